@@ -1,0 +1,31 @@
+// hpgb_host.h -- internal interface between the C-ABI entry points (hpgb_kernels.cu) and the
+// chunked host pipeline (hpgb_host.cu).
+#ifndef HPGB_HOST_H
+#define HPGB_HOST_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <functional>
+
+#include "../../include/hpgb.h"
+
+#define HPGB_PIPE_SLOTS 3
+#define HPGB_PIPE_MAX_ARR 8
+
+// one operand of a host-pointer call: h_in != NULL -> copied to the device before the kernel,
+// h_out != NULL -> copied back after it; bytes_per_point = bytes this operand holds per point
+struct hpgb_pipe_arr {
+    const char *h_in;
+    char *h_out;
+    int64_t bytes_per_point;
+};
+
+// launch(device pointers in operand order, global index of the chunk's first point, points in
+// the chunk, device status, stream) -> HPGB_* code
+typedef std::function<int(void **, int64_t, int64_t, hpgb_status_t *, cudaStream_t)> hpgb_pipe_launch;
+
+int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int narr,
+                       const hpgb_pipe_launch &launch, int64_t *first_bad);
+
+#endif

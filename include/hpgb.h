@@ -1,0 +1,156 @@
+/*
+ * hpgb.h -- C ABI of libhpgb.so, the B200 (sm_100a) implementation of hpgeom's elementwise
+ * HEALPix conversion path.
+ *
+ * This is the drop-in boundary.  The reference has no C ABI of its own for this path: it
+ * exports 15 CPython methods (reference hpgeom/hpgeom.c:3898-3929) whose per-element loops
+ * call scalar cores declared in hpgeom/healpix_geom.h:64-129.  Each entry point below replaces
+ * one of those method bodies (loop + scalar core); the comment above it cites the method.
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / numpy / CUDA types in the signatures
+ *    (`stream` is a cudaStream_t passed as void*; NULL = the legacy default stream);
+ *  - arrays are structure-of-arrays, C-contiguous, int64 / float64, n elements; row outputs
+ *    ((n,8) neighbours, (n,4) interpolation) are row-major;
+ *  - `nside_v` is NULL for a scalar nside (the fast, templated path) or a device array of n
+ *    per-element nside values (the reference broadcasts nside against the data);
+ *  - hpgb_<fn>()      : DEVICE pointers, asynchronous on `stream`, no allocation, no sync;
+ *  - hpgb_host_<fn>() : HOST pointers (pinned or pageable); runs a chunked, multi-stream
+ *    H2D -> kernel -> D2H pipeline on `device` and returns when the outputs are complete;
+ *  - return value: HPGB_OK, an HPGB_E_* argument error, or 1000 + cudaError_t;
+ *  - element errors (the reference's ValueError checks) never trap: the kernel writes -1 / NaN
+ *    for the offending element and records the SMALLEST failing element index with atomicMin
+ *    in `status->first_bad` (device memory, see hpgb_status_reset), so "first bad element wins"
+ *    exactly like the reference's sequential loop (hpgeom/hpgeom.c:309-316).  The caller then
+ *    formats the reference's message for that one element with hpgb_explain_*().
+ */
+#ifndef HPGB_H
+#define HPGB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPGB_OK 0
+#define HPGB_E_NSIDE_NOT_POSITIVE 1 /* hpgeom/hpgeom_utils.c:30-33 */
+#define HPGB_E_NSIDE_NOT_POW2 2     /* hpgeom/hpgeom_utils.c:35-38 */
+#define HPGB_E_NSIDE_TOO_LARGE 3    /* hpgeom/hpgeom_utils.c:40-44 */
+#define HPGB_E_BAD_ARGUMENT 4
+#define HPGB_E_NO_DEVICE 5
+#define HPGB_E_CUDA 1000 /* + cudaError_t */
+
+#define HPGB_NO_BAD_ELEMENT 0xFFFFFFFFFFFFFFFFull
+
+/* element error classes reported by hpgb_explain_* (reference message templates:
+ * hpgeom/hpgeom_utils.c:31,36,41,52,56,66,132,134) */
+#define HPGB_BAD_NONE 0
+#define HPGB_BAD_NSIDE_NOT_POSITIVE 1
+#define HPGB_BAD_NSIDE_NOT_POW2 2
+#define HPGB_BAD_NSIDE_TOO_LARGE 3
+#define HPGB_BAD_THETA 4
+#define HPGB_BAD_PHI 5
+#define HPGB_BAD_LAT 6
+#define HPGB_BAD_PIXEL 7
+
+typedef struct hpgb_status {
+    unsigned long long first_bad; /* smallest failing element index, or HPGB_NO_BAD_ELEMENT */
+} hpgb_status_t;
+
+/* library / device management */
+int hpgb_version(void);
+int hpgb_device_count(void);
+const char *hpgb_error_string(int code);
+/* async memset of *d_status to "no bad element" */
+int hpgb_status_reset(hpgb_status_t *d_status, void *stream);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t hpgb_launch_count(void);
+/* free the cached device scratch / streams used by the hpgb_host_* entry points */
+int hpgb_host_release(void);
+/* pinned host memory for callers that want zero staging in hpgb_host_* */
+int hpgb_pinned_alloc(void **ptr, int64_t bytes);
+int hpgb_pinned_free(void *ptr);
+
+/* ---- nest_to_ring / ring_to_nest: hpgeom/hpgeom.c:1406-1653, :1676-1927 ------------------ */
+int hpgb_nest_to_ring(const int64_t *d_nest, int64_t *d_ring, int64_t n, int64_t nside,
+                      const int64_t *d_nside_v, hpgb_status_t *d_status, void *stream);
+int hpgb_ring_to_nest(const int64_t *d_ring, int64_t *d_nest, int64_t n, int64_t nside,
+                      const int64_t *d_nside_v, hpgb_status_t *d_status, void *stream);
+int hpgb_host_nest_to_ring(const int64_t *nest, int64_t *ring, int64_t n, int64_t nside,
+                           const int64_t *nside_v, int device, int64_t *first_bad);
+int hpgb_host_ring_to_nest(const int64_t *ring, int64_t *nest, int64_t n, int64_t nside,
+                           const int64_t *nside_v, int device, int64_t *first_bad);
+
+/* ---- angle_to_pixel: hpgeom/hpgeom.c:101-380 ---------------------------------------------- */
+int hpgb_angle_to_pixel(const double *d_a, const double *d_b, int64_t *d_pix, int64_t n,
+                        int64_t nside, const int64_t *d_nside_v, int nest, int lonlat, int degrees,
+                        hpgb_status_t *d_status, void *stream);
+int hpgb_host_angle_to_pixel(const double *a, const double *b, int64_t *pix, int64_t n,
+                             int64_t nside, const int64_t *nside_v, int nest, int lonlat,
+                             int degrees, int device, int64_t *first_bad);
+
+/* ---- pixel_to_angle: hpgeom/hpgeom.c:401-676 ---------------------------------------------- */
+int hpgb_pixel_to_angle(const int64_t *d_pix, double *d_a, double *d_b, int64_t n, int64_t nside,
+                        const int64_t *d_nside_v, int nest, int lonlat, int degrees,
+                        hpgb_status_t *d_status, void *stream);
+int hpgb_host_pixel_to_angle(const int64_t *pix, double *a, double *b, int64_t n, int64_t nside,
+                             const int64_t *nside_v, int nest, int lonlat, int degrees, int device,
+                             int64_t *first_bad);
+
+/* ---- vector_to_pixel / pixel_to_vector: hpgeom/hpgeom.c:2298-2566, :2592-2866 -------------- */
+int hpgb_vector_to_pixel(const double *d_x, const double *d_y, const double *d_z, int64_t *d_pix,
+                         int64_t n, int64_t nside, const int64_t *d_nside_v, int nest,
+                         hpgb_status_t *d_status, void *stream);
+int hpgb_pixel_to_vector(const int64_t *d_pix, double *d_x, double *d_y, double *d_z, int64_t n,
+                         int64_t nside, const int64_t *d_nside_v, int nest,
+                         hpgb_status_t *d_status, void *stream);
+int hpgb_host_vector_to_pixel(const double *x, const double *y, const double *z, int64_t *pix,
+                              int64_t n, int64_t nside, const int64_t *nside_v, int nest,
+                              int device, int64_t *first_bad);
+int hpgb_host_pixel_to_vector(const int64_t *pix, double *x, double *y, double *z, int64_t n,
+                              int64_t nside, const int64_t *nside_v, int nest, int device,
+                              int64_t *first_bad);
+
+/* ---- neighbors: hpgeom/hpgeom.c:2889-3184; out is (n,8) row-major, order SW,W,NW,N,NE,E,SE,S */
+int hpgb_neighbors(const int64_t *d_pix, int64_t *d_out_n8, int64_t n, int64_t nside,
+                   const int64_t *d_nside_v, int nest, hpgb_status_t *d_status, void *stream);
+int hpgb_host_neighbors(const int64_t *pix, int64_t *out_n8, int64_t n, int64_t nside,
+                        const int64_t *nside_v, int nest, int device, int64_t *first_bad);
+
+/* ---- get_interpolation_weights: hpgeom/hpgeom.c:3464-3777; (n,4) pixels + (n,4) weights ---- */
+int hpgb_interp_weights(const double *d_a, const double *d_b, int64_t *d_pix_n4, double *d_wgt_n4,
+                        int64_t n, int64_t nside, const int64_t *d_nside_v, int nest, int lonlat,
+                        int degrees, hpgb_status_t *d_status, void *stream);
+int hpgb_host_interp_weights(const double *a, const double *b, int64_t *pix_n4, double *wgt_n4,
+                             int64_t n, int64_t nside, const int64_t *nside_v, int nest,
+                             int lonlat, int degrees, int device, int64_t *first_bad);
+
+/* ---- upgrade_pixels: hpgeom/hpgeom.py:515-556 (+ pixel_ranges_to_pixels, hpgeom.c:3795-3896,
+ * for the equal-length ranges upgrade_pixels produces); out holds n*(nside_upgrade/nside)^2 ---- */
+int hpgb_upgrade_pixels(const int64_t *d_pix, int64_t *d_out, int64_t n, int64_t nside,
+                        int64_t nside_upgrade, int nest, hpgb_status_t *d_status, void *stream);
+int hpgb_host_upgrade_pixels(const int64_t *pix, int64_t *out, int64_t n, int64_t nside,
+                             int64_t nside_upgrade, int nest, int device, int64_t *first_bad);
+
+/* ---- lonlat_to_thetaphi: hpgeom/hpgeom.py:60-88 (numpy formula, not the C one) ------------- */
+int hpgb_lonlat_to_thetaphi(const double *d_lon, const double *d_lat, double *d_theta,
+                            double *d_phi, int64_t n, int degrees, hpgb_status_t *d_status,
+                            void *stream);
+int hpgb_host_lonlat_to_thetaphi(const double *lon, const double *lat, double *theta, double *phi,
+                                 int64_t n, int degrees, int device, int64_t *first_bad);
+
+/* ---- error text for ONE element (host side, pure functions) -------------------------------
+ * Re-evaluates the reference's checks in the reference's order for the element the kernel
+ * flagged and writes the reference's message (at most `cap` bytes, NUL terminated).
+ * Returns the HPGB_BAD_* class (HPGB_BAD_NONE if the element is in fact valid). */
+int hpgb_explain_nside(int64_t nside, int nest, char *msg, int cap);
+int hpgb_explain_angle(int64_t nside, int nest, double a, double b, int lonlat, int degrees,
+                       char *msg, int cap);
+int hpgb_explain_pixel(int64_t nside, int nest, int64_t pix, char *msg, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPGB_H */

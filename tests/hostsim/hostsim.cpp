@@ -1,0 +1,52 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the per-element device functions of hpgeom_b200/csrc (hpgb_core.h, hpgb_math.h,
+// hpgb_fp.h -- all `__host__ __device__`) with g++ and exposes array loops over them, so the
+// bit-level logic of the CUDA kernels can be checked against the oracle in the `-m "not gpu"`
+// test tier (no GPU in the authoring container).  Built with -ffp-contract=off: fused
+// operations happen only where the device code calls fma() explicitly, exactly as under
+// nvcc -fmad=false.  The product (hpgeom_b200) never loads this library.
+#include <stdint.h>
+
+#include "../../hpgeom_b200/csrc/hpgb_core.h"
+#if __has_include("../../hpgeom_b200/csrc/hpgb_fp.h")
+#include "../../hpgeom_b200/csrc/hpgb_fp.h"
+#define HAVE_FP 1
+#endif
+
+extern "C" {
+
+int64_t sim_nest_to_ring(int64_t nside, const int64_t *in, int64_t n, int64_t *out) {
+    hpgb_geom g = hpgb_make_geom(nside, 1);
+    for (int64_t i = 0; i < n; i++) {
+        if (!hpgb_pixel_ok(g, in[i])) return i;
+        out[i] = hpgb_nest2ring(g, in[i]);
+    }
+    return -1;
+}
+
+int64_t sim_ring_to_nest(int64_t nside, const int64_t *in, int64_t n, int64_t *out) {
+    hpgb_geom g = hpgb_make_geom(nside, 1);
+    for (int64_t i = 0; i < n; i++) {
+        if (!hpgb_pixel_ok(g, in[i])) return i;
+        out[i] = hpgb_ring2nest(g, in[i]);
+    }
+    return -1;
+}
+
+// ring -> (ix,iy,face) -> ring through the general-nside path (non powers of two)
+int64_t sim_ring_roundtrip_any(int64_t nside, const int64_t *in, int64_t n, int64_t *out) {
+    hpgb_geom g = hpgb_make_geom(nside, 0);
+    for (int64_t i = 0; i < n; i++) {
+        int32_t ix, iy;
+        uint32_t f;
+        hpgb_ring2xyf_any(g, in[i], ix, iy, f);
+        out[i] = hpgb_xyf2ring(g, ix, iy, f);
+    }
+    return -1;
+}
+
+#ifdef HAVE_FP
+#include "hostsim_fp.inc"
+#endif
+}

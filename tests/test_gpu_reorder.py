@@ -1,0 +1,113 @@
+"""nest_to_ring / ring_to_nest on the GPU, through the public API (which calls the C ABI),
+bit-exact against the oracle, the golden vectors and the round-trip invariant at full size."""
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal, load_golden
+
+pytestmark = pytest.mark.gpu
+
+POW2 = [1, 2, 4, 32, 1024, 4096, 2 ** 20, 2 ** 29]
+
+
+@pytest.fixture(scope="module")
+def hpg():
+    import hpgeom_b200
+    return hpgeom_b200
+
+
+@pytest.mark.parametrize("nside", POW2)
+def test_golden(hpg, nside):
+    g = load_golden("nest_ring")
+    pix = g["pix_%d" % nside]
+    assert_bit_equal(hpg.nest_to_ring(nside, pix), g["n2r_%d" % nside], "n2r")
+    assert_bit_equal(hpg.ring_to_nest(nside, pix), g["r2n_%d" % nside], "r2n")
+
+
+@pytest.mark.parametrize("nside", [1, 2, 8, 64, 256])
+def test_all_pixels(hpg, oracle_port, nside):
+    pix = np.arange(12 * nside * nside, dtype=np.int64)
+    assert_bit_equal(hpg.nest_to_ring(nside, pix), oracle_port.nest_to_ring(nside, pix))
+    assert_bit_equal(hpg.ring_to_nest(nside, pix), oracle_port.ring_to_nest(nside, pix))
+
+
+@pytest.mark.parametrize("nside", [2 ** 10, 2 ** 15, 2 ** 25, 2 ** 29])
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 1_000_003])
+def test_random_vs_oracle(hpg, oracle_port, nside, n):
+    rng = np.random.default_rng(nside + n)
+    pix = rng.integers(0, 12 * nside * nside, n)
+    assert_bit_equal(hpg.nest_to_ring(nside, pix), oracle_port.nest_to_ring(nside, pix))
+    assert_bit_equal(hpg.ring_to_nest(nside, pix), oracle_port.ring_to_nest(nside, pix))
+
+
+def test_torch_device_resident(hpg, oracle_port):
+    import torch
+    nside = 2 ** 29
+    rng = np.random.default_rng(5)
+    pix = rng.integers(0, 12 * nside * nside, 500_001)
+    t = torch.from_numpy(pix).cuda()
+    out = hpg.nest_to_ring(nside, t)
+    assert out.is_cuda and out.dtype == torch.int64
+    assert_bit_equal(out.cpu().numpy(), oracle_port.nest_to_ring(nside, pix))
+    # misaligned view (pointer not 16-byte aligned) takes the scalar kernel
+    out2 = hpg.nest_to_ring(nside, t[1:])
+    assert_bit_equal(out2.cpu().numpy(), oracle_port.nest_to_ring(nside, pix[1:]))
+    # int32 input is safely cast
+    small = torch.arange(0, 48, dtype=torch.int32).cuda()
+    assert_bit_equal(hpg.ring_to_nest(2, small).cpu().numpy(), oracle_port.ring_to_nest(2, np.arange(48)))
+
+
+def test_shapes_and_scalars(hpg):
+    out = hpg.nest_to_ring(1024, 5)
+    assert not isinstance(out, np.ndarray) and out.dtype == np.int64
+    pix = np.arange(24).reshape(2, 3, 4)
+    assert hpg.nest_to_ring(1024, pix).shape == (2, 3, 4)
+    assert hpg.nest_to_ring(1024, np.zeros(0, dtype=np.int64)).shape == (0,)
+    # nside broadcast against the data
+    ns = np.array([1, 2, 4, 8])
+    out = hpg.ring_to_nest(ns, 3)
+    assert out.shape == (4,)
+    for k, n_ in enumerate(ns):
+        assert out[k] == hpg.ring_to_nest(int(n_), 3)
+    with pytest.raises(ValueError, match=r"arrays could not be broadcast together"):
+        hpg.nest_to_ring(np.array([1024, 2048, 4096]), np.zeros(2, dtype=np.int64))
+    with pytest.raises(TypeError):
+        hpg.nest_to_ring(1024, np.array([0.5]))
+
+
+def test_errors(hpg):
+    with pytest.raises(ValueError, match=r"nside .* must be positive"):
+        hpg.nest_to_ring(0, 1)
+    with pytest.raises(ValueError, match=r"nside .* must be power of 2"):
+        hpg.ring_to_nest(1000, 1)
+    with pytest.raises(ValueError, match=r"nside .* must not be greater"):
+        hpg.ring_to_nest(2 ** 30, 1)
+    with pytest.raises(ValueError, match=r"Pixel value -7 out of range for nside 1024"):
+        hpg.nest_to_ring(1024, np.array([1, 2, -7, 12 * 1024 * 1024]))
+    with pytest.raises(ValueError, match=r"Pixel value 12582912 out of range for nside 1024"):
+        hpg.ring_to_nest(1024, 12 * 1024 * 1024)
+    # first bad element wins even when it sits in a late chunk / other bad ones follow
+    pix = np.zeros(3_000_000, dtype=np.int64)
+    pix[2_500_000] = -3
+    pix[2_900_000] = -4
+    with pytest.raises(ValueError, match=r"Pixel value -3 out of range"):
+        hpg.nest_to_ring(1024, pix)
+    # per-element nside: a bad nside is reported for its element
+    with pytest.raises(ValueError, match=r"nside 1000 must be power of 2"):
+        hpg.nest_to_ring(np.array([1024, 1000]), np.array([1, 1]))
+
+
+def test_full_size_round_trip(hpg):
+    """BASELINE config 3: nside=2^29, 1B random pixels, round trip is the identity."""
+    import torch
+    nside = 2 ** 29
+    n = 1 << 30
+    g = torch.Generator(device="cuda").manual_seed(12345)
+    pix = torch.randint(0, 12 * nside * nside, (n,), dtype=torch.int64, device="cuda", generator=g)
+    ring = hpg.nest_to_ring(nside, pix)
+    assert int(ring.min()) >= 0 and int(ring.max()) < 12 * nside * nside
+    back = hpg.ring_to_nest(nside, ring)
+    assert torch.equal(back, pix)
+    del back
+    nest = hpg.ring_to_nest(nside, pix)
+    assert torch.equal(hpg.nest_to_ring(nside, nest), pix)
