@@ -23,7 +23,7 @@
 
 #if defined(__CUDACC__)
 #define HPGB_HD __host__ __device__ __forceinline__
-#define HPGB_HD_NOINLINE __host__ __device__ __noinline__
+#define HPGB_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define HPGB_HD static inline
 #define HPGB_HD_NOINLINE static
@@ -197,7 +197,7 @@ HPGB_HD uint32_t hpgb_special_div(int64_t a, int64_t b) {
 
 // RING pixel -> (face, ix, iy), hpgeom/healpix_geom.c:410-454, general nside (RING allows
 // non-powers of two): 64-bit arithmetic and true divisions, as the reference.
-HPGB_HD void hpgb_ring2xyf_any(const hpgb_geom &g, int64_t pix, int32_t &ix, int32_t &iy, uint32_t &face) {
+HPGB_HD_NOINLINE void hpgb_ring2xyf_any(const hpgb_geom &g, int64_t pix, int32_t &ix, int32_t &iy, uint32_t &face) {
     const int64_t ns = g.nside;
     int64_t iring, iphi, nr;
     uint32_t kshift, f;
@@ -234,6 +234,11 @@ HPGB_HD void hpgb_ring2xyf_any(const hpgb_geom &g, int64_t pix, int32_t &ix, int
 // Same for nside = 2^k: after the ring / in-ring split everything fits 32 bits.  ipt = ix - iy
 // is only needed modulo 8 nside (the reference's "if (ipt >= nl2) ipt -= 8*nside"), and 8 nside
 // divides 2^32, so it is computed mod 2^32 and sign-extended from bit k+2.
+//
+// The reference's isqrt has no correction step (hpgeom/healpix_geom.c:60): for 2*ip-1 > 2^53
+// the int64 -> double rounding can push the last few pixels of a large cap ring into the next
+// ring (in-ring offset < 1 or > 4*ring).  Those pixels must reproduce the reference's int64
+// arithmetic exactly, so they take the general path (rare: ~1e-8 of cap pixels at nside 2^29).
 HPGB_HD void hpgb_ring2xyf_p2(const hpgb_geom &g, int64_t pix, int32_t &ix, int32_t &iy, uint32_t &face) {
     const uint32_t ns = (uint32_t)g.nside;
     const int k = g.order;
@@ -242,11 +247,16 @@ HPGB_HD void hpgb_ring2xyf_p2(const hpgb_geom &g, int64_t pix, int32_t &ix, int3
         const bool north = pix < g.ncap;
         const int64_t ip = north ? pix + 1 : g.npix - pix;
         const uint32_t ir = (uint32_t)((1 + hpgb_isqrt(2 * ip - 1)) >> 1);
-        const uint32_t off = (uint32_t)((uint64_t)ip - 2u * ((uint64_t)ir * (uint64_t)(ir - 1u)));
+        const int64_t off64 = ip - 2 * (int64_t)((uint64_t)ir * (uint64_t)(ir - 1u));
+        if (off64 < 1 || off64 > 4 * (int64_t)ir) {
+            hpgb_ring2xyf_any(g, pix, ix, iy, face);
+            return;
+        }
+        const uint32_t off = (uint32_t)off64;
         iphi = north ? off : 4u * ir + 1u - off;
         kshift = 0u;
         nr = ir;
-        uint32_t a = iphi - 1u;  // special_div(iphi - 1, nr), hpgeom/healpix_geom.c:102-106
+        uint32_t a = iphi - 1u;  // special_div(iphi - 1, nr), hpgeom/healpix_geom.c:102-106; 0 <= a < 4 nr
         const uint32_t t = (a >= 2u * ir) ? 1u : 0u;
         a -= t ? 2u * ir : 0u;
         f = 2u * t + ((a >= ir) ? 1u : 0u) + (north ? 0u : 8u);

@@ -1,0 +1,589 @@
+// hpgb_fp.h -- floating-point per-element cores: angle <-> pixel, vector <-> pixel,
+// interpolation weights, neighbours.  `__host__ __device__` like hpgb_core.h.
+//
+// Parity rules: every +,-,*,/,sqrt,fmod below is a single IEEE operation in the
+// reference's order (the translation units are compiled with implicit FMA contraction off);
+// cos/sin/acos/atan2 come from hpgb_math.h (correctly rounded in practice, which is what the
+// reference's glibc returns for ~99.9 % of arguments).
+#ifndef HPGB_FP_H
+#define HPGB_FP_H
+
+#include "hpgb_core.h"
+#include "hpgb_math.h"
+
+// same decimal literals as hpgeom/healpix_geom.h:31-36
+#define HPGB_PI 3.141592653589793238462643383279502884197
+#define HPGB_TWOPI 6.283185307179586476925286766559005768394
+#define HPGB_HALFPI 1.570796326794896619231321691639751442099
+#define HPGB_INV_HALFPI 0.6366197723675813430755350534900574
+
+// double -> int64 the way C's cast does for in-range values (truncation)
+HPGB_HD int64_t hpgb_d2ll(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2ll_rz(v);
+#else
+    return (int64_t)v;
+#endif
+}
+
+// hpgeom/healpix_geom.c:112-117
+HPGB_HD double hpgb_fmodulo(double v1, double v2) {
+    if (v1 >= 0) return (v1 < v2) ? v1 : fmod(v1, v2);
+    const double t = fmod(v1, v2) + v2;
+    return (t == v2) ? 0. : t;
+}
+
+// Input angles -> (theta, phi), with the reference's range checks.
+// hpgeom/hpgeom_utils.c:119-143 (lonlat) and :48-60 (theta/phi).  Returns true when valid.
+template <bool LONLAT, bool DEGREES>
+HPGB_HD bool hpgb_angles_exact(double a, double b, double &theta, double &phi) {
+    if (LONLAT) {
+        double lon = a, lat = b;
+        if (DEGREES) {
+            lon = hpgb_fmodulo((lon * HPGB_PI) / 180.0, HPGB_TWOPI);
+            lat = (lat * HPGB_PI) / 180.0;
+        } else {
+            lon = hpgb_fmodulo(lon, HPGB_TWOPI);
+        }
+        if (lat < -HPGB_HALFPI || lat > HPGB_HALFPI) return false;
+        phi = lon;
+        theta = -lat + HPGB_HALFPI;
+        return true;
+    }
+    theta = a;
+    phi = b;
+    if (a < 0.0 || a > HPGB_PI) return false;
+    if (b < 0 || b > HPGB_TWOPI) return false;
+    return true;
+}
+
+// (z, phi, sin theta) -> pixel: hpgeom/healpix_geom.c:229-302, operation for operation.
+template <bool NEST>
+HPGB_HD int64_t hpgb_loc2pix_exact(const hpgb_geom &g, double z, double phi, double sth, bool have_sth) {
+    const double za = fabs(z);
+    const double tt = hpgb_fmodulo(phi * HPGB_INV_HALFPI, 4.0);
+    const int64_t ns = g.nside;
+    const double dns = (double)ns;
+    if (!NEST) {
+        if (za <= 2.0 / 3.0) {
+            const int64_t nl4 = 4 * ns;
+            const double t1 = dns * (0.5 + tt);
+            const double t2 = dns * z * 0.75;
+            const int64_t jp = hpgb_d2ll(t1 - t2);
+            const int64_t jm = hpgb_d2ll(t1 + t2);
+            const int64_t ir = ns + 1 + jp - jm;
+            const int64_t kshift = 1 - (ir & 1);
+            const int64_t u = jp + jm - ns + kshift + 1 + nl4 + nl4;
+            const int64_t ip = (g.order > 0) ? ((u >> 1) & (nl4 - 1)) : ((u >> 1) % nl4);
+            return g.ncap + (ir - 1) * nl4 + ip;
+        }
+        const double tp = tt - (double)hpgb_d2ll(tt);
+        const double tmp = ((za < 0.99) || (!have_sth)) ? dns * sqrt(3 * (1 - za)) : dns * sth / sqrt((1. + za) / 3.);
+        const int64_t jp = hpgb_d2ll(tp * tmp);
+        const int64_t jm = hpgb_d2ll((1.0 - tp) * tmp);
+        const int64_t ir = jp + jm + 1;
+        const int64_t ip = hpgb_d2ll(tt * (double)ir);
+        return (z > 0.) ? 2 * ir * (ir - 1) + ip : g.npix - 2 * ir * (ir + 1) + ip;
+    }
+    if (za <= 2.0 / 3.0) {
+        const double t1 = dns * (0.5 + tt);
+        const double t2 = dns * (z * 0.75);
+        const int64_t jp = hpgb_d2ll(t1 - t2);
+        const int64_t jm = hpgb_d2ll(t1 + t2);
+        const int64_t ifp = jp >> g.order;
+        const int64_t ifm = jm >> g.order;
+        const uint32_t face = (uint32_t)((ifp == ifm) ? (ifp | 4) : ((ifp < ifm) ? ifp : (ifm + 8)));
+        const uint32_t ix = (uint32_t)(jm & (ns - 1));
+        const uint32_t iy = (uint32_t)(ns - (jp & (ns - 1)) - 1);
+        return hpgb_xyf2nest(g.order, ix, iy, face);
+    }
+    int ntt = (int)tt;
+    if (ntt >= 4) ntt = 3;
+    const double tp = tt - ntt;
+    const double tmp = ((za < 0.99) || (!have_sth)) ? dns * sqrt(3 * (1 - za)) : dns * sth / sqrt((1. + za) / 3.);
+    int64_t jp = hpgb_d2ll(tp * tmp);
+    int64_t jm = hpgb_d2ll((1.0 - tp) * tmp);
+    if (jp >= ns) jp = ns - 1;
+    if (jm >= ns) jm = ns - 1;
+    return (z >= 0) ? hpgb_xyf2nest(g.order, (uint32_t)(ns - jm - 1), (uint32_t)(ns - jp - 1), (uint32_t)ntt)
+                    : hpgb_xyf2nest(g.order, (uint32_t)jp, (uint32_t)jm, (uint32_t)(ntt + 8));
+}
+
+// hpgeom/healpix_geom.c:153-159 with the accurate cos/sin
+template <bool NEST>
+HPGB_HD int64_t hpgb_ang2pix_exact(const hpgb_geom &g, const double *T, double theta, double phi) {
+    double s, c;
+    hpgb_sincos_cr(T, theta, s, c);
+    if ((theta < 0.01) || (theta > 3.14159 - 0.01)) return hpgb_loc2pix_exact<NEST>(g, c, phi, 0.0, false);
+    return hpgb_loc2pix_exact<NEST>(g, c, phi, s, true);
+}
+
+// Full reference semantics for one (a, b): checks + conversion.  Returns false for a bad element.
+template <bool NEST, bool LONLAT, bool DEGREES>
+HPGB_HD_NOINLINE bool hpgb_angle_to_pixel_exact(const hpgb_geom &g, const double *T, double a, double b,
+                                                int64_t &pix) {
+    double theta, phi;
+    if (!hpgb_angles_exact<LONLAT, DEGREES>(a, b, theta, phi)) {
+        pix = -1;
+        return false;
+    }
+    pix = hpgb_ang2pix_exact<NEST>(g, T, theta, phi);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// angle_to_pixel, NEST, fast path.
+//
+// The pixel index is a step function of the angles; away from the steps it does not care about
+// the last bits of cos(theta).  The fast path therefore uses cheap, branch-free fp64 (~35 fp64
+// pipe operations per point: no division, no sqrt, no full-range cos/sin) with ~1e-15 relative
+// error, keeps the two edge-line coordinates in fixed point, and hands the point to the exact
+// path above only when a coordinate is within `margin` of an integer (a pixel edge) or a
+// discrete decision (equatorial/polar split, face boundary, range check) is closer than its
+// guard band.  margin = nside * 2^-44 covers the fast path's error AND the reference's own
+// rounding noise (its sqrt(3(1-|z|)) amplifies a half-ulp error of cos up to 2^-48 relative),
+// so fast result == exact-path result whenever the fast result is kept.  The exact path is
+// taken for ~1e-4 of uniformly distributed points at nside 2^29 (less at smaller nside).
+//
+// shortcuts ("z and phi shortcuts" of the design):
+//   equatorial |z| <= 2/3 : z = sin(lat)                    (odd polynomial, |lat| <= 0.73)
+//   polar caps            : nside*sqrt(3(1-|z|)) = nside*sqrt(6)*sin(c/2), c = colatitude from the
+//                           nearest pole (same polynomial, argument <= 0.42; no cancellation)
+//   tt = phi*2/pi mod 4   : lon/90 mod 4 directly in degrees
+// ---------------------------------------------------------------------------------------------
+#define HPGB_ASIN_2_3 0.72972765622696636345479665981332  // asin(2/3)
+
+HPGB_HD double hpgb_sin_poly(double a) {  // |a| <= 0.74, error < 1 ulp
+    const double a2 = a * a;
+    double p = fma(a2, -7.6471637318198164759e-13, 1.6059043836821614599e-10);  // -1/15!, 1/13!
+    p = fma(p, a2, -2.5052108385441718775e-8);                                   // -1/11!
+    p = fma(p, a2, 2.7557319223985890653e-6);                                    //  1/9!
+    p = fma(p, a2, -1.9841269841269841270e-4);                                   // -1/7!
+    p = fma(p, a2, 8.3333333333333333333e-3);                                    //  1/5!
+    p = fma(p, a2, -1.6666666666666666667e-1);                                   // -1/3!
+    return fma(a * a2, p, a);
+}
+
+HPGB_HD uint32_t hpgb_hi32(double v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2hiint(v);
+#else
+    union {
+        double d;
+        uint64_t u;
+    } c;
+    c.d = v;
+    return (uint32_t)(c.u >> 32);
+#endif
+}
+
+// per-nside constants of the fast path (host-computed, passed by value with the geometry)
+struct hpgb_a2p_fast {
+    double ns_half;     // 0.5  * nside
+    double ns_075;      // 0.75 * nside
+    double ns_sqrt6;    // sqrt(6) * nside
+    double scale;       // 2^F, F = 58 - order : fixed-point scale of the edge-line coordinates
+    int32_t fbits;      // F
+    int32_t enabled;    // 0 -> always take the exact path (tiny nside)
+};
+
+HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
+    hpgb_a2p_fast f;
+    const double dns = (double)g.nside;
+    f.ns_half = 0.5 * dns;
+    f.ns_075 = 0.75 * dns;
+    f.ns_sqrt6 = 2.4494897427831780981972840747059 * dns;
+    f.fbits = 58 - g.order;
+    f.scale = ldexp(1.0, f.fbits);
+    f.enabled = (g.order >= 0);
+    return f;
+}
+
+// returns true when `pix` is final; false -> caller must run the exact path
+template <bool LONLAT, bool DEGREES>
+HPGB_HD bool hpgb_angle_to_pixel_nest_fast(const hpgb_geom &g, const hpgb_a2p_fast &f, double a, double b,
+                                           int64_t &pix) {
+    // ---- latitude (radians, signed), colatitude from the nearest pole, tt in [0,4) ----
+    double lat, cth, tt;
+    bool guard;
+    if (LONLAT) {
+        if (DEGREES) {
+            lat = b * 1.7453292519943295769e-2;                        // pi/180
+            cth = (90.0 - fabs(b)) * 1.7453292519943295769e-2;         // exact difference
+            const double t = a * 1.1111111111111111111e-2;             // lon/90
+            tt = fma(-4.0, floor(t * 0.25), t);
+            guard = !(fabs(b) < 89.999999) || !(fabs(a) <= 720.0);
+        } else {
+            lat = b;
+            cth = (HPGB_PIO2_1 - fabs(b)) + HPGB_PIO2_2;
+            const double t = a * HPGB_INV_HALFPI;
+            tt = fma(-4.0, floor(t * 0.25), t);
+            guard = !(fabs(b) < 1.5707963) || !(fabs(a) <= 12.5);
+        }
+    } else {
+        lat = (HPGB_PIO2_1 - a) + HPGB_PIO2_2;  // pi/2 - theta, accurate also near the equator
+        cth = (a < HPGB_PIO2_1) ? a : (HPGB_PI_1 - a) + HPGB_PI_2;
+        tt = b * HPGB_INV_HALFPI;               // the reference's own expression
+        guard = !(a > 1e-8 && a < 3.14159265) || !(b >= 0.0 && b < 6.2831853);
+    }
+    const double al = fabs(lat);
+    const bool eq = al <= HPGB_ASIN_2_3;
+    guard = guard || (fabs(al - HPGB_ASIN_2_3) < 1e-11);
+    // tt + 4 has a fixed exponent: its mantissa is tt in fixed point (face index + fraction)
+    const uint32_t thi = hpgb_hi32(tt + 4.0);
+    const uint32_t ntt = (thi >> 18) & 3u;
+    guard = guard || (((thi + 1u) & 0x3FFFFu) < 2u);  // tt within 2^-18 of an integer (face edge / wrap)
+    const double tp = tt - (double)(int32_t)ntt;
+    // ---- one sine for both branches ----
+    const double s = hpgb_sin_poly(eq ? lat : 0.5 * cth);
+    // ---- edge-line coordinates ----
+    const double t1 = fma(2.0 * f.ns_half, tt, f.ns_half);  // nside*(0.5+tt)
+    const double t2 = f.ns_075 * s;
+    const double tmp = f.ns_sqrt6 * s;
+    const double p1 = tp * tmp;
+    const double q1 = eq ? (t1 - t2) : p1;
+    const double q2 = eq ? (t1 + t2) : (tmp - p1);
+    const int64_t x1 = hpgb_d2ll(q1 * f.scale);
+    const int64_t x2 = hpgb_d2ll(q2 * f.scale);
+    const int64_t fmask = ((int64_t)1 << f.fbits) - 1;
+    const int64_t M = (int64_t)1 << 14;  // nside * 2^-44 in fixed-point units
+    guard = guard || (((x1 + M) & fmask) < 2 * M) || (((x2 + M) & fmask) < 2 * M);
+    const uint32_t j1 = (uint32_t)(x1 >> f.fbits), j2 = (uint32_t)(x2 >> f.fbits);
+    const uint32_t ns = (uint32_t)g.nside, nsm1 = ns - 1u;
+    uint32_t ix, iy, face;
+    if (eq) {
+        const uint32_t ifp = j1 >> g.order, ifm = j2 >> g.order;
+        face = (ifp == ifm) ? (ifp | 4u) : ((ifp < ifm) ? ifp : (ifm + 8u));
+        ix = j2 & nsm1;
+        iy = nsm1 - (j1 & nsm1);
+    } else {
+        const uint32_t jp = j1 < nsm1 ? j1 : nsm1, jm = j2 < nsm1 ? j2 : nsm1;
+        const bool north = lat >= 0.0;
+        ix = north ? nsm1 - jm : jp;
+        iy = north ? nsm1 - jp : jm;
+        face = north ? ntt : ntt + 8u;
+    }
+    pix = hpgb_xyf2nest(g.order, ix, iy, face);
+    return !guard && f.enabled;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pixel -> (z, phi, sin theta): hpgeom/healpix_geom.c:304-380, operation for operation
+// (all IEEE-exact: integer work, int->double conversions, *, /, -, sqrt).
+// ---------------------------------------------------------------------------------------------
+template <bool NEST, bool POW2>
+HPGB_HD void hpgb_pix2loc(const hpgb_geom &g, int64_t pix, double &z, double &phi, double &sth, bool &have_sth) {
+    const int64_t ns = g.nside;
+    have_sth = false;
+    sth = 0.0;
+    if (!NEST) {
+        if (pix < g.ncap || pix >= g.npix - g.ncap) {  // polar caps
+            const bool north = pix < g.ncap;
+            const int64_t ip = north ? pix + 1 : g.npix - pix;
+            const int64_t iring = (1 + hpgb_isqrt(2 * ip - 1)) >> 1;  // from the nearest pole
+            const int64_t off = ip - 2 * iring * (iring - 1);
+            const int64_t iphi = north ? off : 4 * iring + 1 - off;
+            const double t = (double)(iring * iring) * g.fact2;
+            z = north ? 1.0 - t : t - 1.0;
+            if (north ? (z > 0.99) : (z < -0.99)) {
+                sth = sqrt(t * (2. - t));
+                have_sth = true;
+            }
+            phi = ((double)iphi - 0.5) * HPGB_HALFPI / (double)iring;
+        } else {
+            const int64_t nl4 = 4 * ns;
+            const int64_t ip = pix - g.ncap;
+            const int64_t t = POW2 ? (ip >> (g.order + 2)) : ip / nl4;
+            const int64_t iring = t + ns, iphi = ip - nl4 * t + 1;
+            const double fodd = ((iring + ns) & 1) ? 1 : 0.5;
+            z = (double)(2 * ns - iring) * g.fact1;
+            phi = ((double)iphi - fodd) * HPGB_PI * 0.75 * g.fact1;
+        }
+        return;
+    }
+    uint32_t ix, iy, face;
+    hpgb_nest2xyf(g, pix, ix, iy, face);
+    const int64_t jr = ((int64_t)hpgb_jrll(face) << g.order) - (int64_t)ix - (int64_t)iy - 1;
+    int64_t nr;
+    if (jr < ns) {
+        nr = jr;
+        const double t = (double)(nr * nr) * g.fact2;
+        z = 1 - t;
+        if (z > 0.99) {
+            sth = sqrt(t * (2. - t));
+            have_sth = true;
+        }
+    } else if (jr > 3 * ns) {
+        nr = ns * 4 - jr;
+        const double t = (double)(nr * nr) * g.fact2;
+        z = t - 1;
+        if (z < -0.99) {
+            sth = sqrt(t * (2. - t));
+            have_sth = true;
+        }
+    } else {
+        nr = ns;
+        z = (double)(2 * ns - jr) * g.fact1;
+    }
+    int64_t t = (int64_t)hpgb_jpll(face) * nr + (int64_t)ix - (int64_t)iy;
+    if (t < 0) t += 8 * nr;
+    phi = (nr == ns) ? 0.75 * HPGB_HALFPI * (double)t * g.fact1 : (0.5 * HPGB_HALFPI * (double)t) / (double)nr;
+}
+
+// pixel -> angles: hpgeom/healpix_geom.c:172-181 + hpgeom/hpgeom_utils.c:145-165
+template <bool NEST, bool POW2, bool LONLAT, bool DEGREES>
+HPGB_HD void hpgb_pix2ang(const hpgb_geom &g, const double *T, int64_t pix, double &a, double &b) {
+    double z, phi, sth;
+    bool have_sth;
+    hpgb_pix2loc<NEST, POW2>(g, pix, z, phi, sth, have_sth);
+    const double theta = have_sth ? hpgb_atan2_cr(T, sth, z) : hpgb_acos_cr(T, z);
+    if (LONLAT) {
+        double lon = phi;
+        double lat = -(theta - HPGB_HALFPI);
+        if (DEGREES) {
+            lon *= 180.0 / HPGB_PI;
+            lat *= 180.0 / HPGB_PI;
+        }
+        a = lon;
+        b = lat;
+    } else {
+        a = theta;
+        b = phi;
+    }
+}
+
+// pixel -> unit vector: hpgeom/healpix_geom.c:183-199
+template <bool NEST, bool POW2>
+HPGB_HD void hpgb_pix2vec(const hpgb_geom &g, const double *T, int64_t pix, double &x, double &y, double &zz) {
+    double z, phi, sth;
+    bool have_sth;
+    hpgb_pix2loc<NEST, POW2>(g, pix, z, phi, sth, have_sth);
+    if (!have_sth) sth = sqrt((1 - z) * (1 + z));
+    double s, c;
+    hpgb_sincos_cr(T, phi, s, c);
+    x = sth * c;
+    y = sth * s;
+    zz = z;
+}
+
+// vector -> pixel: hpgeom/healpix_geom.c:161-170 (+ vec3_length, hpgeom/hpgeom_stack.c:396).
+// No validation, as in the reference.  phi = atan2(y, x) is the only libm call.
+template <bool NEST>
+HPGB_HD int64_t hpgb_vec2pix(const hpgb_geom &g, const double *T, double x, double y, double z) {
+    const double len = sqrt(x * x + y * y + z * z);
+    const double xl = 1. / len;
+    const double phi = ((x == 0.) && (y == 0.)) ? 0.0 : hpgb_atan2_any(T, y, x);
+    const double nz = z * xl;
+    if (fabs(nz) > 0.99) return hpgb_loc2pix_exact<NEST>(g, nz, phi, sqrt(x * x + y * y) * xl, true);
+    return hpgb_loc2pix_exact<NEST>(g, nz, phi, 0, false);
+}
+
+// ---------------------------------------------------------------------------------------------
+// neighbours: hpgeom/healpix_geom.c:890-979.  Order SW, W, NW, N, NE, E, SE, S; -1 = none.
+// The reference's face / swap tables are packed into 64-bit words (4 bits per entry) so the
+// lookup is a shift, not a memory access.
+// ---------------------------------------------------------------------------------------------
+template <bool NEST, bool POW2>
+HPGB_HD int64_t hpgb_xyf2pix(const hpgb_geom &g, int32_t ix, int32_t iy, uint32_t face) {
+    return NEST ? hpgb_xyf2nest(g.order, (uint32_t)ix, (uint32_t)iy, face) : hpgb_xyf2ring(g, ix, iy, face);
+}
+
+// nb_facearray[nbnum][face] (hpgeom/healpix_geom.c:892-900), 0xF = -1, nibble `face` of word `nbnum`
+HPGB_HD uint64_t hpgb_nb_face_word(int nb) {
+    switch (nb) {
+        case 0: return 0x98BAFFFFBA98ull;   // S : 8,9,10,11,-1,-1,-1,-1,10,11,8,9
+        case 1: return 0x8BA9BA984765ull;   // SE: 5,6,7,4,8,9,10,11,9,10,11,8
+        case 2: return 0xFFFF4765FFFFull;   // E : -1 x4, 5,6,7,4, -1 x4
+        case 3: return 0xA98BA98B7654ull;   // SW: 4,5,6,7,11,8,9,10,11,8,9,10
+        case 4: return 0xBA9876543210ull;   // centre
+        case 5: return 0x476532100321ull;   // NE: 1,2,3,0,0,1,2,3,5,6,7,4
+        case 6: return 0xFFFF6547FFFFull;   // W : -1 x4, 7,4,5,6, -1 x4
+        case 7: return 0x765421032103ull;   // NW: 3,0,1,2,3,0,1,2,4,5,6,7
+        default: return 0x3210FFFF1032ull;  // N : 2,3,0,1,-1,-1,-1,-1,0,1,2,3
+    }
+}
+// nb_swaparray[nbnum][face>>2] (hpgeom/healpix_geom.c:901-909), 3 nibbles per row
+HPGB_HD uint32_t hpgb_nb_swap(int nb, uint32_t frow) {
+    // rows: S{0,0,3} SE{0,0,6} E{0,0,0} SW{0,0,5} C{0,0,0} NE{5,0,0} W{0,0,0} NW{6,0,0} N{3,0,0}
+    const uint32_t tab[9] = {0x300u, 0x600u, 0x000u, 0x500u, 0x000u, 0x005u, 0x000u, 0x006u, 0x003u};
+    return (tab[nb] >> (4u * frow)) & 7u;
+}
+
+template <bool NEST, bool POW2>
+HPGB_HD void hpgb_neighbors(const hpgb_geom &g, int64_t pix, int64_t *out) {
+    int32_t ix, iy;
+    uint32_t face;
+    if (NEST) {
+        uint32_t ux, uy;
+        hpgb_nest2xyf(g, pix, ux, uy, face);
+        ix = (int32_t)ux;
+        iy = (int32_t)uy;
+    } else {
+        hpgb_ring2xyf<POW2>(g, pix, ix, iy, face);
+    }
+    const int32_t ns = (int32_t)g.nside;
+    const int32_t dx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+    const int32_t dy[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+    if (ix > 0 && ix < ns - 1 && iy > 0 && iy < ns - 1) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) out[m] = hpgb_xyf2pix<NEST, POW2>(g, ix + dx[m], iy + dy[m], face);
+        return;
+    }
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        int32_t x = ix + dx[m], y = iy + dy[m];
+        int nb = 4;
+        if (x < 0) {
+            x += ns;
+            nb--;
+        } else if (x >= ns) {
+            x -= ns;
+            nb++;
+        }
+        if (y < 0) {
+            y += ns;
+            nb -= 3;
+        } else if (y >= ns) {
+            y -= ns;
+            nb += 3;
+        }
+        const uint32_t f = (uint32_t)((hpgb_nb_face_word(nb) >> (4u * face)) & 0xFull);
+        if (f == 0xFu) {
+            out[m] = -1;
+            continue;
+        }
+        const uint32_t bits = hpgb_nb_swap(nb, face >> 2);
+        if (bits & 1u) x = ns - x - 1;
+        if (bits & 2u) y = ns - y - 1;
+        if (bits & 4u) {
+            const int32_t t = x;
+            x = y;
+            y = t;
+        }
+        out[m] = hpgb_xyf2pix<NEST, POW2>(g, x, y, f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear interpolation: hpgeom/healpix_geom.c:504-510 (ring_above), :1585-1606
+// (get_ring_info2), :1608-1690 (get_interpol)
+// ---------------------------------------------------------------------------------------------
+HPGB_HD int64_t hpgb_ring_above(const hpgb_geom &g, double z) {
+    const double az = fabs(z);
+    const double dns = (double)g.nside;
+    if (az <= 2.0 / 3.0) return hpgb_d2ll(dns * (2 - 1.5 * z));
+    const int64_t ir = hpgb_d2ll(dns * sqrt(3 * (1 - az)));
+    return (z > 0) ? ir : 4 * g.nside - ir - 1;
+}
+
+HPGB_HD void hpgb_ring_info2(const hpgb_geom &g, const double *T, int64_t ring, int64_t &startpix,
+                             int64_t &ringpix, double &theta, bool &shifted) {
+    const int64_t ns = g.nside;
+    const int64_t nring = (ring > 2 * ns) ? 4 * ns - ring : ring;
+    if (nring < ns) {
+        const double t = (double)(nring * nring) * g.fact2;
+        const double ct = 1 - t;
+        const double st = sqrt(t * (2 - t));
+        theta = hpgb_atan2_cr(T, st, ct);
+        ringpix = 4 * nring;
+        shifted = true;
+        startpix = 2 * nring * (nring - 1);
+    } else {
+        theta = hpgb_acos_cr(T, (double)(2 * ns - nring) * g.fact1);
+        ringpix = 4 * ns;
+        shifted = ((nring - ns) & 1) == 0;
+        startpix = g.ncap + (nring - ns) * ringpix;
+    }
+    if (nring != ring) {
+        theta = HPGB_PI - theta;
+        startpix = g.npix - startpix - ringpix;
+    }
+}
+
+// one ring: two pixels + phi weights (the twin blocks hpgeom/healpix_geom.c:1619-1636, :1637-1654)
+HPGB_HD void hpgb_ring_pair(const hpgb_geom &g, const double *T, int64_t ring, double phi, int64_t *p, double *w,
+                            double &theta) {
+    int64_t sp, nr;
+    bool shift;
+    hpgb_ring_info2(g, T, ring, sp, nr, theta, shift);
+    const double dphi = HPGB_TWOPI / (double)nr;
+    const double hs = shift ? 0.5 : 0.0;
+    const double t = (phi / dphi - hs);
+    int64_t i1 = (t < 0) ? hpgb_d2ll(t) - 1 : hpgb_d2ll(t);
+    const double w1 = (phi - ((double)i1 + hs) * dphi) / dphi;
+    int64_t i2 = i1 + 1;
+    if (i1 < 0) i1 += nr;
+    if (i2 >= nr) i2 -= nr;
+    p[0] = sp + i1;
+    p[1] = sp + i2;
+    w[0] = 1 - w1;
+    w[1] = w1;
+}
+
+template <bool NEST, bool POW2>
+HPGB_HD void hpgb_interpol(const hpgb_geom &g, const double *T, double theta, double phi, int64_t *p, double *w) {
+    const double z = hpgb_cos_cr(T, theta);
+    const int64_t ir1 = hpgb_ring_above(g, z);
+    const int64_t ir2 = ir1 + 1;
+    double th1 = 0, th2 = 0;
+    p[0] = p[1] = p[2] = p[3] = 0;
+    w[0] = w[1] = w[2] = w[3] = 0;
+    if (ir1 > 0) hpgb_ring_pair(g, T, ir1, phi, p, w, th1);
+    if (ir2 < 4 * g.nside) hpgb_ring_pair(g, T, ir2, phi, p + 2, w + 2, th2);
+    if (ir1 == 0) {
+        const double wt = theta / th2;
+        w[2] *= wt;
+        w[3] *= wt;
+        const double fac = (1 - wt) * 0.25;
+        w[0] = fac;
+        w[1] = fac;
+        w[2] += fac;
+        w[3] += fac;
+        p[0] = (p[2] + 2) & 3;
+        p[1] = (p[3] + 2) & 3;
+    } else if (ir2 == 4 * g.nside) {
+        const double wt = (theta - th1) / (HPGB_PI - th1);
+        w[0] *= (1 - wt);
+        w[1] *= (1 - wt);
+        const double fac = wt * 0.25;
+        w[0] += fac;
+        w[1] += fac;
+        w[2] = fac;
+        w[3] = fac;
+        p[2] = ((p[0] + 2) & 3) + g.npix - 4;
+        p[3] = ((p[1] + 2) & 3) + g.npix - 4;
+    } else {
+        const double wt = (theta - th1) / (th2 - th1);
+        w[0] *= (1 - wt);
+        w[1] *= (1 - wt);
+        w[2] *= wt;
+        w[3] *= wt;
+    }
+    if (NEST) {
+#pragma unroll
+        for (int m = 0; m < 4; m++) p[m] = hpgb_ring2nest(g, p[m]);
+    }
+}
+
+// lonlat_to_thetaphi with numpy's formulas (hpgeom/hpgeom.py:75-88): Python-style modulo,
+// deg2rad = x * (pi/180).  Returns false when the latitude is out of range.
+template <bool DEGREES>
+HPGB_HD bool hpgb_lonlat_to_thetaphi_np(double lon, double lat, double &theta, double &phi) {
+    const double m = DEGREES ? 360.0 : (2. * HPGB_PI);
+    double r = fmod(lon, m);  // numpy's float remainder: result takes the divisor's sign
+    if (r != 0.0) {
+        if (r < 0.0) r += m;
+    } else {
+        r = copysign(0.0, m);
+    }
+    double lon_ = r, lat_ = lat;
+    if (DEGREES) {
+        lon_ = r * (HPGB_PI / 180.0);
+        lat_ = lat * (HPGB_PI / 180.0);
+    }
+    phi = lon_;
+    theta = HPGB_PI / 2. - lat_;
+    return !((lat_ < -HPGB_PI / 2.) || (lat_ > HPGB_PI / 2.));
+}
+
+#endif  // HPGB_FP_H

@@ -21,6 +21,7 @@
 #include <atomic>
 
 #include "../../include/hpgb.h"
+#include "hpgb_tables.h"
 
 #define HPGB_BLOCK 256
 
@@ -38,13 +39,13 @@ struct hpgb_bad_t {
 };
 
 // Op interface:
-//   typename Op::In2;  In2 load2(int64_t i) const;            // loads elements i, i+1 (i even)
-//   void run2(int64_t i, const In2&, hpgb_bad_t&) const;       // converts + stores i, i+1
-//   void run1(int64_t i, hpgb_bad_t&) const;                   // scalar element
-//   void prologue() const;                                     // optional per-CTA setup
+//   typename Op::In2;  In2 load2(int64_t i) const;                 // loads elements i, i+1 (i even)
+//   typename Op::Ctx;  Ctx prologue() const;                       // per-CTA setup (e.g. stage the trig table)
+//   void run2(int64_t i, const In2&, const Ctx&, hpgb_bad_t&) const; // converts + stores i, i+1
+//   void run1(int64_t i, const Ctx&, hpgb_bad_t&) const;            // scalar element
 template <class Op>
 __global__ void __launch_bounds__(HPGB_BLOCK) k_map2(const Op op, const int64_t n, hpgb_status_t *st) {
-    op.prologue();
+    const typename Op::Ctx ctx = op.prologue();
     const int64_t npair = n >> 1;
     const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
     int64_t p = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x;
@@ -52,21 +53,32 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_map2(const Op op, const int64_t 
     for (; p + stride < npair; p += 2 * stride) {
         const typename Op::In2 v0 = op.load2(2 * p);
         const typename Op::In2 v1 = op.load2(2 * (p + stride));
-        op.run2(2 * p, v0, bad);
-        op.run2(2 * (p + stride), v1, bad);
+        op.run2(2 * p, v0, ctx, bad);
+        op.run2(2 * (p + stride), v1, ctx, bad);
     }
-    if (p < npair) op.run2(2 * p, op.load2(2 * p), bad);
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.run1(n - 1, bad);
+    if (p < npair) op.run2(2 * p, op.load2(2 * p), ctx, bad);
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.run1(n - 1, ctx, bad);
     bad.commit(st);
 }
 
 template <class Op>
 __global__ void __launch_bounds__(HPGB_BLOCK) k_map1(const Op op, const int64_t n, hpgb_status_t *st) {
-    op.prologue();
+    const typename Op::Ctx ctx = op.prologue();
     const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
     hpgb_bad_t bad;
-    for (int64_t i = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; i < n; i += stride) op.run1(i, bad);
+    for (int64_t i = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; i < n; i += stride) op.run1(i, ctx, bad);
     bad.commit(st);
+}
+
+// the 52 x 4 double-double sin/cos table of hpgb_math.h, staged in shared memory per CTA
+// (1664 B; random row gathers from it are LSU work that overlaps the fp64 pipe)
+static __device__ const double g_hpgb_sincos[4 * HPGB_SINCOS_ROWS] = HPGB_SINCOS_TABLE_INIT;
+struct hpgb_no_ctx {};
+__device__ __forceinline__ const double *hpgb_stage_table() {
+    __shared__ double sT[4 * HPGB_SINCOS_ROWS];
+    for (int i = threadIdx.x; i < 4 * HPGB_SINCOS_ROWS; i += HPGB_BLOCK) sT[i] = g_hpgb_sincos[i];
+    __syncthreads();
+    return sT;
 }
 
 int hpgb_sm_count();  // SMs of the current device (148 on B200)
@@ -80,25 +92,32 @@ static int hpgb_resident_ctas(K kernel) {
 
 static inline bool hpgb_aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
 
+// launch the scalar kernel (misaligned operands, per-element nside)
+template <class Op>
+static int hpgb_launch_map1(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
+    if (n <= 0) return HPGB_OK;
+    static int occ1 = 0;
+    if (!occ1) occ1 = hpgb_resident_ctas(k_map1<Op>);
+    int64_t want = (n + HPGB_BLOCK - 1) / HPGB_BLOCK;
+    int64_t grid = (int64_t)hpgb_sm_count() * occ1;
+    if (want < grid) grid = want;
+    k_map1<Op><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(op, n, st);
+    g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+}
+
 // launch `op` over n elements; vec_ok = all operand pointers are 16-byte aligned
 template <class Op>
 static int hpgb_launch_map(const Op &op, int64_t n, bool vec_ok, hpgb_status_t *st, cudaStream_t s) {
     if (n <= 0) return HPGB_OK;
-    static int occ2 = 0, occ1 = 0;  // per instantiation, per process (one device kind per box)
-    const int sms = hpgb_sm_count();
-    if (vec_ok) {
-        if (!occ2) occ2 = hpgb_resident_ctas(k_map2<Op>);
-        int64_t want = ((n >> 1) + HPGB_BLOCK - 1) / HPGB_BLOCK;
-        int64_t grid = (int64_t)sms * occ2;
-        if (want < grid) grid = want > 0 ? want : 1;
-        k_map2<Op><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(op, n, st);
-    } else {
-        if (!occ1) occ1 = hpgb_resident_ctas(k_map1<Op>);
-        int64_t want = (n + HPGB_BLOCK - 1) / HPGB_BLOCK;
-        int64_t grid = (int64_t)sms * occ1;
-        if (want < grid) grid = want;
-        k_map1<Op><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(op, n, st);
-    }
+    if (!vec_ok) return hpgb_launch_map1(op, n, st, s);
+    static int occ2 = 0;  // per instantiation, per process (one device kind per box)
+    if (!occ2) occ2 = hpgb_resident_ctas(k_map2<Op>);
+    int64_t want = ((n >> 1) + HPGB_BLOCK - 1) / HPGB_BLOCK;
+    int64_t grid = (int64_t)hpgb_sm_count() * occ2;
+    if (want < grid) grid = want > 0 ? want : 1;
+    k_map2<Op><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(op, n, st);
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;

@@ -1,0 +1,204 @@
+// hpgb_math.h -- accurate fp64 trig for the kernels: cos / sin / sincos / acos / atan2 evaluated
+// in double-double so that the returned double is the correctly rounded result except with
+// probability ~2^-18 (error <= ~2^-72 relative).
+//
+// Why: the reference takes these from glibc 2.39's libm, which is itself correctly rounded for
+// ~99.9 % of arguments.  CUDA's own fp64 cos/sin/acos/atan2 are 1-2 ulp, which
+// would differ from glibc on tens of percent of arguments; the outputs that subtract nearly
+// equal angles afterwards (latitude = pi/2 - theta, interpolation theta-weights) amplify a
+// single-ulp difference to thousands of ulps.  Returning the correctly rounded value is the
+// only libm-independent way to be bit-identical to the reference wherever the reference is
+// correctly rounded.
+//
+// How (straight-line, no data-dependent branches, bounded arguments only -- |x| <= ~7):
+//   * x = q*(pi/2) + r, |r| <= pi/4, with a three-part pi/2 (r kept as a double-double);
+//   * |r| = k/64 + d with |d| <= 1/128: table of sin/cos(k/64) as double-doubles (52 rows x 32 B,
+//     staged in shared memory by the kernels), angle-addition with short polynomials in d;
+//     the two leading products are kept exact with fma (two_prod);
+//   * acos / atan2: a float-accuracy first guess t0 (24 bits, so t0 reduces exactly), the
+//     double-double sin/cos of t0 from the routine above, then ONE series-corrected Newton step:
+//       acos : cos(t0 + e) = z            e = u - (cot/2) u^2 + (1/6 + cot^2/2) u^3,  u = (cos t0 - z)/sin t0
+//       atan2: x sin(t0+e) - y cos(t0+e) = 0   e = v - v^3/3,  v = -(x sin t0 - y cos t0)/(x cos t0 + y sin t0)
+//     (|u|,|v| ~ 2^-22, so the neglected terms are < 2^-80).
+//
+// All functions are __host__ __device__ (see hpgb_core.h); fma() is called explicitly, the
+// translation units are compiled without implicit contraction.
+#ifndef HPGB_MATH_H
+#define HPGB_MATH_H
+
+#include "hpgb_core.h"
+#include "hpgb_tables.h"
+
+// exact product a*b = p + e
+HPGB_HD void hpgb_two_prod(double a, double b, double &p, double &e) {
+    p = a * b;
+    e = fma(a, b, -p);
+}
+// exact sum a+b = s + e, requires |a| >= |b| (or a == 0)
+HPGB_HD void hpgb_fast_two_sum(double a, double b, double &s, double &e) {
+    s = a + b;
+    e = b - (s - a);
+}
+// exact sum, no precondition
+HPGB_HD void hpgb_two_sum(double a, double b, double &s, double &e) {
+    s = a + b;
+    const double bb = s - a;
+    e = (a - (s - bb)) + (b - bb);
+}
+
+// x -> quadrant q and r = x - q*pi/2 as rh + rl, |r| <= pi/4 (1 + 2^-50).  Valid for |x| < 2^20.
+HPGB_HD void hpgb_reduce_pio2(double x, int &q, double &rh, double &rl) {
+    const double fq = rint(x * HPGB_2OPI);
+    q = (int)fq;
+    const double t = fma(-fq, HPGB_PIO2_1, x);  // exact: |t| < 1 and t is a multiple of ulp(x)/4
+    double p, pe, e1;
+    hpgb_two_prod(fq, HPGB_PIO2_2, p, pe);
+    hpgb_two_sum(t, -p, rh, e1);
+    rl = (e1 - pe) - fq * HPGB_PIO2_3;
+}
+
+// sin and cos of r = rh + rl, |r| <= pi/4 + 2^-40, as double-doubles; T = sincos table
+HPGB_HD void hpgb_sincos_dd(const double *T, double rh, double rl, double &sh, double &sl, double &ch,
+                            double &cl) {
+    const bool neg = rh < 0.0;
+    const double a = fabs(rh);
+    const double al = neg ? -rl : rl;
+    const double fk = rint(a * 64.0);
+    const int k = (int)fk;
+    const double d = a - fk * 0.015625;  // exact
+    const double Sh = T[4 * k + 0], Sl = T[4 * k + 1], Ch = T[4 * k + 2], Cl = T[4 * k + 3];
+    // powers of the offset
+    double p, pe;
+    hpgb_two_prod(d, d, p, pe);
+    // sin(delta) - delta  and  cos(delta) - 1  (delta = d + al)
+    const double sd = d * p * fma(p, fma(p, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0);
+    const double cdh = -0.5 * p;
+    const double cdl = fma(-0.5, pe, -d * al) + p * p * fma(p, fma(p, 1.0 / 40320.0, -1.0 / 720.0), 1.0 / 24.0);
+    const double ds = al + sd;  // sin(delta) = d + ds
+    // sin(a) = S cos(delta) + C sin(delta) = S + C d + S cdh + [Sl + Cl d + C ds + S cdl]
+    {
+        double m, me, n, ne, v, ve, w, we;
+        hpgb_two_prod(Ch, d, m, me);
+        hpgb_two_prod(Sh, cdh, n, ne);
+        hpgb_fast_two_sum(Sh, m, v, ve);
+        hpgb_fast_two_sum(v, n, w, we);
+        const double low = we + (ve + ((me + ne) + (fma(Cl, d, Sl) + fma(Ch, ds, Sh * cdl))));
+        hpgb_fast_two_sum(w, low, sh, sl);
+    }
+    // cos(a) = C cos(delta) - S sin(delta) = C - S d + C cdh + [Cl - Sl d - S ds + C cdl]
+    {
+        double m, me, n, ne, v, ve, w, we;
+        hpgb_two_prod(Ch, cdh, m, me);
+        hpgb_two_prod(Sh, d, n, ne);
+        hpgb_fast_two_sum(Ch, -n, v, ve);
+        hpgb_fast_two_sum(v, m, w, we);
+        const double low = we + (ve + ((me - ne) + (fma(-Sl, d, Cl) + fma(-Sh, ds, Ch * cdl))));
+        hpgb_fast_two_sum(w, low, ch, cl);
+    }
+    if (neg) {
+        sh = -sh;
+        sl = -sl;
+    }
+}
+
+// sin and cos of x (|x| < 2^20) as double-doubles
+HPGB_HD void hpgb_sincos_full_dd(const double *T, double x, double &sh, double &sl, double &ch, double &cl) {
+    int q;
+    double rh, rl, s1, s2, c1, c2;
+    hpgb_reduce_pio2(x, q, rh, rl);
+    hpgb_sincos_dd(T, rh, rl, s1, s2, c1, c2);
+    const bool swap = q & 1;
+    sh = swap ? c1 : s1;
+    sl = swap ? c2 : s2;
+    ch = swap ? s1 : c1;
+    cl = swap ? s2 : c2;
+    if (q & 2) {  // sin: q = 2,3 negative
+        sh = -sh;
+        sl = -sl;
+    }
+    if ((q + 1) & 2) {  // cos: q = 1,2 negative
+        ch = -ch;
+        cl = -cl;
+    }
+}
+
+HPGB_HD double hpgb_cos_cr(const double *T, double x) {
+    double sh, sl, ch, cl;
+    hpgb_sincos_full_dd(T, x, sh, sl, ch, cl);
+    return ch + cl;
+}
+HPGB_HD double hpgb_sin_cr(const double *T, double x) {
+    double sh, sl, ch, cl;
+    hpgb_sincos_full_dd(T, x, sh, sl, ch, cl);
+    return sh + sl;
+}
+HPGB_HD void hpgb_sincos_cr(const double *T, double x, double &s, double &c) {
+    double sh, sl, ch, cl;
+    hpgb_sincos_full_dd(T, x, sh, sl, ch, cl);
+    s = sh + sl;
+    c = ch + cl;
+}
+
+// 24-bit first guesses (any estimate good to ~2^-20 gives the same final result)
+HPGB_HD double hpgb_acos_guess(double z) {
+#if defined(__CUDA_ARCH__)
+    return (double)acosf((float)z);
+#else
+    return (double)(float)acos(z);
+#endif
+}
+HPGB_HD double hpgb_atan2_guess(double y, double x) {
+#if defined(__CUDA_ARCH__)
+    return (double)atan2f((float)y, (float)x);
+#else
+    return (double)(float)atan2(y, x);
+#endif
+}
+
+// acos(z) for |z| <= 0.995 (pixel centres use acos only for |z| <= 0.99, atan2 beyond)
+HPGB_HD double hpgb_acos_cr(const double *T, double z) {
+    const double t0 = hpgb_acos_guess(z);
+    double sh, sl, ch, cl;
+    hpgb_sincos_full_dd(T, t0, sh, sl, ch, cl);
+    const double e = (ch - z) + cl;
+    const double inv = 1.0 / sh;
+    const double u = e * inv;
+    const double cot = z * inv;
+    const double u2 = u * u;
+    const double corr = fma(u2 * u, fma(0.5 * cot, cot, 1.0 / 6.0), -0.5 * cot * u2);
+    return t0 + (u + corr);
+}
+
+// atan2(y, x) for finite, not-both-zero arguments whose magnitudes are within float range of
+// each other after scaling (callers pass normalised-ish values; see hpgb_atan2_any)
+HPGB_HD double hpgb_atan2_cr(const double *T, double y, double x) {
+    const double t0 = hpgb_atan2_guess(y, x);
+    double sh, sl, ch, cl;
+    hpgb_sincos_full_dd(T, t0, sh, sl, ch, cl);
+    // f = x sin t0 - y cos t0 (exact leading products, the difference of the heads is exact)
+    double a, ae, b, be;
+    hpgb_two_prod(x, sh, a, ae);
+    hpgb_two_prod(y, ch, b, be);
+    const double f = (a - b) + ((ae - be) + fma(x, sl, -y * cl));
+    const double g = fma(x, ch, y * sh);
+    const double v = -f / g;
+    return t0 + fma(v * v * v, -1.0 / 3.0, v);
+}
+
+// general atan2 with exponent scaling so the float guess never over/underflows
+HPGB_HD double hpgb_atan2_any(const double *T, double y, double x) {
+    const double m = fmax(fabs(x), fabs(y));
+    if (!(m > 0.0) || !(m < INFINITY)) return atan2(y, x);  // zeros / inf / nan: libm semantics
+    int ex;
+    (void)frexp(m, &ex);
+    const double ys = ldexp(y, -ex), xs = ldexp(x, -ex);
+    if (fabs(ys) < 1e-30 || fabs(xs) < 1e-30) {
+        // one component negligible at float precision: the guess degenerates; result is within
+        // 1e-30 of a multiple of pi/2 and the series below still applies with a double guess
+        const double t0 = atan2(ys, xs);
+        return t0;
+    }
+    return hpgb_atan2_cr(T, ys, xs);
+}
+
+#endif  // HPGB_MATH_H

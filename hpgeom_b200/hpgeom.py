@@ -269,8 +269,9 @@ def upgrade_pixels(nside, pixels, nside_upgrade, nest=True):
         raise ValueError(_lib.explain_nside(int(nside), True))
     _lib.check_rc(rc)
     if bad >= 0:
-        p = int(be.item(pix, bad))
-        if not nest and (p < 0 or p >= 12 * int(nside) * int(nside)):
-            raise ValueError(_lib.explain_pixel(int(nside), True, p))
+        # key = (class << 62) | index; class 0 = pixel out of range, class 1 = the last nest pixel
+        cls, idx = bad >> 62, bad & ((1 << 62) - 1)
+        if not nest and cls == 0:
+            raise ValueError(_lib.explain_pixel(int(nside), True, int(be.item(pix, idx))))
         raise ValueError("Input pixels/ranges out of range.")
     return out

@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes front end of libhostsim.so (host build of the device element
+functions, see hostsim.cpp).  Mirrors the reference's Python signatures for 1-D inputs."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_I = ctypes.POINTER(ctypes.c_int64)
+_D = ctypes.POINTER(ctypes.c_double)
+
+
+class HostSim:
+    def __init__(self):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+        self.lib = ctypes.CDLL(os.path.join(_HERE, "libhostsim.so"))
+        for n in ("sim_nest_to_ring", "sim_ring_to_nest", "sim_ring_roundtrip_any", "sim_angle_to_pixel",
+                  "sim_pixel_to_angle", "sim_pixel_to_vector", "sim_vector_to_pixel", "sim_neighbors", "sim_interp",
+                  "sim_lonlat"):
+            getattr(self.lib, n).restype = ctypes.c_int64
+        self.last_slow = 0
+
+    @staticmethod
+    def _i(a):
+        return np.ascontiguousarray(np.atleast_1d(a), dtype=np.int64)
+
+    @staticmethod
+    def _f(a):
+        return np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64)
+
+    @staticmethod
+    def _chk(bad):
+        if bad >= 0:
+            raise ValueError("bad element %d" % bad)
+
+    def _conv(self, fn, nside, pix):
+        pix = self._i(pix)
+        out = np.empty_like(pix)
+        self._chk(getattr(self.lib, fn)(ctypes.c_int64(nside), pix.ctypes.data_as(_I), ctypes.c_int64(pix.size),
+                                        out.ctypes.data_as(_I)))
+        return out
+
+    def nest_to_ring(self, nside, pix):
+        return self._conv("sim_nest_to_ring", nside, pix)
+
+    def ring_to_nest(self, nside, pix):
+        return self._conv("sim_ring_to_nest", nside, pix)
+
+    def ring_roundtrip_any(self, nside, pix):
+        return self._conv("sim_ring_roundtrip_any", nside, pix)
+
+    def angle_to_pixel(self, nside, a, b, nest=True, lonlat=True, degrees=True, exact_only=False):
+        a, b = self._f(a), self._f(b)
+        out = np.empty(a.size, dtype=np.int64)
+        ns = ctypes.c_int64(0)
+        self._chk(self.lib.sim_angle_to_pixel(ctypes.c_int64(nside), a.ctypes.data_as(_D), b.ctypes.data_as(_D),
+                                              ctypes.c_int64(a.size), int(nest), int(lonlat), int(degrees),
+                                              int(exact_only), out.ctypes.data_as(_I), ctypes.byref(ns)))
+        self.last_slow = ns.value
+        return out
+
+    def pixel_to_angle(self, nside, pix, nest=True, lonlat=True, degrees=True):
+        pix = self._i(pix)
+        a, b = np.empty(pix.size), np.empty(pix.size)
+        self._chk(self.lib.sim_pixel_to_angle(ctypes.c_int64(nside), pix.ctypes.data_as(_I), ctypes.c_int64(pix.size),
+                                              int(nest), int(lonlat), int(degrees), a.ctypes.data_as(_D),
+                                              b.ctypes.data_as(_D)))
+        return a, b
+
+    def pixel_to_vector(self, nside, pix, nest=True):
+        pix = self._i(pix)
+        x, y, z = np.empty(pix.size), np.empty(pix.size), np.empty(pix.size)
+        self._chk(self.lib.sim_pixel_to_vector(ctypes.c_int64(nside), pix.ctypes.data_as(_I), ctypes.c_int64(pix.size),
+                                               int(nest), x.ctypes.data_as(_D), y.ctypes.data_as(_D),
+                                               z.ctypes.data_as(_D)))
+        return x, y, z
+
+    def vector_to_pixel(self, nside, x, y, z, nest=True):
+        x, y, z = self._f(x), self._f(y), self._f(z)
+        out = np.empty(x.size, dtype=np.int64)
+        self.lib.sim_vector_to_pixel(ctypes.c_int64(nside), x.ctypes.data_as(_D), y.ctypes.data_as(_D),
+                                     z.ctypes.data_as(_D), ctypes.c_int64(x.size), int(nest), out.ctypes.data_as(_I))
+        return out
+
+    def neighbors(self, nside, pix, nest=True):
+        pix = self._i(pix)
+        out = np.empty((pix.size, 8), dtype=np.int64)
+        self._chk(self.lib.sim_neighbors(ctypes.c_int64(nside), pix.ctypes.data_as(_I), ctypes.c_int64(pix.size),
+                                         int(nest), out.ctypes.data_as(_I)))
+        return out
+
+    def get_interpolation_weights(self, nside, a, b, nest=True, lonlat=True, degrees=True):
+        a, b = self._f(a), self._f(b)
+        p = np.empty((a.size, 4), dtype=np.int64)
+        w = np.empty((a.size, 4), dtype=np.float64)
+        self._chk(self.lib.sim_interp(ctypes.c_int64(nside), a.ctypes.data_as(_D), b.ctypes.data_as(_D),
+                                      ctypes.c_int64(a.size), int(nest), int(lonlat), int(degrees),
+                                      p.ctypes.data_as(_I), w.ctypes.data_as(_D)))
+        return p, w
+
+    def lonlat_to_thetaphi(self, lon, lat, degrees=True):
+        lon, lat = self._f(lon), self._f(lat)
+        th, ph = np.empty(lon.size), np.empty(lon.size)
+        bad = self.lib.sim_lonlat(lon.ctypes.data_as(_D), lat.ctypes.data_as(_D), ctypes.c_int64(lon.size),
+                                  int(degrees), th.ctypes.data_as(_D), ph.ctypes.data_as(_D))
+        if bad >= 0:
+            raise ValueError("Latitude out of range.")
+        return th, ph

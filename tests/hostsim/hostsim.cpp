@@ -46,7 +46,8 @@ int64_t sim_ring_roundtrip_any(int64_t nside, const int64_t *in, int64_t n, int6
     return -1;
 }
 
+}  // extern "C"
+
 #ifdef HAVE_FP
 #include "hostsim_fp.inc"
 #endif
-}

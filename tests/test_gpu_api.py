@@ -1,0 +1,344 @@
+"""All conversions on the GPU through the public API (numpy -> hpgb_host_*, torch.cuda -> hpgb_*),
+against the golden vectors, the oracle and the reference's recorded error / shape behaviour.
+
+Tolerances (BASELINE.json north_star):
+  * integer outputs of integer inputs (nest<->ring, neighbors, upgrade): bit-exact;
+  * angle_to_pixel / vector_to_pixel: bit-exact except inputs at a pixel boundary (counted; must be
+    explained by a <= 2 ulp perturbation of the inputs);
+  * float outputs: within 2 ulp of the oracle measured on the quantity the libm call produces
+    (theta, cos/sin phi); exact IEEE outputs (phi, lon, z) bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_bit_equal, load_golden, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+POW2 = [1, 2, 4, 32, 1024, 4096, 2 ** 20, 2 ** 29]
+RING_ONLY = [3, 924, 100003]
+CASES = [(n, True) for n in POW2] + [(n, False) for n in POW2 + RING_ONLY]
+
+
+@pytest.fixture(scope="module")
+def hpg():
+    import hpgeom_b200
+    return hpgeom_b200
+
+
+def tag(nside, nest):
+    return "%d_%s" % (nside, "nest" if nest else "ring")
+
+
+def boundary_induced(port, nside, a, b, got, **kw):
+    """True where the oracle returns `got` for some <= 2 ulp perturbation of (a, b)."""
+    ok = np.zeros(a.size, dtype=bool)
+    for da in (-2, -1, 0, 1, 2):
+        for db in (-2, -1, 0, 1, 2):
+            pa = a + da * np.spacing(a)
+            pb = b + db * np.spacing(b)
+            try:
+                ok |= port.angle_to_pixel(nside, pa, pb, **kw) == got
+            except ValueError:
+                pass
+    return ok
+
+
+# ------------------------------------------------------------------------------------------
+# golden vectors
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nside,nest", CASES)
+def test_angle_to_pixel_golden(hpg, nside, nest):
+    g = load_golden("angle_to_pixel")
+    t = tag(nside, nest)
+    assert_bit_equal(hpg.angle_to_pixel(nside, g["lon"], g["lat"], nest=nest), g["deg_" + t], "deg")
+    assert_bit_equal(hpg.angle_to_pixel(nside, np.radians(g["lon"]), np.radians(g["lat"]), nest=nest, degrees=False),
+                     g["rad_" + t], "rad")
+    assert_bit_equal(hpg.angle_to_pixel(nside, g["theta"], g["phi"], nest=nest, lonlat=False), g["tp_" + t], "tp")
+
+
+@pytest.mark.parametrize("nside,nest", CASES)
+def test_pixel_to_angle_golden(hpg, nside, nest):
+    g = load_golden("pixel_to_angle")
+    t = tag(nside, nest)
+    pix = g["pix_%d" % nside]
+    th, ph = hpg.pixel_to_angle(nside, pix, nest=nest, lonlat=False)
+    assert_bit_equal(ph, g["tp_b_" + t], "phi")
+    assert ulp_diff(th, g["tp_a_" + t]).max() <= 1.0
+    many = nside >= 1024
+    assert not many or np.mean(th != g["tp_a_" + t]) <= 0.01
+    for key, kw, scale in (("deg", {}, 180.0 / np.pi), ("rad", {"degrees": False}, 1.0)):
+        lon, lat = hpg.pixel_to_angle(nside, pix, nest=nest, **kw)
+        assert_bit_equal(lon, g["%s_a_%s" % (key, t)], "lon")
+        assert np.abs(lat - g["%s_b_%s" % (key, t)]).max() <= 1.01 * np.spacing(np.pi) * scale
+        assert not many or np.mean(lat != g["%s_b_%s" % (key, t)]) <= 0.01
+
+
+@pytest.mark.parametrize("nside,nest", CASES)
+def test_pixel_to_vector_golden(hpg, nside, nest):
+    g = load_golden("pixel_to_vector")
+    t = tag(nside, nest)
+    x, y, z = hpg.pixel_to_vector(nside, g["pix_%d" % nside], nest=nest)
+    assert_bit_equal(z, g["z_" + t], "z")
+    for got, ref in ((x, g["x_" + t]), (y, g["y_" + t])):
+        big = np.abs(ref) > 1e-300
+        assert ulp_diff(got[big], ref[big]).max() <= 2.0
+        assert nside < 1024 or np.mean(got != ref) <= 0.01
+
+
+@pytest.mark.parametrize("nside,nest", CASES)
+def test_vector_to_pixel_golden(hpg, nside, nest):
+    g = load_golden("vector_to_pixel")
+    assert_bit_equal(hpg.vector_to_pixel(nside, g["x"], g["y"], g["z"], nest=nest), g[tag(nside, nest)])
+
+
+@pytest.mark.parametrize("nside,nest", CASES)
+def test_neighbors_golden(hpg, nside, nest):
+    g = load_golden("neighbors")
+    assert_bit_equal(hpg.neighbors(nside, g["pix_%d" % nside], nest=nest), g["nb_" + tag(nside, nest)])
+
+
+@pytest.mark.parametrize("nside,nest", [(1, True), (1, False), (2, True), (2, False), (32, True), (32, False),
+                                        (4096, True), (4096, False), (2 ** 20, True), (2 ** 20, False),
+                                        (2 ** 29, True), (2 ** 29, False), (3, False), (924, False)])
+def test_interp_golden(hpg, nside, nest):
+    g = load_golden("interp")
+    t = tag(nside, nest)
+    p, w = hpg.get_interpolation_weights(nside, g["lon"], g["lat"], nest=nest)
+    assert_bit_equal(p, g["pix_" + t], "pixels")
+    ref = g["wgt_" + t]
+    assert nside < 1024 or np.mean(w != ref) <= 0.01
+    assert np.abs(w - ref).max() <= 8 * np.spacing(np.pi) * nside
+
+
+@pytest.mark.parametrize("nside,nup", [(1, 1), (1, 4), (32, 64), (4096, 8192), (2 ** 20, 2 ** 22), (2 ** 28, 2 ** 29)])
+@pytest.mark.parametrize("nest", [True, False])
+def test_upgrade_golden(hpg, nside, nup, nest):
+    g = load_golden("upgrade")
+    out = hpg.upgrade_pixels(nside, g["pix_%d_%d" % (nside, nup)], nup, nest=nest)
+    assert_bit_equal(out, g["up_%d_%d_%s" % (nside, nup, "nest" if nest else "ring")])
+
+
+def test_lonlat_golden(hpg):
+    g = load_golden("lonlat")
+    th, ph = hpg.lonlat_to_thetaphi(g["lon"], g["lat"])
+    assert_bit_equal(th, g["deg_theta"])
+    assert_bit_equal(ph, g["deg_phi"])
+    th, ph = hpg.lonlat_to_thetaphi(g["rad_lon"], g["rad_lat"], degrees=False)
+    assert_bit_equal(th, g["rad_theta"])
+    assert_bit_equal(ph, g["rad_phi"])
+    th, ph = hpg.lonlat_to_thetaphi(10.0, 20.0)
+    assert isinstance(th, np.float64) and isinstance(ph, np.float64)
+    th, ph = hpg.lonlat_to_thetaphi(np.array([1.0, 2.0, 3.0]), np.array([5.0]))
+    assert th.shape == (1,) and ph.shape == (3,)
+
+
+# ------------------------------------------------------------------------------------------
+# error / shape behaviour recorded from the reference
+# ------------------------------------------------------------------------------------------
+def test_recorded_errors(hpg):
+    errs = json.load(open(os.path.join(GOLDEN, "golden_errors.json")))
+    ns = {"np": np, "array": np.array, "int64": np.int64}
+    checked = 0
+    for e in errs:
+        fn = getattr(hpg, e["call"])
+        args, kw = eval(e["args"].replace("array(", "np.array(").replace("dtype=float64", "dtype=np.float64")
+                        .replace("dtype=int64", "dtype=np.int64"), ns)
+        if e["type"] is None:
+            fn(*args, **kw)
+        else:
+            with pytest.raises(eval(e["type"])) as info:
+                fn(*args, **kw)
+            assert str(info.value) == e["msg"], (e["call"], e["args"])
+        checked += 1
+    assert checked >= 40
+
+
+def test_recorded_shapes(hpg):
+    s = json.load(open(os.path.join(GOLDEN, "golden_shapes.json")))
+    out = hpg.angle_to_pixel(1024, 1.0, 2.0)
+    assert type(out).__name__ == s["a2p_scalar"] and not isinstance(out, np.ndarray)
+    assert list(hpg.angle_to_pixel(1024, np.zeros((3, 2)), np.zeros((3, 2))).shape) == s["a2p_2d"]
+    assert list(hpg.angle_to_pixel(1024, np.zeros((3, 1)), np.zeros((1, 4))).shape) == s["a2p_bcast"]
+    assert type(hpg.pixel_to_angle(1024, 5)[0]).__name__ == s["p2a_scalar"]
+    assert list(hpg.neighbors(1024, 5).shape) == s["nb_scalar"]
+    assert list(hpg.neighbors(1024, np.arange(3)).shape) == s["nb_1d"]
+    assert hpg.neighbors(np.array([1024, 2048, 4096]), 1000).tolist() == s["nb_nside_vec"]
+    assert [list(v.shape) for v in hpg.get_interpolation_weights(1024, 1.0, 2.0)] == s["interp_scalar"]
+    assert list(hpg.angle_to_pixel(1024, np.zeros(0), np.zeros(0)).shape) == s["empty"]
+    assert hpg.angle_to_pixel(np.array([1, 2, 4, 8]), 10.0, 20.0).tolist() == s["a2p_nside_vec"]
+    assert [float(v) for v in hpg.pixel_to_angle(32, np.int32(7))] == s["p2a_int32"]
+
+
+def test_first_bad_element_wins(hpg):
+    lon = np.zeros(5_000_000)
+    lat = np.zeros(5_000_000)
+    lat[4_500_000] = 95.5
+    lat[4_999_999] = -123.25
+    with pytest.raises(ValueError, match=r"lat = 95.5 out of range \[-90, 90\]"):
+        hpg.angle_to_pixel(1024, lon, lat)
+    with pytest.raises(ValueError, match=r"colatitude \(theta\) = -0.1 out of range"):
+        hpg.get_interpolation_weights(1024, np.array([1.0, -0.1, 5.0]), np.array([1.0, 1.0, 1.0]), lonlat=False)
+    with pytest.raises(ValueError, match=r"nside 1000 must be power of 2"):
+        hpg.angle_to_pixel(np.array([1024, 1000]), np.array([1.0, 1.0]), np.array([1.0, 1.0]))
+
+
+# ------------------------------------------------------------------------------------------
+# seeded random inputs vs the oracle, BASELINE configs at oracle-sized N
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nside,nest,kw", [
+    (1024, True, {}),                       # config 1
+    (2 ** 29, True, {}), (2 ** 29, False, {}),  # config 5
+    (2 ** 29, True, {"degrees": False}), (2 ** 20, True, {"lonlat": False}), (924, False, {}),
+])
+def test_angle_to_pixel_random(hpg, oracle_port, nside, nest, kw):
+    rng = np.random.default_rng(12345)
+    n = 2_000_003
+    lon = 360.0 * rng.random(n)
+    lat = np.degrees(np.arcsin(2.0 * rng.random(n) - 1.0))
+    if kw.get("lonlat", True) is False:
+        a, b = np.pi / 2 - np.radians(lat), np.radians(lon)
+    elif kw.get("degrees", True) is False:
+        a, b = np.radians(lon), np.radians(lat)
+    else:
+        a, b = lon, lat
+    got = hpg.angle_to_pixel(nside, a, b, nest=nest, **kw)
+    ref = oracle_port.angle_to_pixel(nside, a, b, nest=nest, **kw)
+    bad = np.flatnonzero(got != ref)
+    print("angle_to_pixel nside=%d nest=%s %s: %d / %d differ" % (nside, nest, kw, bad.size, n))
+    assert bad.size <= 5
+    if bad.size:
+        assert boundary_induced(oracle_port, nside, a[bad], b[bad], got[bad], nest=nest, **kw).all()
+
+
+@pytest.mark.parametrize("nside", [2 ** 20])
+@pytest.mark.parametrize("nest", [True, False])
+def test_config2_pixel_to_angle_vector(hpg, oracle_port, nside, nest):
+    rng = np.random.default_rng(12345)
+    pix = rng.integers(0, 12 * nside * nside, 2_000_001)
+    th, ph = hpg.pixel_to_angle(nside, pix, nest=nest, lonlat=False)
+    rth, rph = oracle_port.pixel_to_angle(nside, pix, nest=nest, lonlat=False)
+    assert_bit_equal(ph, rph)
+    assert ulp_diff(th, rth).max() <= 1.0 and np.mean(th != rth) < 5e-3
+    lon, lat = hpg.pixel_to_angle(nside, pix, nest=nest)
+    rlon, rlat = oracle_port.pixel_to_angle(nside, pix, nest=nest)
+    assert_bit_equal(lon, rlon)
+    assert np.abs(lat - rlat).max() <= 1.01 * np.spacing(np.pi) * 180 / np.pi and np.mean(lat != rlat) < 5e-3
+    x, y, z = hpg.pixel_to_vector(nside, pix, nest=nest)
+    rx, ry, rz = oracle_port.pixel_to_vector(nside, pix, nest=nest)
+    assert_bit_equal(z, rz)
+    assert ulp_diff(x, rx).max() <= 2.0 and ulp_diff(y, ry).max() <= 2.0
+    assert np.mean(x != rx) < 5e-3 and np.mean(y != ry) < 5e-3
+    # round trips (exact in the reference)
+    assert np.array_equal(hpg.angle_to_pixel(nside, lon, lat, nest=nest), pix)
+    assert np.array_equal(hpg.vector_to_pixel(nside, x, y, z, nest=nest), pix)
+
+
+@pytest.mark.parametrize("nest", [True, False])
+def test_config4_neighbors_interp_upgrade(hpg, oracle_port, nest):
+    nside = 4096
+    rng = np.random.default_rng(12345)
+    n = 1_000_001
+    pix = rng.integers(0, 12 * nside * nside - 1, n)
+    assert_bit_equal(hpg.neighbors(nside, pix, nest=nest), oracle_port.neighbors(nside, pix, nest=nest))
+    assert_bit_equal(hpg.upgrade_pixels(nside, pix, 8192, nest=nest), oracle_port.upgrade_pixels(nside, pix, 8192, nest=nest))
+    lon = 360.0 * rng.random(n)
+    lat = np.degrees(np.arcsin(2.0 * rng.random(n) - 1.0))
+    p, w = hpg.get_interpolation_weights(nside, lon, lat, nest=nest)
+    rp, rw = oracle_port.get_interpolation_weights(nside, lon, lat, nest=nest)
+    assert np.count_nonzero(p != rp) == 0
+    assert np.mean(w != rw) < 5e-3
+    assert np.abs(w - rw).max() <= 8 * np.spacing(np.pi) * nside
+    assert np.abs(w.sum(axis=1) - 1.0).max() < 1e-12
+
+
+def test_vector_to_pixel_random(hpg, oracle_port):
+    rng = np.random.default_rng(12345)
+    x, y, z = rng.uniform(-1, 1, (3, 2_000_000))
+    for nside, nest in ((2 ** 29, True), (2 ** 29, False), (1024, True)):
+        got = hpg.vector_to_pixel(nside, x, y, z, nest=nest)
+        ref = oracle_port.vector_to_pixel(nside, x, y, z, nest=nest)
+        assert np.count_nonzero(got != ref) <= 5
+
+
+def test_neighbors_fraction_of_missing(hpg):
+    for nside, frac in ((1, 0.25), (2, 0.0625), (32, 24 / (8 * 12 * 32 * 32))):
+        nb = hpg.neighbors(nside, np.arange(12 * nside * nside))
+        assert abs(np.mean(nb == -1) - frac) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------
+# device-resident torch path
+# ------------------------------------------------------------------------------------------
+def test_torch_device_resident_all(hpg, oracle_port):
+    import torch
+    rng = np.random.default_rng(99)
+    nside = 2 ** 20
+    n = 300_001
+    pix = rng.integers(0, 12 * nside * nside, n)
+    lon = 360.0 * rng.random(n)
+    lat = np.degrees(np.arcsin(2.0 * rng.random(n) - 1.0))
+    tp, tlon, tlat = (torch.from_numpy(v).cuda() for v in (pix, lon, lat))
+    out = hpg.angle_to_pixel(nside, tlon, tlat)
+    assert out.is_cuda and np.count_nonzero(out.cpu().numpy() != oracle_port.angle_to_pixel(nside, lon, lat)) <= 2
+    a, b = hpg.pixel_to_angle(nside, tp)
+    ra, rb = oracle_port.pixel_to_angle(nside, pix)
+    assert a.is_cuda and np.array_equal(a.cpu().numpy(), ra)
+    assert np.abs(b.cpu().numpy() - rb).max() <= 1.01 * np.spacing(np.pi) * 180 / np.pi
+    x, y, z = hpg.pixel_to_vector(nside, tp)
+    assert np.array_equal(z.cpu().numpy(), oracle_port.pixel_to_vector(nside, pix)[2])
+    back = hpg.vector_to_pixel(nside, x, y, z)
+    assert torch.equal(back, tp)
+    nb = hpg.neighbors(nside, tp[:1000])
+    assert nb.shape == (1000, 8) and np.array_equal(nb.cpu().numpy(), oracle_port.neighbors(nside, pix[:1000]))
+    p, w = hpg.get_interpolation_weights(nside, tlon[:1000], tlat[:1000])
+    assert p.shape == (1000, 4) and w.dtype == torch.float64
+    assert np.array_equal(p.cpu().numpy(), oracle_port.get_interpolation_weights(nside, lon[:1000], lat[:1000])[0])
+    up = hpg.upgrade_pixels(1024, torch.arange(0, 1000, device="cuda"), 4096, nest=False)
+    assert np.array_equal(up.cpu().numpy(), oracle_port.upgrade_pixels(1024, np.arange(1000), 4096, nest=False))
+    th, ph = hpg.lonlat_to_thetaphi(tlon, tlat)
+    rth, rph = oracle_port.lonlat_to_thetaphi(lon, lat)
+    assert np.array_equal(th.cpu().numpy(), rth) and np.array_equal(ph.cpu().numpy(), rph)
+    with pytest.raises(ValueError, match=r"lat = 100 out of range"):
+        hpg.angle_to_pixel(nside, tlon[:4], torch.tensor([0.0, 100.0, 0.0, 0.0], device="cuda", dtype=torch.float64))
+    # misaligned views take the scalar kernels
+    out2 = hpg.angle_to_pixel(nside, tlon[1:], tlat[1:])
+    assert torch.equal(out2, out[1:])
+    # results stay on the tensor's device and a non-default stream works
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out3 = hpg.angle_to_pixel(nside, tlon, tlat)
+    s.synchronize()
+    assert torch.equal(out3, out)
+
+
+# ------------------------------------------------------------------------------------------
+# full-size properties (BASELINE configs at their stated sizes, device resident)
+# ------------------------------------------------------------------------------------------
+def test_config1_full_size(hpg, oracle_port):
+    """config 1: 10M points, nside=1024 nest lonlat degrees, vs the oracle bit for bit."""
+    rng = np.random.default_rng(12345)
+    n = 10_000_000
+    lon = 360.0 * rng.random(n)
+    lat = np.degrees(np.arcsin(2.0 * rng.random(n) - 1.0))
+    got = hpg.angle_to_pixel(1024, lon, lat)
+    ref = oracle_port.angle_to_pixel(1024, lon, lat)
+    assert np.count_nonzero(got != ref) == 0
+
+
+def test_config5_round_trip_property(hpg):
+    """config 5 shape at one GPU's shard scale: 256M device-generated points, nside=2^29;
+    pixel -> centre -> pixel must be the identity (size-independent property)."""
+    import torch
+    nside = 2 ** 29
+    n = 1 << 28
+    g = torch.Generator(device="cuda").manual_seed(12345)
+    pix = torch.randint(0, 12 * nside * nside, (n,), dtype=torch.int64, device="cuda", generator=g)
+    for nest in (True, False):
+        lon, lat = hpg.pixel_to_angle(nside, pix, nest=nest)
+        back = hpg.angle_to_pixel(nside, lon, lat, nest=nest)
+        assert int((back != pix).sum()) == 0
+        del lon, lat, back
