@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libhpgb.so kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref)
+
+Workload (config.workload): angle_to_pixel, nside=2^29, nest, lonlat, degrees -- one shard of
+BASELINE config 5 per GPU (2^30 uniform-on-sphere points = 16 GiB in + 8 GiB out per GPU, weak
+scaling: 8 GPUs = 8.6e9 points).  A step is ONE pass of the kernel over the resident shard.
+Inputs (24 GB) are ~200x larger than L2, so nothing survives between steps.
+
+value  : whole-job Gpoints/s, inputs resident in HBM, CUDA events on the launch stream,
+         barrier + synchronize on both sides, max over ranks.
+e2e    : same metric through the C ABI with HOST buffers (hpgb_host_angle_to_pixel: pinned host
+         memory -> chunked H2D / kernel / D2H pipeline -> pinned host memory), timed on the host
+         around the blocking call, max over ranks.
+roofline: 24 algorithmic bytes per point / the kernel's mean launch time, against the measured
+         HBM copy bandwidth of MEASURED_PEAKS.json.
+cpu_baseline: the reference's own C (oracle/_ref, all host threads) on a bounded sample, rank 0, N=1.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NSIDE = 2 ** 29
+BYTES_PER_POINT = {"angle_to_pixel": 24, "nest_to_ring": 16}
+METRIC = "Gpoints/s angle_to_pixel @nside=2^29 nest lonlat degrees (device-resident)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-points", type=int, default=30, help="points per GPU = 2^this")
+    ap.add_argument("--log2-e2e-points", type=int, default=27, help="host-buffer batch per GPU = 2^this")
+    ap.add_argument("--log2-ref-points", type=int, default=25, help="reference arm: points per step = 2^this")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def sky_points_host(n, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    lon = 360.0 * rng.random(n)
+    lat = np.degrees(np.arcsin(2.0 * rng.random(n) - 1.0))
+    return lon, lat
+
+
+def cpu_reference_rate(n, threads, reps=1):
+    """Gpoints/s of the reference's own C path (oracle/_ref) -- or the scalar port -- on n points."""
+    import oracle
+    lon, lat = sky_points_host(n, 12345)
+    if oracle.ref is not None:
+        kind, cores = "reference", threads
+        fn = lambda: oracle.ref.angle_to_pixel(NSIDE, lon, lat, nest=True, lonlat=True, degrees=True, n_threads=threads)
+    else:
+        kind, cores = "port", 1
+        port = oracle.port()
+        fn = lambda: port.angle_to_pixel(NSIDE, lon, lat)
+    fn()
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return n / best / 1e9, kind, cores, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the same path, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n = 1 << args.log2_ref_points
+    import oracle
+    lon, lat = sky_points_host(n, 12345)
+    if oracle.ref is not None:
+        kind, cores = "reference", threads
+        step = lambda: oracle.ref.angle_to_pixel(NSIDE, lon, lat, nest=True, lonlat=True, degrees=True, n_threads=threads)
+    else:
+        kind, cores = "port", 1
+        port = oracle.port()
+        step = lambda: port.angle_to_pixel(NSIDE, lon, lat)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt / 1e9
+    sample = "2^%d uniform-on-sphere points per step (bounded sample of the 2^%d-point-per-GPU workload)" % (
+        args.log2_ref_points, args.log2_points)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "angle_to_pixel nside=2^29 nest lonlat degrees; reference CPU path "
+                               "(unmodified hpgeom C compiled into oracle/_ref), n_threads=%d, %s" % (cores, sample)},
+        "cpu_baseline": {"value": value, "unit": "Gpoints/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from hpgeom_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    n = 1 << args.log2_points
+    gen = torch.Generator(device=dev).manual_seed(12345 + rank)
+    lon = torch.rand(n, dtype=torch.float64, device=dev, generator=gen).mul_(360.0)
+    lat = torch.rand(n, dtype=torch.float64, device=dev, generator=gen).mul_(2.0).sub_(1.0).asin_().mul_(180.0 / 3.141592653589793)
+    pix = torch.empty(n, dtype=torch.int64, device=dev)
+    status = torch.empty(2, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    stp = ctypes.c_void_p(status.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_a2p():
+        rc = L.hpgb_angle_to_pixel(lon.data_ptr(), lat.data_ptr(), pix.data_ptr(), n, NSIDE, None, 1, 1, 1, stp, sp)
+        assert rc == 0, _lib.error_string(rc)
+
+    def timed(step, steps, warmup):
+        L.hpgb_status_reset(stp, sp)
+        for _ in range(warmup):
+            step()
+        barrier()
+        l0 = L.hpgb_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = L.hpgb_launch_count() - l0
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = t.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            return float(mx[0]), int(sm[1])
+        return ms, launches
+
+    # ---- headline: angle_to_pixel, device resident ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_a2p, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    assert int(status[0].item()) == -1, "kernel flagged a bad element in valid synthetic input"
+    ms_per_step = ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e9
+
+    # ---- second headline of the metric: nest_to_ring on the pixels just produced ----
+    ring = lon.view(torch.int64)  # reuse the 8 GiB buffer as the output (lon is no longer needed after e2e setup)
+
+    def step_n2r():
+        rc = L.hpgb_nest_to_ring(pix.data_ptr(), ring.data_ptr(), n, NSIDE, None, stp, sp)
+        assert rc == 0, _lib.error_string(rc)
+
+    ms_n2r, _ = timed(step_n2r, args.steps, max(args.warmup, 3))
+    ms_n2r /= args.steps
+    n2r_value = world * n / (ms_n2r * 1e-3) / 1e9
+    del ring, lon, lat, pix
+    torch.cuda.empty_cache()
+
+    # ---- e2e: the C ABI with HOST (pinned) buffers, copies inside the timed region ----
+    ne = 1 << args.log2_e2e_points
+    hlon = torch.empty(ne, dtype=torch.float64).pin_memory()
+    hlat = torch.empty(ne, dtype=torch.float64).pin_memory()
+    hpix = torch.empty(ne, dtype=torch.int64).pin_memory()
+    g = torch.Generator().manual_seed(777 + rank)
+    hlon.copy_(torch.rand(ne, dtype=torch.float64, generator=g) * 360.0)
+    hlat.copy_(torch.rad2deg(torch.asin(torch.rand(ne, dtype=torch.float64, generator=g) * 2.0 - 1.0)))
+    fb = ctypes.c_int64(-1)
+
+    def step_e2e():
+        rc = L.hpgb_host_angle_to_pixel(hlon.data_ptr(), hlat.data_ptr(), hpix.data_ptr(), ne, NSIDE, None, 1, 1, 1,
+                                        local, ctypes.byref(fb))
+        assert rc == 0 and fb.value == -1, (rc, fb.value)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * ne * e2e_steps / float(t[0]) / 1e9
+    checksum = int(hpix[:1024].sum().item())  # the step's result is read on the host
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = BYTES_PER_POINT["angle_to_pixel"] * n / (ms_per_step * 1e-3) / 1e9
+        kernel = "k_map2<OpAng2Pix<nest,lonlat,degrees>>"
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "angle_to_pixel nside=2^29 nest lonlat degrees, 2^%d uniform-on-sphere points per GPU "
+                                   "(BASELINE config 5 shard), device-resident; inputs 16 B + output 8 B per point "
+                                   "(%.1f GB per GPU) >> L2, no flush needed" % (args.log2_points, 24 * n / 1e9),
+                       "sharding": "contiguous shards, one process per GPU, no data-path collective",
+                       "e2e_batch_points_per_gpu": ne},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic("angle_to_pixel"), "kernel": kernel, "peak_source": peak_src,
+                         "bytes_per_point": 24, "points_per_launch": n},
+            "e2e": {"value": e2e_value, "unit": "Gpoints/s", "h2d_bytes_per_step": 16 * ne, "d2h_bytes_per_step": 8 * ne,
+                    "api": "hpgb_host_angle_to_pixel (C ABI, pinned host buffers)", "steps": e2e_steps,
+                    "result_checksum": checksum},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "also": {"nest_to_ring": {"value": n2r_value, "unit": "Gpoints/s", "ms_per_step": ms_n2r,
+                                      "roofline_frac": 16 * n / (ms_n2r * 1e-3) / 1e9 / peak,
+                                      "workload": "nest_to_ring nside=2^29 on the 2^%d pixels per GPU" % args.log2_points}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            probe, kind, cores, _ = cpu_reference_rate(1 << 22, threads)
+            # size the sample for ~10 s of CPU work, bounded to 2^27 points (3 GB of host arrays)
+            ns = int(min(max(probe * 1e9 * 10.0, 1 << 22), 1 << 27))
+            rate, kind, cores, secs = cpu_reference_rate(ns, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "Gpoints/s", "cores": cores, "kind": kind,
+                                    "sample": "%d uniform-on-sphere points of the same workload, %.1f s" % (ns, secs)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

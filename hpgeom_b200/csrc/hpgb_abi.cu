@@ -1,0 +1,132 @@
+// hpgb_abi.cu -- the C ABI of include/hpgb.h: thin extern "C" wrappers over the kernel launchers
+// (device-pointer entry points) and over the chunked host pipeline (host-pointer entry points).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hpgb_core.h"
+#include "hpgb_host.h"
+#include "hpgb_internal.h"
+
+typedef const char *cc;
+
+// =============================================================================================
+// C ABI (include/hpgb.h)
+// =============================================================================================
+extern "C" {
+
+#define S(x) ((cudaStream_t)(x))
+
+int hpgb_nest_to_ring(const int64_t *d_nest, int64_t *d_ring, int64_t n, int64_t nside, const int64_t *d_nside_v,
+                      hpgb_status_t *d_status, void *stream) {
+    return launch_n2r(d_nest, d_ring, n, nside, d_nside_v, 0, d_status, S(stream));
+}
+int hpgb_ring_to_nest(const int64_t *d_ring, int64_t *d_nest, int64_t n, int64_t nside, const int64_t *d_nside_v,
+                      hpgb_status_t *d_status, void *stream) {
+    return launch_r2n(d_ring, d_nest, n, nside, d_nside_v, 0, d_status, S(stream));
+}
+int hpgb_angle_to_pixel(const double *d_a, const double *d_b, int64_t *d_pix, int64_t n, int64_t nside,
+                        const int64_t *d_nside_v, int nest, int lonlat, int degrees, hpgb_status_t *d_status,
+                        void *stream) {
+    return launch_a2p(d_a, d_b, d_pix, n, nside, d_nside_v, nest, lonlat, degrees, 0, d_status, S(stream));
+}
+int hpgb_pixel_to_angle(const int64_t *d_pix, double *d_a, double *d_b, int64_t n, int64_t nside,
+                        const int64_t *d_nside_v, int nest, int lonlat, int degrees, hpgb_status_t *d_status,
+                        void *stream) {
+    return launch_p2a(d_pix, d_a, d_b, n, nside, d_nside_v, nest, lonlat, degrees, 0, d_status, S(stream));
+}
+int hpgb_vector_to_pixel(const double *d_x, const double *d_y, const double *d_z, int64_t *d_pix, int64_t n,
+                         int64_t nside, const int64_t *d_nside_v, int nest, hpgb_status_t *d_status, void *stream) {
+    return launch_v2p(d_x, d_y, d_z, d_pix, n, nside, d_nside_v, nest, 0, d_status, S(stream));
+}
+int hpgb_pixel_to_vector(const int64_t *d_pix, double *d_x, double *d_y, double *d_z, int64_t n, int64_t nside,
+                         const int64_t *d_nside_v, int nest, hpgb_status_t *d_status, void *stream) {
+    return launch_p2v(d_pix, d_x, d_y, d_z, n, nside, d_nside_v, nest, 0, d_status, S(stream));
+}
+int hpgb_neighbors(const int64_t *d_pix, int64_t *d_out_n8, int64_t n, int64_t nside, const int64_t *d_nside_v,
+                   int nest, hpgb_status_t *d_status, void *stream) {
+    return launch_neighbors(d_pix, d_out_n8, n, nside, d_nside_v, nest, 0, d_status, S(stream));
+}
+int hpgb_interp_weights(const double *d_a, const double *d_b, int64_t *d_pix_n4, double *d_wgt_n4, int64_t n,
+                        int64_t nside, const int64_t *d_nside_v, int nest, int lonlat, int degrees,
+                        hpgb_status_t *d_status, void *stream) {
+    return launch_interp(d_a, d_b, d_pix_n4, d_wgt_n4, n, nside, d_nside_v, nest, lonlat, degrees, 0, d_status, S(stream));
+}
+int hpgb_upgrade_pixels(const int64_t *d_pix, int64_t *d_out, int64_t n, int64_t nside, int64_t nside_upgrade,
+                        int nest, hpgb_status_t *d_status, void *stream) {
+    return launch_upgrade(d_pix, d_out, n, nside, nside_upgrade, nest, 0, d_status, S(stream));
+}
+int hpgb_lonlat_to_thetaphi(const double *d_lon, const double *d_lat, double *d_theta, double *d_phi, int64_t n,
+                            int degrees, hpgb_status_t *d_status, void *stream) {
+    return launch_lonlat(d_lon, d_lat, d_theta, d_phi, n, degrees, 0, d_status, S(stream));
+}
+
+// ---- host-pointer entry points: operands in C-argument order, then the optional nside array ----
+#define IN(p, b) {(cc)(p), nullptr, (b)}
+#define OUT(p, b) {nullptr, (char *)(p), (b)}
+#define PIPE(arrs, narr, call)                                                                          \
+    return hpgb_host_pipeline(device, n, arrs, narr,                                                    \
+                              [&](void **d, int64_t base, int64_t cn, hpgb_status_t *st, cudaStream_t s) { return call; }, \
+                              first_bad)
+#define NSV(k) (nside_v ? (const int64_t *)d[k] : nullptr)
+
+int hpgb_host_nest_to_ring(const int64_t *nest, int64_t *ring, int64_t n, int64_t nside, const int64_t *nside_v,
+                           int device, int64_t *first_bad) {
+    hpgb_pipe_arr arrs[3] = {IN(nest, 8), OUT(ring, 8), IN(nside_v, 8)};
+    PIPE(arrs, nside_v ? 3 : 2, launch_n2r((const int64_t *)d[0], (int64_t *)d[1], cn, nside, NSV(2), base, st, s));
+}
+int hpgb_host_ring_to_nest(const int64_t *ring, int64_t *nest, int64_t n, int64_t nside, const int64_t *nside_v,
+                           int device, int64_t *first_bad) {
+    hpgb_pipe_arr arrs[3] = {IN(ring, 8), OUT(nest, 8), IN(nside_v, 8)};
+    PIPE(arrs, nside_v ? 3 : 2, launch_r2n((const int64_t *)d[0], (int64_t *)d[1], cn, nside, NSV(2), base, st, s));
+}
+int hpgb_host_angle_to_pixel(const double *a, const double *b, int64_t *pix, int64_t n, int64_t nside,
+                             const int64_t *nside_v, int nest, int lonlat, int degrees, int device, int64_t *first_bad) {
+    hpgb_pipe_arr arrs[4] = {IN(a, 8), IN(b, 8), OUT(pix, 8), IN(nside_v, 8)};
+    PIPE(arrs, nside_v ? 4 : 3,
+         launch_a2p((const double *)d[0], (const double *)d[1], (int64_t *)d[2], cn, nside, NSV(3), nest, lonlat, degrees, base, st, s));
+}
+int hpgb_host_pixel_to_angle(const int64_t *pix, double *a, double *b, int64_t n, int64_t nside,
+                             const int64_t *nside_v, int nest, int lonlat, int degrees, int device, int64_t *first_bad) {
+    hpgb_pipe_arr arrs[4] = {IN(pix, 8), OUT(a, 8), OUT(b, 8), IN(nside_v, 8)};
+    PIPE(arrs, nside_v ? 4 : 3,
+         launch_p2a((const int64_t *)d[0], (double *)d[1], (double *)d[2], cn, nside, NSV(3), nest, lonlat, degrees, base, st, s));
+}
+int hpgb_host_vector_to_pixel(const double *x, const double *y, const double *z, int64_t *pix, int64_t n,
+                              int64_t nside, const int64_t *nside_v, int nest, int device, int64_t *first_bad) {
+    hpgb_pipe_arr arrs[5] = {IN(x, 8), IN(y, 8), IN(z, 8), OUT(pix, 8), IN(nside_v, 8)};
+    PIPE(arrs, nside_v ? 5 : 4,
+         launch_v2p((const double *)d[0], (const double *)d[1], (const double *)d[2], (int64_t *)d[3], cn, nside, NSV(4), nest, base, st, s));
+}
+int hpgb_host_pixel_to_vector(const int64_t *pix, double *x, double *y, double *z, int64_t n, int64_t nside,
+                              const int64_t *nside_v, int nest, int device, int64_t *first_bad) {
+    hpgb_pipe_arr arrs[5] = {IN(pix, 8), OUT(x, 8), OUT(y, 8), OUT(z, 8), IN(nside_v, 8)};
+    PIPE(arrs, nside_v ? 5 : 4,
+         launch_p2v((const int64_t *)d[0], (double *)d[1], (double *)d[2], (double *)d[3], cn, nside, NSV(4), nest, base, st, s));
+}
+int hpgb_host_neighbors(const int64_t *pix, int64_t *out_n8, int64_t n, int64_t nside, const int64_t *nside_v,
+                        int nest, int device, int64_t *first_bad) {
+    hpgb_pipe_arr arrs[3] = {IN(pix, 8), OUT(out_n8, 64), IN(nside_v, 8)};
+    PIPE(arrs, nside_v ? 3 : 2, launch_neighbors((const int64_t *)d[0], (int64_t *)d[1], cn, nside, NSV(2), nest, base, st, s));
+}
+int hpgb_host_interp_weights(const double *a, const double *b, int64_t *pix_n4, double *wgt_n4, int64_t n,
+                             int64_t nside, const int64_t *nside_v, int nest, int lonlat, int degrees, int device,
+                             int64_t *first_bad) {
+    hpgb_pipe_arr arrs[5] = {IN(a, 8), IN(b, 8), OUT(pix_n4, 32), OUT(wgt_n4, 32), IN(nside_v, 8)};
+    PIPE(arrs, nside_v ? 5 : 4,
+         launch_interp((const double *)d[0], (const double *)d[1], (int64_t *)d[2], (double *)d[3], cn, nside, NSV(4), nest, lonlat, degrees, base, st, s));
+}
+int hpgb_host_upgrade_pixels(const int64_t *pix, int64_t *out, int64_t n, int64_t nside, int64_t nside_upgrade,
+                             int nest, int device, int64_t *first_bad) {
+    if (hpgb_check_nside(nside, 1)) return hpgb_check_nside(nside, 1);
+    if (hpgb_check_nside(nside_upgrade, 1) || nside_upgrade < nside) return HPGB_E_BAD_ARGUMENT;
+    const int64_t ratio = (nside_upgrade / nside) * (nside_upgrade / nside);
+    hpgb_pipe_arr arrs[2] = {IN(pix, 8), OUT(out, 8 * ratio)};
+    PIPE(arrs, 2, launch_upgrade((const int64_t *)d[0], (int64_t *)d[1], cn, nside, nside_upgrade, nest, base, st, s));
+}
+int hpgb_host_lonlat_to_thetaphi(const double *lon, const double *lat, double *theta, double *phi, int64_t n,
+                                 int degrees, int device, int64_t *first_bad) {
+    hpgb_pipe_arr arrs[4] = {IN(lon, 8), IN(lat, 8), OUT(theta, 8), OUT(phi, 8)};
+    PIPE(arrs, 4, launch_lonlat((const double *)d[0], (const double *)d[1], (double *)d[2], (double *)d[3], cn, degrees, base, st, s));
+}
+
+}  // extern "C"

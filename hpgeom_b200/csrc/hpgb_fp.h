@@ -153,17 +153,6 @@ HPGB_HD_NOINLINE bool hpgb_angle_to_pixel_exact(const hpgb_geom &g, const double
 // ---------------------------------------------------------------------------------------------
 #define HPGB_ASIN_2_3 0.72972765622696636345479665981332  // asin(2/3)
 
-HPGB_HD double hpgb_sin_poly(double a) {  // |a| <= 0.74, error < 1 ulp
-    const double a2 = a * a;
-    double p = fma(a2, -7.6471637318198164759e-13, 1.6059043836821614599e-10);  // -1/15!, 1/13!
-    p = fma(p, a2, -2.5052108385441718775e-8);                                   // -1/11!
-    p = fma(p, a2, 2.7557319223985890653e-6);                                    //  1/9!
-    p = fma(p, a2, -1.9841269841269841270e-4);                                   // -1/7!
-    p = fma(p, a2, 8.3333333333333333333e-3);                                    //  1/5!
-    p = fma(p, a2, -1.6666666666666666667e-1);                                   // -1/3!
-    return fma(a * a2, p, a);
-}
-
 HPGB_HD uint32_t hpgb_hi32(double v) {
 #if defined(__CUDA_ARCH__)
     return (uint32_t)__double2hiint(v);
@@ -177,29 +166,77 @@ HPGB_HD uint32_t hpgb_hi32(double v) {
 #endif
 }
 
-// per-nside constants of the fast path (host-computed, passed by value with the geometry)
+// Per-nside constants of the fast path, host-computed and passed by value with the geometry.
+// The polynomial coefficients and unit factors travel here too: kernel parameters live in the
+// constant bank, so fp64 instructions read them as operands instead of materialising 64-bit
+// immediates (two extra instructions per constant per element otherwise).
 struct hpgb_a2p_fast {
-    double ns_half;     // 0.5  * nside
-    double ns_075;      // 0.75 * nside
-    double ns_sqrt6;    // sqrt(6) * nside
-    double scale;       // 2^F, F = 58 - order : fixed-point scale of the edge-line coordinates
-    int32_t fbits;      // F
-    int32_t enabled;    // 0 -> always take the exact path (tiny nside)
+    double ns, ns_half, ns_075, ns_sqrt6;  // nside, 0.5 nside, 0.75 nside, sqrt(6) nside
+    double scale;                          // 2^F: fixed-point scale of the edge-line coordinates
+    double c3, c5, c7, c9, c11, c13, c15;  // sin(a) = a + a^3 (c3 + c5 a^2 + ...), |a| <= 0.74
+    double k_lat, k_lon;                   // radians per input latitude unit; tt per input longitude unit
+    double pole;                           // input latitude of the pole (90 or pi/2 head)
+    double pole_lo;                        // tail of the pole constant (0 in degrees)
+    double lat_max, lon_max;               // fast-path range guards
+    double asin23;                         // asin(2/3): equatorial / polar split in latitude
+    uint32_t fbits, fmask, margin, enabled;
 };
 
+template <bool LONLAT, bool DEGREES>
 HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
     hpgb_a2p_fast f;
     const double dns = (double)g.nside;
+    const int order = g.order < 0 ? 0 : g.order;
+    f.ns = dns;
     f.ns_half = 0.5 * dns;
     f.ns_075 = 0.75 * dns;
     f.ns_sqrt6 = 2.4494897427831780981972840747059 * dns;
-    f.fbits = 58 - g.order;
-    f.scale = ldexp(1.0, f.fbits);
-    f.enabled = (g.order >= 0);
+    // F fraction bits, always inside the low 32-bit word; margin = nside * 2^-44 in fixed-point
+    // units (never below 16 units), see the derivation above hpgb_angle_to_pixel_nest_fast
+    f.fbits = order >= 27 ? (uint32_t)(58 - order) : 32u;
+    f.fmask = f.fbits >= 32 ? 0xFFFFFFFFu : ((1u << f.fbits) - 1u);
+    f.margin = order >= 26 ? (1u << 14) : (order >= 16 ? (1u << (order - 12)) : 16u);
+    f.scale = ldexp(1.0, (int)f.fbits);
+    f.c3 = -1.6666666666666666667e-1;
+    f.c5 = 8.3333333333333333333e-3;
+    f.c7 = -1.9841269841269841270e-4;
+    f.c9 = 2.7557319223985890653e-6;
+    f.c11 = -2.5052108385441718775e-8;
+    f.c13 = 1.6059043836821614599e-10;
+    f.c15 = -7.6471637318198164759e-13;
+    if (LONLAT && DEGREES) {
+        f.k_lat = 1.7453292519943295769e-2;  // pi/180
+        f.k_lon = 1.1111111111111111111e-2;  // 1/90
+        f.pole = 90.0;
+        f.pole_lo = 0.0;
+        f.lat_max = 89.999999;
+        f.lon_max = 720.0;
+    } else {
+        f.k_lat = 1.0;
+        f.k_lon = HPGB_INV_HALFPI;
+        f.pole = HPGB_PIO2_1;
+        f.pole_lo = HPGB_PIO2_2;
+        f.lat_max = 1.5707963;
+        f.lon_max = 12.5;
+    }
+    f.asin23 = 0.72972765622696636345479665981332;
+    f.enabled = (g.order >= 0) ? 1u : 0u;
     return f;
 }
 
-// returns true when `pix` is final; false -> caller must run the exact path
+HPGB_HD double hpgb_sin_poly(const hpgb_a2p_fast &f, double a) {  // |a| <= 0.74, error < 1 ulp
+    const double a2 = a * a;
+    double p = fma(a2, f.c15, f.c13);
+    p = fma(p, a2, f.c11);
+    p = fma(p, a2, f.c9);
+    p = fma(p, a2, f.c7);
+    p = fma(p, a2, f.c5);
+    p = fma(p, a2, f.c3);
+    return fma(a * a2, p, a);
+}
+
+// Result of the fast path for one point: the candidate pixel and whether it can be trusted.
+// Branch-free up to the final select; `ok == false` -> the caller runs the exact path.
 template <bool LONLAT, bool DEGREES>
 HPGB_HD bool hpgb_angle_to_pixel_nest_fast(const hpgb_geom &g, const hpgb_a2p_fast &f, double a, double b,
                                            int64_t &pix) {
@@ -207,47 +244,39 @@ HPGB_HD bool hpgb_angle_to_pixel_nest_fast(const hpgb_geom &g, const hpgb_a2p_fa
     double lat, cth, tt;
     bool guard;
     if (LONLAT) {
-        if (DEGREES) {
-            lat = b * 1.7453292519943295769e-2;                        // pi/180
-            cth = (90.0 - fabs(b)) * 1.7453292519943295769e-2;         // exact difference
-            const double t = a * 1.1111111111111111111e-2;             // lon/90
-            tt = fma(-4.0, floor(t * 0.25), t);
-            guard = !(fabs(b) < 89.999999) || !(fabs(a) <= 720.0);
-        } else {
-            lat = b;
-            cth = (HPGB_PIO2_1 - fabs(b)) + HPGB_PIO2_2;
-            const double t = a * HPGB_INV_HALFPI;
-            tt = fma(-4.0, floor(t * 0.25), t);
-            guard = !(fabs(b) < 1.5707963) || !(fabs(a) <= 12.5);
-        }
+        lat = DEGREES ? b * f.k_lat : b;
+        cth = DEGREES ? (f.pole - fabs(b)) * f.k_lat : (f.pole - fabs(b)) + f.pole_lo;
+        const double t = a * f.k_lon;  // lon/90 or lon*2/pi
+        tt = fma(-4.0, floor(t * 0.25), t);
+        guard = !(fabs(b) < f.lat_max) || !(fabs(a) <= f.lon_max);
     } else {
-        lat = (HPGB_PIO2_1 - a) + HPGB_PIO2_2;  // pi/2 - theta, accurate also near the equator
-        cth = (a < HPGB_PIO2_1) ? a : (HPGB_PI_1 - a) + HPGB_PI_2;
-        tt = b * HPGB_INV_HALFPI;               // the reference's own expression
+        lat = (f.pole - a) + f.pole_lo;  // pi/2 - theta, accurate also near the equator
+        cth = (a < f.pole) ? a : (HPGB_PI_1 - a) + HPGB_PI_2;
+        tt = b * f.k_lon;                // the reference's own expression
         guard = !(a > 1e-8 && a < 3.14159265) || !(b >= 0.0 && b < 6.2831853);
     }
     const double al = fabs(lat);
-    const bool eq = al <= HPGB_ASIN_2_3;
-    guard = guard || (fabs(al - HPGB_ASIN_2_3) < 1e-11);
+    const bool eq = al <= f.asin23;
+    guard = guard || (fabs(al - f.asin23) < 1e-11);
     // tt + 4 has a fixed exponent: its mantissa is tt in fixed point (face index + fraction)
     const uint32_t thi = hpgb_hi32(tt + 4.0);
     const uint32_t ntt = (thi >> 18) & 3u;
     guard = guard || (((thi + 1u) & 0x3FFFFu) < 2u);  // tt within 2^-18 of an integer (face edge / wrap)
     const double tp = tt - (double)(int32_t)ntt;
     // ---- one sine for both branches ----
-    const double s = hpgb_sin_poly(eq ? lat : 0.5 * cth);
-    // ---- edge-line coordinates ----
-    const double t1 = fma(2.0 * f.ns_half, tt, f.ns_half);  // nside*(0.5+tt)
+    const double s = hpgb_sin_poly(f, eq ? lat : 0.5 * cth);
+    // ---- edge-line coordinates, fixed point with F fraction bits ----
+    const double t1 = fma(f.ns, tt, f.ns_half);  // nside*(0.5+tt)
     const double t2 = f.ns_075 * s;
     const double tmp = f.ns_sqrt6 * s;
     const double p1 = tp * tmp;
     const double q1 = eq ? (t1 - t2) : p1;
     const double q2 = eq ? (t1 + t2) : (tmp - p1);
-    const int64_t x1 = hpgb_d2ll(q1 * f.scale);
-    const int64_t x2 = hpgb_d2ll(q2 * f.scale);
-    const int64_t fmask = ((int64_t)1 << f.fbits) - 1;
-    const int64_t M = (int64_t)1 << 14;  // nside * 2^-44 in fixed-point units
-    guard = guard || (((x1 + M) & fmask) < 2 * M) || (((x2 + M) & fmask) < 2 * M);
+    const uint64_t x1 = (uint64_t)hpgb_d2ll(q1 * f.scale);
+    const uint64_t x2 = (uint64_t)hpgb_d2ll(q2 * f.scale);
+    // within `margin` of an integer?  (the fraction sits in the low word)
+    const uint32_t n1 = ((uint32_t)x1 + f.margin) & f.fmask, n2 = ((uint32_t)x2 + f.margin) & f.fmask;
+    guard = guard || ((n1 < n2 ? n1 : n2) < 2u * f.margin);
     const uint32_t j1 = (uint32_t)(x1 >> f.fbits), j2 = (uint32_t)(x2 >> f.fbits);
     const uint32_t ns = (uint32_t)g.nside, nsm1 = ns - 1u;
     uint32_t ix, iy, face;

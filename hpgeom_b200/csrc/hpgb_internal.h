@@ -1,0 +1,32 @@
+// hpgb_internal.h -- kernel launchers shared between the k_*.cu translation units and hpgb_abi.cu.
+// All take DEVICE pointers, the global index `base` of element 0 (chunked host pipeline) and
+// launch asynchronously on `s`; return HPGB_OK / HPGB_E_*.
+#ifndef HPGB_INTERNAL_H
+#define HPGB_INTERNAL_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hpgb.h"
+
+int launch_n2r(const int64_t *in, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v, int64_t base,
+               hpgb_status_t *st, cudaStream_t s);
+int launch_r2n(const int64_t *in, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v, int64_t base,
+               hpgb_status_t *st, cudaStream_t s);
+int launch_a2p(const double *a, const double *b, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v,
+               int nest, int lonlat, int degrees, int64_t base, hpgb_status_t *st, cudaStream_t s);
+int launch_p2a(const int64_t *pix, double *a, double *b, int64_t n, int64_t nside, const int64_t *nside_v, int nest,
+               int lonlat, int degrees, int64_t base, hpgb_status_t *st, cudaStream_t s);
+int launch_v2p(const double *x, const double *y, const double *z, int64_t *out, int64_t n, int64_t nside,
+               const int64_t *nside_v, int nest, int64_t base, hpgb_status_t *st, cudaStream_t s);
+int launch_p2v(const int64_t *pix, double *x, double *y, double *z, int64_t n, int64_t nside, const int64_t *nside_v,
+               int nest, int64_t base, hpgb_status_t *st, cudaStream_t s);
+int launch_neighbors(const int64_t *pix, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v, int nest,
+                     int64_t base, hpgb_status_t *st, cudaStream_t s);
+int launch_interp(const double *a, const double *b, int64_t *pix, double *wgt, int64_t n, int64_t nside,
+                  const int64_t *nside_v, int nest, int lonlat, int degrees, int64_t base, hpgb_status_t *st,
+                  cudaStream_t s);
+int launch_upgrade(const int64_t *pix, int64_t *out, int64_t n, int64_t nside, int64_t nside_upgrade, int nest,
+                   int64_t base, hpgb_status_t *st, cudaStream_t s);
+int launch_lonlat(const double *lon, const double *lat, double *theta, double *phi, int64_t n, int degrees,
+                  int64_t base, hpgb_status_t *st, cudaStream_t s);
+#endif

@@ -42,6 +42,7 @@ struct hpgb_bad_t {
 //   typename Op::In2;  In2 load2(int64_t i) const;                 // loads elements i, i+1 (i even)
 //   typename Op::Ctx;  Ctx prologue() const;                       // per-CTA setup (e.g. stage the trig table)
 //   void run2(int64_t i, const In2&, const Ctx&, hpgb_bad_t&) const; // converts + stores i, i+1
+//   void run4(i0, v0, i1, v1, ctx, bad) const;                      // two pairs (ILP across both)
 //   void run1(int64_t i, const Ctx&, hpgb_bad_t&) const;            // scalar element
 template <class Op>
 __global__ void __launch_bounds__(HPGB_BLOCK) k_map2(const Op op, const int64_t n, hpgb_status_t *st) {
@@ -53,8 +54,7 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_map2(const Op op, const int64_t 
     for (; p + stride < npair; p += 2 * stride) {
         const typename Op::In2 v0 = op.load2(2 * p);
         const typename Op::In2 v1 = op.load2(2 * (p + stride));
-        op.run2(2 * p, v0, ctx, bad);
-        op.run2(2 * (p + stride), v1, ctx, bad);
+        op.run4(2 * p, v0, 2 * (p + stride), v1, ctx, bad);
     }
     if (p < npair) op.run2(2 * p, op.load2(2 * p), ctx, bad);
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.run1(n - 1, ctx, bad);
@@ -74,6 +74,13 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_map1(const Op op, const int64_t 
 // (1664 B; random row gathers from it are LSU work that overlaps the fp64 pipe)
 static __device__ const double g_hpgb_sincos[4 * HPGB_SINCOS_ROWS] = HPGB_SINCOS_TABLE_INIT;
 struct hpgb_no_ctx {};
+// default run4 = two run2 calls
+#define HPGB_DEFAULT_RUN4                                                                                      \
+    __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &c, \
+                                         hpgb_bad_t &bad) const {                                             \
+        run2(i0, v0, c, bad);                                                                                 \
+        run2(i1, v1, c, bad);                                                                                 \
+    }
 __device__ __forceinline__ const double *hpgb_stage_table() {
     __shared__ double sT[4 * HPGB_SINCOS_ROWS];
     for (int i = threadIdx.x; i < 4 * HPGB_SINCOS_ROWS; i += HPGB_BLOCK) sT[i] = g_hpgb_sincos[i];

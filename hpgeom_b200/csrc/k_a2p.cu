@@ -1,0 +1,142 @@
+// k_a2p.cu -- angle_to_pixel kernels (the headline path)
+// (one Op struct per API function, see hpgb_launch.cuh for the kernel skeleton they plug into;
+// templated on the flags the reference tests per element -- nest / lonlat / degrees,
+// hpgeom/hpgeom.c:143-153 -- so those branches are compile-time here.  A scalar instantiation
+// (VAR) serves per-element nside arrays.)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hpgb_core.h"
+#include "hpgb_fp.h"
+#include "hpgb_host.h"
+#include "hpgb_internal.h"
+#include "hpgb_launch.cuh"
+
+namespace {
+
+// per-element geometry for nside arrays; flags the element and returns false on a bad nside
+// (the reference re-checks nside whenever it changes, hpgeom/hpgeom.c:133-140)
+__device__ __forceinline__ bool var_geom(const int64_t *nside_v, int64_t i, int nest, hpgb_geom &g) {
+    const int64_t ns = hpgb_ld1(nside_v + i);
+    if (hpgb_check_nside(ns, nest)) return false;
+    g = hpgb_make_geom(ns, nest);
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------
+// angle_to_pixel   (reference loop: hpgeom/hpgeom.c:126-157)   16 B in + 8 B out per point.
+// NEST: fast path (hpgb_fp.h) with the exact path as a rare, non-inlined fallback.
+// RING: exact path (ring fast path: next).
+// -------------------------------------------------------------------------------------------
+template <bool NEST, bool LONLAT, bool DEGREES, bool VAR>
+struct OpAng2Pix {
+    const double *a, *b;
+    int64_t *out;
+    const int64_t *nside_v;
+    int64_t base;
+    hpgb_geom g;
+    hpgb_a2p_fast f;
+    struct In2 {
+        double2 a, b;
+    };
+    typedef const double *Ctx;
+
+    __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
+    __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(a + i), hpgb_ld2(b + i)}; }
+    // exact path for one element (rare): non-inlined call, flags the element when it is invalid
+    __device__ __forceinline__ int64_t slow(const hpgb_geom &gg, double va, double vb, int64_t i, Ctx T,
+                                            hpgb_bad_t &bad) const {
+        int64_t pix;
+        if (!hpgb_angle_to_pixel_exact<NEST, LONLAT, DEGREES>(gg, T, va, vb, pix)) bad.flag(base + i);
+        return pix;
+    }
+    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &bad) const {
+        int64_t p0 = 0, p1 = 0;
+        bool ok0 = false, ok1 = false;
+        if (NEST) {  // both fast paths first (independent -> the fp64 chains interleave), exact path after
+            ok0 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v.a.x, v.b.x, p0);
+            ok1 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v.a.y, v.b.y, p1);
+        }
+        if (!ok0) p0 = slow(g, v.a.x, v.b.x, i, T, bad);
+        if (!ok1) p1 = slow(g, v.a.y, v.b.y, i + 1, T, bad);
+        hpgb_st2(out + i, p0, p1);
+    }
+    __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
+                                         hpgb_bad_t &bad) const {
+        int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+        bool ok0 = false, ok1 = false, ok2 = false, ok3 = false;
+        if (NEST) {
+            ok0 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v0.a.x, v0.b.x, p0);
+            ok1 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v0.a.y, v0.b.y, p1);
+            ok2 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v1.a.x, v1.b.x, p2);
+            ok3 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v1.a.y, v1.b.y, p3);
+        }
+        if (!(ok0 && ok1 && ok2 && ok3)) {
+            if (!ok0) p0 = slow(g, v0.a.x, v0.b.x, i0, T, bad);
+            if (!ok1) p1 = slow(g, v0.a.y, v0.b.y, i0 + 1, T, bad);
+            if (!ok2) p2 = slow(g, v1.a.x, v1.b.x, i1, T, bad);
+            if (!ok3) p3 = slow(g, v1.a.y, v1.b.y, i1 + 1, T, bad);
+        }
+        hpgb_st2(out + i0, p0, p1);
+        hpgb_st2(out + i1, p2, p3);
+    }
+    __device__ __forceinline__ void run1(int64_t i, const Ctx &T, hpgb_bad_t &bad) const {
+        hpgb_geom gg = g;
+        hpgb_a2p_fast ff = f;
+        if (VAR) {
+            if (!var_geom(nside_v, i, NEST, gg)) {
+                bad.flag(base + i);
+                hpgb_st1(out + i, -1);
+                return;
+            }
+            ff = hpgb_make_a2p_fast<LONLAT, DEGREES>(gg);
+        }
+        const double va = hpgb_ld1(a + i), vb = hpgb_ld1(b + i);
+        int64_t pix;
+        if (!(NEST && hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(gg, ff, va, vb, pix))) pix = slow(gg, va, vb, i, T, bad);
+        hpgb_st1(out + i, pix);
+    }
+};
+
+template <bool NEST, bool LONLAT, bool DEGREES>
+int launch_a2p_t(const double *a, const double *b, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v,
+                 int64_t base, hpgb_status_t *st, cudaStream_t s) {
+    if (nside_v) {
+        OpAng2Pix<NEST, LONLAT, DEGREES, true> op{a, b, out, nside_v, base, hpgb_geom(), hpgb_a2p_fast()};
+        return hpgb_launch_map1(op, n, st, s);
+    }
+    const hpgb_geom g = hpgb_make_geom(nside, NEST);
+    OpAng2Pix<NEST, LONLAT, DEGREES, false> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g)};
+    return hpgb_launch_map(op, n, hpgb_aligned16(a) && hpgb_aligned16(b) && hpgb_aligned16(out), st, s);
+}
+
+}  // namespace
+
+int launch_a2p(const double *a, const double *b, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v,
+               int nest, int lonlat, int degrees, int64_t base, hpgb_status_t *st, cudaStream_t s) {
+    if (n < 0 || (n > 0 && (!a || !b || !out || !st))) return HPGB_E_BAD_ARGUMENT;
+    if (n == 0) return HPGB_OK;
+    if (!nside_v) {
+        int c = hpgb_check_nside(nside, nest);
+        if (c) return c;
+    }
+#define GO(N, L, D) return launch_a2p_t<N, L, D>(a, b, out, n, nside, nside_v, base, st, s)
+    if (nest) {
+        if (lonlat) {
+            if (degrees) GO(true, true, true);
+            GO(true, true, false);
+        }
+        GO(true, false, false);
+    }
+    if (lonlat) {
+        if (degrees) GO(false, true, true);
+        GO(false, true, false);
+    }
+    GO(false, false, false);
+#undef GO
+}
+
+namespace {
+
+
+}  // namespace

@@ -1,0 +1,252 @@
+// k_p2a.cu -- pixel_to_angle / pixel_to_vector kernels
+// (one Op struct per API function, see hpgb_launch.cuh for the kernel skeleton they plug into;
+// templated on the flags the reference tests per element -- nest / lonlat / degrees,
+// hpgeom/hpgeom.c:143-153 -- so those branches are compile-time here.  A scalar instantiation
+// (VAR) serves per-element nside arrays.)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hpgb_core.h"
+#include "hpgb_fp.h"
+#include "hpgb_host.h"
+#include "hpgb_internal.h"
+#include "hpgb_launch.cuh"
+
+namespace {
+
+// per-element geometry for nside arrays; flags the element and returns false on a bad nside
+// (the reference re-checks nside whenever it changes, hpgeom/hpgeom.c:133-140)
+__device__ __forceinline__ bool var_geom(const int64_t *nside_v, int64_t i, int nest, hpgb_geom &g) {
+    const int64_t ns = hpgb_ld1(nside_v + i);
+    if (hpgb_check_nside(ns, nest)) return false;
+    g = hpgb_make_geom(ns, nest);
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------
+// pixel_to_angle   (reference loop: hpgeom/hpgeom.c:426-457)   8 B in + 16 B out per pixel
+// -------------------------------------------------------------------------------------------
+template <bool NEST, bool POW2, bool LONLAT, bool DEGREES, bool VAR>
+struct OpPix2Ang {
+    const int64_t *pix;
+    double *a, *b;
+    const int64_t *nside_v;
+    int64_t base;
+    hpgb_geom g;
+    typedef longlong2 In2;
+    typedef const double *Ctx;
+    HPGB_DEFAULT_RUN4
+
+    __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
+    __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
+    __device__ __forceinline__ void conv(const hpgb_geom &gg, int64_t p, int64_t i, Ctx T, hpgb_bad_t &bad, double &va,
+                                         double &vb) const {
+        if (!hpgb_pixel_ok(gg, p)) {
+            bad.flag(base + i);
+            va = vb = 0.0;
+            return;
+        }
+        hpgb_pix2ang<NEST, POW2, LONLAT, DEGREES>(gg, T, p, va, vb);
+    }
+    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &bad) const {
+        double a0, b0, a1, b1;
+        conv(g, v.x, i, T, bad, a0, b0);
+        conv(g, v.y, i + 1, T, bad, a1, b1);
+        hpgb_st2(a + i, a0, a1);
+        hpgb_st2(b + i, b0, b1);
+    }
+    __device__ __forceinline__ void run1(int64_t i, const Ctx &T, hpgb_bad_t &bad) const {
+        double va = 0.0, vb = 0.0;
+        if (VAR) {
+            hpgb_geom gg;
+            if (!var_geom(nside_v, i, NEST, gg))
+                bad.flag(base + i);
+            else
+                conv(gg, hpgb_ld1(pix + i), i, T, bad, va, vb);
+        } else {
+            conv(g, hpgb_ld1(pix + i), i, T, bad, va, vb);
+        }
+        hpgb_st1(a + i, va);
+        hpgb_st1(b + i, vb);
+    }
+};
+
+template <bool NEST, bool LONLAT, bool DEGREES>
+int launch_p2a_t(const int64_t *pix, double *a, double *b, int64_t n, int64_t nside, const int64_t *nside_v,
+                 int64_t base, hpgb_status_t *st, cudaStream_t s) {
+    if (nside_v) {  // per-element nside: the general-nside code path handles powers of two as well
+        OpPix2Ang<NEST, NEST, LONLAT, DEGREES, true> op{pix, a, b, nside_v, base, hpgb_geom()};
+        return hpgb_launch_map1(op, n, st, s);
+    }
+    const hpgb_geom g = hpgb_make_geom(nside, NEST);
+    const bool vec = hpgb_aligned16(pix) && hpgb_aligned16(a) && hpgb_aligned16(b);
+    if (NEST || g.order >= 0) {
+        OpPix2Ang<NEST, true, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g};
+        return hpgb_launch_map(op, n, vec, st, s);
+    }
+    OpPix2Ang<false, false, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g};
+    return hpgb_launch_map(op, n, vec, st, s);
+}
+
+}  // namespace
+
+int launch_p2a(const int64_t *pix, double *a, double *b, int64_t n, int64_t nside, const int64_t *nside_v, int nest,
+               int lonlat, int degrees, int64_t base, hpgb_status_t *st, cudaStream_t s) {
+    if (n < 0 || (n > 0 && (!pix || !a || !b || !st))) return HPGB_E_BAD_ARGUMENT;
+    if (n == 0) return HPGB_OK;
+    if (!nside_v) {
+        int c = hpgb_check_nside(nside, nest);
+        if (c) return c;
+    }
+#define GO(N, L, D) return launch_p2a_t<N, L, D>(pix, a, b, n, nside, nside_v, base, st, s)
+    if (nest) {
+        if (lonlat) {
+            if (degrees) GO(true, true, true);
+            GO(true, true, false);
+        }
+        GO(true, false, false);
+    }
+    if (lonlat) {
+        if (degrees) GO(false, true, true);
+        GO(false, true, false);
+    }
+    GO(false, false, false);
+#undef GO
+}
+
+namespace {
+
+// -------------------------------------------------------------------------------------------
+// vector_to_pixel / pixel_to_vector   (hpgeom/hpgeom.c:2323-2345, :2617-2643)   32 B per element
+// -------------------------------------------------------------------------------------------
+template <bool NEST, bool VAR>
+struct OpVec2Pix {
+    const double *x, *y, *z;
+    int64_t *out;
+    const int64_t *nside_v;
+    int64_t base;
+    hpgb_geom g;
+    struct In2 {
+        double2 x, y, z;
+    };
+    typedef const double *Ctx;
+    HPGB_DEFAULT_RUN4
+    __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
+    __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(x + i), hpgb_ld2(y + i), hpgb_ld2(z + i)}; }
+    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &) const {
+        hpgb_st2(out + i, hpgb_vec2pix<NEST>(g, T, v.x.x, v.y.x, v.z.x), hpgb_vec2pix<NEST>(g, T, v.x.y, v.y.y, v.z.y));
+    }
+    __device__ __forceinline__ void run1(int64_t i, const Ctx &T, hpgb_bad_t &bad) const {
+        hpgb_geom gg = g;
+        if (VAR && !var_geom(nside_v, i, NEST, gg)) {
+            bad.flag(base + i);
+            hpgb_st1(out + i, -1);
+            return;
+        }
+        hpgb_st1(out + i, hpgb_vec2pix<NEST>(gg, T, hpgb_ld1(x + i), hpgb_ld1(y + i), hpgb_ld1(z + i)));
+    }
+};
+
+template <bool NEST>
+int launch_v2p_t(const double *x, const double *y, const double *z, int64_t *out, int64_t n, int64_t nside,
+                 const int64_t *nside_v, int64_t base, hpgb_status_t *st, cudaStream_t s) {
+    if (nside_v) {
+        OpVec2Pix<NEST, true> op{x, y, z, out, nside_v, base, hpgb_geom()};
+        return hpgb_launch_map1(op, n, st, s);
+    }
+    OpVec2Pix<NEST, false> op{x, y, z, out, nullptr, base, hpgb_make_geom(nside, NEST)};
+    return hpgb_launch_map(op, n, hpgb_aligned16(x) && hpgb_aligned16(y) && hpgb_aligned16(z) && hpgb_aligned16(out), st, s);
+}
+
+}  // namespace
+
+int launch_v2p(const double *x, const double *y, const double *z, int64_t *out, int64_t n, int64_t nside,
+               const int64_t *nside_v, int nest, int64_t base, hpgb_status_t *st, cudaStream_t s) {
+    if (n < 0 || (n > 0 && (!x || !y || !z || !out || !st))) return HPGB_E_BAD_ARGUMENT;
+    if (n == 0) return HPGB_OK;
+    if (!nside_v) {
+        int c = hpgb_check_nside(nside, nest);
+        if (c) return c;
+    }
+    return nest ? launch_v2p_t<true>(x, y, z, out, n, nside, nside_v, base, st, s)
+                : launch_v2p_t<false>(x, y, z, out, n, nside, nside_v, base, st, s);
+}
+
+namespace {
+
+template <bool NEST, bool POW2, bool VAR>
+struct OpPix2Vec {
+    const int64_t *pix;
+    double *x, *y, *z;
+    const int64_t *nside_v;
+    int64_t base;
+    hpgb_geom g;
+    typedef longlong2 In2;
+    typedef const double *Ctx;
+    HPGB_DEFAULT_RUN4
+    __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
+    __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
+    __device__ __forceinline__ void conv(const hpgb_geom &gg, int64_t p, int64_t i, Ctx T, hpgb_bad_t &bad, double &vx,
+                                         double &vy, double &vz) const {
+        if (!hpgb_pixel_ok(gg, p)) {
+            bad.flag(base + i);
+            vx = vy = vz = 0.0;
+            return;
+        }
+        hpgb_pix2vec<NEST, POW2>(gg, T, p, vx, vy, vz);
+    }
+    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &bad) const {
+        double x0, y0, z0, x1, y1, z1;
+        conv(g, v.x, i, T, bad, x0, y0, z0);
+        conv(g, v.y, i + 1, T, bad, x1, y1, z1);
+        hpgb_st2(x + i, x0, x1);
+        hpgb_st2(y + i, y0, y1);
+        hpgb_st2(z + i, z0, z1);
+    }
+    __device__ __forceinline__ void run1(int64_t i, const Ctx &T, hpgb_bad_t &bad) const {
+        double vx = 0.0, vy = 0.0, vz = 0.0;
+        hpgb_geom gg = g;
+        if (VAR && !var_geom(nside_v, i, NEST, gg))
+            bad.flag(base + i);
+        else
+            conv(gg, hpgb_ld1(pix + i), i, T, bad, vx, vy, vz);
+        hpgb_st1(x + i, vx);
+        hpgb_st1(y + i, vy);
+        hpgb_st1(z + i, vz);
+    }
+};
+
+}  // namespace
+
+int launch_p2v(const int64_t *pix, double *x, double *y, double *z, int64_t n, int64_t nside, const int64_t *nside_v,
+               int nest, int64_t base, hpgb_status_t *st, cudaStream_t s) {
+    if (n < 0 || (n > 0 && (!pix || !x || !y || !z || !st))) return HPGB_E_BAD_ARGUMENT;
+    if (n == 0) return HPGB_OK;
+    if (nside_v) {
+        if (nest) {
+            OpPix2Vec<true, true, true> op{pix, x, y, z, nside_v, base, hpgb_geom()};
+            return hpgb_launch_map1(op, n, st, s);
+        }
+        OpPix2Vec<false, false, true> op{pix, x, y, z, nside_v, base, hpgb_geom()};
+        return hpgb_launch_map1(op, n, st, s);
+    }
+    int c = hpgb_check_nside(nside, nest);
+    if (c) return c;
+    const hpgb_geom g = hpgb_make_geom(nside, nest);
+    const bool vec = hpgb_aligned16(pix) && hpgb_aligned16(x) && hpgb_aligned16(y) && hpgb_aligned16(z);
+    if (nest) {
+        OpPix2Vec<true, true, false> op{pix, x, y, z, nullptr, base, g};
+        return hpgb_launch_map(op, n, vec, st, s);
+    }
+    if (g.order >= 0) {
+        OpPix2Vec<false, true, false> op{pix, x, y, z, nullptr, base, g};
+        return hpgb_launch_map(op, n, vec, st, s);
+    }
+    OpPix2Vec<false, false, false> op{pix, x, y, z, nullptr, base, g};
+    return hpgb_launch_map(op, n, vec, st, s);
+}
+
+namespace {
+
+
+}  // namespace

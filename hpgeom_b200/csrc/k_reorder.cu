@@ -1,0 +1,279 @@
+// k_reorder.cu -- integer kernels: nest_to_ring / ring_to_nest, neighbors, upgrade_pixels, lonlat_to_thetaphi
+// (one Op struct per API function, see hpgb_launch.cuh for the kernel skeleton they plug into;
+// templated on the flags the reference tests per element -- nest / lonlat / degrees,
+// hpgeom/hpgeom.c:143-153 -- so those branches are compile-time here.  A scalar instantiation
+// (VAR) serves per-element nside arrays.)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hpgb_core.h"
+#include "hpgb_fp.h"
+#include "hpgb_host.h"
+#include "hpgb_internal.h"
+#include "hpgb_launch.cuh"
+
+namespace {
+
+// per-element geometry for nside arrays; flags the element and returns false on a bad nside
+// (the reference re-checks nside whenever it changes, hpgeom/hpgeom.c:133-140)
+__device__ __forceinline__ bool var_geom(const int64_t *nside_v, int64_t i, int nest, hpgb_geom &g) {
+    const int64_t ns = hpgb_ld1(nside_v + i);
+    if (hpgb_check_nside(ns, nest)) return false;
+    g = hpgb_make_geom(ns, nest);
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------
+// nest_to_ring / ring_to_nest   (reference loops: hpgeom/hpgeom.c:1429-1450, :1699-1720)
+// 8 B in + 8 B out per pixel, integer only.
+// -------------------------------------------------------------------------------------------
+template <bool TO_RING, bool VAR>
+struct OpReorder {
+    const int64_t *in;
+    int64_t *out;
+    const int64_t *nside_v;
+    int64_t base;  // global index of element 0 (chunked host pipeline)
+    hpgb_geom g;
+    typedef longlong2 In2;
+    typedef hpgb_no_ctx Ctx;
+    HPGB_DEFAULT_RUN4
+
+    __device__ __forceinline__ Ctx prologue() const { return Ctx(); }
+    __device__ __forceinline__ int64_t conv(const hpgb_geom &gg, int64_t p, int64_t i, hpgb_bad_t &bad) const {
+        if (!hpgb_pixel_ok(gg, p)) {
+            bad.flag(base + i);
+            return -1;
+        }
+        return TO_RING ? hpgb_nest2ring(gg, p) : hpgb_ring2nest(gg, p);
+    }
+    __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(in + i); }
+    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &, hpgb_bad_t &bad) const {
+        hpgb_st2(out + i, conv(g, v.x, i, bad), conv(g, v.y, i + 1, bad));
+    }
+    __device__ __forceinline__ void run1(int64_t i, const Ctx &, hpgb_bad_t &bad) const {
+        if (VAR) {
+            hpgb_geom gg;
+            if (!var_geom(nside_v, i, 1, gg)) {
+                bad.flag(base + i);
+                hpgb_st1(out + i, -1);
+                return;
+            }
+            hpgb_st1(out + i, conv(gg, hpgb_ld1(in + i), i, bad));
+        } else {
+            hpgb_st1(out + i, conv(g, hpgb_ld1(in + i), i, bad));
+        }
+    }
+};
+
+template <bool TO_RING>
+int launch_reorder(const int64_t *in, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v, int64_t base,
+                   hpgb_status_t *st, cudaStream_t s) {
+    if (n < 0 || (n > 0 && (!in || !out || !st))) return HPGB_E_BAD_ARGUMENT;
+    if (n == 0) return HPGB_OK;  // the reference checks nside inside the loop: no elements, no error
+    if (nside_v) {
+        OpReorder<TO_RING, true> op{in, out, nside_v, base, hpgb_geom()};
+        return hpgb_launch_map1(op, n, st, s);
+    }
+    int c = hpgb_check_nside(nside, 1);
+    if (c) return c;
+    OpReorder<TO_RING, false> op{in, out, nullptr, base, hpgb_make_geom(nside, 1)};
+    return hpgb_launch_map(op, n, hpgb_aligned16(in) && hpgb_aligned16(out), st, s);
+}
+
+// -------------------------------------------------------------------------------------------
+// neighbors   (hpgeom/hpgeom.c:2928-2959)   8 B in + 64 B out per pixel, rows of 8 (row-major)
+// One thread per pixel; the row leaves as four 128-bit streaming stores.
+// -------------------------------------------------------------------------------------------
+template <bool NEST, bool POW2, bool VAR>
+struct OpNeighbors {
+    const int64_t *pix;
+    int64_t *out;
+    const int64_t *nside_v;
+    int64_t base;
+    hpgb_geom g;
+    typedef longlong2 In2;
+    typedef hpgb_no_ctx Ctx;
+    HPGB_DEFAULT_RUN4
+    __device__ __forceinline__ Ctx prologue() const { return Ctx(); }
+    __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
+    __device__ __forceinline__ void row(const hpgb_geom &gg, int64_t p, int64_t i, hpgb_bad_t &bad) const {
+        int64_t r[8];
+        if (!hpgb_pixel_ok(gg, p)) {
+            bad.flag(base + i);
+#pragma unroll
+            for (int m = 0; m < 8; m++) r[m] = -1;
+        } else {
+            hpgb_neighbors<NEST, POW2>(gg, p, r);
+        }
+        int64_t *o = out + 8 * i;  // 64-byte rows: always 16-byte aligned when `out` is
+#pragma unroll
+        for (int m = 0; m < 8; m += 2) hpgb_st2(o + m, r[m], r[m + 1]);
+    }
+    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &, hpgb_bad_t &bad) const {
+        row(g, v.x, i, bad);
+        row(g, v.y, i + 1, bad);
+    }
+    __device__ __forceinline__ void run1(int64_t i, const Ctx &, hpgb_bad_t &bad) const {
+        hpgb_geom gg = g;
+        if (VAR && !var_geom(nside_v, i, NEST, gg)) {
+            bad.flag(base + i);
+            for (int m = 0; m < 8; m++) out[8 * i + m] = -1;
+            return;
+        }
+        row(gg, hpgb_ld1(pix + i), i, bad);
+    }
+};
+
+}  // namespace
+
+int launch_neighbors(const int64_t *pix, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v, int nest,
+                     int64_t base, hpgb_status_t *st, cudaStream_t s) {
+    if (n < 0 || (n > 0 && (!pix || !out || !st))) return HPGB_E_BAD_ARGUMENT;
+    if (n == 0) return HPGB_OK;
+    if (!hpgb_aligned16(out)) return HPGB_E_BAD_ARGUMENT;  // rows are written with 128-bit stores
+    if (nside_v) {
+        if (nest) {
+            OpNeighbors<true, true, true> op{pix, out, nside_v, base, hpgb_geom()};
+            return hpgb_launch_map1(op, n, st, s);
+        }
+        OpNeighbors<false, false, true> op{pix, out, nside_v, base, hpgb_geom()};
+        return hpgb_launch_map1(op, n, st, s);
+    }
+    int c = hpgb_check_nside(nside, nest);
+    if (c) return c;
+    const hpgb_geom g = hpgb_make_geom(nside, nest);
+    const bool vec = hpgb_aligned16(pix);
+    if (nest) {
+        OpNeighbors<true, true, false> op{pix, out, nullptr, base, g};
+        return hpgb_launch_map(op, n, vec, st, s);
+    }
+    if (g.order >= 0) {
+        OpNeighbors<false, true, false> op{pix, out, nullptr, base, g};
+        return hpgb_launch_map(op, n, vec, st, s);
+    }
+    OpNeighbors<false, false, false> op{pix, out, nullptr, base, g};
+    return hpgb_launch_map(op, n, vec, st, s);
+}
+
+namespace {
+
+// -------------------------------------------------------------------------------------------
+// upgrade_pixels   (hpgeom/hpgeom.py:515-556 fused: [ring->nest] -> children -> [nest->ring])
+// One thread per OUTPUT pixel (coalesced 8 B..16 B stores); the parent is re-read through L1/L2
+// by its 4^k children.  Element error classes (priority via the high bits of the atomicMin key):
+//   class 0: pixel out of range              (the reference's ring_to_nest check)
+//   class 1: nest pixel == npix-1            (the reference range-checks p+1, hpgeom.py:505)
+// -------------------------------------------------------------------------------------------
+#define HPGB_UPGRADE_CLASS1 ((int64_t)1 << 62)
+
+template <bool NEST>
+__global__ void __launch_bounds__(HPGB_BLOCK) k_upgrade(const int64_t *__restrict__ pix, int64_t *__restrict__ out,
+                                                        const int64_t n_out, const int shift, const hpgb_geom g,
+                                                        const hpgb_geom gu, const int64_t base, hpgb_status_t *st) {
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    hpgb_bad_t bad;
+    for (int64_t o = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; o < n_out; o += stride) {
+        const int64_t i = o >> shift;
+        const int64_t j = o & (((int64_t)1 << shift) - 1);
+        int64_t p = __ldg(pix + i);
+        int64_t r = -1;
+        if (!hpgb_pixel_ok(g, p)) {
+            bad.flag(base + i);
+        } else {
+            if (!NEST) p = hpgb_ring2nest(g, p);
+            if (p == g.npix - 1) bad.flag(HPGB_UPGRADE_CLASS1 | (base + i));
+            r = (p << shift) + j;
+            if (!NEST) r = hpgb_nest2ring(gu, r);
+        }
+        __stcs(out + o, r);
+    }
+    bad.commit(st);
+}
+
+}  // namespace
+
+int launch_upgrade(const int64_t *pix, int64_t *out, int64_t n, int64_t nside, int64_t nside_upgrade, int nest,
+                   int64_t base, hpgb_status_t *st, cudaStream_t s) {
+    if (n < 0 || (n > 0 && (!pix || !out || !st))) return HPGB_E_BAD_ARGUMENT;
+    int c = hpgb_check_nside(nside, 1);
+    if (c) return c;
+    c = hpgb_check_nside(nside_upgrade, 1);
+    if (c || nside_upgrade < nside) return HPGB_E_BAD_ARGUMENT;
+    if (n == 0) return HPGB_OK;
+    const hpgb_geom g = hpgb_make_geom(nside, 1), gu = hpgb_make_geom(nside_upgrade, 1);
+    const int shift = 2 * (gu.order - g.order);
+    const int64_t n_out = n << shift;
+    static int occ[2] = {0, 0};
+    if (!occ[nest ? 1 : 0])
+        occ[nest ? 1 : 0] = nest ? hpgb_resident_ctas(k_upgrade<true>) : hpgb_resident_ctas(k_upgrade<false>);
+    int64_t grid = (int64_t)hpgb_sm_count() * occ[nest ? 1 : 0];
+    const int64_t want = (n_out + HPGB_BLOCK - 1) / HPGB_BLOCK;
+    if (want < grid) grid = want;
+    if (nest)
+        k_upgrade<true><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n_out, shift, g, gu, base, st);
+    else
+        k_upgrade<false><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n_out, shift, g, gu, base, st);
+    g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+}
+
+namespace {
+
+// -------------------------------------------------------------------------------------------
+// lonlat_to_thetaphi   (hpgeom/hpgeom.py:60-88, numpy formulas)   16 B in + 16 B out
+// -------------------------------------------------------------------------------------------
+template <bool DEGREES>
+struct OpLonLat {
+    const double *lon, *lat;
+    double *theta, *phi;
+    int64_t base;
+    struct In2 {
+        double2 lon, lat;
+    };
+    typedef hpgb_no_ctx Ctx;
+    HPGB_DEFAULT_RUN4
+    __device__ __forceinline__ Ctx prologue() const { return Ctx(); }
+    __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(lon + i), hpgb_ld2(lat + i)}; }
+    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &, hpgb_bad_t &bad) const {
+        double t0, p0, t1, p1;
+        if (!hpgb_lonlat_to_thetaphi_np<DEGREES>(v.lon.x, v.lat.x, t0, p0)) bad.flag(base + i);
+        if (!hpgb_lonlat_to_thetaphi_np<DEGREES>(v.lon.y, v.lat.y, t1, p1)) bad.flag(base + i + 1);
+        hpgb_st2(theta + i, t0, t1);
+        hpgb_st2(phi + i, p0, p1);
+    }
+    __device__ __forceinline__ void run1(int64_t i, const Ctx &, hpgb_bad_t &bad) const {
+        double t, p;
+        if (!hpgb_lonlat_to_thetaphi_np<DEGREES>(hpgb_ld1(lon + i), hpgb_ld1(lat + i), t, p)) bad.flag(base + i);
+        hpgb_st1(theta + i, t);
+        hpgb_st1(phi + i, p);
+    }
+};
+
+}  // namespace
+
+int launch_lonlat(const double *lon, const double *lat, double *theta, double *phi, int64_t n, int degrees,
+                  int64_t base, hpgb_status_t *st, cudaStream_t s) {
+    if (n < 0 || (n > 0 && (!lon || !lat || !theta || !phi || !st))) return HPGB_E_BAD_ARGUMENT;
+    const bool vec = hpgb_aligned16(lon) && hpgb_aligned16(lat) && hpgb_aligned16(theta) && hpgb_aligned16(phi);
+    if (degrees) {
+        OpLonLat<true> op{lon, lat, theta, phi, base};
+        return hpgb_launch_map(op, n, vec, st, s);
+    }
+    OpLonLat<false> op{lon, lat, theta, phi, base};
+    return hpgb_launch_map(op, n, vec, st, s);
+}
+
+namespace {
+
+
+}  // namespace
+
+int launch_n2r(const int64_t *in, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v, int64_t base,
+               hpgb_status_t *st, cudaStream_t s) {
+    return launch_reorder<true>(in, out, n, nside, nside_v, base, st, s);
+}
+int launch_r2n(const int64_t *in, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v, int64_t base,
+               hpgb_status_t *st, cudaStream_t s) {
+    return launch_reorder<false>(in, out, n, nside, nside_v, base, st, s);
+}

@@ -1,0 +1,46 @@
+"""Small fixed workload for ncu: each hot kernel launched a few times on 2^LOG2 points."""
+import ctypes
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from hpgeom_b200 import _lib
+
+L = _lib.lib()
+log2 = int(sys.argv[1]) if len(sys.argv) > 1 else 26
+which = sys.argv[2] if len(sys.argv) > 2 else "all"
+n = 1 << log2
+nside = 2 ** 29
+g = torch.Generator(device="cuda").manual_seed(1)
+lon = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 360.0
+lat = torch.rad2deg(torch.asin(torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1))
+pix = torch.randint(0, 12 * nside * nside, (n,), dtype=torch.int64, device="cuda", generator=g)
+out = torch.randint(0, 12 * nside * nside, (n,), dtype=torch.int64, device="cuda", generator=g)
+a = torch.empty(n, dtype=torch.float64, device="cuda")
+b = torch.empty(n, dtype=torch.float64, device="cuda")
+c = torch.empty(n, dtype=torch.float64, device="cuda")
+st = torch.empty(2, dtype=torch.int64, device="cuda")
+s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+L.hpgb_status_reset(st.data_ptr(), s)
+reps = 3
+for _ in range(reps):
+    if which in ("all", "a2p"):
+        assert L.hpgb_angle_to_pixel(lon.data_ptr(), lat.data_ptr(), pix.data_ptr(), n, nside, None, 1, 1, 1, st.data_ptr(), s) == 0
+    if which in ("all", "a2p_ring"):
+        assert L.hpgb_angle_to_pixel(lon.data_ptr(), lat.data_ptr(), out.data_ptr(), n, nside, None, 0, 1, 1, st.data_ptr(), s) == 0
+    if which == "a2p_ring":
+        continue
+    if which in ("all", "n2r"):
+        assert L.hpgb_nest_to_ring(pix.data_ptr(), out.data_ptr(), n, nside, None, st.data_ptr(), s) == 0
+    if which in ("all", "r2n"):
+        assert L.hpgb_ring_to_nest(out.data_ptr(), pix.data_ptr(), n, nside, None, st.data_ptr(), s) == 0
+    if which in ("all", "p2a"):
+        assert L.hpgb_pixel_to_angle(pix.data_ptr(), a.data_ptr(), b.data_ptr(), n, nside, None, 1, 1, 1, st.data_ptr(), s) == 0
+    if which in ("all", "p2v"):
+        assert L.hpgb_pixel_to_vector(pix.data_ptr(), a.data_ptr(), b.data_ptr(), c.data_ptr(), n, nside, None, 1, st.data_ptr(), s) == 0
+    if which in ("all", "v2p"):
+        assert L.hpgb_vector_to_pixel(a.data_ptr(), b.data_ptr(), c.data_ptr(), out.data_ptr(), n, nside, None, 1, st.data_ptr(), s) == 0
+torch.cuda.synchronize()
+assert st[0].item() == -1
+print("ok", n)
