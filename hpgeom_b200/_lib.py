@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhpgb.so")
+# HPGEOM_B200_LIB selects an alternative build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("HPGEOM_B200_LIB") or os.path.join(_HERE, "libhpgb.so")
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

@@ -169,17 +169,19 @@ HPGB_HD uint32_t hpgb_hi32(double v) {
 // Per-nside constants of the fast path, host-computed and passed by value with the geometry.
 // The polynomial coefficients and unit factors travel here too: kernel parameters live in the
 // constant bank, so fp64 instructions read them as operands instead of materialising 64-bit
-// immediates (two extra instructions per constant per element otherwise).
+// immediates (two extra instructions per constant per element otherwise).  Everything that
+// multiplies an edge-line coordinate is pre-scaled by 2^F (exact), so the coordinates come out
+// directly in fixed point.
 struct hpgb_a2p_fast {
-    double ns, ns_half, ns_075, ns_sqrt6;  // nside, 0.5 nside, 0.75 nside, sqrt(6) nside
-    double scale;                          // 2^F: fixed-point scale of the edge-line coordinates
-    double c3, c5, c7, c9, c11, c13, c15;  // sin(a) = a + a^3 (c3 + c5 a^2 + ...), |a| <= 0.74
-    double k_lat, k_lon;                   // radians per input latitude unit; tt per input longitude unit
-    double pole;                           // input latitude of the pole (90 or pi/2 head)
-    double pole_lo;                        // tail of the pole constant (0 in degrees)
-    double lat_max, lon_max;               // fast-path range guards
-    double asin23;                         // asin(2/3): equatorial / polar split in latitude
+    double ns_s, ns_half_s, ns_075_s, ns_sqrt6_s;  // (nside, nside/2, 0.75 nside, sqrt(6) nside) * 2^F
+    double c3, c5, c7, c9, c11, c13, c15;          // sin(a) = a + a^3 (c3 + c5 a^2 + ...), |a| <= 0.74
+    double k_lat, k_hcth, k_lon;  // radians per latitude unit; half of it; tt per longitude unit
+    double pole, pole_lo;         // input latitude of the pole (90, or pi/2 as head + tail)
+    double lat_max, lon_max;      // fast-path range guards
+    double asin23;                // asin(2/3): equatorial / polar split in latitude
     uint32_t fbits, fmask, margin, enabled;
+    uint32_t face_shift_hi;       // 2*order - 32 when order >= 16 (face bits live in the high word)
+    uint32_t pad_;
 };
 
 template <bool LONLAT, bool DEGREES>
@@ -187,16 +189,16 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
     hpgb_a2p_fast f;
     const double dns = (double)g.nside;
     const int order = g.order < 0 ? 0 : g.order;
-    f.ns = dns;
-    f.ns_half = 0.5 * dns;
-    f.ns_075 = 0.75 * dns;
-    f.ns_sqrt6 = 2.4494897427831780981972840747059 * dns;
     // F fraction bits, always inside the low 32-bit word; margin = nside * 2^-44 in fixed-point
     // units (never below 16 units), see the derivation above hpgb_angle_to_pixel_nest_fast
     f.fbits = order >= 27 ? (uint32_t)(58 - order) : 32u;
     f.fmask = f.fbits >= 32 ? 0xFFFFFFFFu : ((1u << f.fbits) - 1u);
     f.margin = order >= 26 ? (1u << 14) : (order >= 16 ? (1u << (order - 12)) : 16u);
-    f.scale = ldexp(1.0, (int)f.fbits);
+    const double scale = ldexp(1.0, (int)f.fbits);
+    f.ns_s = dns * scale;
+    f.ns_half_s = 0.5 * dns * scale;
+    f.ns_075_s = 0.75 * dns * scale;
+    f.ns_sqrt6_s = 2.4494897427831780981972840747059 * dns * scale;
     f.c3 = -1.6666666666666666667e-1;
     f.c5 = 8.3333333333333333333e-3;
     f.c7 = -1.9841269841269841270e-4;
@@ -205,14 +207,16 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
     f.c13 = 1.6059043836821614599e-10;
     f.c15 = -7.6471637318198164759e-13;
     if (LONLAT && DEGREES) {
-        f.k_lat = 1.7453292519943295769e-2;  // pi/180
-        f.k_lon = 1.1111111111111111111e-2;  // 1/90
+        f.k_lat = 1.7453292519943295769e-2;   // pi/180
+        f.k_hcth = 8.7266462599716478846e-3;  // pi/360
+        f.k_lon = 1.1111111111111111111e-2;   // 1/90
         f.pole = 90.0;
         f.pole_lo = 0.0;
         f.lat_max = 89.999999;
         f.lon_max = 720.0;
     } else {
         f.k_lat = 1.0;
+        f.k_hcth = 0.5;
         f.k_lon = HPGB_INV_HALFPI;
         f.pole = HPGB_PIO2_1;
         f.pole_lo = HPGB_PIO2_2;
@@ -221,6 +225,8 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
     }
     f.asin23 = 0.72972765622696636345479665981332;
     f.enabled = (g.order >= 0) ? 1u : 0u;
+    f.face_shift_hi = order >= 16 ? (uint32_t)(2 * order - 32) : 0u;
+    f.pad_ = 0;
     return f;
 }
 
@@ -235,65 +241,70 @@ HPGB_HD double hpgb_sin_poly(const hpgb_a2p_fast &f, double a) {  // |a| <= 0.74
     return fma(a * a2, p, a);
 }
 
-// Result of the fast path for one point: the candidate pixel and whether it can be trusted.
-// Branch-free up to the final select; `ok == false` -> the caller runs the exact path.
-template <bool LONLAT, bool DEGREES>
+// Fast path for one point: candidate pixel + whether it can be trusted (false -> the caller runs
+// the exact path).  Branch-free apart from the equatorial/polar integer tail; the guard
+// conditions are accumulated bitwise so no short-circuit branches appear in the hot loop.
+// HI: nside >= 2^16, i.e. the face number only touches the high word of the pixel.
+template <bool LONLAT, bool DEGREES, bool HI>
 HPGB_HD bool hpgb_angle_to_pixel_nest_fast(const hpgb_geom &g, const hpgb_a2p_fast &f, double a, double b,
                                            int64_t &pix) {
-    // ---- latitude (radians, signed), colatitude from the nearest pole, tt in [0,4) ----
-    double lat, cth, tt;
-    bool guard;
+    // ---- latitude (radians, signed), half colatitude from the nearest pole, tt in [0,4) ----
+    double lat, hcth, tt;
+    unsigned guard;
     if (LONLAT) {
         lat = DEGREES ? b * f.k_lat : b;
-        cth = DEGREES ? (f.pole - fabs(b)) * f.k_lat : (f.pole - fabs(b)) + f.pole_lo;
+        hcth = DEGREES ? (f.pole - fabs(b)) * f.k_hcth : ((f.pole - fabs(b)) + f.pole_lo) * 0.5;
         const double t = a * f.k_lon;  // lon/90 or lon*2/pi
         tt = fma(-4.0, floor(t * 0.25), t);
-        guard = !(fabs(b) < f.lat_max) || !(fabs(a) <= f.lon_max);
+        guard = (unsigned)!(fabs(b) < f.lat_max) | (unsigned)!(fabs(a) <= f.lon_max);
     } else {
         lat = (f.pole - a) + f.pole_lo;  // pi/2 - theta, accurate also near the equator
-        cth = (a < f.pole) ? a : (HPGB_PI_1 - a) + HPGB_PI_2;
+        hcth = 0.5 * ((a < f.pole) ? a : (HPGB_PI_1 - a) + HPGB_PI_2);
         tt = b * f.k_lon;                // the reference's own expression
-        guard = !(a > 1e-8 && a < 3.14159265) || !(b >= 0.0 && b < 6.2831853);
+        guard = (unsigned)!(a > 1e-8) | (unsigned)!(a < 3.14159265) | (unsigned)!(b >= 0.0) | (unsigned)!(b < 6.2831853);
     }
     const double al = fabs(lat);
     const bool eq = al <= f.asin23;
-    guard = guard || (fabs(al - f.asin23) < 1e-11);
+    guard |= (unsigned)(fabs(al - f.asin23) < 1e-11);
     // tt + 4 has a fixed exponent: its mantissa is tt in fixed point (face index + fraction)
     const uint32_t thi = hpgb_hi32(tt + 4.0);
     const uint32_t ntt = (thi >> 18) & 3u;
-    guard = guard || (((thi + 1u) & 0x3FFFFu) < 2u);  // tt within 2^-18 of an integer (face edge / wrap)
+    guard |= (unsigned)(((thi + 1u) & 0x3FFFFu) < 2u);  // tt within 2^-18 of an integer (face edge / wrap)
     const double tp = tt - (double)(int32_t)ntt;
     // ---- one sine for both branches ----
-    const double s = hpgb_sin_poly(f, eq ? lat : 0.5 * cth);
-    // ---- edge-line coordinates, fixed point with F fraction bits ----
-    const double t1 = fma(f.ns, tt, f.ns_half);  // nside*(0.5+tt)
-    const double t2 = f.ns_075 * s;
-    const double tmp = f.ns_sqrt6 * s;
+    const double s = hpgb_sin_poly(f, eq ? lat : hcth);
+    // ---- edge-line coordinates, already scaled to fixed point with F fraction bits ----
+    const double t1 = fma(f.ns_s, tt, f.ns_half_s);  // nside*(0.5+tt)
+    const double t2 = f.ns_075_s * s;
+    const double tmp = f.ns_sqrt6_s * s;
     const double p1 = tp * tmp;
-    const double q1 = eq ? (t1 - t2) : p1;
-    const double q2 = eq ? (t1 + t2) : (tmp - p1);
-    const uint64_t x1 = (uint64_t)hpgb_d2ll(q1 * f.scale);
-    const uint64_t x2 = (uint64_t)hpgb_d2ll(q2 * f.scale);
+    const uint64_t x1 = (uint64_t)hpgb_d2ll(eq ? (t1 - t2) : p1);
+    const uint64_t x2 = (uint64_t)hpgb_d2ll(eq ? (t1 + t2) : (tmp - p1));
     // within `margin` of an integer?  (the fraction sits in the low word)
     const uint32_t n1 = ((uint32_t)x1 + f.margin) & f.fmask, n2 = ((uint32_t)x2 + f.margin) & f.fmask;
-    guard = guard || ((n1 < n2 ? n1 : n2) < 2u * f.margin);
+    guard |= (unsigned)((n1 < n2 ? n1 : n2) < 2u * f.margin);
     const uint32_t j1 = (uint32_t)(x1 >> f.fbits), j2 = (uint32_t)(x2 >> f.fbits);
-    const uint32_t ns = (uint32_t)g.nside, nsm1 = ns - 1u;
+    const uint32_t nsm1 = (uint32_t)g.nside - 1u;
     uint32_t ix, iy, face;
     if (eq) {
         const uint32_t ifp = j1 >> g.order, ifm = j2 >> g.order;
         face = (ifp == ifm) ? (ifp | 4u) : ((ifp < ifm) ? ifp : (ifm + 8u));
         ix = j2 & nsm1;
-        iy = nsm1 - (j1 & nsm1);
+        iy = ~j1 & nsm1;  // nside - 1 - (j1 mod nside)
     } else {
         const uint32_t jp = j1 < nsm1 ? j1 : nsm1, jm = j2 < nsm1 ? j2 : nsm1;
         const bool north = lat >= 0.0;
-        ix = north ? nsm1 - jm : jp;
-        iy = north ? nsm1 - jp : jm;
+        ix = north ? (nsm1 ^ jm) : jp;  // nside - 1 - jm
+        iy = north ? (nsm1 ^ jp) : jm;
         face = north ? ntt : ntt + 8u;
     }
-    pix = hpgb_xyf2nest(g.order, ix, iy, face);
-    return !guard && f.enabled;
+    if (HI) {
+        const uint64_t m = hpgb_interleave(ix, iy);
+        pix = (int64_t)(m + ((uint64_t)(face << f.face_shift_hi) << 32));
+    } else {
+        pix = hpgb_xyf2nest(g.order, ix, iy, face);
+    }
+    return (guard == 0u) & (f.enabled != 0u);
 }
 
 // ---------------------------------------------------------------------------------------------

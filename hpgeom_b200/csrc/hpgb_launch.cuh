@@ -25,6 +25,7 @@
 
 #define HPGB_BLOCK 256
 
+
 extern std::atomic<int64_t> g_hpgb_launches;
 
 struct hpgb_bad_t {
@@ -88,6 +89,100 @@ __device__ __forceinline__ const double *hpgb_stage_table() {
     return sT;
 }
 
+// -------------------------------------------------------------------------------------------
+// k_stream: TMA-fed persistent streaming kernel (the fast path for 16-byte aligned operands).
+//
+// One elected thread per CTA keeps a ring of STAGES shared-memory tiles full with 1-D bulk
+// async copies (cp.async.bulk.shared.global + mbarrier complete_tx -> SASS UBLKCP); every tile
+// holds HPGB_TILE consecutive elements of each input array.  The 256 threads wait on the
+// stage's mbarrier, pull their elements out of shared memory with conflict-free 128-bit LDS,
+// release the stage (one CTA barrier) so the producer can refill it while they compute, and
+// write results straight to HBM with 128-bit streaming stores.  Global-load latency is thus
+// hidden by the ring, not by occupancy: no registers are tied up by loads in flight and the
+// kernel stays busy even at the 2-3 CTAs/SM the fp64 register footprint allows.
+// Thread t owns elements {2t, 2t+1} and {TILE/2 + 2t, TILE/2 + 2t + 1} of a tile, so each warp
+// LDS / STG instruction covers one contiguous 512-byte span.
+// Op additionally provides:  static constexpr int NIN, MINB (min resident CTAs/SM -> register cap);
+//                            const void *src(int k) const;
+//                            In2 load2s(const unsigned char *stage, int elem) const;
+// -------------------------------------------------------------------------------------------
+#define HPGB_TILE 1024
+
+__device__ __forceinline__ uint32_t hpgb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void hpgb_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hpgb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hpgb_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hpgb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hpgb_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     hpgb_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(hpgb_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void hpgb_mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = hpgb_smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+template <class Op, int STAGES>
+__global__ void __launch_bounds__(HPGB_BLOCK, Op::MINB) k_stream(const Op op, const int64_t n, hpgb_status_t *st) {
+    constexpr int NIN = Op::NIN;
+    constexpr uint32_t ARR_BYTES = HPGB_TILE * 8;
+    extern __shared__ __align__(128) unsigned char hpgb_stage_smem[];
+    __shared__ uint64_t full[STAGES];
+    const typename Op::Ctx ctx = op.prologue();
+    const int tid = threadIdx.x;
+    const int64_t ntiles = n / HPGB_TILE;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) hpgb_mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int s, int64_t tile) {
+        hpgb_mbar_expect_tx(&full[s], NIN * ARR_BYTES);
+#pragma unroll
+        for (int k = 0; k < NIN; k++)
+            hpgb_bulk_g2s(hpgb_stage_smem + (size_t)(s * NIN + k) * ARR_BYTES,
+                          (const unsigned char *)op.src(k) + (size_t)tile * ARR_BYTES, ARR_BYTES, &full[s]);
+    };
+    if (tid == 0) {
+        int64_t t = blockIdx.x;
+        for (int s = 0; s < STAGES && t < ntiles; s++, t += gridDim.x) issue(s, t);
+    }
+    hpgb_bad_t bad;
+    int s = 0;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        hpgb_mbar_wait(&full[s], phase);
+        const unsigned char *stage = hpgb_stage_smem + (size_t)s * NIN * ARR_BYTES;
+        const typename Op::In2 v0 = op.load2s(stage, 2 * tid);
+        const typename Op::In2 v1 = op.load2s(stage, HPGB_TILE / 2 + 2 * tid);
+        __syncthreads();  // every thread has its elements: the stage may be refilled
+        if (tid == 0) {
+            const int64_t tn = t + (int64_t)STAGES * gridDim.x;
+            if (tn < ntiles) issue(s, tn);
+        }
+        const int64_t e0 = t * HPGB_TILE + 2 * tid;
+        op.run4(e0, v0, e0 + HPGB_TILE / 2, v1, ctx, bad);
+        if (++s == STAGES) {
+            s = 0;
+            phase ^= 1u;
+        }
+    }
+    if (blockIdx.x == 0)  // fewer than HPGB_TILE leftover elements
+        for (int64_t i = ntiles * HPGB_TILE + tid; i < n; i += HPGB_BLOCK) op.run1(i, ctx, bad);
+    bad.commit(st);
+}
+
 int hpgb_sm_count();  // SMs of the current device (148 on B200)
 
 template <class K>
@@ -125,6 +220,27 @@ static int hpgb_launch_map(const Op &op, int64_t n, bool vec_ok, hpgb_status_t *
     int64_t grid = (int64_t)hpgb_sm_count() * occ2;
     if (want < grid) grid = want > 0 ? want : 1;
     k_map2<Op><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(op, n, st);
+    g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+}
+
+// launch the TMA streaming kernel (operands 16-byte aligned); falls back to k_map2 for small n
+template <class Op, int STAGES>
+static int hpgb_launch_stream(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
+    if (n < 4 * HPGB_TILE) return hpgb_launch_map(op, n, true, st, s);
+    const int smem = STAGES * Op::NIN * HPGB_TILE * 8;
+    static int occ = 0;
+    if (!occ) {
+        cudaFuncSetAttribute(k_stream<Op, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream<Op, STAGES>, HPGB_BLOCK, smem);
+        occ = per_sm > 0 ? per_sm : 1;
+    }
+    int64_t grid = (int64_t)hpgb_sm_count() * occ;
+    const int64_t ntiles = n / HPGB_TILE;
+    if (ntiles < grid) grid = ntiles;
+    k_stream<Op, STAGES><<<(unsigned)grid, HPGB_BLOCK, smem, s>>>(op, n, st);
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;

@@ -28,7 +28,7 @@ __device__ __forceinline__ bool var_geom(const int64_t *nside_v, int64_t i, int 
 // NEST: fast path (hpgb_fp.h) with the exact path as a rare, non-inlined fallback.
 // RING: exact path (ring fast path: next).
 // -------------------------------------------------------------------------------------------
-template <bool NEST, bool LONLAT, bool DEGREES, bool VAR>
+template <bool NEST, bool LONLAT, bool DEGREES, bool VAR, bool HI>
 struct OpAng2Pix {
     const double *a, *b;
     int64_t *out;
@@ -43,6 +43,13 @@ struct OpAng2Pix {
 
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(a + i), hpgb_ld2(b + i)}; }
+    static constexpr int NIN = 2;
+    static constexpr int MINB = 3;  // <= 80 registers: 3 CTAs/SM measured best on B200 (2: 190, 3: 201, 4: 192 Gpts/s)
+    __device__ __forceinline__ const void *src(int k) const { return k == 0 ? (const void *)a : (const void *)b; }
+    __device__ __forceinline__ In2 load2s(const unsigned char *stage, int e) const {
+        return In2{*reinterpret_cast<const double2 *>(stage + 8 * e),
+                   *reinterpret_cast<const double2 *>(stage + 8 * HPGB_TILE + 8 * e)};
+    }
     // exact path for one element (rare): non-inlined call, flags the element when it is invalid
     __device__ __forceinline__ int64_t slow(const hpgb_geom &gg, double va, double vb, int64_t i, Ctx T,
                                             hpgb_bad_t &bad) const {
@@ -54,8 +61,8 @@ struct OpAng2Pix {
         int64_t p0 = 0, p1 = 0;
         bool ok0 = false, ok1 = false;
         if (NEST) {  // both fast paths first (independent -> the fp64 chains interleave), exact path after
-            ok0 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v.a.x, v.b.x, p0);
-            ok1 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v.a.y, v.b.y, p1);
+            ok0 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v.a.x, v.b.x, p0);
+            ok1 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v.a.y, v.b.y, p1);
         }
         if (!ok0) p0 = slow(g, v.a.x, v.b.x, i, T, bad);
         if (!ok1) p1 = slow(g, v.a.y, v.b.y, i + 1, T, bad);
@@ -66,10 +73,10 @@ struct OpAng2Pix {
         int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
         bool ok0 = false, ok1 = false, ok2 = false, ok3 = false;
         if (NEST) {
-            ok0 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v0.a.x, v0.b.x, p0);
-            ok1 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v0.a.y, v0.b.y, p1);
-            ok2 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v1.a.x, v1.b.x, p2);
-            ok3 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(g, f, v1.a.y, v1.b.y, p3);
+            ok0 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v0.a.x, v0.b.x, p0);
+            ok1 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v0.a.y, v0.b.y, p1);
+            ok2 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v1.a.x, v1.b.x, p2);
+            ok3 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v1.a.y, v1.b.y, p3);
         }
         if (!(ok0 && ok1 && ok2 && ok3)) {
             if (!ok0) p0 = slow(g, v0.a.x, v0.b.x, i0, T, bad);
@@ -93,7 +100,7 @@ struct OpAng2Pix {
         }
         const double va = hpgb_ld1(a + i), vb = hpgb_ld1(b + i);
         int64_t pix;
-        if (!(NEST && hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES>(gg, ff, va, vb, pix))) pix = slow(gg, va, vb, i, T, bad);
+        if (!(NEST && hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(gg, ff, va, vb, pix))) pix = slow(gg, va, vb, i, T, bad);
         hpgb_st1(out + i, pix);
     }
 };
@@ -102,12 +109,18 @@ template <bool NEST, bool LONLAT, bool DEGREES>
 int launch_a2p_t(const double *a, const double *b, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v,
                  int64_t base, hpgb_status_t *st, cudaStream_t s) {
     if (nside_v) {
-        OpAng2Pix<NEST, LONLAT, DEGREES, true> op{a, b, out, nside_v, base, hpgb_geom(), hpgb_a2p_fast()};
+        OpAng2Pix<NEST, LONLAT, DEGREES, true, false> op{a, b, out, nside_v, base, hpgb_geom(), hpgb_a2p_fast()};
         return hpgb_launch_map1(op, n, st, s);
     }
     const hpgb_geom g = hpgb_make_geom(nside, NEST);
-    OpAng2Pix<NEST, LONLAT, DEGREES, false> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g)};
-    return hpgb_launch_map(op, n, hpgb_aligned16(a) && hpgb_aligned16(b) && hpgb_aligned16(out), st, s);
+    const bool vec = hpgb_aligned16(a) && hpgb_aligned16(b) && hpgb_aligned16(out);
+    if (NEST && g.order >= 16) {  // face bits only in the high word of the pixel: cheaper assembly
+        OpAng2Pix<NEST, LONLAT, DEGREES, false, NEST> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g)};
+        if (vec) return hpgb_launch_stream<decltype(op), 3>(op, n, st, s);
+        return hpgb_launch_map(op, n, vec, st, s);
+    }
+    OpAng2Pix<NEST, LONLAT, DEGREES, false, false> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g)};
+    return hpgb_launch_map(op, n, vec, st, s);
 }
 
 }  // namespace

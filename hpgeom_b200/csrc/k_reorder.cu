@@ -47,6 +47,12 @@ struct OpReorder {
         return TO_RING ? hpgb_nest2ring(gg, p) : hpgb_ring2nest(gg, p);
     }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(in + i); }
+    static constexpr int NIN = 1;
+    static constexpr int MINB = 1;
+    __device__ __forceinline__ const void *src(int) const { return in; }
+    __device__ __forceinline__ In2 load2s(const unsigned char *stage, int e) const {
+        return *reinterpret_cast<const longlong2 *>(stage + 8 * e);
+    }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &, hpgb_bad_t &bad) const {
         hpgb_st2(out + i, conv(g, v.x, i, bad), conv(g, v.y, i + 1, bad));
     }
@@ -77,7 +83,8 @@ int launch_reorder(const int64_t *in, int64_t *out, int64_t n, int64_t nside, co
     int c = hpgb_check_nside(nside, 1);
     if (c) return c;
     OpReorder<TO_RING, false> op{in, out, nullptr, base, hpgb_make_geom(nside, 1)};
-    return hpgb_launch_map(op, n, hpgb_aligned16(in) && hpgb_aligned16(out), st, s);
+    if (hpgb_aligned16(in) && hpgb_aligned16(out)) return hpgb_launch_stream<decltype(op), 4>(op, n, st, s);
+    return hpgb_launch_map(op, n, false, st, s);
 }
 
 // -------------------------------------------------------------------------------------------
