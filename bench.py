@@ -57,17 +57,23 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def ncu_traffic(kernel, points):
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json holds measured bytes per point at 2^26 points), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(kernel)
+            return json.load(f)[kernel + "_bytes_per_point"] * points
     except Exception:
         return None
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    The sampler process is started before the warm-up (nvidia-smi needs ~100 ms to produce its
+    first row); every row is stamped on arrival and only rows that arrived inside
+    [mark_begin(), mark_end()] are summarised (all rows under load if that window is too short
+    to contain three samples)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -75,37 +81,59 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            time.sleep(0.3)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is not None:
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except Exception:
                 pass
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if len(r) >= 9 and self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) + 0.03]
+        window = "timed region"
+        if len(rows) < 3:
+            rows = [r for _, r in self.rows if len(r) >= 9]
+            window = "warm-up + timed region"
+
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+
+        sm = [num(r[1]) for r in rows if num(r[1]) is not None]
+        mx = [num(r[2]) for r in rows if num(r[2]) is not None]
+        pw = [num(r[3]) for r in rows if num(r[3]) is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def sky_points_host(n, seed):
@@ -214,18 +242,22 @@ def main():
         rc = L.hpgb_angle_to_pixel(lon.data_ptr(), lat.data_ptr(), pix.data_ptr(), n, NSIDE, None, 1, 1, 1, stp, sp)
         assert rc == 0, _lib.error_string(rc)
 
-    def timed(step, steps, warmup):
+    def timed(step, steps, warmup, sampler=None):
         L.hpgb_status_reset(stp, sp)
         for _ in range(warmup):
             step()
         barrier()
         l0 = L.hpgb_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.mark_begin()
         e0.record(stream)
         for _ in range(steps):
             step()
         e1.record(stream)
         barrier()
+        if sampler is not None:
+            sampler.mark_end()
         ms = e0.elapsed_time(e1)
         launches = L.hpgb_launch_count() - l0
         t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
@@ -241,7 +273,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, launches = timed(step_a2p, args.steps, max(args.warmup, 3))
+    ms, launches = timed(step_a2p, args.steps, max(args.warmup, 3), sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     assert int(status[0].item()) == -1, "kernel flagged a bad element in valid synthetic input"
     ms_per_step = ms / args.steps
@@ -292,7 +324,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = BYTES_PER_POINT["angle_to_pixel"] * n / (ms_per_step * 1e-3) / 1e9
-        kernel = "k_map2<OpAng2Pix<nest,lonlat,degrees>>"
+        kernel = "k_stream<OpAng2Pix<nest,lonlat,degrees>,3>"
         line = {
             "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -303,7 +335,7 @@ def main():
                        "sharding": "contiguous shards, one process per GPU, no data-path collective",
                        "e2e_batch_points_per_gpu": ne},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("angle_to_pixel"), "kernel": kernel, "peak_source": peak_src,
+                         "traffic": ncu_traffic("angle_to_pixel", n), "kernel": kernel, "peak_source": peak_src,
                          "bytes_per_point": 24, "points_per_launch": n},
             "e2e": {"value": e2e_value, "unit": "Gpoints/s", "h2d_bytes_per_step": 16 * ne, "d2h_bytes_per_step": 8 * ne,
                     "api": "hpgb_host_angle_to_pixel (C ABI, pinned host buffers)", "steps": e2e_steps,
@@ -317,11 +349,13 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             probe, kind, cores, _ = cpu_reference_rate(1 << 22, threads)
-            # size the sample for ~10 s of CPU work, bounded to 2^27 points (3 GB of host arrays)
-            ns = int(min(max(probe * 1e9 * 10.0, 1 << 22), 1 << 27))
-            rate, kind, cores, secs = cpu_reference_rate(ns, threads)
+            # ~10 s of CPU work: a 2^26-point sample (1.5 GB of host arrays) repeated as often as needed
+            ns = 1 << 26
+            reps = int(min(max(10.0 / (ns / (probe * 1e9)), 1), 200))
+            rate, kind, cores, secs = cpu_reference_rate(ns, threads, reps=reps)
             line["cpu_baseline"] = {"value": rate, "unit": "Gpoints/s", "cores": cores, "kind": kind,
-                                    "sample": "%d uniform-on-sphere points of the same workload, %.1f s" % (ns, secs)}
+                                    "sample": "%d uniform-on-sphere points of the same workload x %d passes "
+                                              "(best pass %.2f s), n_threads=%d" % (ns, reps, secs, cores)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
