@@ -1,0 +1,154 @@
+// hpgb_reorder.h -- minimum-instruction NEST <-> RING cores for nside = 2^k (the nest_to_ring /
+// ring_to_nest kernels are bound by the integer ALU pipe, not by HBM, so every instruction
+// counts: see DESIGN.md 4.2).  Bit-identical to nest2ring / ring2nest of the reference
+// (hpgeom/healpix_geom.c:217-227 = nest2xyf/xyf2ring/ring2xyf/xyf2nest, :382-454, :512-528).
+//
+// In-face coordinates (ix, iy), ring numbers and in-ring offsets are 32-bit; a pixel number is
+// produced by ONE unsigned 32x32+64 multiply-add (IMAD.WIDE.U32) whose three operands are
+// selected per zone.  With t = jr - nside (jr = ring, 1-based from the north pole), fc = face & 3:
+//
+//   NEST -> RING, pix_ring = A * B + C
+//     north cap (t < 0)       nr = t + nside         A = nr  B = 2nr - 2 + fc     C = nside-1-iy
+//     south cap (t >= 2nside) nr = 3nside - t        A = nr  B = -(2nr + 2 - fc)  C = npix + ix - (nr << 32)
+//     belt                    A = t + nside/2 - 1    B = 4nside                   C = 2nside + ro
+//                             ro = ((jpll*nside + ix - iy + (t&1) - 1) >> 1) mod 4nside
+//   derivation: xyf2ring's jp = (jpll*nr + ix - iy + 1 + kshift)/2 reduces to fc*nr + (nside-1-iy) + 1
+//   in the north cap and fc*nr + ix + 1 in the south cap (nr = (nside-1-ix)+(nside-1-iy)+1 resp.
+//   ix+iy+1); ncap + t*4nside = 4nside*(t + nside/2 - 1) + 2nside; the south product is taken
+//   modulo 2^64 (B = 2^32 - (2nr+2-fc), compensated by the -nr in the high word of C).
+//
+//   RING -> NEST: belt pixels use the edge-line coordinates of the reference's loc2pix
+//     jp = ip + (tmp >> 1), jm = jp + nside - tmp   (ip = in-ring index, tmp = ring - nside)
+//     face from (jp >> k, jm >> k), ix = jm mod nside, iy = nside-1 - (jp mod nside)
+//   (identical to ring2xyf's ifp / ifm, hpgeom/healpix_geom.c:427-436, and its irt / ipt tail);
+//   cap pixels: ring from the reference's isqrt (same fp64 expression), q = 0-based in-ring index
+//   counted eastward, fc = q div nr, rem = q mod nr (special_div);
+//     north: ix = nside - nr + rem, iy = nside-1 - rem      south: ix = rem, iy = nr-1 - rem
+//   The reference's isqrt has no correction step, so for 2*ip-1 >~ 2^50 it can put the first / last
+//   pixels of a huge cap ring into the neighbouring ring; whenever the in-ring index comes out
+//   outside [0, 4nr) the element is handed to the general 64-bit path (hpgb_ring2xyf_any), which
+//   replays the reference's arithmetic literally.
+#ifndef HPGB_REORDER_H
+#define HPGB_REORDER_H
+
+#include "hpgb_core.h"
+
+struct hpgb_rk {
+    uint32_t ns, nsm1, ns2, ns3, ns4, ns4m1;
+    uint32_t belt_a0, belt_c0;          // nside/2 - 1, 2 nside  (0, 0 for nside = 1)
+    uint32_t npix_lo, npix_hi;          // 12 nside^2
+    uint32_t npm1_lo, npm1_hi;          // npix - 1
+    uint32_t ncap_lo, ncap_hi;          // 2 nside (nside - 1)
+    uint32_t lmask, hmask;              // nside^2 - 1
+    uint32_t k, k2;                     // order, 2 * order
+    uint32_t fsh_hi, fmul_hi;           // order >= 16: 2k - 32 and 1 << (2k - 32)
+};
+
+HPGB_HD hpgb_rk hpgb_make_rk(const hpgb_geom &g) {
+    hpgb_rk c;
+    const uint32_t ns = (uint32_t)g.nside;
+    const uint32_t k = (uint32_t)(g.order < 0 ? 0 : g.order);
+    c.ns = ns;
+    c.nsm1 = ns - 1u;
+    c.ns2 = 2u * ns;
+    c.ns3 = 3u * ns;
+    c.ns4 = 4u * ns;
+    c.ns4m1 = 4u * ns - 1u;
+    c.belt_a0 = k >= 1 ? ns / 2u - 1u : 0u;
+    c.belt_c0 = k >= 1 ? 2u * ns : 0u;
+    c.npix_lo = (uint32_t)(uint64_t)g.npix;
+    c.npix_hi = (uint32_t)((uint64_t)g.npix >> 32);
+    c.npm1_lo = (uint32_t)(uint64_t)(g.npix - 1);
+    c.npm1_hi = (uint32_t)((uint64_t)(g.npix - 1) >> 32);
+    c.ncap_lo = (uint32_t)(uint64_t)g.ncap;
+    c.ncap_hi = (uint32_t)((uint64_t)g.ncap >> 32);
+    c.lmask = (uint32_t)(uint64_t)(g.npface - 1);
+    c.hmask = (uint32_t)((uint64_t)(g.npface - 1) >> 32);
+    c.k = k;
+    c.k2 = 2u * k;
+    c.fsh_hi = k >= 16 ? 2u * k - 32u : 0u;
+    c.fmul_hi = k >= 16 ? (1u << (2u * k - 32u)) : 0u;
+    return c;
+}
+
+// jpll[face] = {1,3,5,7,0,2,4,6,1,3,5,7} as a byte lookup done by one PRMT: selector nibble 0 =
+// face & 7 picks the entry, nibbles 1-3 = 4 pick the zero byte.
+HPGB_HD uint32_t hpgb_jpll_lut(uint32_t face) { return hpgb_prmt(0x07050301u, 0x06040200u, (face & 7u) | 0x4440u); }
+
+// NEST pixel (lo, hi words; must be < npix) -> RING pixel.  HI: order >= 16.
+template <bool HI>
+HPGB_HD int64_t hpgb_nest2ring_k(const hpgb_rk &c, uint32_t lo, uint32_t hi) {
+    const uint32_t face = HI ? (hi >> c.fsh_hi) : (uint32_t)((((uint64_t)hi << 32) | lo) >> c.k2);
+    uint32_t wl = HI ? lo : (lo & c.lmask), wh = hi & c.hmask;
+    HPGB_DSWAP(wl, 0x22222222u, 1);
+    HPGB_DSWAP(wh, 0x22222222u, 1);
+    HPGB_DSWAP(wl, 0x0C0C0C0Cu, 2);
+    HPGB_DSWAP(wh, 0x0C0C0C0Cu, 2);
+    HPGB_DSWAP(wl, 0x00F000F0u, 4);
+    HPGB_DSWAP(wh, 0x00F000F0u, 4);
+    const uint32_t ix = hpgb_prmt(wl, wh, 0x6420), iy = hpgb_prmt(wl, wh, 0x7531);
+    const uint32_t fr = face >> 2, fc = face & 3u;
+    const uint32_t t = fr * c.ns + c.nsm1 - ix - iy;  // jr - nside, two's complement
+    const bool cap = t >= c.ns2;                       // t < 0 wraps to a huge unsigned value
+    const bool north = (int32_t)t < 0;
+    // operands of the final multiply-add, selected per zone (branch-free: with random pixels
+    // every warp holds cap and belt pixels anyway, and straight-line code lets the four elements a
+    // thread owns interleave)
+    const uint32_t X = hpgb_jpll_lut(face) * c.ns + (ix - iy) + (t & 1u) - 1u;
+    const uint32_t nr = north ? t + c.ns : c.ns3 - t;
+    const uint32_t fm2 = fc - 2u;
+    const uint32_t A = cap ? nr : t + c.belt_a0;
+    const uint32_t B = cap ? (north ? fm2 + 2u * nr : fm2 - 2u * nr) : c.ns4;
+    const uint32_t Cl = cap ? (north ? (~iy & c.nsm1) : (c.npix_lo | ix)) : ((X >> 1) & c.ns4m1) + c.belt_c0;
+    const uint32_t Ch = (cap && !north) ? c.npix_hi - nr : 0u;
+    return (int64_t)((uint64_t)A * (uint64_t)B + (((uint64_t)Ch << 32) | Cl));
+}
+
+// RING pixel (must be < npix) -> NEST pixel.  HI: order >= 16.
+template <bool HI>
+HPGB_HD int64_t hpgb_ring2nest_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix) {
+    const uint64_t up = (uint64_t)pix;
+    const uint64_t ipb = up - (((uint64_t)c.ncap_hi << 32) | c.ncap_lo);  // index inside the belt (negative: north cap)
+    const uint32_t tmp = (uint32_t)((int64_t)ipb >> (c.k + 2u));          // ring - nside; fits int32
+    uint32_t ix, iy, face;
+    if (tmp > c.ns2) {  // polar caps (tmp < 0 wraps)
+        const bool north = (int32_t)tmp < 0;
+        const uint64_t ipm1 = north ? up : ((((uint64_t)c.npm1_hi << 32) | c.npm1_lo) - up);  // 0-based from the pole
+        const uint32_t ir = (uint32_t)((1 + hpgb_isqrt((int64_t)(2 * ipm1 + 1))) >> 1);
+        const uint64_t q0 = ipm1 - (uint64_t)ir * (uint64_t)(2u * ir - 2u);  // in-ring index, eastward from the pole side
+        if (q0 >= 4ull * ir) {  // the reference's isqrt mis-rounded: replay its 64-bit arithmetic
+            int32_t sx, sy;
+            hpgb_ring2xyf_any(g, pix, sx, sy, face);
+            ix = (uint32_t)sx;
+            iy = (uint32_t)sy;
+        } else {
+            uint32_t q = north ? (uint32_t)q0 : 4u * ir - 1u - (uint32_t)q0;
+            const uint32_t t1 = (q >= 2u * ir) ? 1u : 0u;
+            q -= t1 ? 2u * ir : 0u;
+            const uint32_t t2 = (q >= ir) ? 1u : 0u;
+            q -= t2 ? ir : 0u;
+            face = 2u * t1 + t2 + (north ? 0u : 8u);
+            ix = north ? c.ns - ir + q : q;
+            iy = north ? c.nsm1 - q : ir - 1u - q;
+        }
+    } else {
+        const uint32_t ip = (uint32_t)ipb & c.ns4m1;
+        const uint32_t jp = ip + (tmp >> 1);
+        const uint32_t jm = jp + c.ns - tmp;
+        const uint32_t ifp = jp >> c.k, ifm = jm >> c.k;
+        face = (ifp == ifm) ? (ifp | 4u) : ((ifp < ifm) ? ifp : (ifm + 8u));
+        ix = jm & c.nsm1;
+        iy = ~jp & c.nsm1;
+    }
+    uint32_t lo = hpgb_prmt(ix, iy, 0x5140), hi = hpgb_prmt(ix, iy, 0x7362);
+    HPGB_DSWAP(lo, 0x00F000F0u, 4);
+    HPGB_DSWAP(hi, 0x00F000F0u, 4);
+    HPGB_DSWAP(lo, 0x0C0C0C0Cu, 2);
+    HPGB_DSWAP(hi, 0x0C0C0C0Cu, 2);
+    HPGB_DSWAP(lo, 0x22222222u, 1);
+    HPGB_DSWAP(hi, 0x22222222u, 1);
+    if (HI) return (int64_t)(((uint64_t)(hi + face * c.fmul_hi) << 32) | lo);
+    return (int64_t)((((uint64_t)hi << 32) | lo) + ((uint64_t)face << c.k2));
+}
+
+#endif  // HPGB_REORDER_H

@@ -11,6 +11,7 @@
 #include "hpgb_host.h"
 #include "hpgb_internal.h"
 #include "hpgb_launch.cuh"
+#include "hpgb_reorder.h"
 
 namespace {
 
@@ -27,24 +28,34 @@ __device__ __forceinline__ bool var_geom(const int64_t *nside_v, int64_t i, int 
 // nest_to_ring / ring_to_nest   (reference loops: hpgeom/hpgeom.c:1429-1450, :1699-1720)
 // 8 B in + 8 B out per pixel, integer only.
 // -------------------------------------------------------------------------------------------
-template <bool TO_RING, bool VAR>
+template <bool TO_RING, bool VAR, bool HI>
 struct OpReorder {
     const int64_t *in;
     int64_t *out;
     const int64_t *nside_v;
     int64_t base;  // global index of element 0 (chunked host pipeline)
     hpgb_geom g;
+    hpgb_rk c;     // per-nside constants of the minimum-instruction cores (hpgb_reorder.h)
     typedef longlong2 In2;
     typedef hpgb_no_ctx Ctx;
-    HPGB_DEFAULT_RUN4
 
     __device__ __forceinline__ Ctx prologue() const { return Ctx(); }
-    __device__ __forceinline__ int64_t conv(const hpgb_geom &gg, int64_t p, int64_t i, hpgb_bad_t &bad) const {
-        if (!hpgb_pixel_ok(gg, p)) {
+    // scalar-nside hot path.  HI (nside >= 2^16): npix is a multiple of 2^32, so the range check is
+    // one 32-bit compare.  The conversion itself is evaluated unconditionally (pure arithmetic, any
+    // input is safe); invalid elements are patched afterwards, off the hot path.
+    __device__ __forceinline__ bool ok(int64_t p) const {
+        return HI ? ((uint32_t)((uint64_t)p >> 32) < c.npix_hi) : hpgb_pixel_ok(g, p);
+    }
+    __device__ __forceinline__ int64_t core(int64_t p) const {
+        return TO_RING ? hpgb_nest2ring_k<HI>(c, (uint32_t)(uint64_t)p, (uint32_t)((uint64_t)p >> 32))
+                       : hpgb_ring2nest_k<HI>(c, g, p);
+    }
+    __device__ __forceinline__ int64_t conv(int64_t p, int64_t i, hpgb_bad_t &bad) const {
+        if (!ok(p)) {
             bad.flag(base + i);
             return -1;
         }
-        return TO_RING ? hpgb_nest2ring(gg, p) : hpgb_ring2nest(gg, p);
+        return core(p);
     }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(in + i); }
     static constexpr int NIN = 1;
@@ -54,19 +65,33 @@ struct OpReorder {
         return *reinterpret_cast<const longlong2 *>(stage + 8 * e);
     }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &, hpgb_bad_t &bad) const {
-        hpgb_st2(out + i, conv(g, v.x, i, bad), conv(g, v.y, i + 1, bad));
+        hpgb_st2(out + i, conv(v.x, i, bad), conv(v.y, i + 1, bad));
+    }
+    __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &,
+                                         hpgb_bad_t &bad) const {
+        int64_t r0 = core(v0.x), r1 = core(v0.y), r2 = core(v1.x), r3 = core(v1.y);
+        const bool k0 = ok(v0.x), k1 = ok(v0.y), k2 = ok(v1.x), k3 = ok(v1.y);
+        if (!(k0 & k1 & k2 & k3)) {  // rare: at least one pixel out of range
+            if (!k0) r0 = -1, bad.flag(base + i0);
+            if (!k1) r1 = -1, bad.flag(base + i0 + 1);
+            if (!k2) r2 = -1, bad.flag(base + i1);
+            if (!k3) r3 = -1, bad.flag(base + i1 + 1);
+        }
+        hpgb_st2(out + i0, r0, r1);
+        hpgb_st2(out + i1, r2, r3);
     }
     __device__ __forceinline__ void run1(int64_t i, const Ctx &, hpgb_bad_t &bad) const {
-        if (VAR) {
+        if (VAR) {  // per-element nside: general cores
             hpgb_geom gg;
-            if (!var_geom(nside_v, i, 1, gg)) {
+            const int64_t p = hpgb_ld1(in + i);
+            if (!var_geom(nside_v, i, 1, gg) || !hpgb_pixel_ok(gg, p)) {
                 bad.flag(base + i);
                 hpgb_st1(out + i, -1);
                 return;
             }
-            hpgb_st1(out + i, conv(gg, hpgb_ld1(in + i), i, bad));
+            hpgb_st1(out + i, TO_RING ? hpgb_nest2ring(gg, p) : hpgb_ring2nest(gg, p));
         } else {
-            hpgb_st1(out + i, conv(g, hpgb_ld1(in + i), i, bad));
+            hpgb_st1(out + i, conv(hpgb_ld1(in + i), i, bad));
         }
     }
 };
@@ -77,13 +102,20 @@ int launch_reorder(const int64_t *in, int64_t *out, int64_t n, int64_t nside, co
     if (n < 0 || (n > 0 && (!in || !out || !st))) return HPGB_E_BAD_ARGUMENT;
     if (n == 0) return HPGB_OK;  // the reference checks nside inside the loop: no elements, no error
     if (nside_v) {
-        OpReorder<TO_RING, true> op{in, out, nside_v, base, hpgb_geom()};
+        OpReorder<TO_RING, true, false> op{in, out, nside_v, base, hpgb_geom(), hpgb_rk()};
         return hpgb_launch_map1(op, n, st, s);
     }
     int c = hpgb_check_nside(nside, 1);
     if (c) return c;
-    OpReorder<TO_RING, false> op{in, out, nullptr, base, hpgb_make_geom(nside, 1)};
-    if (hpgb_aligned16(in) && hpgb_aligned16(out)) return hpgb_launch_stream<decltype(op), 4>(op, n, st, s);
+    const hpgb_geom g = hpgb_make_geom(nside, 1);
+    const bool vec = hpgb_aligned16(in) && hpgb_aligned16(out);
+    if (g.order >= 16) {
+        OpReorder<TO_RING, false, true> op{in, out, nullptr, base, g, hpgb_make_rk(g)};
+        if (vec) return hpgb_launch_stream<decltype(op), 4>(op, n, st, s);
+        return hpgb_launch_map(op, n, false, st, s);
+    }
+    OpReorder<TO_RING, false, false> op{in, out, nullptr, base, g, hpgb_make_rk(g)};
+    if (vec) return hpgb_launch_stream<decltype(op), 4>(op, n, st, s);
     return hpgb_launch_map(op, n, false, st, s);
 }
 

@@ -17,7 +17,7 @@ class HostSim:
         self.lib = ctypes.CDLL(os.path.join(_HERE, "libhostsim.so"))
         for n in ("sim_nest_to_ring", "sim_ring_to_nest", "sim_ring_roundtrip_any", "sim_angle_to_pixel",
                   "sim_pixel_to_angle", "sim_pixel_to_vector", "sim_vector_to_pixel", "sim_neighbors", "sim_interp",
-                  "sim_lonlat"):
+                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k"):
             getattr(self.lib, n).restype = ctypes.c_int64
         self.last_slow = 0
 
@@ -46,6 +46,20 @@ class HostSim:
 
     def ring_to_nest(self, nside, pix):
         return self._conv("sim_ring_to_nest", nside, pix)
+
+    def _conv_k(self, fn, nside, pix, hi):
+        pix = self._i(pix)
+        out = np.empty_like(pix)
+        self._chk(getattr(self.lib, fn)(ctypes.c_int64(nside), pix.ctypes.data_as(_I), ctypes.c_int64(pix.size),
+                                        out.ctypes.data_as(_I), int(hi)))
+        return out
+
+    def nest_to_ring_k(self, nside, pix, hi=None):
+        """hpgb_reorder.h core; hi=None picks the instantiation the kernel launcher would."""
+        return self._conv_k("sim_nest_to_ring_k", nside, pix, nside >= 2 ** 16 if hi is None else hi)
+
+    def ring_to_nest_k(self, nside, pix, hi=None):
+        return self._conv_k("sim_ring_to_nest_k", nside, pix, nside >= 2 ** 16 if hi is None else hi)
 
     def ring_roundtrip_any(self, nside, pix):
         return self._conv("sim_ring_roundtrip_any", nside, pix)

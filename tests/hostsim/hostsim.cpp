@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "../../hpgeom_b200/csrc/hpgb_core.h"
+#include "../../hpgeom_b200/csrc/hpgb_reorder.h"
 #if __has_include("../../hpgeom_b200/csrc/hpgb_fp.h")
 #include "../../hpgeom_b200/csrc/hpgb_fp.h"
 #define HAVE_FP 1
@@ -30,6 +31,29 @@ int64_t sim_ring_to_nest(int64_t nside, const int64_t *in, int64_t n, int64_t *o
     for (int64_t i = 0; i < n; i++) {
         if (!hpgb_pixel_ok(g, in[i])) return i;
         out[i] = hpgb_ring2nest(g, in[i]);
+    }
+    return -1;
+}
+
+// the minimum-instruction cores the scalar-nside kernels use (hpgb_reorder.h); hi = 1 selects the
+// nside >= 2^16 instantiation (only valid for such nside), 0 the general power-of-two one
+int64_t sim_nest_to_ring_k(int64_t nside, const int64_t *in, int64_t n, int64_t *out, int hi) {
+    hpgb_geom g = hpgb_make_geom(nside, 1);
+    hpgb_rk c = hpgb_make_rk(g);
+    for (int64_t i = 0; i < n; i++) {
+        if (!hpgb_pixel_ok(g, in[i])) return i;
+        const uint32_t lo = (uint32_t)(uint64_t)in[i], h = (uint32_t)((uint64_t)in[i] >> 32);
+        out[i] = hi ? hpgb_nest2ring_k<true>(c, lo, h) : hpgb_nest2ring_k<false>(c, lo, h);
+    }
+    return -1;
+}
+
+int64_t sim_ring_to_nest_k(int64_t nside, const int64_t *in, int64_t n, int64_t *out, int hi) {
+    hpgb_geom g = hpgb_make_geom(nside, 1);
+    hpgb_rk c = hpgb_make_rk(g);
+    for (int64_t i = 0; i < n; i++) {
+        if (!hpgb_pixel_ok(g, in[i])) return i;
+        out[i] = hi ? hpgb_ring2nest_k<true>(c, g, in[i]) : hpgb_ring2nest_k<false>(c, g, in[i]);
     }
     return -1;
 }

@@ -32,6 +32,10 @@ def test_reorder_golden(sim, nside):
     pix = g["pix_%d" % nside]
     assert_bit_equal(sim.nest_to_ring(nside, pix), g["n2r_%d" % nside], "n2r")
     assert_bit_equal(sim.ring_to_nest(nside, pix), g["r2n_%d" % nside], "r2n")
+    assert_bit_equal(sim.nest_to_ring_k(nside, pix), g["n2r_%d" % nside], "n2r (kernel core)")
+    assert_bit_equal(sim.ring_to_nest_k(nside, pix), g["r2n_%d" % nside], "r2n (kernel core)")
+    assert_bit_equal(sim.nest_to_ring_k(nside, pix, hi=False), g["n2r_%d" % nside], "n2r (kernel core, general)")
+    assert_bit_equal(sim.ring_to_nest_k(nside, pix, hi=False), g["r2n_%d" % nside], "r2n (kernel core, general)")
 
 
 def test_reorder_isqrt_quirk_region(sim, oracle_port):
@@ -44,14 +48,37 @@ def test_reorder_isqrt_quirk_region(sim, oracle_port):
     pn = 2 * r * (r + 1) - 1 + rng.integers(-40, 41, r.size)
     pn = np.concatenate([pn, [2 * nside * (nside - 1) - 1, 2 * nside * (nside - 1) - 2, 2 * nside * (nside - 1)]])
     for pix in (pn, npix - 1 - pn):
-        assert_bit_equal(sim.ring_to_nest(nside, pix), oracle_port.ring_to_nest(nside, pix))
+        ref = oracle_port.ring_to_nest(nside, pix)
+        assert_bit_equal(sim.ring_to_nest(nside, pix), ref)
+        assert_bit_equal(sim.ring_to_nest_k(nside, pix), ref)
+        assert_bit_equal(sim.ring_to_nest_k(nside, pix, hi=False), ref)
 
 
-@pytest.mark.parametrize("nside", [1, 2, 8, 64])
+@pytest.mark.parametrize("nside", [1, 2, 4, 8, 64, 256])
 def test_reorder_all_pixels(sim, oracle_port, nside):
     pix = np.arange(12 * nside * nside, dtype=np.int64)
-    assert_bit_equal(sim.nest_to_ring(nside, pix), oracle_port.nest_to_ring(nside, pix))
-    assert_bit_equal(sim.ring_to_nest(nside, pix), oracle_port.ring_to_nest(nside, pix))
+    n2r, r2n = oracle_port.nest_to_ring(nside, pix), oracle_port.ring_to_nest(nside, pix)
+    assert_bit_equal(sim.nest_to_ring(nside, pix), n2r)
+    assert_bit_equal(sim.ring_to_nest(nside, pix), r2n)
+    assert_bit_equal(sim.nest_to_ring_k(nside, pix), n2r)
+    assert_bit_equal(sim.ring_to_nest_k(nside, pix), r2n)
+
+
+@pytest.mark.parametrize("nside", [2 ** 15, 2 ** 16, 2 ** 17, 2 ** 24, 2 ** 28, 2 ** 29])
+def test_reorder_kernel_cores_random(sim, oracle_port, nside):
+    """hpgb_reorder.h cores (both instantiations where valid) on random pixels plus every zone
+    boundary: first/last pixels of the caps and of the belt, face corners."""
+    rng = np.random.default_rng(nside)
+    npix = 12 * nside * nside
+    ncap = 2 * nside * (nside - 1)
+    edges = np.concatenate([np.arange(0, 64), ncap + np.arange(-64, 64), npix - ncap + np.arange(-64, 64),
+                            npix - 1 - np.arange(0, 64), 4 * nside * np.arange(1, 64) + ncap,
+                            nside * nside * np.arange(0, 12), nside * nside * np.arange(1, 13) - 1])
+    pix = np.concatenate([rng.integers(0, npix, 400000), edges]).astype(np.int64)
+    n2r, r2n = oracle_port.nest_to_ring(nside, pix), oracle_port.ring_to_nest(nside, pix)
+    for hi in ([False, True] if nside >= 2 ** 16 else [False]):
+        assert_bit_equal(sim.nest_to_ring_k(nside, pix, hi=hi), n2r, "n2r hi=%s" % hi)
+        assert_bit_equal(sim.ring_to_nest_k(nside, pix, hi=hi), r2n, "r2n hi=%s" % hi)
 
 
 @pytest.mark.parametrize("nside", [3, 5, 12, 924, 2 ** 29 - 1])
