@@ -106,10 +106,22 @@ HPGB_HD uint32_t hpgb_xor3(uint32_t a, uint32_t b, uint32_t c) {  // a ^ b ^ c
     return a ^ b ^ c;
 #endif
 }
-#define HPGB_DSWAP(w, m, s)                                  \
-    do {                                                     \
-        uint32_t t_ = hpgb_xor_and((w), (w) >> (s), (m));    \
-        (w) = hpgb_xor3((w), t_, t_ << (s));                 \
+// w >> s.  With HPGB_SHR_MULHI the device version is a multiply-high by 2^(32-s) whose multiplier
+// is laundered through an empty asm so ptxas keeps it an IMAD.HI (FMA pipe) instead of strength-
+// reducing it back to SHF (ALU pipe): the integer kernels are ALU-pipe bound.
+HPGB_HD uint32_t hpgb_shr(uint32_t w, int s) {
+#if defined(__CUDA_ARCH__) && defined(HPGB_SHR_MULHI)
+    uint32_t mul = 1u << (32 - s);
+    asm("" : "+r"(mul));
+    return __umulhi(w, mul);
+#else
+    return w >> s;
+#endif
+}
+#define HPGB_DSWAP(w, m, s)                                       \
+    do {                                                          \
+        uint32_t t_ = hpgb_xor_and((w), hpgb_shr((w), (s)), (m)); \
+        (w) = hpgb_xor3((w), t_, t_ << (s));                      \
     } while (0)
 
 // Morton-interleave two 29-bit coordinates: bit i of ix -> bit 2i, bit i of iy -> bit 2i+1.

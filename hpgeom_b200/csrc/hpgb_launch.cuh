@@ -93,20 +93,25 @@ __device__ __forceinline__ const double *hpgb_stage_table() {
 // k_stream: TMA-fed persistent streaming kernel (the fast path for 16-byte aligned operands).
 //
 // One elected thread per CTA keeps a ring of STAGES shared-memory tiles full with 1-D bulk
-// async copies (cp.async.bulk.shared.global + mbarrier complete_tx -> SASS UBLKCP); every tile
-// holds HPGB_TILE consecutive elements of each input array.  The 256 threads wait on the
-// stage's mbarrier, pull their elements out of shared memory with conflict-free 128-bit LDS,
-// release the stage (one CTA barrier) so the producer can refill it while they compute, and
-// write results straight to HBM with 128-bit streaming stores.  Global-load latency is thus
-// hidden by the ring, not by occupancy: no registers are tied up by loads in flight and the
-// kernel stays busy even at the 2-3 CTAs/SM the fp64 register footprint allows.
-// Thread t owns elements {2t, 2t+1} and {TILE/2 + 2t, TILE/2 + 2t + 1} of a tile, so each warp
-// LDS / STG instruction covers one contiguous 512-byte span.
+// async copies (cp.async.bulk.shared.global + mbarrier complete_tx -> SASS UBLKCP); a tile holds
+// TILE = 1024*H consecutive elements of each input array.  Producer/consumer hand-over is two
+// mbarriers per stage and NO CTA-wide barrier:
+//   full[s]  (count 1, + transaction bytes) : the TMA engine completes it when the tile has landed;
+//   empty[s] (count 8 = warps per CTA)      : each warp arrives once it has pulled its elements out
+//                                             of the stage with conflict-free 128-bit LDS.
+// The eight warps therefore drift freely (a warp that hits the rare exact path does not stall the
+// other seven); only the producer thread ever waits on `empty`, and it refills the stage that was
+// consumed one iteration EARLIER, whose readers have normally long gone.  Results go straight to
+// HBM with 128-bit streaming stores.  Global-load latency is hidden by the ring, not by occupancy:
+// no registers are tied up by loads in flight and the kernel stays busy even at the 2-3 CTAs/SM the
+// fp64 register footprint allows.
+// Within sub-block h of a tile, thread t owns elements {2t, 2t+1} and {512 + 2t, 512 + 2t + 1}, so
+// each warp LDS / STG instruction covers one contiguous 512-byte span.
 // Op additionally provides:  static constexpr int NIN, MINB (min resident CTAs/SM -> register cap);
 //                            const void *src(int k) const;
-//                            In2 load2s(const unsigned char *stage, int elem) const;
+//                            In2 load2s(const unsigned char *stage, int tile_elems, int elem) const;
 // -------------------------------------------------------------------------------------------
-#define HPGB_TILE 1024
+#define HPGB_SUB 1024  // elements per sub-block (4 per thread)
 
 __device__ __forceinline__ uint32_t hpgb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void hpgb_mbar_init(uint64_t *bar, uint32_t count) {
@@ -114,6 +119,9 @@ __device__ __forceinline__ void hpgb_mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void hpgb_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hpgb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hpgb_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hpgb_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void hpgb_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -133,17 +141,21 @@ __device__ __forceinline__ void hpgb_mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
-template <class Op, int STAGES>
+template <class Op, int STAGES, int H>
 __global__ void __launch_bounds__(HPGB_BLOCK, Op::MINB) k_stream(const Op op, const int64_t n, hpgb_status_t *st) {
     constexpr int NIN = Op::NIN;
-    constexpr uint32_t ARR_BYTES = HPGB_TILE * 8;
+    constexpr int TILE = HPGB_SUB * H;
+    constexpr uint32_t ARR_BYTES = TILE * 8;
     extern __shared__ __align__(128) unsigned char hpgb_stage_smem[];
-    __shared__ uint64_t full[STAGES];
+    __shared__ uint64_t full[STAGES], empty[STAGES];
     const typename Op::Ctx ctx = op.prologue();
     const int tid = threadIdx.x;
-    const int64_t ntiles = n / HPGB_TILE;
+    const int64_t ntiles = n / TILE;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) hpgb_mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; s++) {
+            hpgb_mbar_init(&full[s], 1);
+            hpgb_mbar_init(&empty[s], HPGB_BLOCK / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -159,27 +171,40 @@ __global__ void __launch_bounds__(HPGB_BLOCK, Op::MINB) k_stream(const Op op, co
         for (int s = 0; s < STAGES && t < ntiles; s++, t += gridDim.x) issue(s, t);
     }
     hpgb_bad_t bad;
-    int s = 0;
-    uint32_t phase = 0;
+    int s = 0, sprev = STAGES - 1;
+    uint32_t phase = 0, phase_prev = 1;  // parity of full[s] now / of empty[sprev] for the refill
+    bool first = true;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (tid == 0 && !first) {  // refill the stage every warp left one iteration ago
+            const int64_t tn = t + (int64_t)(STAGES - 1) * gridDim.x;
+            if (tn < ntiles) {
+                hpgb_mbar_wait(&empty[sprev], phase_prev);
+                issue(sprev, tn);
+            }
+        }
+        first = false;
         hpgb_mbar_wait(&full[s], phase);
         const unsigned char *stage = hpgb_stage_smem + (size_t)s * NIN * ARR_BYTES;
-        const typename Op::In2 v0 = op.load2s(stage, 2 * tid);
-        const typename Op::In2 v1 = op.load2s(stage, HPGB_TILE / 2 + 2 * tid);
-        __syncthreads();  // every thread has its elements: the stage may be refilled
-        if (tid == 0) {
-            const int64_t tn = t + (int64_t)STAGES * gridDim.x;
-            if (tn < ntiles) issue(s, tn);
+#pragma unroll
+        for (int h = 0; h < H; h++) {
+            const typename Op::In2 v0 = op.load2s(stage, TILE, h * HPGB_SUB + 2 * tid);
+            const typename Op::In2 v1 = op.load2s(stage, TILE, h * HPGB_SUB + HPGB_SUB / 2 + 2 * tid);
+            if (h == H - 1) {  // this warp is done with the stage
+                __syncwarp();
+                if ((tid & 31) == 0) hpgb_mbar_arrive(&empty[s]);
+            }
+            const int64_t e0 = t * TILE + h * HPGB_SUB + 2 * tid;
+            op.run4(e0, v0, e0 + HPGB_SUB / 2, v1, ctx, bad);
         }
-        const int64_t e0 = t * HPGB_TILE + 2 * tid;
-        op.run4(e0, v0, e0 + HPGB_TILE / 2, v1, ctx, bad);
+        sprev = s;
+        phase_prev = phase;
         if (++s == STAGES) {
             s = 0;
             phase ^= 1u;
         }
     }
-    if (blockIdx.x == 0)  // fewer than HPGB_TILE leftover elements
-        for (int64_t i = ntiles * HPGB_TILE + tid; i < n; i += HPGB_BLOCK) op.run1(i, ctx, bad);
+    if (blockIdx.x == 0)  // fewer than TILE leftover elements
+        for (int64_t i = ntiles * TILE + tid; i < n; i += HPGB_BLOCK) op.run1(i, ctx, bad);
     bad.commit(st);
 }
 
@@ -226,21 +251,22 @@ static int hpgb_launch_map(const Op &op, int64_t n, bool vec_ok, hpgb_status_t *
 }
 
 // launch the TMA streaming kernel (operands 16-byte aligned); falls back to k_map2 for small n
-template <class Op, int STAGES>
+template <class Op, int STAGES, int H = 1>
 static int hpgb_launch_stream(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
-    if (n < 4 * HPGB_TILE) return hpgb_launch_map(op, n, true, st, s);
-    const int smem = STAGES * Op::NIN * HPGB_TILE * 8;
+    constexpr int TILE = HPGB_SUB * H;
+    if (n < 4 * TILE) return hpgb_launch_map(op, n, true, st, s);
+    const int smem = STAGES * Op::NIN * TILE * 8;
     static int occ = 0;
     if (!occ) {
-        cudaFuncSetAttribute(k_stream<Op, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_stream<Op, STAGES, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream<Op, STAGES>, HPGB_BLOCK, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream<Op, STAGES, H>, HPGB_BLOCK, smem);
         occ = per_sm > 0 ? per_sm : 1;
     }
     int64_t grid = (int64_t)hpgb_sm_count() * occ;
-    const int64_t ntiles = n / HPGB_TILE;
+    const int64_t ntiles = n / TILE;
     if (ntiles < grid) grid = ntiles;
-    k_stream<Op, STAGES><<<(unsigned)grid, HPGB_BLOCK, smem, s>>>(op, n, st);
+    k_stream<Op, STAGES, H><<<(unsigned)grid, HPGB_BLOCK, smem, s>>>(op, n, st);
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;

@@ -42,6 +42,7 @@ struct hpgb_rk {
     uint32_t lmask, hmask;              // nside^2 - 1
     uint32_t k, k2;                     // order, 2 * order
     uint32_t fsh_hi, fmul_hi;           // order >= 16: 2k - 32 and 1 << (2k - 32)
+    uint32_t ns3p1, dnr;                // 3 nside + 1, nside - (3 nside + 1)
 };
 
 HPGB_HD hpgb_rk hpgb_make_rk(const hpgb_geom &g) {
@@ -68,7 +69,20 @@ HPGB_HD hpgb_rk hpgb_make_rk(const hpgb_geom &g) {
     c.k2 = 2u * k;
     c.fsh_hi = k >= 16 ? 2u * k - 32u : 0u;
     c.fmul_hi = k >= 16 ? (1u << (2u * k - 32u)) : 0u;
+    c.ns3p1 = 3u * ns + 1u;
+    c.dnr = ns - (3u * ns + 1u);
     return c;
+}
+
+// select that stays a select (inline selp: the compiler cannot turn it back into a branch)
+HPGB_HD uint32_t hpgb_sel(bool p, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tselp.u32 %0, %1, %2, q;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((uint32_t)p));
+    return r;
+#else
+    return p ? a : b;
+#endif
 }
 
 // jpll[face] = {1,3,5,7,0,2,4,6,1,3,5,7} as a byte lookup done by one PRMT: selector nibble 0 =
@@ -87,21 +101,72 @@ HPGB_HD int64_t hpgb_nest2ring_k(const hpgb_rk &c, uint32_t lo, uint32_t hi) {
     HPGB_DSWAP(wl, 0x00F000F0u, 4);
     HPGB_DSWAP(wh, 0x00F000F0u, 4);
     const uint32_t ix = hpgb_prmt(wl, wh, 0x6420), iy = hpgb_prmt(wl, wh, 0x7531);
+#if defined(__CUDA_ARCH__)
+    // Zone selection written as predicated PTX so that it stays ~20 instructions: belt operands by
+    // default, overwritten under the north / south predicates (the C++ below is the same arithmetic;
+    // left to the compiler it becomes either a divergent branch per element or ~35 selects).
+    uint64_t res;
+    asm("{\n\t"
+        ".reg .pred pn, ps;\n\t"
+        ".reg .u32 fc, fr, fm2, frns, t, v, d, w, ks, X, A, B, Cl, Ch, niy;\n\t"
+        ".reg .u64 C;\n\t"
+        "and.b32 fc, %3, 3;\n\t"
+        "shr.u32 fr, %3, 2;\n\t"
+        "mul.lo.u32 frns, fr, %4;\n\t"
+        "sub.u32 t, %5, %1;\n\t"
+        "sub.u32 t, t, %2;\n\t"
+        "add.u32 t, t, frns;\n\t"          // t = fr*ns + (ns-1) - ix - iy = ring - nside
+        "setp.lt.s32 pn, t, 0;\n\t"        // north cap
+        "setp.ge.s32 ps, t, %6;\n\t"       // south cap (t >= 2 nside)
+        "and.b32 v, frns, %4;\n\t"         // (fr & 1) * nside
+        "sub.u32 d, %1, %2;\n\t"
+        "mad.lo.u32 w, fc, %6, d;\n\t"     // fc * 2 nside + ix - iy
+        "and.b32 ks, t, 1;\n\t"
+        "add.u32 X, w, ks;\n\t"
+        "add.u32 X, X, %5;\n\t"
+        "sub.u32 X, X, v;\n\t"             // jpll * nside + ix - iy + kshift - 1
+        "shr.u32 X, X, 1;\n\t"
+        "and.b32 X, X, %9;\n\t"
+        "add.u32 Cl, X, %11;\n\t"          // belt: 2 nside + in-ring offset
+        "add.u32 A, t, %10;\n\t"           // belt: t + nside/2 - 1
+        "mov.u32 B, %8;\n\t"               // belt: 4 nside
+        "mov.u32 Ch, 0;\n\t"
+        "sub.u32 fm2, fc, 2;\n\t"
+        "@pn add.u32 A, t, %4;\n\t"        // north: nr = t + nside
+        "@ps sub.u32 A, %7, t;\n\t"        // south: nr = 3 nside - t
+        "@pn mad.lo.u32 B, A, 2, fm2;\n\t"
+        "@ps mad.lo.u32 B, A, 0xfffffffe, fm2;\n\t"
+        "not.b32 niy, %2;\n\t"
+        "@pn and.b32 Cl, niy, %5;\n\t"     // north: nside - 1 - iy
+        "@ps or.b32 Cl, %12, %1;\n\t"      // south: npix_lo + ix
+        "@ps sub.u32 Ch, %13, A;\n\t"      // south: npix_hi - nr (compensates B = 2^32 - ...)
+        "mov.b64 C, {Cl, Ch};\n\t"
+        "mad.wide.u32 %0, A, B, C;\n\t"
+        "}"
+        : "=l"(res)
+        : "r"(ix), "r"(iy), "r"(face), "r"(c.ns), "r"(c.nsm1), "r"(c.ns2), "r"(c.ns3), "r"(c.ns4), "r"(c.ns4m1),
+          "r"(c.belt_a0), "r"(c.belt_c0), "r"(c.npix_lo), "r"(c.npix_hi));
+    return (int64_t)res;
+#else
     const uint32_t fr = face >> 2, fc = face & 3u;
     const uint32_t t = fr * c.ns + c.nsm1 - ix - iy;  // jr - nside, two's complement
-    const bool cap = t >= c.ns2;                       // t < 0 wraps to a huge unsigned value
-    const bool north = (int32_t)t < 0;
-    // operands of the final multiply-add, selected per zone (branch-free: with random pixels
-    // every warp holds cap and belt pixels anyway, and straight-line code lets the four elements a
-    // thread owns interleave)
-    const uint32_t X = hpgb_jpll_lut(face) * c.ns + (ix - iy) + (t & 1u) - 1u;
-    const uint32_t nr = north ? t + c.ns : c.ns3 - t;
+    const bool north = (int32_t)t < 0, south = (int32_t)t >= (int32_t)c.ns2;
+    // jpll = 2 fc + 1 - (fr & 1)
+    const uint32_t X = fc * c.ns2 + (ix - iy) + (t & 1u) + c.nsm1 - ((fr * c.ns) & c.ns);
+    uint32_t A = t + c.belt_a0, B = c.ns4, Cl = ((X >> 1) & c.ns4m1) + c.belt_c0, Ch = 0u;
     const uint32_t fm2 = fc - 2u;
-    const uint32_t A = cap ? nr : t + c.belt_a0;
-    const uint32_t B = cap ? (north ? fm2 + 2u * nr : fm2 - 2u * nr) : c.ns4;
-    const uint32_t Cl = cap ? (north ? (~iy & c.nsm1) : (c.npix_lo | ix)) : ((X >> 1) & c.ns4m1) + c.belt_c0;
-    const uint32_t Ch = (cap && !north) ? c.npix_hi - nr : 0u;
+    if (north) {
+        A = t + c.ns;
+        B = 2u * A + fm2;
+        Cl = ~iy & c.nsm1;
+    } else if (south) {
+        A = c.ns3 - t;
+        B = fm2 - 2u * A;
+        Cl = c.npix_lo | ix;
+        Ch = c.npix_hi - A;
+    }
     return (int64_t)((uint64_t)A * (uint64_t)B + (((uint64_t)Ch << 32) | Cl));
+#endif
 }
 
 // RING pixel (must be < npix) -> NEST pixel.  HI: order >= 16.

@@ -12,6 +12,17 @@
 #include "hpgb_internal.h"
 #include "hpgb_launch.cuh"
 
+// ring depth / sub-blocks per tile / min resident CTAs of the streaming kernel (tunable per build)
+#ifndef HPGB_A2P_ST
+#define HPGB_A2P_ST 3
+#endif
+#ifndef HPGB_A2P_H
+#define HPGB_A2P_H 1
+#endif
+#ifndef HPGB_A2P_MINB
+#define HPGB_A2P_MINB 3
+#endif
+
 namespace {
 
 // per-element geometry for nside arrays; flags the element and returns false on a bad nside
@@ -44,11 +55,11 @@ struct OpAng2Pix {
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(a + i), hpgb_ld2(b + i)}; }
     static constexpr int NIN = 2;
-    static constexpr int MINB = 3;  // <= 80 registers: 3 CTAs/SM measured best on B200 (2: 190, 3: 201, 4: 192 Gpts/s)
+    static constexpr int MINB = HPGB_A2P_MINB;  // <= 80 registers: 3 CTAs/SM measured best on B200 (2: 190, 3: 201, 4: 192 Gpts/s)
     __device__ __forceinline__ const void *src(int k) const { return k == 0 ? (const void *)a : (const void *)b; }
-    __device__ __forceinline__ In2 load2s(const unsigned char *stage, int e) const {
+    __device__ __forceinline__ In2 load2s(const unsigned char *stage, int tile, int e) const {
         return In2{*reinterpret_cast<const double2 *>(stage + 8 * e),
-                   *reinterpret_cast<const double2 *>(stage + 8 * HPGB_TILE + 8 * e)};
+                   *reinterpret_cast<const double2 *>(stage + 8 * tile + 8 * e)};
     }
     // exact path for one element (rare): non-inlined call, flags the element when it is invalid
     __device__ __forceinline__ int64_t slow(const hpgb_geom &gg, double va, double vb, int64_t i, Ctx T,
@@ -116,7 +127,7 @@ int launch_a2p_t(const double *a, const double *b, int64_t *out, int64_t n, int6
     const bool vec = hpgb_aligned16(a) && hpgb_aligned16(b) && hpgb_aligned16(out);
     if (NEST && g.order >= 16) {  // face bits only in the high word of the pixel: cheaper assembly
         OpAng2Pix<NEST, LONLAT, DEGREES, false, NEST> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g)};
-        if (vec) return hpgb_launch_stream<decltype(op), 3>(op, n, st, s);
+        if (vec) return hpgb_launch_stream<decltype(op), HPGB_A2P_ST, HPGB_A2P_H>(op, n, st, s);
         return hpgb_launch_map(op, n, vec, st, s);
     }
     OpAng2Pix<NEST, LONLAT, DEGREES, false, false> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g)};

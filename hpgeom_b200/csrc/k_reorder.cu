@@ -13,6 +13,14 @@
 #include "hpgb_launch.cuh"
 #include "hpgb_reorder.h"
 
+// ring depth / sub-blocks per tile of the streaming kernel (tunable per build for A/B timing)
+#ifndef HPGB_RE_ST
+#define HPGB_RE_ST 3
+#endif
+#ifndef HPGB_RE_H
+#define HPGB_RE_H 2
+#endif
+
 namespace {
 
 // per-element geometry for nside arrays; flags the element and returns false on a bad nside
@@ -61,7 +69,7 @@ struct OpReorder {
     static constexpr int NIN = 1;
     static constexpr int MINB = 1;
     __device__ __forceinline__ const void *src(int) const { return in; }
-    __device__ __forceinline__ In2 load2s(const unsigned char *stage, int e) const {
+    __device__ __forceinline__ In2 load2s(const unsigned char *stage, int, int e) const {
         return *reinterpret_cast<const longlong2 *>(stage + 8 * e);
     }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &, hpgb_bad_t &bad) const {
@@ -111,11 +119,11 @@ int launch_reorder(const int64_t *in, int64_t *out, int64_t n, int64_t nside, co
     const bool vec = hpgb_aligned16(in) && hpgb_aligned16(out);
     if (g.order >= 16) {
         OpReorder<TO_RING, false, true> op{in, out, nullptr, base, g, hpgb_make_rk(g)};
-        if (vec) return hpgb_launch_stream<decltype(op), 4>(op, n, st, s);
+        if (vec) return hpgb_launch_stream<decltype(op), HPGB_RE_ST, HPGB_RE_H>(op, n, st, s);
         return hpgb_launch_map(op, n, false, st, s);
     }
     OpReorder<TO_RING, false, false> op{in, out, nullptr, base, g, hpgb_make_rk(g)};
-    if (vec) return hpgb_launch_stream<decltype(op), 4>(op, n, st, s);
+    if (vec) return hpgb_launch_stream<decltype(op), HPGB_RE_ST, HPGB_RE_H>(op, n, st, s);
     return hpgb_launch_map(op, n, false, st, s);
 }
 
