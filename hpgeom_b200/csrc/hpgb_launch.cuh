@@ -110,6 +110,9 @@ __device__ __forceinline__ const double *hpgb_stage_table() {
 // Op additionally provides:  static constexpr int NIN, MINB (min resident CTAs/SM -> register cap);
 //                            const void *src(int k) const;
 //                            In2 load2s(const unsigned char *stage, int tile_elems, int elem) const;
+//                            static constexpr bool TILE_HOOK; static constexpr int EXTRA_SMEM;
+//   TILE_HOOK ops replace the per-thread run4 calls by  tile<TILE>(stage, extra_smem, first_element,
+//   tid, ctx, bad, empty_barrier)  and may rewrite the stage in place (see OpReorder, ring -> nest).
 // -------------------------------------------------------------------------------------------
 #define HPGB_SUB 1024  // elements per sub-block (4 per thread)
 
@@ -185,16 +188,22 @@ __global__ void __launch_bounds__(HPGB_BLOCK, Op::MINB) k_stream(const Op op, co
         first = false;
         hpgb_mbar_wait(&full[s], phase);
         const unsigned char *stage = hpgb_stage_smem + (size_t)s * NIN * ARR_BYTES;
+        if constexpr (Op::TILE_HOOK) {
+            // the op processes the whole tile itself (warp-cooperative) and arrives on empty[s]
+            op.template tile<TILE>(const_cast<unsigned char *>(stage), hpgb_stage_smem + (size_t)STAGES * NIN * ARR_BYTES,
+                                   t * TILE, tid, ctx, bad, &empty[s]);
+        } else {
 #pragma unroll
-        for (int h = 0; h < H; h++) {
-            const typename Op::In2 v0 = op.load2s(stage, TILE, h * HPGB_SUB + 2 * tid);
-            const typename Op::In2 v1 = op.load2s(stage, TILE, h * HPGB_SUB + HPGB_SUB / 2 + 2 * tid);
-            if (h == H - 1) {  // this warp is done with the stage
-                __syncwarp();
-                if ((tid & 31) == 0) hpgb_mbar_arrive(&empty[s]);
+            for (int h = 0; h < H; h++) {
+                const typename Op::In2 v0 = op.load2s(stage, TILE, h * HPGB_SUB + 2 * tid);
+                const typename Op::In2 v1 = op.load2s(stage, TILE, h * HPGB_SUB + HPGB_SUB / 2 + 2 * tid);
+                if (h == H - 1) {  // this warp is done with the stage
+                    __syncwarp();
+                    if ((tid & 31) == 0) hpgb_mbar_arrive(&empty[s]);
+                }
+                const int64_t e0 = t * TILE + h * HPGB_SUB + 2 * tid;
+                op.run4(e0, v0, e0 + HPGB_SUB / 2, v1, ctx, bad);
             }
-            const int64_t e0 = t * TILE + h * HPGB_SUB + 2 * tid;
-            op.run4(e0, v0, e0 + HPGB_SUB / 2, v1, ctx, bad);
         }
         sprev = s;
         phase_prev = phase;
@@ -255,7 +264,7 @@ template <class Op, int STAGES, int H = 1>
 static int hpgb_launch_stream(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
     constexpr int TILE = HPGB_SUB * H;
     if (n < 4 * TILE) return hpgb_launch_map(op, n, true, st, s);
-    const int smem = STAGES * Op::NIN * TILE * 8;
+    const int smem = STAGES * Op::NIN * TILE * 8 + Op::EXTRA_SMEM;
     static int occ = 0;
     if (!occ) {
         cudaFuncSetAttribute(k_stream<Op, STAGES, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -169,42 +169,61 @@ HPGB_HD int64_t hpgb_nest2ring_k(const hpgb_rk &c, uint32_t lo, uint32_t hi) {
 #endif
 }
 
-// RING pixel (must be < npix) -> NEST pixel.  HI: order >= 16.
-template <bool HI>
-HPGB_HD int64_t hpgb_ring2nest_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix) {
-    const uint64_t up = (uint64_t)pix;
-    const uint64_t ipb = up - (((uint64_t)c.ncap_hi << 32) | c.ncap_lo);  // index inside the belt (negative: north cap)
-    const uint32_t tmp = (uint32_t)((int64_t)ipb >> (c.k + 2u));          // ring - nside; fits int32
-    uint32_t ix, iy, face;
-    if (tmp > c.ns2) {  // polar caps (tmp < 0 wraps)
-        const bool north = (int32_t)tmp < 0;
-        const uint64_t ipm1 = north ? up : ((((uint64_t)c.npm1_hi << 32) | c.npm1_lo) - up);  // 0-based from the pole
-        const uint32_t ir = (uint32_t)((1 + hpgb_isqrt((int64_t)(2 * ipm1 + 1))) >> 1);
-        const uint64_t q0 = ipm1 - (uint64_t)ir * (uint64_t)(2u * ir - 2u);  // in-ring index, eastward from the pole side
-        if (q0 >= 4ull * ir) {  // the reference's isqrt mis-rounded: replay its 64-bit arithmetic
-            int32_t sx, sy;
-            hpgb_ring2xyf_any(g, pix, sx, sy, face);
-            ix = (uint32_t)sx;
-            iy = (uint32_t)sy;
-        } else {
-            uint32_t q = north ? (uint32_t)q0 : 4u * ir - 1u - (uint32_t)q0;
-            const uint32_t t1 = (q >= 2u * ir) ? 1u : 0u;
-            q -= t1 ? 2u * ir : 0u;
-            const uint32_t t2 = (q >= ir) ? 1u : 0u;
-            q -= t2 ? ir : 0u;
-            face = 2u * t1 + t2 + (north ? 0u : 8u);
-            ix = north ? c.ns - ir + q : q;
-            iy = north ? c.nsm1 - q : ir - 1u - q;
-        }
-    } else {
-        const uint32_t ip = (uint32_t)ipb & c.ns4m1;
-        const uint32_t jp = ip + (tmp >> 1);
-        const uint32_t jm = jp + c.ns - tmp;
-        const uint32_t ifp = jp >> c.k, ifm = jm >> c.k;
-        face = (ifp == ifm) ? (ifp | 4u) : ((ifp < ifm) ? ifp : (ifm + 8u));
-        ix = jm & c.nsm1;
-        iy = ~jp & c.nsm1;
+// ---- RING -> NEST, in pieces (the streaming kernel runs the belt and the cap part in different
+// phases, see OpReorder::tile in k_reorder.cu; hpgb_ring2nest_k below is the plain composition) ----
+
+// ring - nside of a valid RING pixel (two's complement: negative in the north cap, > 2 nside in the
+// south cap) and the low word of its index inside the belt
+HPGB_HD uint32_t hpgb_r2n_zone(const hpgb_rk &c, uint64_t up, uint32_t &ipb_lo) {
+    const uint64_t ipb = up - (((uint64_t)c.ncap_hi << 32) | c.ncap_lo);
+    ipb_lo = (uint32_t)ipb;
+    return (uint32_t)((int64_t)ipb >> (c.k + 2u));  // fits int32
+}
+HPGB_HD bool hpgb_r2n_is_cap(const hpgb_rk &c, uint32_t tmp) { return tmp > c.ns2; }
+
+HPGB_HD void hpgb_r2n_belt(const hpgb_rk &c, uint32_t tmp, uint32_t ipb_lo, uint32_t &ix, uint32_t &iy, uint32_t &face) {
+    const uint32_t ip = ipb_lo & c.ns4m1;
+    const uint32_t jp = ip + (tmp >> 1);
+    const uint32_t jm = jp + c.ns - tmp;
+    const uint32_t ifp = jp >> c.k, ifm = jm >> c.k;
+    face = (ifp == ifm) ? (ifp | 4u) : ((ifp < ifm) ? ifp : (ifm + 8u));
+    ix = jm & c.nsm1;
+    iy = ~jp & c.nsm1;
+}
+
+// polar-cap pixel.  Everything after the reference's isqrt is 32-bit: the ring number is < 2^30
+// and the in-ring index is compared modulo 2^32, which still detects a ring that is off by one
+// (|error| of the uncorrected isqrt <= 1, and 4 * ring <= 2^31).
+HPGB_HD void hpgb_r2n_cap(const hpgb_rk &c, const hpgb_geom &g, uint64_t up, bool north, uint32_t &ix, uint32_t &iy,
+                          uint32_t &face) {
+    const uint64_t ipm1 = north ? up : ((((uint64_t)c.npm1_hi << 32) | c.npm1_lo) - up);  // 0-based from the pole
+    // isqrt of the reference: (int64)sqrt((double)(2 ip - 1) + 0.5), hpgeom/healpix_geom.c:60; < 2^31
+#if defined(__CUDA_ARCH__)
+    const uint32_t isq = __double2uint_rz(sqrt((double)(int64_t)(2 * ipm1 + 1) + 0.5));
+#else
+    const uint32_t isq = (uint32_t)(int64_t)sqrt((double)(int64_t)(2 * ipm1 + 1) + 0.5);
+#endif
+    const uint32_t ir = (isq + 1u) >> 1;
+    const uint32_t q0 = (uint32_t)ipm1 - ir * (2u * ir - 2u);  // in-ring index, eastward, counted from the pole side
+    if (q0 >= 4u * ir) {  // the reference's isqrt mis-rounded: replay its 64-bit arithmetic
+        int32_t sx, sy;
+        hpgb_ring2xyf_any(g, (int64_t)up, sx, sy, face);
+        ix = (uint32_t)sx;
+        iy = (uint32_t)sy;
+        return;
     }
+    uint32_t q = north ? q0 : 4u * ir - 1u - q0;
+    const uint32_t t1 = (q >= 2u * ir) ? 1u : 0u;
+    q -= t1 ? 2u * ir : 0u;
+    const uint32_t t2 = (q >= ir) ? 1u : 0u;
+    q -= t2 ? ir : 0u;
+    face = 2u * t1 + t2 + (north ? 0u : 8u);
+    ix = north ? c.ns - ir + q : q;
+    iy = north ? c.nsm1 - q : ir - 1u - q;
+}
+
+template <bool HI>
+HPGB_HD int64_t hpgb_xyf2nest_k(const hpgb_rk &c, uint32_t ix, uint32_t iy, uint32_t face) {
     uint32_t lo = hpgb_prmt(ix, iy, 0x5140), hi = hpgb_prmt(ix, iy, 0x7362);
     HPGB_DSWAP(lo, 0x00F000F0u, 4);
     HPGB_DSWAP(hi, 0x00F000F0u, 4);
@@ -214,6 +233,18 @@ HPGB_HD int64_t hpgb_ring2nest_k(const hpgb_rk &c, const hpgb_geom &g, int64_t p
     HPGB_DSWAP(hi, 0x22222222u, 1);
     if (HI) return (int64_t)(((uint64_t)(hi + face * c.fmul_hi) << 32) | lo);
     return (int64_t)((((uint64_t)hi << 32) | lo) + ((uint64_t)face << c.k2));
+}
+
+// RING pixel (must be < npix) -> NEST pixel.  HI: order >= 16.
+template <bool HI>
+HPGB_HD int64_t hpgb_ring2nest_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix) {
+    uint32_t ipb_lo, ix, iy, face;
+    const uint32_t tmp = hpgb_r2n_zone(c, (uint64_t)pix, ipb_lo);
+    if (hpgb_r2n_is_cap(c, tmp))
+        hpgb_r2n_cap(c, g, (uint64_t)pix, (int32_t)tmp < 0, ix, iy, face);
+    else
+        hpgb_r2n_belt(c, tmp, ipb_lo, ix, iy, face);
+    return hpgb_xyf2nest_k<HI>(c, ix, iy, face);
 }
 
 #endif  // HPGB_REORDER_H

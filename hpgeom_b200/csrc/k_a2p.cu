@@ -55,6 +55,8 @@ struct OpAng2Pix {
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(a + i), hpgb_ld2(b + i)}; }
     static constexpr int NIN = 2;
+    static constexpr bool TILE_HOOK = false;
+    static constexpr int EXTRA_SMEM = 0;
     static constexpr int MINB = HPGB_A2P_MINB;  // <= 80 registers: 3 CTAs/SM measured best on B200 (2: 190, 3: 201, 4: 192 Gpts/s)
     __device__ __forceinline__ const void *src(int k) const { return k == 0 ? (const void *)a : (const void *)b; }
     __device__ __forceinline__ In2 load2s(const unsigned char *stage, int tile, int e) const {

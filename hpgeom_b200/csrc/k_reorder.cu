@@ -68,7 +68,90 @@ struct OpReorder {
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(in + i); }
     static constexpr int NIN = 1;
     static constexpr int MINB = 1;
+    // ring -> nest runs the warp-cooperative tile routine below; nest -> ring the per-thread run4
+    static constexpr bool TILE_HOOK = !TO_RING && !VAR;
+    static constexpr int EXTRA_SMEM = TILE_HOOK ? (HPGB_BLOCK / 32) * 256 * (8 + 2) : 0;
     __device__ __forceinline__ const void *src(int) const { return in; }
+
+    // ---------------------------------------------------------------------------------------
+    // ring -> nest, one tile.  Cap pixels need the (long) isqrt path, belt pixels a dozen
+    // instructions; with random pixels a third of every warp's lanes would drag the other two
+    // thirds through the cap path.  So the warp sorts them instead:
+    //   phase 1  every thread converts its 8 pixels as if they were belt pixels and writes the
+    //            results over the inputs in the shared-memory stage; cap pixels are appended to a
+    //            per-warp queue (ballot + popc) with their slot number;
+    //   phase 2  the warp drains the queue 32 cap pixels at a time (dense lanes) and writes those
+    //            results into their slots;
+    //   phase 3  the finished tile goes to HBM with 128-bit streaming stores.
+    // A warp only ever touches its own 256 slots, so __syncwarp() is the only synchronisation.
+    // ---------------------------------------------------------------------------------------
+    template <int TILE>
+    __device__ __forceinline__ void tile(unsigned char *stage, unsigned char *extra, int64_t e_base, int tid, const Ctx &,
+                                         hpgb_bad_t &bad, uint64_t *empty_bar) const {
+        static_assert(TILE == 2048, "queue sizes assume 8 elements per thread");
+        const int lane = tid & 31, warp = tid >> 5;
+        unsigned long long *qpix = reinterpret_cast<unsigned long long *>(extra) + warp * 256;
+        unsigned short *qslot = reinterpret_cast<unsigned short *>(extra + (HPGB_BLOCK / 32) * 256 * 8) + warp * 256;
+        longlong2 *st2 = reinterpret_cast<longlong2 *>(stage);
+        unsigned long long *st1 = reinterpret_cast<unsigned long long *>(stage);
+        const unsigned lt = (1u << lane) - 1u;
+        int ncap = 0;
+        bool all_ok = true;
+#pragma unroll
+        for (int j = 0; j < TILE / 512; j++) {
+            const int slot = j * 512 + 2 * tid;
+            const longlong2 v = st2[slot >> 1];
+            int64_t r[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int64_t p = e ? v.y : v.x;
+                const bool good = ok(p);
+                all_ok &= good;
+                uint32_t ipb_lo, ix, iy, face;
+                const uint32_t tmp = hpgb_r2n_zone(c, (uint64_t)p, ipb_lo);
+                const bool cap = hpgb_r2n_is_cap(c, tmp) && good;
+                hpgb_r2n_belt(c, tmp, ipb_lo, ix, iy, face);
+                r[e] = hpgb_xyf2nest_k<HI>(c, ix, iy, face);
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, cap);
+                if (cap) {
+                    const int pos = ncap + __popc(m & lt);
+                    qpix[pos] = (unsigned long long)p;
+                    qslot[pos] = (unsigned short)(slot + e);
+                }
+                ncap += __popc(m);
+            }
+            st2[slot >> 1] = make_longlong2(r[0], r[1]);
+        }
+        __syncwarp();
+        for (int j = lane; j < ncap; j += 32) {
+            const uint64_t p = qpix[j];
+            uint32_t ix, iy, face;
+            hpgb_r2n_cap(c, g, p, p < (((uint64_t)c.ncap_hi << 32) | c.ncap_lo), ix, iy, face);
+            st1[qslot[j]] = (unsigned long long)hpgb_xyf2nest_k<HI>(c, ix, iy, face);
+        }
+        if (!all_ok) {  // rare: out-of-range pixels among this thread's 8 -> re-read them from HBM, flag, patch
+#pragma unroll 1
+            for (int j = 0; j < TILE / 512; j++)
+                for (int e = 0; e < 2; e++) {
+                    const int slot = j * 512 + 2 * tid + e;
+                    if (!ok(in[e_base + slot])) {
+                        bad.flag(base + e_base + slot);
+                        st1[slot] = ~0ull;
+                    }
+                }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < TILE / 512; j++) {
+            const int slot = j * 512 + 2 * tid;
+            const longlong2 v = st2[slot >> 1];
+            hpgb_st2(out + e_base + slot, v.x, v.y);
+        }
+        // generic-proxy writes to the stage must be ordered before the TMA refill (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) hpgb_mbar_arrive(empty_bar);
+    }
     __device__ __forceinline__ In2 load2s(const unsigned char *stage, int, int e) const {
         return *reinterpret_cast<const longlong2 *>(stage + 8 * e);
     }

@@ -97,6 +97,40 @@ def test_errors(hpg):
         hpg.nest_to_ring(np.array([1024, 1000]), np.array([1, 1]))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("nside", [2 ** 12, 2 ** 29])
+def test_bad_pixels_in_streaming_tiles(hpg, oracle_port, nside):
+    """Out-of-range pixels inside the TMA-streamed tiles (both directions, both nside classes): the
+    smallest bad index is reported, every other element is still converted, bad ones come out -1."""
+    import ctypes
+
+    import torch
+
+    from hpgeom_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    npix = 12 * nside * nside
+    n = 300_007
+    pix = rng.integers(0, npix, n)
+    badpos = np.array([299_999, 70_001, 150_000, 70_002])
+    pix[badpos] = [npix, -1, npix + 12345, 2 ** 62]
+    good = np.ones(n, bool)
+    good[badpos] = False
+    t = torch.from_numpy(pix).cuda()
+    out = torch.empty_like(t)
+    st = torch.empty(1, dtype=torch.int64, device="cuda")
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for name, ref in (("hpgb_nest_to_ring", oracle_port.nest_to_ring), ("hpgb_ring_to_nest", oracle_port.ring_to_nest)):
+        L.hpgb_status_reset(st.data_ptr(), s)
+        assert getattr(L, name)(t.data_ptr(), out.data_ptr(), n, nside, None, st.data_ptr(), s) == 0
+        assert int(st.item()) == 70_001
+        got = out.cpu().numpy()
+        assert np.all(got[badpos] == -1)
+        assert np.array_equal(got[good], ref(nside, pix[good]))
+    with pytest.raises(ValueError, match=r"Pixel value -1 out of range"):
+        hpg.ring_to_nest(nside, t)
+
+
 def test_full_size_round_trip(hpg, oracle_port):
     """BASELINE config 3: nside=2^29, 1B random pixels.  ring_to_nest(nest_to_ring(p)) == p except
     on the reference's own isqrt quirk (hpgeom/healpix_geom.c:60: the last few pixels of cap rings
