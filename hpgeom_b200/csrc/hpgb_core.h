@@ -151,6 +151,17 @@ HPGB_HD void hpgb_deinterleave(uint64_t v, uint32_t &ix, uint32_t &iy) {
     iy = hpgb_prmt(lo, hi, 0x7531);
 }
 
+// select that stays a select (inline selp: the compiler cannot turn it back into a branch)
+HPGB_HD uint32_t hpgb_sel(bool p, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tselp.u32 %0, %1, %2, q;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((uint32_t)p));
+    return r;
+#else
+    return p ? a : b;
+#endif
+}
+
 // jrll[f] = 2 + (f >> 2); jpll[f] = {1,3,5,7,0,2,4,6,1,3,5,7}  (hpgeom/healpix_geom.c:57-58)
 HPGB_HD uint32_t hpgb_jrll(uint32_t f) { return 2u + (f >> 2); }
 HPGB_HD uint32_t hpgb_jpll(uint32_t f) { return 2u * (f & 3u) + 1u - (((f >> 2) == 1u) ? 1u : 0u); }

@@ -246,8 +246,8 @@ HPGB_HD double hpgb_sin_poly(const hpgb_a2p_fast &f, double a) {  // |a| <= 0.74
 // conditions are accumulated bitwise so no short-circuit branches appear in the hot loop.
 // HI: nside >= 2^16, i.e. the face number only touches the high word of the pixel.
 template <bool LONLAT, bool DEGREES, bool HI>
-HPGB_HD bool hpgb_angle_to_pixel_nest_fast(const hpgb_geom &g, const hpgb_a2p_fast &f, double a, double b,
-                                           int64_t &pix) {
+HPGB_HD uint32_t hpgb_angle_to_pixel_nest_fast_g(const hpgb_geom &g, const hpgb_a2p_fast &f, double a, double b,
+                                                 int64_t &pix) {
     // ---- latitude (radians, signed), half colatitude from the nearest pole, tt in [0,4) ----
     double lat, hcth, tt;
     unsigned guard;
@@ -285,27 +285,29 @@ HPGB_HD bool hpgb_angle_to_pixel_nest_fast(const hpgb_geom &g, const hpgb_a2p_fa
     guard |= (unsigned)((n1 < n2 ? n1 : n2) < 2u * f.margin);
     const uint32_t j1 = (uint32_t)(x1 >> f.fbits), j2 = (uint32_t)(x2 >> f.fbits);
     const uint32_t nsm1 = (uint32_t)g.nside - 1u;
-    uint32_t ix, iy, face;
-    if (eq) {
-        const uint32_t ifp = j1 >> g.order, ifm = j2 >> g.order;
-        face = (ifp == ifm) ? (ifp | 4u) : ((ifp < ifm) ? ifp : (ifm + 8u));
-        ix = j2 & nsm1;
-        iy = ~j1 & nsm1;  // nside - 1 - (j1 mod nside)
-    } else {
-        const uint32_t jp = j1 < nsm1 ? j1 : nsm1, jm = j2 < nsm1 ? j2 : nsm1;
-        const bool north = lat >= 0.0;
-        ix = north ? (nsm1 ^ jm) : jp;  // nside - 1 - jm
-        iy = north ? (nsm1 ^ jp) : jm;
-        face = north ? ntt : ntt + 8u;
-    }
+    // equatorial and polar candidates, then selects: no per-element branch, so the four points a
+    // thread owns interleave in the instruction stream
+    const uint32_t ifp = j1 >> g.order, ifm = j2 >> g.order;
+    const uint32_t face_eq = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
+    const uint32_t jp = j1 < nsm1 ? j1 : nsm1, jm = j2 < nsm1 ? j2 : nsm1;
+    const bool north = lat >= 0.0;
+    const uint32_t ix = hpgb_sel(eq, j2 & nsm1, hpgb_sel(north, nsm1 ^ jm, jp));   // nside - 1 - jm
+    const uint32_t iy = hpgb_sel(eq, ~j1 & nsm1, hpgb_sel(north, nsm1 ^ jp, jm));  // eq: nside - 1 - (j1 mod nside)
+    const uint32_t face = hpgb_sel(eq, face_eq, hpgb_sel(north, ntt, ntt + 8u));
     if (HI) {
         const uint64_t m = hpgb_interleave(ix, iy);
         pix = (int64_t)(m + ((uint64_t)(face << f.face_shift_hi) << 32));
     } else {
         pix = hpgb_xyf2nest(g.order, ix, iy, face);
     }
-    return (guard == 0u) & (f.enabled != 0u);
+    return guard | (f.enabled ^ 1u);
 }
+
+template <bool LONLAT, bool DEGREES, bool HI>
+HPGB_HD bool hpgb_angle_to_pixel_nest_fast(const hpgb_geom &g, const hpgb_a2p_fast &f, double a, double b, int64_t &pix) {
+    return hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, a, b, pix) == 0u;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // pixel -> (z, phi, sin theta): hpgeom/healpix_geom.c:304-380, operation for operation

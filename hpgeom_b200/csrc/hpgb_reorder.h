@@ -74,17 +74,6 @@ HPGB_HD hpgb_rk hpgb_make_rk(const hpgb_geom &g) {
     return c;
 }
 
-// select that stays a select (inline selp: the compiler cannot turn it back into a branch)
-HPGB_HD uint32_t hpgb_sel(bool p, uint32_t a, uint32_t b) {
-#if defined(__CUDA_ARCH__)
-    uint32_t r;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tselp.u32 %0, %1, %2, q;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((uint32_t)p));
-    return r;
-#else
-    return p ? a : b;
-#endif
-}
-
 // jpll[face] = {1,3,5,7,0,2,4,6,1,3,5,7} as a byte lookup done by one PRMT: selector nibble 0 =
 // face & 7 picks the entry, nibbles 1-3 = 4 pick the zero byte.
 HPGB_HD uint32_t hpgb_jpll_lut(uint32_t face) { return hpgb_prmt(0x07050301u, 0x06040200u, (face & 7u) | 0x4440u); }

@@ -17,10 +17,10 @@
 #define HPGB_A2P_ST 3
 #endif
 #ifndef HPGB_A2P_H
-#define HPGB_A2P_H 1
+#define HPGB_A2P_H 2
 #endif
 #ifndef HPGB_A2P_MINB
-#define HPGB_A2P_MINB 3
+#define HPGB_A2P_MINB 2
 #endif
 
 namespace {
@@ -57,7 +57,7 @@ struct OpAng2Pix {
     static constexpr int NIN = 2;
     static constexpr bool TILE_HOOK = false;
     static constexpr int EXTRA_SMEM = 0;
-    static constexpr int MINB = HPGB_A2P_MINB;  // <= 80 registers: 3 CTAs/SM measured best on B200 (2: 190, 3: 201, 4: 192 Gpts/s)
+    static constexpr int MINB = HPGB_A2P_MINB;  // 2 CTAs/SM (<= 128 registers): measured best with 2048-point tiles
     __device__ __forceinline__ const void *src(int k) const { return k == 0 ? (const void *)a : (const void *)b; }
     __device__ __forceinline__ In2 load2s(const unsigned char *stage, int tile, int e) const {
         return In2{*reinterpret_cast<const double2 *>(stage + 8 * e),
@@ -84,18 +84,18 @@ struct OpAng2Pix {
     __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
                                          hpgb_bad_t &bad) const {
         int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-        bool ok0 = false, ok1 = false, ok2 = false, ok3 = false;
+        uint32_t g0 = 1u, g1 = 1u, g2 = 1u, g3 = 1u;  // guard words: 0 = the fast result can be trusted
         if (NEST) {
-            ok0 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v0.a.x, v0.b.x, p0);
-            ok1 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v0.a.y, v0.b.y, p1);
-            ok2 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v1.a.x, v1.b.x, p2);
-            ok3 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v1.a.y, v1.b.y, p3);
+            g0 = hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, v0.a.x, v0.b.x, p0);
+            g1 = hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, v0.a.y, v0.b.y, p1);
+            g2 = hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, v1.a.x, v1.b.x, p2);
+            g3 = hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, v1.a.y, v1.b.y, p3);
         }
-        if (!(ok0 && ok1 && ok2 && ok3)) {
-            if (!ok0) p0 = slow(g, v0.a.x, v0.b.x, i0, T, bad);
-            if (!ok1) p1 = slow(g, v0.a.y, v0.b.y, i0 + 1, T, bad);
-            if (!ok2) p2 = slow(g, v1.a.x, v1.b.x, i1, T, bad);
-            if (!ok3) p3 = slow(g, v1.a.y, v1.b.y, i1 + 1, T, bad);
+        if ((g0 | g1 | g2 | g3) != 0u) {
+            if (g0) p0 = slow(g, v0.a.x, v0.b.x, i0, T, bad);
+            if (g1) p1 = slow(g, v0.a.y, v0.b.y, i0 + 1, T, bad);
+            if (g2) p2 = slow(g, v1.a.x, v1.b.x, i1, T, bad);
+            if (g3) p3 = slow(g, v1.a.y, v1.b.y, i1 + 1, T, bad);
         }
         hpgb_st2(out + i0, p0, p1);
         hpgb_st2(out + i1, p2, p3);
