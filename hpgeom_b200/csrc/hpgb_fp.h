@@ -145,6 +145,12 @@ HPGB_HD_NOINLINE bool hpgb_angle_to_pixel_exact(const hpgb_geom &g, const double
 // so fast result == exact-path result whenever the fast result is kept.  The exact path is
 // taken for ~1e-4 of uniformly distributed points at nside 2^29 (less at smaller nside).
 //
+// Within 0.01 rad of a pole the reference itself is noisy: it skips sin(theta) there
+// (hpgeom/healpix_geom.c:154-157) and falls back on nside*sqrt(3(1-|z|)), where the rounding of
+// z = cos(theta) alone moves the result by up to nside * 7e-17 / theta -- more than the margin for
+// theta < ~5e-3.  Those points (1e-4 of the sphere) always take the exact path, which reproduces
+// the reference's rounding bit for bit.
+//
 // shortcuts ("z and phi shortcuts" of the design):
 //   equatorial |z| <= 2/3 : z = sin(lat)                    (odd polynomial, |lat| <= 0.73)
 //   polar caps            : nside*sqrt(3(1-|z|)) = nside*sqrt(6)*sin(c/2), c = colatitude from the
@@ -152,6 +158,15 @@ HPGB_HD_NOINLINE bool hpgb_angle_to_pixel_exact(const hpgb_geom &g, const double
 //   tt = phi*2/pi mod 4   : lon/90 mod 4 directly in degrees
 // ---------------------------------------------------------------------------------------------
 #define HPGB_ASIN_2_3 0.72972765622696636345479665981332  // asin(2/3)
+
+// v with its sign flipped when s is negative (one LOP3 on the high word)
+HPGB_HD double hpgb_copysign_xor(double v, double s) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (__double2hiint(s) & (int)0x80000000), __double2loint(v));
+#else
+    return signbit(s) ? -v : v;
+#endif
+}
 
 HPGB_HD uint32_t hpgb_hi32(double v) {
 #if defined(__CUDA_ARCH__)
@@ -179,7 +194,9 @@ struct hpgb_a2p_fast {
     double pole, pole_lo;         // input latitude of the pole (90, or pi/2 as head + tail)
     double lat_max, lon_max;      // fast-path range guards
     double asin23;                // asin(2/3): equatorial / polar split in latitude
+    double d_ns_m;                // (0.75 - sqrt(6)) nside * 2^F: equatorial minus polar multiplier of the sine
     uint32_t fbits, fmask, margin, enabled;
+    uint32_t mask_hi, pad2_;      // fraction bits at or above 2 * margin
     uint32_t face_shift_hi;       // 2*order - 32 when order >= 16 (face bits live in the high word)
     uint32_t pad_;
 };
@@ -199,6 +216,7 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
     f.ns_half_s = 0.5 * dns * scale;
     f.ns_075_s = 0.75 * dns * scale;
     f.ns_sqrt6_s = 2.4494897427831780981972840747059 * dns * scale;
+    f.d_ns_m = f.ns_075_s - f.ns_sqrt6_s;
     f.c3 = -1.6666666666666666667e-1;
     f.c5 = 8.3333333333333333333e-3;
     f.c7 = -1.9841269841269841270e-4;
@@ -212,7 +230,7 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
         f.k_lon = 1.1111111111111111111e-2;   // 1/90
         f.pole = 90.0;
         f.pole_lo = 0.0;
-        f.lat_max = 89.999999;
+        f.lat_max = 89.42;  // see below: colatitude < 0.0101 rad goes to the exact path
         f.lon_max = 720.0;
     } else {
         f.k_lat = 1.0;
@@ -220,13 +238,15 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
         f.k_lon = HPGB_INV_HALFPI;
         f.pole = HPGB_PIO2_1;
         f.pole_lo = HPGB_PIO2_2;
-        f.lat_max = 1.5707963;
+        f.lat_max = 1.5606;
         f.lon_max = 12.5;
     }
     f.asin23 = 0.72972765622696636345479665981332;
     f.enabled = (g.order >= 0) ? 1u : 0u;
     f.face_shift_hi = order >= 16 ? (uint32_t)(2 * order - 32) : 0u;
     f.pad_ = 0;
+    f.mask_hi = f.fmask & ~(2u * f.margin - 1u);
+    f.pad2_ = 0;
     return f;
 }
 
@@ -261,39 +281,46 @@ HPGB_HD uint32_t hpgb_angle_to_pixel_nest_fast_g(const hpgb_geom &g, const hpgb_
         lat = (f.pole - a) + f.pole_lo;  // pi/2 - theta, accurate also near the equator
         hcth = 0.5 * ((a < f.pole) ? a : (HPGB_PI_1 - a) + HPGB_PI_2);
         tt = b * f.k_lon;                // the reference's own expression
-        guard = (unsigned)!(a > 1e-8) | (unsigned)!(a < 3.14159265) | (unsigned)!(b >= 0.0) | (unsigned)!(b < 6.2831853);
+        guard = (unsigned)!(a > 0.0102) | (unsigned)!(a < 3.1313) | (unsigned)!(b >= 0.0) | (unsigned)!(b < 6.2831853);
     }
     const double al = fabs(lat);
     const bool eq = al <= f.asin23;
     guard |= (unsigned)(fabs(al - f.asin23) < 1e-11);
-    // tt + 4 has a fixed exponent: its mantissa is tt in fixed point (face index + fraction)
-    const uint32_t thi = hpgb_hi32(tt + 4.0);
-    const uint32_t ntt = (thi >> 18) & 3u;
-    guard |= (unsigned)(((thi + 1u) & 0x3FFFFu) < 2u);  // tt within 2^-18 of an integer (face edge / wrap)
-    const double tp = tt - (double)(int32_t)ntt;
-    // ---- one sine for both branches ----
-    const double s = hpgb_sin_poly(f, eq ? lat : hcth);
+    // The integer ALU pipe is what bounds this kernel, so the equatorial / polar split is resolved
+    // in fp64 arithmetic (a blend with e = 1.0 / 0.0) instead of integer selects, and BOTH zones are
+    // brought to the same pair of edge-line coordinates, so one integer tail serves both:
+    //   x1 = S + D, x2 = S - D,   S = nside (ntt + 1) + (tp - 1/2) W
+    //     equatorial : W = nside,  D = -(3/4) nside sin(lat)           -> nside (1/2 + tt) -+ (3/4) nside z
+    //     polar      : W = w,      D = +-(w/2 - nside)  (+ north)      ,  w = sqrt(6) nside sin(colat/2)
+    //                  north: x1 = nside ntt + tp w,  x2 = nside (ntt + 2) - (1 - tp) w;  south: swapped
+    //   For a polar point floor(x1), floor(x2) are  nside ntt + jp  and  nside (ntt + 1) + (nside-1-jm)
+    //   (jp, jm as in the reference, hpgeom/healpix_geom.c:289-292), so the equatorial rule "face
+    //   from (x1 >> k, x2 >> k), ix = x2 mod nside, iy = nside-1 - x1 mod nside" yields the
+    //   reference's polar (face, ix, iy) too: north face = ntt, (nside-1-jm, nside-1-jp); south
+    //   face = ntt + 8, (jp, jm).  The reference's clamps jp, jm <= nside-1 only act at |z| = 2/3
+    //   exactly, inside the guard band above.
+    const double e = eq ? 1.0 : 0.0;
+    const double nttd = floor(tt);
+    const double tq = (tt - nttd) - 0.5;  // tp - 1/2
+    guard |= (unsigned)!(fabs(tq) < 0.5 - 3.8146972656250000e-06);  // tt within 2^-18 of an integer (face edge / wrap)
+    // ---- one sine for both zones ----
+    const double s = hpgb_sin_poly(f, fma(e, lat - hcth, hcth));
     // ---- edge-line coordinates, already scaled to fixed point with F fraction bits ----
-    const double t1 = fma(f.ns_s, tt, f.ns_half_s);  // nside*(0.5+tt)
-    const double t2 = f.ns_075_s * s;
-    const double tmp = f.ns_sqrt6_s * s;
-    const double p1 = tp * tmp;
-    const uint64_t x1 = (uint64_t)hpgb_d2ll(eq ? (t1 - t2) : p1);
-    const uint64_t x2 = (uint64_t)hpgb_d2ll(eq ? (t1 + t2) : (tmp - p1));
-    // within `margin` of an integer?  (the fraction sits in the low word)
-    const uint32_t n1 = ((uint32_t)x1 + f.margin) & f.fmask, n2 = ((uint32_t)x2 + f.margin) & f.fmask;
-    guard |= (unsigned)((n1 < n2 ? n1 : n2) < 2u * f.margin);
+    const double v = fma(e, f.d_ns_m, f.ns_sqrt6_s) * s;  // (3/4) nside z   or   w
+    const double W = fma(e, f.ns_s - v, v);
+    const double S = fma(tq, W, fma(nttd, f.ns_s, f.ns_s));
+    const double Dp = hpgb_copysign_xor(fma(0.5, v, -f.ns_s), lat);  // +-(w/2 - nside)
+    const double D = fma(e, -v - Dp, Dp);
+    const uint64_t x1 = (uint64_t)hpgb_d2ll(S + D);
+    const uint64_t x2 = (uint64_t)hpgb_d2ll(S - D);
+    // within `margin` of an integer?  (the fraction sits in the low word; 2 * margin is a power of two)
+    guard |= (unsigned)((((uint32_t)x1 + f.margin) & f.mask_hi) == 0u) | (unsigned)((((uint32_t)x2 + f.margin) & f.mask_hi) == 0u);
     const uint32_t j1 = (uint32_t)(x1 >> f.fbits), j2 = (uint32_t)(x2 >> f.fbits);
     const uint32_t nsm1 = (uint32_t)g.nside - 1u;
-    // equatorial and polar candidates, then selects: no per-element branch, so the four points a
-    // thread owns interleave in the instruction stream
     const uint32_t ifp = j1 >> g.order, ifm = j2 >> g.order;
-    const uint32_t face_eq = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
-    const uint32_t jp = j1 < nsm1 ? j1 : nsm1, jm = j2 < nsm1 ? j2 : nsm1;
-    const bool north = lat >= 0.0;
-    const uint32_t ix = hpgb_sel(eq, j2 & nsm1, hpgb_sel(north, nsm1 ^ jm, jp));   // nside - 1 - jm
-    const uint32_t iy = hpgb_sel(eq, ~j1 & nsm1, hpgb_sel(north, nsm1 ^ jp, jm));  // eq: nside - 1 - (j1 mod nside)
-    const uint32_t face = hpgb_sel(eq, face_eq, hpgb_sel(north, ntt, ntt + 8u));
+    const uint32_t face = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
+    const uint32_t ix = j2 & nsm1;
+    const uint32_t iy = ~j1 & nsm1;  // nside - 1 - (j1 mod nside)
     if (HI) {
         const uint64_t m = hpgb_interleave(ix, iy);
         pix = (int64_t)(m + ((uint64_t)(face << f.face_shift_hi) << 32));

@@ -127,10 +127,21 @@ __device__ __forceinline__ void hpgb_mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hpgb_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void hpgb_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+#if defined(HPGB_TMA_EVICT_FIRST)
+    // the tile is read exactly once: mark its L2 lines evict-first so that they, not the dirty
+    // output lines waiting for write-back, are the victims
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     hpgb_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(hpgb_smem_u32(bar)), "l"(pol)
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      hpgb_smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(hpgb_smem_u32(bar))
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void hpgb_mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = hpgb_smem_u32(bar);
@@ -284,8 +295,19 @@ static int hpgb_launch_stream(const Op &op, int64_t n, hpgb_status_t *st, cudaSt
 // streaming 128-bit accessors
 __device__ __forceinline__ longlong2 hpgb_ld2(const int64_t *p) { return __ldcs(reinterpret_cast<const longlong2 *>(p)); }
 __device__ __forceinline__ double2 hpgb_ld2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+#if defined(HPGB_ST_MODE) && HPGB_ST_MODE == 1   // plain write-back stores
+__device__ __forceinline__ void hpgb_st2(int64_t *p, int64_t a, int64_t b) { *reinterpret_cast<longlong2 *>(p) = make_longlong2(a, b); }
+__device__ __forceinline__ void hpgb_st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
+#elif defined(HPGB_ST_MODE) && HPGB_ST_MODE == 2  // cache-global
+__device__ __forceinline__ void hpgb_st2(int64_t *p, int64_t a, int64_t b) { __stcg(reinterpret_cast<longlong2 *>(p), make_longlong2(a, b)); }
+__device__ __forceinline__ void hpgb_st2(double *p, double a, double b) { __stcg(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
+#elif defined(HPGB_ST_MODE) && HPGB_ST_MODE == 3  // write-through
+__device__ __forceinline__ void hpgb_st2(int64_t *p, int64_t a, int64_t b) { __stwt(reinterpret_cast<longlong2 *>(p), make_longlong2(a, b)); }
+__device__ __forceinline__ void hpgb_st2(double *p, double a, double b) { __stwt(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
+#else
 __device__ __forceinline__ void hpgb_st2(int64_t *p, int64_t a, int64_t b) { __stcs(reinterpret_cast<longlong2 *>(p), make_longlong2(a, b)); }
 __device__ __forceinline__ void hpgb_st2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
+#endif
 __device__ __forceinline__ int64_t hpgb_ld1(const int64_t *p) { return __ldcs(p); }
 __device__ __forceinline__ double hpgb_ld1(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void hpgb_st1(int64_t *p, int64_t a) { __stcs(p, a); }

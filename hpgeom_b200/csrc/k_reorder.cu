@@ -199,7 +199,15 @@ int launch_reorder(const int64_t *in, int64_t *out, int64_t n, int64_t nside, co
     int c = hpgb_check_nside(nside, 1);
     if (c) return c;
     const hpgb_geom g = hpgb_make_geom(nside, 1);
+#if defined(HPGB_NO_STREAM)
+    const bool vec = false;
+    if (g.order >= 16) {
+        OpReorder<TO_RING, false, true> op{in, out, nullptr, base, g, hpgb_make_rk(g)};
+        return hpgb_launch_map(op, n, true, st, s);
+    }
+#else
     const bool vec = hpgb_aligned16(in) && hpgb_aligned16(out);
+#endif
     if (g.order >= 16) {
         OpReorder<TO_RING, false, true> op{in, out, nullptr, base, g, hpgb_make_rk(g)};
         if (vec) return hpgb_launch_stream<decltype(op), HPGB_RE_ST, HPGB_RE_H>(op, n, st, s);

@@ -131,6 +131,35 @@ def test_angle_to_pixel_fast_path_equals_exact_path(sim, oracle_port, nside):
     assert bad.size <= 20
 
 
+@pytest.mark.parametrize("nside", [2 ** 29, 2 ** 28, 2 ** 16, 2 ** 15, 8, 1])
+def test_angle_to_pixel_fast_path_adversarial(sim, oracle_port, nside):
+    """Fast path + fallback == exact path on points concentrated where the fast path is weakest:
+    next to the poles (where the reference itself is noisy: it drops sin(theta) within 0.01 rad,
+    hpgeom/healpix_geom.c:154-157), the |z| = 2/3 transition, face edges in longitude, the equator and
+    wrapped longitudes; all three angle conventions.  Both sides use our correctly rounded trig, so
+    the comparison is exact; the near-pole points are also compared with the oracle."""
+    rng = np.random.default_rng(nside + 1)
+    n = 240_000
+    k = n // 8
+    lon = rng.uniform(0, 360, n)
+    lat = np.degrees(np.arcsin(rng.uniform(-1, 1, n)))
+    lat[:k] = np.sign(rng.uniform(-1, 1, k)) * (90 - 10 ** rng.uniform(-9, 1, k))
+    lat[k:2 * k] = np.sign(rng.uniform(-1, 1, k)) * (41.810314895778596 + rng.normal(0, 1, k) * 10 ** rng.uniform(-12, 0, k))
+    lon[2 * k:3 * k] = 45.0 * rng.integers(0, 9, k) + rng.normal(0, 1, k) * 10 ** rng.uniform(-12, -1, k)
+    lat[3 * k:4 * k] = rng.normal(0, 1, k) * 10 ** rng.uniform(-12, 0, k)
+    lon[4 * k:5 * k] = rng.uniform(-720, 720, k)
+    lat = np.clip(lat, -90, 90)
+    cases = {"deg": (lon, lat, dict(lonlat=True, degrees=True)),
+             "rad": (np.radians(lon), np.radians(lat), dict(lonlat=True, degrees=False)),
+             "tp": (np.clip(np.pi / 2 - np.radians(lat), 0, np.pi), np.radians(lon % 360), dict(lonlat=False, degrees=False))}
+    for name, (a, b, kw) in cases.items():
+        fast = sim.angle_to_pixel(nside, a, b, nest=True, **kw)
+        exact = sim.angle_to_pixel(nside, a, b, nest=True, exact_only=True, **kw)
+        assert_bit_equal(fast, exact, "fast path vs exact path (%s)" % name)
+    ref = oracle_port.angle_to_pixel(nside, lon[:k], lat[:k])
+    assert np.count_nonzero(sim.angle_to_pixel(nside, lon[:k], lat[:k]) != ref) <= 1  # glibc mis-rounding only
+
+
 @pytest.mark.parametrize("nside,nest", CASES)
 def test_vector_to_pixel_golden(sim, nside, nest):
     g = load_golden("vector_to_pixel")
