@@ -292,6 +292,48 @@ static int hpgb_launch_stream(const Op &op, int64_t n, hpgb_status_t *st, cudaSt
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
 }
 
+// launch `op` on the fastest skeleton its operands allow: the TMA streaming kernel when every pointer
+// is 16-byte aligned, else the scalar kernel
+template <class Op, int STAGES = 3, int H = 2>
+static int hpgb_launch_auto(const Op &op, int64_t n, bool vec_ok, hpgb_status_t *st, cudaStream_t s) {
+    if (vec_ok) return hpgb_launch_stream<Op, STAGES, H>(op, n, st, s);
+    return hpgb_launch_map(op, n, false, st, s);
+}
+
+// members a streaming op needs when its only input array is int64 pixels / two or three float64 arrays
+#define HPGB_STREAM_IN_I64(ptr, minb)                                                                       \
+    static constexpr int NIN = 1;                                                                           \
+    static constexpr int MINB = minb;                                                                       \
+    static constexpr bool TILE_HOOK = false;                                                                \
+    static constexpr int EXTRA_SMEM = 0;                                                                    \
+    __device__ __forceinline__ const void *src(int) const { return ptr; }                                  \
+    __device__ __forceinline__ In2 load2s(const unsigned char *stage, int, int e) const {                  \
+        return *reinterpret_cast<const longlong2 *>(stage + 8 * e);                                         \
+    }
+#define HPGB_STREAM_IN_F64x2(p0, p1, minb)                                                                  \
+    static constexpr int NIN = 2;                                                                           \
+    static constexpr int MINB = minb;                                                                       \
+    static constexpr bool TILE_HOOK = false;                                                                \
+    static constexpr int EXTRA_SMEM = 0;                                                                    \
+    __device__ __forceinline__ const void *src(int k) const { return k == 0 ? (const void *)p0 : (const void *)p1; } \
+    __device__ __forceinline__ In2 load2s(const unsigned char *stage, int tile, int e) const {              \
+        return In2{*reinterpret_cast<const double2 *>(stage + 8 * e),                                       \
+                   *reinterpret_cast<const double2 *>(stage + 8 * tile + 8 * e)};                           \
+    }
+#define HPGB_STREAM_IN_F64x3(p0, p1, p2, minb)                                                              \
+    static constexpr int NIN = 3;                                                                           \
+    static constexpr int MINB = minb;                                                                       \
+    static constexpr bool TILE_HOOK = false;                                                                \
+    static constexpr int EXTRA_SMEM = 0;                                                                    \
+    __device__ __forceinline__ const void *src(int k) const {                                              \
+        return k == 0 ? (const void *)p0 : (k == 1 ? (const void *)p1 : (const void *)p2);                  \
+    }                                                                                                       \
+    __device__ __forceinline__ In2 load2s(const unsigned char *stage, int tile, int e) const {              \
+        return In2{*reinterpret_cast<const double2 *>(stage + 8 * e),                                       \
+                   *reinterpret_cast<const double2 *>(stage + 8 * tile + 8 * e),                            \
+                   *reinterpret_cast<const double2 *>(stage + 16 * tile + 8 * e)};                          \
+    }
+
 // streaming 128-bit accessors
 __device__ __forceinline__ longlong2 hpgb_ld2(const int64_t *p) { return __ldcs(reinterpret_cast<const longlong2 *>(p)); }
 __device__ __forceinline__ double2 hpgb_ld2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }

@@ -133,6 +133,7 @@ int launch_a2p_t(const double *a, const double *b, int64_t *out, int64_t n, int6
         return hpgb_launch_map(op, n, vec, st, s);
     }
     OpAng2Pix<NEST, LONLAT, DEGREES, false, false> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g)};
+    if (vec) return hpgb_launch_stream<decltype(op), HPGB_A2P_ST, HPGB_A2P_H>(op, n, st, s);
     return hpgb_launch_map(op, n, vec, st, s);
 }
 

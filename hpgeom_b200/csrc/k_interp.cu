@@ -39,6 +39,7 @@ struct OpInterp {
     };
     typedef const double *Ctx;
     HPGB_DEFAULT_RUN4
+    HPGB_STREAM_IN_F64x2(a, b, 2)
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(a + i), hpgb_ld2(b + i)}; }
     __device__ __forceinline__ void row(const hpgb_geom &gg, double va, double vb, int64_t i, Ctx T, hpgb_bad_t &bad) const {

@@ -36,6 +36,7 @@ struct OpPix2Ang {
     typedef longlong2 In2;
     typedef const double *Ctx;
     HPGB_DEFAULT_RUN4
+    HPGB_STREAM_IN_I64(pix, 2)
 
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
@@ -131,6 +132,7 @@ struct OpVec2Pix {
     };
     typedef const double *Ctx;
     HPGB_DEFAULT_RUN4
+    HPGB_STREAM_IN_F64x3(x, y, z, 2)
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(x + i), hpgb_ld2(y + i), hpgb_ld2(z + i)}; }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &) const {
@@ -184,6 +186,7 @@ struct OpPix2Vec {
     typedef longlong2 In2;
     typedef const double *Ctx;
     HPGB_DEFAULT_RUN4
+    HPGB_STREAM_IN_I64(pix, 2)
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
     __device__ __forceinline__ void conv(const hpgb_geom &gg, int64_t p, int64_t i, Ctx T, hpgb_bad_t &bad, double &vx,

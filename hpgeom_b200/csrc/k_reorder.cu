@@ -232,6 +232,7 @@ struct OpNeighbors {
     typedef longlong2 In2;
     typedef hpgb_no_ctx Ctx;
     HPGB_DEFAULT_RUN4
+    HPGB_STREAM_IN_I64(pix, 2)
     __device__ __forceinline__ Ctx prologue() const { return Ctx(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
     __device__ __forceinline__ void row(const hpgb_geom &gg, int64_t p, int64_t i, hpgb_bad_t &bad) const {
@@ -371,6 +372,7 @@ struct OpLonLat {
     };
     typedef hpgb_no_ctx Ctx;
     HPGB_DEFAULT_RUN4
+    HPGB_STREAM_IN_F64x2(lon, lat, 4)
     __device__ __forceinline__ Ctx prologue() const { return Ctx(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(lon + i), hpgb_ld2(lat + i)}; }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &, hpgb_bad_t &bad) const {
@@ -396,10 +398,10 @@ int launch_lonlat(const double *lon, const double *lat, double *theta, double *p
     const bool vec = hpgb_aligned16(lon) && hpgb_aligned16(lat) && hpgb_aligned16(theta) && hpgb_aligned16(phi);
     if (degrees) {
         OpLonLat<true> op{lon, lat, theta, phi, base};
-        return hpgb_launch_map(op, n, vec, st, s);
+        return hpgb_launch_auto(op, n, vec, st, s);
     }
     OpLonLat<false> op{lon, lat, theta, phi, base};
-    return hpgb_launch_map(op, n, vec, st, s);
+    return hpgb_launch_auto(op, n, vec, st, s);
 }
 
 namespace {
