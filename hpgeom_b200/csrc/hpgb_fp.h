@@ -478,10 +478,36 @@ HPGB_HD uint32_t hpgb_nb_swap(int nb, uint32_t frow) {
     return (tab[nb] >> (4u * frow)) & 7u;
 }
 
+// NEST pixel strictly inside its base face (0 < ix, iy < nside-1): the eight neighbours are
+// obtained by +-1 on the even (ix) and odd (iy) bit planes of the Morton code itself -- dilated-
+// integer arithmetic, no de-interleave / re-interleave.  Returns false (out untouched) for a pixel
+// on a face edge; those (4/nside of all pixels) take the general path below.
+HPGB_HD bool hpgb_neighbors_nest_interior(const hpgb_geom &g, int64_t pix, int64_t *out) {
+    const uint64_t m = (uint64_t)(g.npface - 1);
+    const uint64_t EV = 0x5555555555555555ull & m, OD = 0xAAAAAAAAAAAAAAAAull & m;
+    const uint64_t v = (uint64_t)pix & m, fb = (uint64_t)pix - v;
+    const uint64_t X = v & EV, Y = v & OD;
+    if (X == 0 || X == EV || Y == 0 || Y == OD) return false;
+    const uint64_t xp = ((X | OD) + 1) & EV;  // ix + 1: the carry rides over the odd plane
+    const uint64_t xm = (X - 1) & EV;         // ix - 1: the borrow rides over the (zero) odd plane
+    const uint64_t yp = ((Y | EV) + 2) & OD;
+    const uint64_t ym = (Y - 2) & OD;
+    out[0] = (int64_t)(fb + (xm | Y));   // SW (-1,  0)
+    out[1] = (int64_t)(fb + (xm | yp));  // W  (-1, +1)
+    out[2] = (int64_t)(fb + (X | yp));   // NW ( 0, +1)
+    out[3] = (int64_t)(fb + (xp | yp));  // N  (+1, +1)
+    out[4] = (int64_t)(fb + (xp | Y));   // NE (+1,  0)
+    out[5] = (int64_t)(fb + (xp | ym));  // E  (+1, -1)
+    out[6] = (int64_t)(fb + (X | ym));   // SE ( 0, -1)
+    out[7] = (int64_t)(fb + (xm | ym));  // S  (-1, -1)
+    return true;
+}
+
 template <bool NEST, bool POW2>
 HPGB_HD void hpgb_neighbors(const hpgb_geom &g, int64_t pix, int64_t *out) {
     int32_t ix, iy;
     uint32_t face;
+    if (NEST && hpgb_neighbors_nest_interior(g, pix, out)) return;
     if (NEST) {
         uint32_t ux, uy;
         hpgb_nest2xyf(g, pix, ux, uy, face);

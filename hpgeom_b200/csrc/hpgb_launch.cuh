@@ -355,4 +355,26 @@ __device__ __forceinline__ double hpgb_ld1(const double *p) { return __ldcs(p); 
 __device__ __forceinline__ void hpgb_st1(int64_t *p, int64_t a) { __stcs(p, a); }
 __device__ __forceinline__ void hpgb_st1(double *p, double a) { __stcs(p, a); }
 
+// Row outputs ((n,8) neighbours, (n,4)+(n,4) interpolation): a lane holds NU consecutive 16-byte
+// units, the warp's 32*NU units are contiguous in HBM.  Storing them lane by lane would make every
+// warp store touch 32 half-filled sectors; instead the units take a turn through shared memory
+// (XOR-swizzled, conflict-free both ways) so that each store instruction writes 512 contiguous
+// bytes.  Full warps only (callers fall back to direct stores otherwise).  NU = 4 or 8.
+template <int NU>
+__device__ __forceinline__ void hpgb_warp_store_units(longlong2 *warp_dst, const longlong2 (&u)[NU], longlong2 *warp_smem) {
+    const int lane = threadIdx.x & 31;
+    constexpr int M = NU - 1;
+    const int sw = NU == 8 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+    for (int j = 0; j < NU; j++) warp_smem[lane * NU + (j ^ sw)] = u[j];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < NU; k++) {
+        const int idx = k * 32 + lane, src = idx / NU, j = idx & M;
+        const int ssw = NU == 8 ? (src & 7) : ((src >> 1) & 3);
+        __stcs(warp_dst + idx, warp_smem[src * NU + (j ^ ssw)]);
+    }
+    __syncwarp();
+}
+
 #endif  // HPGB_LAUNCH_CUH

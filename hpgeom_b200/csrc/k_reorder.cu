@@ -235,8 +235,7 @@ struct OpNeighbors {
     HPGB_STREAM_IN_I64(pix, 2)
     __device__ __forceinline__ Ctx prologue() const { return Ctx(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
-    __device__ __forceinline__ void row(const hpgb_geom &gg, int64_t p, int64_t i, hpgb_bad_t &bad) const {
-        int64_t r[8];
+    __device__ __forceinline__ void compute(const hpgb_geom &gg, int64_t p, int64_t i, hpgb_bad_t &bad, int64_t *r) const {
         if (!hpgb_pixel_ok(gg, p)) {
             bad.flag(base + i);
 #pragma unroll
@@ -244,13 +243,37 @@ struct OpNeighbors {
         } else {
             hpgb_neighbors<NEST, POW2>(gg, p, r);
         }
+    }
+    __device__ __forceinline__ void row(const hpgb_geom &gg, int64_t p, int64_t i, hpgb_bad_t &bad) const {
+        int64_t r[8];
+        compute(gg, p, i, bad, r);
         int64_t *o = out + 8 * i;  // 64-byte rows: always 16-byte aligned when `out` is
 #pragma unroll
         for (int m = 0; m < 8; m += 2) hpgb_st2(o + m, r[m], r[m + 1]);
     }
+    // two consecutive pixels per lane = 128 contiguous output bytes per lane, 4 KiB per warp:
+    // transposed through shared memory so every store instruction is fully coalesced
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &, hpgb_bad_t &bad) const {
-        row(g, v.x, i, bad);
-        row(g, v.y, i + 1, bad);
+        __shared__ longlong2 sbuf[HPGB_BLOCK / 32][32 * 8];
+        int64_t r0[8], r1[8];
+        compute(g, v.x, i, bad, r0);
+        compute(g, v.y, i + 1, bad, r1);
+        if (__activemask() == 0xFFFFFFFFu) {
+            longlong2 u[8];
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                u[m] = make_longlong2(r0[2 * m], r0[2 * m + 1]);
+                u[4 + m] = make_longlong2(r1[2 * m], r1[2 * m + 1]);
+            }
+            const int lane = threadIdx.x & 31;
+            hpgb_warp_store_units<8>(reinterpret_cast<longlong2 *>(out + 8 * (i - 2 * lane)), u, sbuf[threadIdx.x >> 5]);
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; m += 2) {
+                hpgb_st2(out + 8 * i + m, r0[m], r0[m + 1]);
+                hpgb_st2(out + 8 * i + 8 + m, r1[m], r1[m + 1]);
+            }
+        }
     }
     __device__ __forceinline__ void run1(int64_t i, const Ctx &, hpgb_bad_t &bad) const {
         hpgb_geom gg = g;
@@ -305,27 +328,56 @@ namespace {
 // -------------------------------------------------------------------------------------------
 #define HPGB_UPGRADE_CLASS1 ((int64_t)1 << 62)
 
-template <bool NEST>
+// One thread per group of C consecutive children (NEST: 2 = one 16-byte unit, every warp store is
+// 512 contiguous bytes; RING: 4 = two 128-bit stores).  The parent is converted ring -> nest once per group,
+// each child nest -> ring with the minimum-instruction cores of hpgb_reorder.h.  For
+// nside_upgrade == nside (one child) the group is the single child.
+template <bool NEST, int C>
 __global__ void __launch_bounds__(HPGB_BLOCK) k_upgrade(const int64_t *__restrict__ pix, int64_t *__restrict__ out,
-                                                        const int64_t n_out, const int shift, const hpgb_geom g,
-                                                        const hpgb_geom gu, const int64_t base, hpgb_status_t *st) {
+                                                        const int64_t n_groups, const int gshift, const hpgb_geom g,
+                                                        const hpgb_rk c, const hpgb_rk cu, const int64_t base,
+                                                        hpgb_status_t *st) {
     const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
     hpgb_bad_t bad;
-    for (int64_t o = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; o < n_out; o += stride) {
-        const int64_t i = o >> shift;
-        const int64_t j = o & (((int64_t)1 << shift) - 1);
-        int64_t p = __ldg(pix + i);
-        int64_t r = -1;
+    auto emit = [&](int64_t w, int64_t p) {
+        const int64_t i = w >> gshift;  // parent
+        int64_t r[C];
         if (!hpgb_pixel_ok(g, p)) {
             bad.flag(base + i);
+#pragma unroll
+            for (int j = 0; j < C; j++) r[j] = -1;
         } else {
-            if (!NEST) p = hpgb_ring2nest(g, p);
+            if (!NEST) p = hpgb_ring2nest_k<false>(c, g, p);
             if (p == g.npix - 1) bad.flag(HPGB_UPGRADE_CLASS1 | (base + i));
-            r = (p << shift) + j;
-            if (!NEST) r = hpgb_nest2ring(gu, r);
+            // first child of the group: parent << 2k, plus C * (group index within the parent)
+            const int64_t first = (p << (gshift + (C == 4 ? 2 : (C == 2 ? 1 : 0)))) + ((w & (((int64_t)1 << gshift) - 1)) * C);
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                const uint64_t q = (uint64_t)(first + j);
+                r[j] = NEST ? (int64_t)q : hpgb_nest2ring_k<false>(cu, (uint32_t)q, (uint32_t)(q >> 32));
+            }
         }
-        __stcs(out + o, r);
+        if (C == 4) {
+            hpgb_st2(out + 4 * w, r[0], r[1]);
+            hpgb_st2(out + 4 * w + 2, r[2], r[3]);
+        } else if (C == 2) {
+            hpgb_st2(out + 2 * w, r[0], r[C - 1]);
+        } else {
+            hpgb_st1(out + w, r[0]);
+        }
+    };
+    // four parent loads in flight per thread: each warp-wide load only brings in 8..32 distinct
+    // parents, so without this the kernel is bound by load latency, not bandwidth
+    constexpr int U = NEST ? 4 : 2;
+    int64_t w = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x;
+    for (; w + (U - 1) * stride < n_groups; w += U * stride) {
+        int64_t p[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) p[u] = __ldg(pix + ((w + u * stride) >> gshift));
+#pragma unroll
+        for (int u = 0; u < U; u++) emit(w + u * stride, p[u]);
     }
+    for (; w < n_groups; w += stride) emit(w, __ldg(pix + (w >> gshift)));
     bad.commit(st);
 }
 
@@ -340,18 +392,23 @@ int launch_upgrade(const int64_t *pix, int64_t *out, int64_t n, int64_t nside, i
     if (c || nside_upgrade < nside) return HPGB_E_BAD_ARGUMENT;
     if (n == 0) return HPGB_OK;
     const hpgb_geom g = hpgb_make_geom(nside, 1), gu = hpgb_make_geom(nside_upgrade, 1);
+    const hpgb_rk rk = hpgb_make_rk(g), rku = hpgb_make_rk(gu);
     const int shift = 2 * (gu.order - g.order);
-    const int64_t n_out = n << shift;
-    static int occ[2] = {0, 0};
-    if (!occ[nest ? 1 : 0])
-        occ[nest ? 1 : 0] = nest ? hpgb_resident_ctas(k_upgrade<true>) : hpgb_resident_ctas(k_upgrade<false>);
-    int64_t grid = (int64_t)hpgb_sm_count() * occ[nest ? 1 : 0];
-    const int64_t want = (n_out + HPGB_BLOCK - 1) / HPGB_BLOCK;
+    // children per thread: NEST 2 (one fully coalesced 16-byte unit per lane), RING 4 (the parent's
+    // ring -> nest conversion is shared by the four), 1 when nside_upgrade == nside or `out` is misaligned
+    const bool four = shift >= 2 && hpgb_aligned16(out) && !nest, two = shift >= 2 && hpgb_aligned16(out) && nest;
+    const int gshift = four ? shift - 2 : (two ? shift - 1 : shift);  // log2(groups per parent)
+    const int64_t n_groups = n << gshift;
+    int64_t grid = (int64_t)hpgb_sm_count() * 8;
+    const int64_t want = (n_groups + HPGB_BLOCK - 1) / HPGB_BLOCK;
     if (want < grid) grid = want;
-    if (nest)
-        k_upgrade<true><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n_out, shift, g, gu, base, st);
-    else
-        k_upgrade<false><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n_out, shift, g, gu, base, st);
+#define GO(N, C) k_upgrade<N, C><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n_groups, gshift, g, rk, rku, base, st)
+    if (nest) {
+        if (two) GO(true, 2); else GO(true, 1);
+    } else {
+        if (four) GO(false, 4); else GO(false, 1);
+    }
+#undef GO
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
