@@ -261,6 +261,36 @@ HPGB_HD double hpgb_sin_poly(const hpgb_a2p_fast &f, double a) {  // |a| <= 0.74
     return fma(a * a2, p, a);
 }
 
+// Shared tail of the NEST fast paths (angle_to_pixel, vector_to_pixel): from floor(tt), tp - 1/2,
+// the zone flag e (1.0 equatorial / 0.0 polar), v = (3/4) nside z (equatorial) or w (polar), both
+// scaled by 2^F, and the hemisphere (sign of `hemi`) to the pixel.  Returns the margin guard bit.
+template <bool HI>
+HPGB_HD unsigned hpgb_sd_to_nest(const hpgb_geom &g, const hpgb_a2p_fast &f, double nttd, double tq, double e, double v,
+                                 double hemi, int64_t &pix) {
+    // ---- edge-line coordinates, already scaled to fixed point with F fraction bits ----
+    const double W = fma(e, f.ns_s - v, v);
+    const double S = fma(tq, W, fma(nttd, f.ns_s, f.ns_s));
+    const double Dp = hpgb_copysign_xor(fma(0.5, v, -f.ns_s), hemi);  // +-(w/2 - nside)
+    const double D = fma(e, -v - Dp, Dp);
+    const uint64_t x1 = (uint64_t)hpgb_d2ll(S + D);
+    const uint64_t x2 = (uint64_t)hpgb_d2ll(S - D);
+    // within `margin` of an integer?  (the fraction sits in the low word; 2 * margin is a power of two)
+    const unsigned guard = (unsigned)((((uint32_t)x1 + f.margin) & f.mask_hi) == 0u) | (unsigned)((((uint32_t)x2 + f.margin) & f.mask_hi) == 0u);
+    const uint32_t j1 = (uint32_t)(x1 >> f.fbits), j2 = (uint32_t)(x2 >> f.fbits);
+    const uint32_t nsm1 = (uint32_t)g.nside - 1u;
+    const uint32_t ifp = j1 >> g.order, ifm = j2 >> g.order;
+    const uint32_t face = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
+    const uint32_t ix = j2 & nsm1;
+    const uint32_t iy = ~j1 & nsm1;  // nside - 1 - (j1 mod nside)
+    if (HI) {
+        const uint64_t m = hpgb_interleave(ix, iy);
+        pix = (int64_t)(m + ((uint64_t)(face << f.face_shift_hi) << 32));
+    } else {
+        pix = hpgb_xyf2nest(g.order, ix, iy, face);
+    }
+    return guard;
+}
+
 // Fast path for one point: candidate pixel + whether it can be trusted (false -> the caller runs
 // the exact path).  Branch-free apart from the equatorial/polar integer tail; the guard
 // conditions are accumulated bitwise so no short-circuit branches appear in the hot loop.
@@ -305,28 +335,8 @@ HPGB_HD uint32_t hpgb_angle_to_pixel_nest_fast_g(const hpgb_geom &g, const hpgb_
     guard |= (unsigned)!(fabs(tq) < 0.5 - 3.8146972656250000e-06);  // tt within 2^-18 of an integer (face edge / wrap)
     // ---- one sine for both zones ----
     const double s = hpgb_sin_poly(f, fma(e, lat - hcth, hcth));
-    // ---- edge-line coordinates, already scaled to fixed point with F fraction bits ----
     const double v = fma(e, f.d_ns_m, f.ns_sqrt6_s) * s;  // (3/4) nside z   or   w
-    const double W = fma(e, f.ns_s - v, v);
-    const double S = fma(tq, W, fma(nttd, f.ns_s, f.ns_s));
-    const double Dp = hpgb_copysign_xor(fma(0.5, v, -f.ns_s), lat);  // +-(w/2 - nside)
-    const double D = fma(e, -v - Dp, Dp);
-    const uint64_t x1 = (uint64_t)hpgb_d2ll(S + D);
-    const uint64_t x2 = (uint64_t)hpgb_d2ll(S - D);
-    // within `margin` of an integer?  (the fraction sits in the low word; 2 * margin is a power of two)
-    guard |= (unsigned)((((uint32_t)x1 + f.margin) & f.mask_hi) == 0u) | (unsigned)((((uint32_t)x2 + f.margin) & f.mask_hi) == 0u);
-    const uint32_t j1 = (uint32_t)(x1 >> f.fbits), j2 = (uint32_t)(x2 >> f.fbits);
-    const uint32_t nsm1 = (uint32_t)g.nside - 1u;
-    const uint32_t ifp = j1 >> g.order, ifm = j2 >> g.order;
-    const uint32_t face = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
-    const uint32_t ix = j2 & nsm1;
-    const uint32_t iy = ~j1 & nsm1;  // nside - 1 - (j1 mod nside)
-    if (HI) {
-        const uint64_t m = hpgb_interleave(ix, iy);
-        pix = (int64_t)(m + ((uint64_t)(face << f.face_shift_hi) << 32));
-    } else {
-        pix = hpgb_xyf2nest(g.order, ix, iy, face);
-    }
+    guard |= hpgb_sd_to_nest<HI>(g, f, nttd, tq, e, v, lat, pix);
     return guard | (f.enabled ^ 1u);
 }
 
@@ -335,6 +345,93 @@ HPGB_HD bool hpgb_angle_to_pixel_nest_fast(const hpgb_geom &g, const hpgb_a2p_fa
     return hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, a, b, pix) == 0u;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// vector_to_pixel, NEST, fast path (same contract as the angle_to_pixel one: candidate pixel + a
+// guard word, 0 = trusted; anything else re-runs on hpgb_vec2pix, the reference's operation order).
+//   z/|v| and sin^2(theta) from ONE reciprocal square root (no IEEE sqrt + division);
+//   polar zone: 1 - |z| = sin^2 / (1 + |z|), no cancellation at any latitude;
+//   phi: atan2 reduced to atan(r), |r| <= 1/31, with r = (num - c den) / (den + c num), c = k/16 picked
+//   from an approximate quotient, 17-entry table of atan(k/16), odd polynomial of degree 11; the
+//   quadrant only fixes floor(tt) and whether tp = u or 1 - u, so tt itself is never formed.
+// All approximations are good to a few 2^-52, far inside the margin nside * 2^-44.
+// T = the shared-memory table block (atan part at T + 4 * HPGB_SINCOS_ROWS).
+// ---------------------------------------------------------------------------------------------
+HPGB_HD double hpgb_rsqrt_fast(double x) {  // 1/sqrt(x), ~1 ulp, x normal and positive
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    return y;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+HPGB_HD double hpgb_rcp_fast(double x) {  // 1/x, ~1 ulp, x normal
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+#else
+    return 1.0 / x;
+#endif
+}
+HPGB_HD double hpgb_rcp_rough(double x) {  // ~2^-20 relative: only used to pick a table row
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#else
+    return 1.0 / x;
+#endif
+}
+
+template <bool HI>
+HPGB_HD uint32_t hpgb_vector_to_pixel_nest_fast_g(const hpgb_geom &g, const hpgb_a2p_fast &f, const double *T, double x,
+                                                  double y, double z, int64_t &pix) {
+    const double r2 = fma(y, y, x * x);
+    const double len2 = fma(z, z, r2);
+    // squares must stay normal numbers; |x| = |y| = 0 (phi = 0 by convention) goes to the exact path
+    unsigned guard = (unsigned)!(len2 > 1e-280) | (unsigned)!(len2 < 1e280) | (unsigned)!(r2 > 1e-32 * len2);
+    const double il = hpgb_rsqrt_fast(len2);
+    const double nz = z * il;
+    const double za = fabs(nz);
+    const double s2 = (r2 * il) * il;  // sin^2(theta)
+    const bool eq = za <= 2.0 / 3.0;
+    guard |= (unsigned)(fabs(za - 2.0 / 3.0) < 1e-11);
+    const double e = eq ? 1.0 : 0.0;
+    const double q = (3.0 * s2) * hpgb_rcp_fast(1.0 + za);  // 3 (1 - |z|)
+    const double w = f.ns_s * (q * hpgb_rsqrt_fast(q));      // nside sqrt(3 (1 - |z|))
+    const double v = fma(e, f.ns_075_s * nz - w, w);
+    // ---- phi ----
+    const double ax = fabs(x), ay = fabs(y);
+    const bool swap = ay > ax;
+    const double num = swap ? ax : ay, den = swap ? ay : ax;  // 0 <= num <= den, den > 0
+    double fk = rint(16.0 * (num * hpgb_rcp_rough(den)));
+    fk = fk >= 0.0 ? (fk <= 16.0 ? fk : 16.0) : 0.0;  // NaN / zero vectors (guarded above) must still index the table safely
+    const double c = fk * 0.0625;
+    const double r = fma(-c, den, num) * hpgb_rcp_fast(fma(c, num, den));
+    const double rr = r * r;
+    double p = fma(rr, -1.0 / 11.0, 1.0 / 9.0);
+    p = fma(p, rr, -1.0 / 7.0);
+    p = fma(p, rr, 1.0 / 5.0);
+    p = fma(p, rr, -1.0 / 3.0);
+    const double at = T[4 * HPGB_SINCOS_ROWS + (int)fk] + fma(r * rr, p, r);  // atan(num/den) in [0, pi/4]
+    const double u = at * HPGB_INV_HALFPI;                                    // in quarter turns, [0, 1/2]
+    // quadrant: floor(tt) from the signs alone; tp = u or 1 - u by the parity of (swap, x < 0, y < 0)
+    const uint32_t xs = hpgb_hi32(x) >> 31, ys = hpgb_hi32(y) >> 31;
+    const double xn = xs ? 1.0 : 0.0;
+    const double nttd = ys ? 3.0 - xn : xn;
+    const bool flip = ((uint32_t)swap ^ xs ^ ys) != 0u;
+    const double tq = flip ? 0.5 - u : u - 0.5;  // tp - 1/2
+    guard |= (unsigned)!(fabs(tq) < 0.5 - 3.8146972656250000e-06);  // tt within 2^-18 of an integer (face edge / wrap)
+    guard |= hpgb_sd_to_nest<HI>(g, f, nttd, tq, e, v, nz, pix);
+    return guard | (f.enabled ^ 1u);
+}
 
 // ---------------------------------------------------------------------------------------------
 // pixel -> (z, phi, sin theta): hpgeom/healpix_geom.c:304-380, operation for operation

@@ -71,9 +71,12 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_map1(const Op op, const int64_t 
     bad.commit(st);
 }
 
-// the 52 x 4 double-double sin/cos table of hpgb_math.h, staged in shared memory per CTA
-// (1664 B; random row gathers from it are LSU work that overlaps the fp64 pipe)
+// the 52 x 4 double-double sin/cos table of hpgb_math.h followed by the 17-entry atan(k/16) table of
+// the vector_to_pixel fast path, staged in shared memory per CTA (1800 B; random row gathers from it
+// are LSU work that overlaps the fp64 pipe)
+#define HPGB_TABLE_DOUBLES (4 * HPGB_SINCOS_ROWS + HPGB_ATAN16_ROWS)
 static __device__ const double g_hpgb_sincos[4 * HPGB_SINCOS_ROWS] = HPGB_SINCOS_TABLE_INIT;
+static __device__ const double g_hpgb_atan16[HPGB_ATAN16_ROWS] = HPGB_ATAN16_TABLE_INIT;
 struct hpgb_no_ctx {};
 // default run4 = two run2 calls
 #define HPGB_DEFAULT_RUN4                                                                                      \
@@ -83,8 +86,9 @@ struct hpgb_no_ctx {};
         run2(i1, v1, c, bad);                                                                                 \
     }
 __device__ __forceinline__ const double *hpgb_stage_table() {
-    __shared__ double sT[4 * HPGB_SINCOS_ROWS];
+    __shared__ double sT[HPGB_TABLE_DOUBLES];
     for (int i = threadIdx.x; i < 4 * HPGB_SINCOS_ROWS; i += HPGB_BLOCK) sT[i] = g_hpgb_sincos[i];
+    for (int i = threadIdx.x; i < HPGB_ATAN16_ROWS; i += HPGB_BLOCK) sT[4 * HPGB_SINCOS_ROWS + i] = g_hpgb_atan16[i];
     __syncthreads();
     return sT;
 }

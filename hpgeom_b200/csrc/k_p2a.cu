@@ -120,23 +120,57 @@ namespace {
 // -------------------------------------------------------------------------------------------
 // vector_to_pixel / pixel_to_vector   (hpgeom/hpgeom.c:2323-2345, :2617-2643)   32 B per element
 // -------------------------------------------------------------------------------------------
-template <bool NEST, bool VAR>
+// NEST: fast path (hpgb_vector_to_pixel_nest_fast_g) with the reference-order path as the rare,
+// non-inlined fallback, exactly like angle_to_pixel.  RING: reference-order path.
+template <bool NEST, bool VAR, bool HI>
 struct OpVec2Pix {
     const double *x, *y, *z;
     int64_t *out;
     const int64_t *nside_v;
     int64_t base;
     hpgb_geom g;
+    hpgb_a2p_fast f;
     struct In2 {
         double2 x, y, z;
     };
     typedef const double *Ctx;
-    HPGB_DEFAULT_RUN4
     HPGB_STREAM_IN_F64x3(x, y, z, 2)
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(x + i), hpgb_ld2(y + i), hpgb_ld2(z + i)}; }
+    static __device__ __noinline__ int64_t slow(const hpgb_geom &gg, Ctx T, double vx, double vy, double vz) {
+        return hpgb_vec2pix<NEST>(gg, T, vx, vy, vz);
+    }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &) const {
-        hpgb_st2(out + i, hpgb_vec2pix<NEST>(g, T, v.x.x, v.y.x, v.z.x), hpgb_vec2pix<NEST>(g, T, v.x.y, v.y.y, v.z.y));
+        int64_t p0 = 0, p1 = 0;
+        uint32_t g0 = 1u, g1 = 1u;
+        if (NEST) {
+            g0 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v.x.x, v.y.x, v.z.x, p0);
+            g1 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v.x.y, v.y.y, v.z.y, p1);
+        }
+        if ((g0 | g1) != 0u) {
+            if (g0) p0 = slow(g, T, v.x.x, v.y.x, v.z.x);
+            if (g1) p1 = slow(g, T, v.x.y, v.y.y, v.z.y);
+        }
+        hpgb_st2(out + i, p0, p1);
+    }
+    __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
+                                         hpgb_bad_t &) const {
+        int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+        uint32_t g0 = 1u, g1 = 1u, g2 = 1u, g3 = 1u;
+        if (NEST) {
+            g0 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v0.x.x, v0.y.x, v0.z.x, p0);
+            g1 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v0.x.y, v0.y.y, v0.z.y, p1);
+            g2 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v1.x.x, v1.y.x, v1.z.x, p2);
+            g3 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v1.x.y, v1.y.y, v1.z.y, p3);
+        }
+        if ((g0 | g1 | g2 | g3) != 0u) {
+            if (g0) p0 = slow(g, T, v0.x.x, v0.y.x, v0.z.x);
+            if (g1) p1 = slow(g, T, v0.x.y, v0.y.y, v0.z.y);
+            if (g2) p2 = slow(g, T, v1.x.x, v1.y.x, v1.z.x);
+            if (g3) p3 = slow(g, T, v1.x.y, v1.y.y, v1.z.y);
+        }
+        hpgb_st2(out + i0, p0, p1);
+        hpgb_st2(out + i1, p2, p3);
     }
     __device__ __forceinline__ void run1(int64_t i, const Ctx &T, hpgb_bad_t &bad) const {
         hpgb_geom gg = g;
@@ -145,7 +179,10 @@ struct OpVec2Pix {
             hpgb_st1(out + i, -1);
             return;
         }
-        hpgb_st1(out + i, hpgb_vec2pix<NEST>(gg, T, hpgb_ld1(x + i), hpgb_ld1(y + i), hpgb_ld1(z + i)));
+        const double vx = hpgb_ld1(x + i), vy = hpgb_ld1(y + i), vz = hpgb_ld1(z + i);
+        int64_t pix = 0;
+        if (VAR || !NEST || hpgb_vector_to_pixel_nest_fast_g<HI>(gg, f, T, vx, vy, vz, pix) != 0u) pix = slow(gg, T, vx, vy, vz);
+        hpgb_st1(out + i, pix);
     }
 };
 
@@ -153,11 +190,18 @@ template <bool NEST>
 int launch_v2p_t(const double *x, const double *y, const double *z, int64_t *out, int64_t n, int64_t nside,
                  const int64_t *nside_v, int64_t base, hpgb_status_t *st, cudaStream_t s) {
     if (nside_v) {
-        OpVec2Pix<NEST, true> op{x, y, z, out, nside_v, base, hpgb_geom()};
+        OpVec2Pix<NEST, true, false> op{x, y, z, out, nside_v, base, hpgb_geom(), hpgb_a2p_fast()};
         return hpgb_launch_map1(op, n, st, s);
     }
-    OpVec2Pix<NEST, false> op{x, y, z, out, nullptr, base, hpgb_make_geom(nside, NEST)};
-    return hpgb_launch_map(op, n, hpgb_aligned16(x) && hpgb_aligned16(y) && hpgb_aligned16(z) && hpgb_aligned16(out), st, s);
+    const hpgb_geom g = hpgb_make_geom(nside, NEST);
+    const bool vec = hpgb_aligned16(x) && hpgb_aligned16(y) && hpgb_aligned16(z) && hpgb_aligned16(out);
+    if (NEST && g.order >= 16) {
+        OpVec2Pix<NEST, false, NEST> op{x, y, z, out, nullptr, base, g, hpgb_make_a2p_fast<true, true>(g)};
+        return hpgb_launch_auto(op, n, vec, st, s);
+    }
+    OpVec2Pix<NEST, false, false> op{x, y, z, out, nullptr, base, g, hpgb_make_a2p_fast<true, true>(g)};
+    if (NEST) return hpgb_launch_auto(op, n, vec, st, s);
+    return hpgb_launch_map(op, n, vec, st, s);
 }
 
 }  // namespace

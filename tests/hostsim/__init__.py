@@ -90,11 +90,12 @@ class HostSim:
                                                z.ctypes.data_as(_D)))
         return x, y, z
 
-    def vector_to_pixel(self, nside, x, y, z, nest=True):
+    def vector_to_pixel(self, nside, x, y, z, nest=True, exact_only=False):
         x, y, z = self._f(x), self._f(y), self._f(z)
         out = np.empty(x.size, dtype=np.int64)
-        self.lib.sim_vector_to_pixel(ctypes.c_int64(nside), x.ctypes.data_as(_D), y.ctypes.data_as(_D),
-                                     z.ctypes.data_as(_D), ctypes.c_int64(x.size), int(nest), out.ctypes.data_as(_I))
+        self.last_slow = self.lib.sim_vector_to_pixel(ctypes.c_int64(nside), x.ctypes.data_as(_D), y.ctypes.data_as(_D),
+                                                      z.ctypes.data_as(_D), ctypes.c_int64(x.size), int(nest),
+                                                      int(exact_only), out.ctypes.data_as(_I))
         return out
 
     def neighbors(self, nside, pix, nest=True):

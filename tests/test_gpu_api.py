@@ -264,6 +264,38 @@ def test_vector_to_pixel_random(hpg, oracle_port):
         assert np.count_nonzero(got != ref) <= 5
 
 
+@pytest.mark.parametrize("nside", [2 ** 29, 2 ** 20, 1024, 1])
+def test_fast_paths_adversarial(hpg, oracle_port, nside):
+    """angle_to_pixel / vector_to_pixel NEST fast paths on the DEVICE (its rsqrt / rcp approximations
+    differ from the host simulation's) against the oracle, on points concentrated next to the poles,
+    the |z| = 2/3 transition, face edges / octant seams in longitude and the equator, with
+    un-normalised vectors.  Allowed mismatches: glibc mis-rounding at a pixel edge (~1e-9 per point)."""
+    rng = np.random.default_rng(nside + 17)
+    n = 400_000
+    k = n // 8
+    lon = rng.uniform(0, 2 * np.pi, n)
+    zz = rng.uniform(-1, 1, n)
+    zz[:k] = np.sign(rng.uniform(-1, 1, k)) * (1 - 10 ** rng.uniform(-16, -1, k))
+    zz[k:2 * k] = np.sign(rng.uniform(-1, 1, k)) * (2 / 3 + rng.normal(0, 1, k) * 10 ** rng.uniform(-14, -2, k))
+    lon[2 * k:3 * k] = (np.pi / 4) * rng.integers(0, 9, k) + rng.normal(0, 1, k) * 10 ** rng.uniform(-14, -2, k)
+    zz[3 * k:4 * k] = rng.normal(0, 1, k) * 10 ** rng.uniform(-14, -1, k)
+    zz = np.clip(zz, -1, 1)
+    st = np.sqrt((1 - zz) * (1 + zz))
+    scale = 10.0 ** rng.uniform(-100, 100, n)
+    scale[: n // 2] = 1.0
+    x, y, z = st * np.cos(lon) * scale, st * np.sin(lon) * scale, zz * scale
+    x[4 * k:4 * k + 100] = 0.0
+    y[4 * k + 50:4 * k + 150] = 0.0
+    got = hpg.vector_to_pixel(nside, x, y, z)
+    assert np.count_nonzero(got != oracle_port.vector_to_pixel(nside, x, y, z)) <= 2
+    lon_d, lat_d = np.degrees(lon) % 360, np.degrees(np.arcsin(zz))
+    got = hpg.angle_to_pixel(nside, lon_d, lat_d)
+    assert np.count_nonzero(got != oracle_port.angle_to_pixel(nside, lon_d, lat_d)) <= 2
+    theta, phi = np.arccos(zz), lon % (2 * np.pi)
+    got = hpg.angle_to_pixel(nside, theta, phi, lonlat=False)
+    assert np.count_nonzero(got != oracle_port.angle_to_pixel(nside, theta, phi, lonlat=False)) <= 2
+
+
 def test_neighbors_fraction_of_missing(hpg):
     for nside, frac in ((1, 0.25), (2, 0.0625), (32, 24 / (8 * 12 * 32 * 32))):
         nb = hpg.neighbors(nside, np.arange(12 * nside * nside))

@@ -167,6 +167,35 @@ def test_vector_to_pixel_golden(sim, nside, nest):
     assert np.count_nonzero(got != g[tag(nside, nest)]) == 0
 
 
+@pytest.mark.parametrize("nside", [2 ** 29, 2 ** 16, 2 ** 15, 8, 1])
+def test_vector_to_pixel_fast_path_adversarial(sim, oracle_port, nside):
+    """vector_to_pixel fast path + fallback == reference-order path (and the oracle) on vectors
+    concentrated at the poles, the |z| = 2/3 transition, octant seams, the equator, with random
+    overall scale and exact zeros in x / y."""
+    rng = np.random.default_rng(nside + 3)
+    n = 200_000
+    k = n // 8
+    lon = rng.uniform(0, 2 * np.pi, n)
+    zz = rng.uniform(-1, 1, n)
+    zz[:k] = np.sign(rng.uniform(-1, 1, k)) * (1 - 10 ** rng.uniform(-16, -1, k))
+    zz[k:2 * k] = np.sign(rng.uniform(-1, 1, k)) * (2 / 3 + rng.normal(0, 1, k) * 10 ** rng.uniform(-14, -2, k))
+    lon[2 * k:3 * k] = (np.pi / 4) * rng.integers(0, 9, k) + rng.normal(0, 1, k) * 10 ** rng.uniform(-14, -2, k)
+    zz[3 * k:4 * k] = rng.normal(0, 1, k) * 10 ** rng.uniform(-14, -1, k)
+    zz = np.clip(zz, -1, 1)
+    st = np.sqrt((1 - zz) * (1 + zz))
+    scale = 10.0 ** rng.uniform(-100, 100, n)
+    scale[: n // 2] = 1.0
+    x, y, z = st * np.cos(lon) * scale, st * np.sin(lon) * scale, zz * scale
+    x[4 * k:4 * k + 100] = 0.0
+    y[4 * k + 50:4 * k + 150] = 0.0
+    fast = sim.vector_to_pixel(nside, x, y, z)
+    assert_bit_equal(fast, sim.vector_to_pixel(nside, x, y, z, exact_only=True), "fast path vs reference-order path")
+    assert np.count_nonzero(fast != oracle_port.vector_to_pixel(nside, x, y, z)) <= 1  # glibc atan2 mis-rounding only
+    u = rng.uniform(-1, 1, (3, 100_000))
+    sim.vector_to_pixel(nside, *u)
+    assert sim.last_slow < 2e-3 * u.shape[1]  # the reference-order path is the rare path
+
+
 @pytest.mark.parametrize("nside,nest", CASES)
 def test_neighbors_golden(sim, nside, nest):
     g = load_golden("neighbors")
