@@ -10,6 +10,7 @@
 
 #include "hpgb_core.h"
 #include "hpgb_math.h"
+#include "hpgb_reorder.h"
 
 // same decimal literals as hpgeom/healpix_geom.h:31-36
 #define HPGB_PI 3.141592653589793238462643383279502884197
@@ -132,7 +133,7 @@ HPGB_HD_NOINLINE bool hpgb_angle_to_pixel_exact(const hpgb_geom &g, const double
 }
 
 // ---------------------------------------------------------------------------------------------
-// angle_to_pixel, NEST, fast path.
+// angle_to_pixel, fast path (NEST and, for power-of-two nside, RING).
 //
 // The pixel index is a step function of the angles; away from the steps it does not care about
 // the last bits of cos(theta).  The fast path therefore uses cheap, branch-free fp64 (~35 fp64
@@ -198,7 +199,7 @@ struct hpgb_a2p_fast {
     uint32_t fbits, fmask, margin, enabled;
     uint32_t mask_hi, pad2_;      // fraction bits at or above 2 * margin
     uint32_t face_shift_hi;       // 2*order - 32 when order >= 16 (face bits live in the high word)
-    uint32_t pad_;
+    uint32_t ord;                 // order, 0 when nside is not a power of two (fast path disabled then)
 };
 
 template <bool LONLAT, bool DEGREES>
@@ -244,7 +245,7 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
     f.asin23 = 0.72972765622696636345479665981332;
     f.enabled = (g.order >= 0) ? 1u : 0u;
     f.face_shift_hi = order >= 16 ? (uint32_t)(2 * order - 32) : 0u;
-    f.pad_ = 0;
+    f.ord = (uint32_t)order;
     f.mask_hi = f.fmask & ~(2u * f.margin - 1u);
     f.pad2_ = 0;
     return f;
@@ -264,9 +265,16 @@ HPGB_HD double hpgb_sin_poly(const hpgb_a2p_fast &f, double a) {  // |a| <= 0.74
 // Shared tail of the NEST fast paths (angle_to_pixel, vector_to_pixel): from floor(tt), tp - 1/2,
 // the zone flag e (1.0 equatorial / 0.0 polar), v = (3/4) nside z (equatorial) or w (polar), both
 // scaled by 2^F, and the hemisphere (sign of `hemi`) to the pixel.  Returns the margin guard bit.
-template <bool HI>
-HPGB_HD unsigned hpgb_sd_to_nest(const hpgb_geom &g, const hpgb_a2p_fast &f, double nttd, double tq, double e, double v,
-                                 double hemi, int64_t &pix) {
+// NEST: Morton interleave (HI: nside >= 2^16, face bits in the high word only).  RING: the same
+// (face, ix, iy) goes through xyf2ring -- equal to the reference's direct ring formulas
+// (hpgeom/healpix_geom.c:236-262): the equatorial branch uses the same jp, jm; in the caps the
+// reference takes ip = floor(tt * ir), which equals ntt * ir + jp whenever tp * tmp and
+// (1 - tp) * tmp are at least `margin` away from integers (a convex-combination argument:
+// frac(tp * ir) lies between frac(tp * tmp) and 1 - frac((1 - tp) * tmp)), i.e. whenever the
+// fast result is kept.  rk is only read for RING.
+template <bool NEST, bool HI>
+HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, double nttd, double tq,
+                                double e, double v, double hemi, int64_t &pix) {
     // ---- edge-line coordinates, already scaled to fixed point with F fraction bits ----
     const double W = fma(e, f.ns_s - v, v);
     const double S = fma(tq, W, fma(nttd, f.ns_s, f.ns_s));
@@ -278,15 +286,17 @@ HPGB_HD unsigned hpgb_sd_to_nest(const hpgb_geom &g, const hpgb_a2p_fast &f, dou
     const unsigned guard = (unsigned)((((uint32_t)x1 + f.margin) & f.mask_hi) == 0u) | (unsigned)((((uint32_t)x2 + f.margin) & f.mask_hi) == 0u);
     const uint32_t j1 = (uint32_t)(x1 >> f.fbits), j2 = (uint32_t)(x2 >> f.fbits);
     const uint32_t nsm1 = (uint32_t)g.nside - 1u;
-    const uint32_t ifp = j1 >> g.order, ifm = j2 >> g.order;
+    const uint32_t ifp = j1 >> f.ord, ifm = j2 >> f.ord;
     const uint32_t face = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
     const uint32_t ix = j2 & nsm1;
     const uint32_t iy = ~j1 & nsm1;  // nside - 1 - (j1 mod nside)
-    if (HI) {
+    if (!NEST) {
+        pix = hpgb_xyf2ring_k(rk, ix, iy, face);
+    } else if (HI) {
         const uint64_t m = hpgb_interleave(ix, iy);
         pix = (int64_t)(m + ((uint64_t)(face << f.face_shift_hi) << 32));
     } else {
-        pix = hpgb_xyf2nest(g.order, ix, iy, face);
+        pix = hpgb_xyf2nest((int)f.ord, ix, iy, face);
     }
     return guard;
 }
@@ -295,9 +305,9 @@ HPGB_HD unsigned hpgb_sd_to_nest(const hpgb_geom &g, const hpgb_a2p_fast &f, dou
 // the exact path).  Branch-free apart from the equatorial/polar integer tail; the guard
 // conditions are accumulated bitwise so no short-circuit branches appear in the hot loop.
 // HI: nside >= 2^16, i.e. the face number only touches the high word of the pixel.
-template <bool LONLAT, bool DEGREES, bool HI>
-HPGB_HD uint32_t hpgb_angle_to_pixel_nest_fast_g(const hpgb_geom &g, const hpgb_a2p_fast &f, double a, double b,
-                                                 int64_t &pix) {
+template <bool NEST, bool LONLAT, bool DEGREES, bool HI>
+HPGB_HD uint32_t hpgb_angle_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, double a,
+                                            double b, int64_t &pix) {
     // ---- latitude (radians, signed), half colatitude from the nearest pole, tt in [0,4) ----
     double lat, hcth, tt;
     unsigned guard;
@@ -336,18 +346,14 @@ HPGB_HD uint32_t hpgb_angle_to_pixel_nest_fast_g(const hpgb_geom &g, const hpgb_
     // ---- one sine for both zones ----
     const double s = hpgb_sin_poly(f, fma(e, lat - hcth, hcth));
     const double v = fma(e, f.d_ns_m, f.ns_sqrt6_s) * s;  // (3/4) nside z   or   w
-    guard |= hpgb_sd_to_nest<HI>(g, f, nttd, tq, e, v, lat, pix);
+    guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, nttd, tq, e, v, lat, pix);
     return guard | (f.enabled ^ 1u);
 }
 
-template <bool LONLAT, bool DEGREES, bool HI>
-HPGB_HD bool hpgb_angle_to_pixel_nest_fast(const hpgb_geom &g, const hpgb_a2p_fast &f, double a, double b, int64_t &pix) {
-    return hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, a, b, pix) == 0u;
-}
 
 
 // ---------------------------------------------------------------------------------------------
-// vector_to_pixel, NEST, fast path (same contract as the angle_to_pixel one: candidate pixel + a
+// vector_to_pixel, fast path (same contract as the angle_to_pixel one: candidate pixel + a
 // guard word, 0 = trusted; anything else re-runs on hpgb_vec2pix, the reference's operation order).
 //   z/|v| and sin^2(theta) from ONE reciprocal square root (no IEEE sqrt + division);
 //   polar zone: 1 - |z| = sin^2 / (1 + |z|), no cancellation at any latitude;
@@ -390,9 +396,9 @@ HPGB_HD double hpgb_rcp_rough(double x) {  // ~2^-20 relative: only used to pick
 #endif
 }
 
-template <bool HI>
-HPGB_HD uint32_t hpgb_vector_to_pixel_nest_fast_g(const hpgb_geom &g, const hpgb_a2p_fast &f, const double *T, double x,
-                                                  double y, double z, int64_t &pix) {
+template <bool NEST, bool HI>
+HPGB_HD uint32_t hpgb_vector_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, const double *T,
+                                             double x, double y, double z, int64_t &pix) {
     const double r2 = fma(y, y, x * x);
     const double len2 = fma(z, z, r2);
     // squares must stay normal numbers; |x| = |y| = 0 (phi = 0 by convention) goes to the exact path
@@ -429,7 +435,7 @@ HPGB_HD uint32_t hpgb_vector_to_pixel_nest_fast_g(const hpgb_geom &g, const hpgb
     const bool flip = ((uint32_t)swap ^ xs ^ ys) != 0u;
     const double tq = flip ? 0.5 - u : u - 0.5;  // tp - 1/2
     guard |= (unsigned)!(fabs(tq) < 0.5 - 3.8146972656250000e-06);  // tt within 2^-18 of an integer (face edge / wrap)
-    guard |= hpgb_sd_to_nest<HI>(g, f, nttd, tq, e, v, nz, pix);
+    guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, nttd, tq, e, v, nz, pix);
     return guard | (f.enabled ^ 1u);
 }
 

@@ -78,18 +78,9 @@ HPGB_HD hpgb_rk hpgb_make_rk(const hpgb_geom &g) {
 // face & 7 picks the entry, nibbles 1-3 = 4 pick the zero byte.
 HPGB_HD uint32_t hpgb_jpll_lut(uint32_t face) { return hpgb_prmt(0x07050301u, 0x06040200u, (face & 7u) | 0x4440u); }
 
-// NEST pixel (lo, hi words; must be < npix) -> RING pixel.  HI: order >= 16.
-template <bool HI>
-HPGB_HD int64_t hpgb_nest2ring_k(const hpgb_rk &c, uint32_t lo, uint32_t hi) {
-    const uint32_t face = HI ? (hi >> c.fsh_hi) : (uint32_t)((((uint64_t)hi << 32) | lo) >> c.k2);
-    uint32_t wl = HI ? lo : (lo & c.lmask), wh = hi & c.hmask;
-    HPGB_DSWAP(wl, 0x22222222u, 1);
-    HPGB_DSWAP(wh, 0x22222222u, 1);
-    HPGB_DSWAP(wl, 0x0C0C0C0Cu, 2);
-    HPGB_DSWAP(wh, 0x0C0C0C0Cu, 2);
-    HPGB_DSWAP(wl, 0x00F000F0u, 4);
-    HPGB_DSWAP(wh, 0x00F000F0u, 4);
-    const uint32_t ix = hpgb_prmt(wl, wh, 0x6420), iy = hpgb_prmt(wl, wh, 0x7531);
+// (face, ix, iy) -> RING pixel (xyf2ring of the reference, hpgeom/healpix_geom.c:394-408, in the
+// three-zone multiply-add form described at the top of this file)
+HPGB_HD int64_t hpgb_xyf2ring_k(const hpgb_rk &c, uint32_t ix, uint32_t iy, uint32_t face) {
 #if defined(__CUDA_ARCH__)
     // Zone selection written as predicated PTX so that it stays ~20 instructions: belt operands by
     // default, overwritten under the north / south predicates (the C++ below is the same arithmetic;
@@ -156,6 +147,20 @@ HPGB_HD int64_t hpgb_nest2ring_k(const hpgb_rk &c, uint32_t lo, uint32_t hi) {
     }
     return (int64_t)((uint64_t)A * (uint64_t)B + (((uint64_t)Ch << 32) | Cl));
 #endif
+}
+
+// NEST pixel (lo, hi words; must be < npix) -> RING pixel.  HI: order >= 16.
+template <bool HI>
+HPGB_HD int64_t hpgb_nest2ring_k(const hpgb_rk &c, uint32_t lo, uint32_t hi) {
+    const uint32_t face = HI ? (hi >> c.fsh_hi) : (uint32_t)((((uint64_t)hi << 32) | lo) >> c.k2);
+    uint32_t wl = HI ? lo : (lo & c.lmask), wh = hi & c.hmask;
+    HPGB_DSWAP(wl, 0x22222222u, 1);
+    HPGB_DSWAP(wh, 0x22222222u, 1);
+    HPGB_DSWAP(wl, 0x0C0C0C0Cu, 2);
+    HPGB_DSWAP(wh, 0x0C0C0C0Cu, 2);
+    HPGB_DSWAP(wl, 0x00F000F0u, 4);
+    HPGB_DSWAP(wh, 0x00F000F0u, 4);
+    return hpgb_xyf2ring_k(c, hpgb_prmt(wl, wh, 0x6420), hpgb_prmt(wl, wh, 0x7531), face);
 }
 
 // ---- RING -> NEST, in pieces (the streaming kernel runs the belt and the cap part in different

@@ -36,8 +36,8 @@ __device__ __forceinline__ bool var_geom(const int64_t *nside_v, int64_t i, int 
 
 // -------------------------------------------------------------------------------------------
 // angle_to_pixel   (reference loop: hpgeom/hpgeom.c:126-157)   16 B in + 8 B out per point.
-// NEST: fast path (hpgb_fp.h) with the exact path as a rare, non-inlined fallback.
-// RING: exact path (ring fast path: next).
+// Fast path (hpgb_fp.h) with the exact path as a rare, non-inlined fallback; RING with a
+// non-power-of-two nside has no fast path (f.enabled = 0) and runs the exact path throughout.
 // -------------------------------------------------------------------------------------------
 template <bool NEST, bool LONLAT, bool DEGREES, bool VAR, bool HI>
 struct OpAng2Pix {
@@ -47,6 +47,7 @@ struct OpAng2Pix {
     int64_t base;
     hpgb_geom g;
     hpgb_a2p_fast f;
+    hpgb_rk rk;  // RING only
     struct In2 {
         double2 a, b;
     };
@@ -71,26 +72,21 @@ struct OpAng2Pix {
         return pix;
     }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &bad) const {
-        int64_t p0 = 0, p1 = 0;
-        bool ok0 = false, ok1 = false;
-        if (NEST) {  // both fast paths first (independent -> the fp64 chains interleave), exact path after
-            ok0 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v.a.x, v.b.x, p0);
-            ok1 = hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(g, f, v.a.y, v.b.y, p1);
-        }
-        if (!ok0) p0 = slow(g, v.a.x, v.b.x, i, T, bad);
-        if (!ok1) p1 = slow(g, v.a.y, v.b.y, i + 1, T, bad);
+        int64_t p0 = 0, p1 = 0;  // both fast paths first (independent -> the fp64 chains interleave), exact path after
+        const uint32_t g0 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v.a.x, v.b.x, p0);
+        const uint32_t g1 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v.a.y, v.b.y, p1);
+        if (g0) p0 = slow(g, v.a.x, v.b.x, i, T, bad);
+        if (g1) p1 = slow(g, v.a.y, v.b.y, i + 1, T, bad);
         hpgb_st2(out + i, p0, p1);
     }
     __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
                                          hpgb_bad_t &bad) const {
         int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-        uint32_t g0 = 1u, g1 = 1u, g2 = 1u, g3 = 1u;  // guard words: 0 = the fast result can be trusted
-        if (NEST) {
-            g0 = hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, v0.a.x, v0.b.x, p0);
-            g1 = hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, v0.a.y, v0.b.y, p1);
-            g2 = hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, v1.a.x, v1.b.x, p2);
-            g3 = hpgb_angle_to_pixel_nest_fast_g<LONLAT, DEGREES, HI>(g, f, v1.a.y, v1.b.y, p3);
-        }
+        // guard words: 0 = the fast result can be trusted
+        const uint32_t g0 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.x, v0.b.x, p0);
+        const uint32_t g1 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.y, v0.b.y, p1);
+        const uint32_t g2 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.x, v1.b.x, p2);
+        const uint32_t g3 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.y, v1.b.y, p3);
         if ((g0 | g1 | g2 | g3) != 0u) {
             if (g0) p0 = slow(g, v0.a.x, v0.b.x, i0, T, bad);
             if (g1) p1 = slow(g, v0.a.y, v0.b.y, i0 + 1, T, bad);
@@ -113,7 +109,7 @@ struct OpAng2Pix {
         }
         const double va = hpgb_ld1(a + i), vb = hpgb_ld1(b + i);
         int64_t pix;
-        if (!(NEST && hpgb_angle_to_pixel_nest_fast<LONLAT, DEGREES, HI>(gg, ff, va, vb, pix))) pix = slow(gg, va, vb, i, T, bad);
+        if (VAR || hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(gg, ff, rk, va, vb, pix) != 0u) pix = slow(gg, va, vb, i, T, bad);
         hpgb_st1(out + i, pix);
     }
 };
@@ -122,17 +118,17 @@ template <bool NEST, bool LONLAT, bool DEGREES>
 int launch_a2p_t(const double *a, const double *b, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v,
                  int64_t base, hpgb_status_t *st, cudaStream_t s) {
     if (nside_v) {
-        OpAng2Pix<NEST, LONLAT, DEGREES, true, false> op{a, b, out, nside_v, base, hpgb_geom(), hpgb_a2p_fast()};
+        OpAng2Pix<NEST, LONLAT, DEGREES, true, false> op{a, b, out, nside_v, base, hpgb_geom(), hpgb_a2p_fast(), hpgb_rk()};
         return hpgb_launch_map1(op, n, st, s);
     }
     const hpgb_geom g = hpgb_make_geom(nside, NEST);
     const bool vec = hpgb_aligned16(a) && hpgb_aligned16(b) && hpgb_aligned16(out);
     if (NEST && g.order >= 16) {  // face bits only in the high word of the pixel: cheaper assembly
-        OpAng2Pix<NEST, LONLAT, DEGREES, false, NEST> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g)};
+        OpAng2Pix<NEST, LONLAT, DEGREES, false, NEST> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g), hpgb_make_rk(g)};
         if (vec) return hpgb_launch_stream<decltype(op), HPGB_A2P_ST, HPGB_A2P_H>(op, n, st, s);
         return hpgb_launch_map(op, n, vec, st, s);
     }
-    OpAng2Pix<NEST, LONLAT, DEGREES, false, false> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g)};
+    OpAng2Pix<NEST, LONLAT, DEGREES, false, false> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g), hpgb_make_rk(g)};
     if (vec) return hpgb_launch_stream<decltype(op), HPGB_A2P_ST, HPGB_A2P_H>(op, n, st, s);
     return hpgb_launch_map(op, n, vec, st, s);
 }

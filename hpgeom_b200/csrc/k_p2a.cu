@@ -120,8 +120,8 @@ namespace {
 // -------------------------------------------------------------------------------------------
 // vector_to_pixel / pixel_to_vector   (hpgeom/hpgeom.c:2323-2345, :2617-2643)   32 B per element
 // -------------------------------------------------------------------------------------------
-// NEST: fast path (hpgb_vector_to_pixel_nest_fast_g) with the reference-order path as the rare,
-// non-inlined fallback, exactly like angle_to_pixel.  RING: reference-order path.
+// Fast path (hpgb_vector_to_pixel_fast_g) with the reference-order path as the rare, non-inlined
+// fallback, exactly like angle_to_pixel.
 template <bool NEST, bool VAR, bool HI>
 struct OpVec2Pix {
     const double *x, *y, *z;
@@ -130,6 +130,7 @@ struct OpVec2Pix {
     int64_t base;
     hpgb_geom g;
     hpgb_a2p_fast f;
+    hpgb_rk rk;  // RING only
     struct In2 {
         double2 x, y, z;
     };
@@ -142,11 +143,8 @@ struct OpVec2Pix {
     }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &) const {
         int64_t p0 = 0, p1 = 0;
-        uint32_t g0 = 1u, g1 = 1u;
-        if (NEST) {
-            g0 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v.x.x, v.y.x, v.z.x, p0);
-            g1 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v.x.y, v.y.y, v.z.y, p1);
-        }
+        const uint32_t g0 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v.x.x, v.y.x, v.z.x, p0);
+        const uint32_t g1 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v.x.y, v.y.y, v.z.y, p1);
         if ((g0 | g1) != 0u) {
             if (g0) p0 = slow(g, T, v.x.x, v.y.x, v.z.x);
             if (g1) p1 = slow(g, T, v.x.y, v.y.y, v.z.y);
@@ -156,13 +154,10 @@ struct OpVec2Pix {
     __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
                                          hpgb_bad_t &) const {
         int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-        uint32_t g0 = 1u, g1 = 1u, g2 = 1u, g3 = 1u;
-        if (NEST) {
-            g0 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v0.x.x, v0.y.x, v0.z.x, p0);
-            g1 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v0.x.y, v0.y.y, v0.z.y, p1);
-            g2 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v1.x.x, v1.y.x, v1.z.x, p2);
-            g3 = hpgb_vector_to_pixel_nest_fast_g<HI>(g, f, T, v1.x.y, v1.y.y, v1.z.y, p3);
-        }
+        const uint32_t g0 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v0.x.x, v0.y.x, v0.z.x, p0);
+        const uint32_t g1 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v0.x.y, v0.y.y, v0.z.y, p1);
+        const uint32_t g2 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v1.x.x, v1.y.x, v1.z.x, p2);
+        const uint32_t g3 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v1.x.y, v1.y.y, v1.z.y, p3);
         if ((g0 | g1 | g2 | g3) != 0u) {
             if (g0) p0 = slow(g, T, v0.x.x, v0.y.x, v0.z.x);
             if (g1) p1 = slow(g, T, v0.x.y, v0.y.y, v0.z.y);
@@ -181,7 +176,7 @@ struct OpVec2Pix {
         }
         const double vx = hpgb_ld1(x + i), vy = hpgb_ld1(y + i), vz = hpgb_ld1(z + i);
         int64_t pix = 0;
-        if (VAR || !NEST || hpgb_vector_to_pixel_nest_fast_g<HI>(gg, f, T, vx, vy, vz, pix) != 0u) pix = slow(gg, T, vx, vy, vz);
+        if (VAR || hpgb_vector_to_pixel_fast_g<NEST, HI>(gg, f, rk, T, vx, vy, vz, pix) != 0u) pix = slow(gg, T, vx, vy, vz);
         hpgb_st1(out + i, pix);
     }
 };
@@ -190,18 +185,17 @@ template <bool NEST>
 int launch_v2p_t(const double *x, const double *y, const double *z, int64_t *out, int64_t n, int64_t nside,
                  const int64_t *nside_v, int64_t base, hpgb_status_t *st, cudaStream_t s) {
     if (nside_v) {
-        OpVec2Pix<NEST, true, false> op{x, y, z, out, nside_v, base, hpgb_geom(), hpgb_a2p_fast()};
+        OpVec2Pix<NEST, true, false> op{x, y, z, out, nside_v, base, hpgb_geom(), hpgb_a2p_fast(), hpgb_rk()};
         return hpgb_launch_map1(op, n, st, s);
     }
     const hpgb_geom g = hpgb_make_geom(nside, NEST);
     const bool vec = hpgb_aligned16(x) && hpgb_aligned16(y) && hpgb_aligned16(z) && hpgb_aligned16(out);
     if (NEST && g.order >= 16) {
-        OpVec2Pix<NEST, false, NEST> op{x, y, z, out, nullptr, base, g, hpgb_make_a2p_fast<true, true>(g)};
+        OpVec2Pix<NEST, false, NEST> op{x, y, z, out, nullptr, base, g, hpgb_make_a2p_fast<true, true>(g), hpgb_make_rk(g)};
         return hpgb_launch_auto(op, n, vec, st, s);
     }
-    OpVec2Pix<NEST, false, false> op{x, y, z, out, nullptr, base, g, hpgb_make_a2p_fast<true, true>(g)};
-    if (NEST) return hpgb_launch_auto(op, n, vec, st, s);
-    return hpgb_launch_map(op, n, vec, st, s);
+    OpVec2Pix<NEST, false, false> op{x, y, z, out, nullptr, base, g, hpgb_make_a2p_fast<true, true>(g), hpgb_make_rk(g)};
+    return hpgb_launch_auto(op, n, vec, st, s);
 }
 
 }  // namespace

@@ -286,14 +286,15 @@ def test_fast_paths_adversarial(hpg, oracle_port, nside):
     x, y, z = st * np.cos(lon) * scale, st * np.sin(lon) * scale, zz * scale
     x[4 * k:4 * k + 100] = 0.0
     y[4 * k + 50:4 * k + 150] = 0.0
-    got = hpg.vector_to_pixel(nside, x, y, z)
-    assert np.count_nonzero(got != oracle_port.vector_to_pixel(nside, x, y, z)) <= 2
     lon_d, lat_d = np.degrees(lon) % 360, np.degrees(np.arcsin(zz))
-    got = hpg.angle_to_pixel(nside, lon_d, lat_d)
-    assert np.count_nonzero(got != oracle_port.angle_to_pixel(nside, lon_d, lat_d)) <= 2
     theta, phi = np.arccos(zz), lon % (2 * np.pi)
-    got = hpg.angle_to_pixel(nside, theta, phi, lonlat=False)
-    assert np.count_nonzero(got != oracle_port.angle_to_pixel(nside, theta, phi, lonlat=False)) <= 2
+    for nest in (True, False):
+        got = hpg.vector_to_pixel(nside, x, y, z, nest=nest)
+        assert np.count_nonzero(got != oracle_port.vector_to_pixel(nside, x, y, z, nest=nest)) <= 2
+        got = hpg.angle_to_pixel(nside, lon_d, lat_d, nest=nest)
+        assert np.count_nonzero(got != oracle_port.angle_to_pixel(nside, lon_d, lat_d, nest=nest)) <= 2
+        got = hpg.angle_to_pixel(nside, theta, phi, lonlat=False, nest=nest)
+        assert np.count_nonzero(got != oracle_port.angle_to_pixel(nside, theta, phi, nest=nest, lonlat=False)) <= 2
 
 
 def test_neighbors_fraction_of_missing(hpg):

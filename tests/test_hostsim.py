@@ -153,9 +153,10 @@ def test_angle_to_pixel_fast_path_adversarial(sim, oracle_port, nside):
              "rad": (np.radians(lon), np.radians(lat), dict(lonlat=True, degrees=False)),
              "tp": (np.clip(np.pi / 2 - np.radians(lat), 0, np.pi), np.radians(lon % 360), dict(lonlat=False, degrees=False))}
     for name, (a, b, kw) in cases.items():
-        fast = sim.angle_to_pixel(nside, a, b, nest=True, **kw)
-        exact = sim.angle_to_pixel(nside, a, b, nest=True, exact_only=True, **kw)
-        assert_bit_equal(fast, exact, "fast path vs exact path (%s)" % name)
+        for nest in (True, False):
+            fast = sim.angle_to_pixel(nside, a, b, nest=nest, **kw)
+            exact = sim.angle_to_pixel(nside, a, b, nest=nest, exact_only=True, **kw)
+            assert_bit_equal(fast, exact, "fast path vs exact path (%s, %s)" % (name, "nest" if nest else "ring"))
     ref = oracle_port.angle_to_pixel(nside, lon[:k], lat[:k])
     assert np.count_nonzero(sim.angle_to_pixel(nside, lon[:k], lat[:k]) != ref) <= 1  # glibc mis-rounding only
 
@@ -188,9 +189,11 @@ def test_vector_to_pixel_fast_path_adversarial(sim, oracle_port, nside):
     x, y, z = st * np.cos(lon) * scale, st * np.sin(lon) * scale, zz * scale
     x[4 * k:4 * k + 100] = 0.0
     y[4 * k + 50:4 * k + 150] = 0.0
-    fast = sim.vector_to_pixel(nside, x, y, z)
-    assert_bit_equal(fast, sim.vector_to_pixel(nside, x, y, z, exact_only=True), "fast path vs reference-order path")
-    assert np.count_nonzero(fast != oracle_port.vector_to_pixel(nside, x, y, z)) <= 1  # glibc atan2 mis-rounding only
+    for nest in (True, False):
+        fast = sim.vector_to_pixel(nside, x, y, z, nest=nest)
+        assert_bit_equal(fast, sim.vector_to_pixel(nside, x, y, z, nest=nest, exact_only=True),
+                         "fast path vs reference-order path (%s)" % ("nest" if nest else "ring"))
+        assert np.count_nonzero(fast != oracle_port.vector_to_pixel(nside, x, y, z, nest=nest)) <= 1  # glibc atan2 only
     u = rng.uniform(-1, 1, (3, 100_000))
     sim.vector_to_pixel(nside, *u)
     assert sim.last_slow < 2e-3 * u.shape[1]  # the reference-order path is the rare path

@@ -22,11 +22,12 @@ for nside in [2 ** 29, 2 ** 28, 2 ** 20, 2 ** 16, 2 ** 15, 2 ** 10, 8, 1]:
     for kw, (a, b) in {"deg": (lon, lat), "rad": (np.radians(lon), np.radians(lat)),
                        "tp": (np.clip(np.pi / 2 - np.radians(lat), 0, np.pi), np.radians(lon % 360))}.items():
         flags = dict(lonlat=kw != "tp", degrees=kw == "deg")
-        fast = sim.angle_to_pixel(nside, a, b, nest=True, **flags)
-        slow_n = sim.last_slow
-        exact = sim.angle_to_pixel(nside, a, b, nest=True, exact_only=True, **flags)
-        bad = np.flatnonzero(fast != exact)
-        tot_bad += bad.size
-        print("nside 2^%-4.1f %-3s: %d points, exact-path fraction %.2e, fast != exact: %d %s" % (
-            np.log2(nside), kw, n, slow_n / n, bad.size, (a[bad[:3]], b[bad[:3]]) if bad.size else ""))
+        for nest in (True, False):
+            fast = sim.angle_to_pixel(nside, a, b, nest=nest, **flags)
+            slow_n = sim.last_slow
+            exact = sim.angle_to_pixel(nside, a, b, nest=nest, exact_only=True, **flags)
+            bad = np.flatnonzero(fast != exact)
+            tot_bad += bad.size
+            print("nside 2^%-4.1f %-3s %s: %d points, exact-path fraction %.2e, fast != exact: %d %s" % (
+                np.log2(nside), kw, "nest" if nest else "ring", n, slow_n / n, bad.size, (a[bad[:3]], b[bad[:3]]) if bad.size else ""))
 print("TOTAL mismatches:", tot_bad)

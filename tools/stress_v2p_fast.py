@@ -21,11 +21,12 @@ for nside in [2 ** 29, 2 ** 28, 2 ** 20, 2 ** 16, 2 ** 15, 1024, 8, 1]:
     scale[: n // 2] = 1.0
     x, y, z = st * np.cos(lon) * scale, st * np.sin(lon) * scale, zz * scale
     x[4 * k:4 * k + 100] = 0.0; y[4 * k + 50:4 * k + 150] = 0.0
-    fast = sim.vector_to_pixel(nside, x, y, z)
-    slow_n = sim.last_slow
-    exact = sim.vector_to_pixel(nside, x, y, z, exact_only=True)
-    bad = np.flatnonzero(fast != exact)
-    tot += bad.size
-    print("nside 2^%-4.1f: %d vectors, exact-path fraction %.2e, fast != exact: %d %s" % (
-        np.log2(nside), n, slow_n / n, bad.size, (x[bad[:3]], y[bad[:3]], z[bad[:3]]) if bad.size else ""))
+    for nest in (True, False):
+        fast = sim.vector_to_pixel(nside, x, y, z, nest=nest)
+        slow_n = sim.last_slow
+        exact = sim.vector_to_pixel(nside, x, y, z, nest=nest, exact_only=True)
+        bad = np.flatnonzero(fast != exact)
+        tot += bad.size
+        print("nside 2^%-4.1f %s: %d vectors, exact-path fraction %.2e, fast != exact: %d %s" % (
+            np.log2(nside), "nest" if nest else "ring", n, slow_n / n, bad.size, (x[bad[:3]], y[bad[:3]], z[bad[:3]]) if bad.size else ""))
 print("TOTAL mismatches:", tot)
