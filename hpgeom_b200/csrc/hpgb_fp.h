@@ -502,13 +502,89 @@ HPGB_HD void hpgb_pix2loc(const hpgb_geom &g, int64_t pix, double &z, double &ph
     phi = (nr == ns) ? 0.75 * HPGB_HALFPI * (double)t * g.fact1 : (0.5 * HPGB_HALFPI * (double)t) / (double)nr;
 }
 
-// pixel -> angles: hpgeom/healpix_geom.c:172-181 + hpgeom/hpgeom_utils.c:145-165
+// Same results as hpgb_pix2loc for nside = 2^k, organised for the GPU: 32-bit integer work, one
+// straight-line body for caps and belt (selects, no per-element branch, so the pixels a thread owns
+// interleave), and sin(theta) left to the caller (only needed for |z| > 0.99, 1 % of the pixels):
+// `tcap` is the reference's `tmp` = nr^2 * fact2 (sth = sqrt(tcap (2 - tcap))), `polar` tells
+// whether the reference would have set have_sth.  Returns false for the ~1e-8 of RING cap pixels
+// where the reference's uncorrected isqrt mis-rounds (the caller then uses hpgb_pix2loc).
+template <bool NEST>
+HPGB_HD bool hpgb_pix2loc_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, double &z, double &phi, double &tcap,
+                            bool &polar) {
+    uint32_t nr, tphi;    // ring size / 4, and the integer the reference converts for phi
+    int32_t zb;           // belt: 2 nside - ring
+    bool north, cap, ok = true;
+    double phi_off = 0.0;  // RING: subtracted from the in-ring index before scaling
+    if (NEST) {
+        const uint32_t lo = (uint32_t)(uint64_t)pix, hi = (uint32_t)((uint64_t)pix >> 32);
+        const uint32_t face = (uint32_t)((uint64_t)pix >> c.k2);
+        uint32_t wl = lo & c.lmask, wh = hi & c.hmask;
+        HPGB_DSWAP(wl, 0x22222222u, 1);
+        HPGB_DSWAP(wh, 0x22222222u, 1);
+        HPGB_DSWAP(wl, 0x0C0C0C0Cu, 2);
+        HPGB_DSWAP(wh, 0x0C0C0C0Cu, 2);
+        HPGB_DSWAP(wl, 0x00F000F0u, 4);
+        HPGB_DSWAP(wh, 0x00F000F0u, 4);
+        const uint32_t ix = hpgb_prmt(wl, wh, 0x6420), iy = hpgb_prmt(wl, wh, 0x7531);
+        const uint32_t t = (face >> 2) * c.ns + c.nsm1 - ix - iy;  // ring - nside (two's complement)
+        north = (int32_t)t < 0;
+        cap = t > c.ns2;  // jr > 3 nside, or jr < nside (wraps)
+        nr = cap ? (north ? t + c.ns : c.ns3 - t) : c.ns;
+        zb = (int32_t)(c.ns - t);
+        // jpll * nr + ix - iy, + 8 nr when negative (only face row 1, jpll = 0, can be negative)
+        const uint32_t jp = 2u * (face & 3u) + 1u - ((face >> 2) & 1u);
+        const uint32_t v = jp * nr + ix - iy;
+        tphi = (jp == 0u && ix < iy) ? v + 8u * nr : v;
+    } else {
+        uint32_t ipb_lo;
+        const uint32_t tmp = hpgb_r2n_zone(c, (uint64_t)pix, ipb_lo);  // ring - nside
+        north = (int32_t)tmp < 0;
+        cap = hpgb_r2n_is_cap(c, tmp);
+        // caps: the reference's isqrt (hpgeom/healpix_geom.c:60,307-310,326-329)
+        const uint64_t up = (uint64_t)pix;
+        const uint64_t ipm1 = north ? up : ((((uint64_t)c.npm1_hi << 32) | c.npm1_lo) - up);
+#if defined(__CUDA_ARCH__)
+        const uint32_t isq = __double2uint_rz(sqrt((double)(int64_t)(2 * ipm1 + 1) + 0.5));
+#else
+        const uint32_t isq = (uint32_t)(int64_t)sqrt((double)(int64_t)(2 * ipm1 + 1) + 0.5);
+#endif
+        const uint32_t ir = (isq + 1u) >> 1;
+        const uint32_t q0 = (uint32_t)ipm1 - ir * (2u * ir - 2u);  // 0-based in-ring index counted from the pole side
+        ok = !cap || q0 < 4u * ir;
+        const uint32_t iphi_cap = north ? q0 + 1u : 4u * ir - q0;
+        nr = cap ? ir : c.ns;
+        zb = (int32_t)(c.ns - tmp);
+        tphi = cap ? iphi_cap : (ipb_lo & c.ns4m1) + 1u;
+        phi_off = cap ? 0.5 : ((tmp & 1u) ? 1.0 : 0.5);  // belt: (iring + nside) & 1 ? 1 : 0.5, iring + nside = tmp + 2 nside
+    }
+    const double dnr = (double)nr;
+    tcap = (dnr * dnr) * g.fact2;  // RN(nr^2) either way: same double as (double)(nr * nr)
+    const double zc = north ? 1.0 - tcap : tcap - 1.0;
+    z = cap ? zc : (double)zb * g.fact1;
+    polar = cap && fabs(zc) > 0.99;
+    const double dt = (double)tphi;
+    if (NEST) {
+        const double pb = 0.75 * HPGB_HALFPI * dt * g.fact1;
+        const double pc = (0.5 * HPGB_HALFPI * dt) / dnr;
+        phi = cap ? pc : pb;
+    } else {
+        const double d = dt - phi_off;
+        const double pb = d * HPGB_PI * 0.75 * g.fact1;
+        const double pc = d * HPGB_HALFPI / dnr;
+        phi = cap ? pc : pb;
+    }
+    return ok;
+}
+
+// pixel -> angles: hpgeom/healpix_geom.c:172-181 + hpgeom/hpgeom_utils.c:145-165.
+// TA / TQ: the acos / atan tables of hpgb_math.h (table-driven, correctly rounded in practice).
 template <bool NEST, bool POW2, bool LONLAT, bool DEGREES>
-HPGB_HD void hpgb_pix2ang(const hpgb_geom &g, const double *T, int64_t pix, double &a, double &b) {
+HPGB_HD void hpgb_pix2ang(const hpgb_geom &g, const double *TA, const double *TQ, int64_t pix, double &a, double &b) {
     double z, phi, sth;
     bool have_sth;
     hpgb_pix2loc<NEST, POW2>(g, pix, z, phi, sth, have_sth);
-    const double theta = have_sth ? hpgb_atan2_cr(T, sth, z) : hpgb_acos_cr(T, z);
+    // have_sth <=> |z| > 0.99 (hpgeom/healpix_geom.c:317,347-360): the reference takes atan2(sth, z) there
+    const double theta = have_sth ? hpgb_atan2_tab(TQ, sth, z) : hpgb_acos_tab(TA, z);
     if (LONLAT) {
         double lon = phi;
         double lat = -(theta - HPGB_HALFPI);
@@ -522,6 +598,41 @@ HPGB_HD void hpgb_pix2ang(const hpgb_geom &g, const double *T, int64_t pix, doub
         a = theta;
         b = phi;
     }
+}
+
+// theta -> output pair (hpgeom/hpgeom_utils.c:145-165)
+template <bool LONLAT, bool DEGREES>
+HPGB_HD void hpgb_thetaphi_out(double theta, double phi, double &a, double &b) {
+    if (LONLAT) {
+        double lon = phi;
+        double lat = -(theta - HPGB_HALFPI);
+        if (DEGREES) {
+            lon *= 180.0 / HPGB_PI;
+            lat *= 180.0 / HPGB_PI;
+        }
+        a = lon;
+        b = lat;
+    } else {
+        a = theta;
+        b = phi;
+    }
+}
+
+// pixel_to_angle for nside = 2^k, hot part: everything except the two rare cases, which the caller
+// resolves afterwards (so that its pixels interleave): returns 0 = done, 1 = |z| > 0.99 (theta =
+// atan2(sth, z), hpgb_pix2ang_polar), 2 = isqrt quirk (hpgb_pix2ang).
+template <bool NEST, bool LONLAT, bool DEGREES>
+HPGB_HD int hpgb_pix2ang_k(const hpgb_rk &c, const hpgb_geom &g, const double *TA, int64_t pix, double &a, double &b,
+                           double &z, double &phi, double &tcap) {
+    bool polar;
+    const bool ok = hpgb_pix2loc_k<NEST>(c, g, pix, z, phi, tcap, polar);
+    hpgb_thetaphi_out<LONLAT, DEGREES>(hpgb_acos_tab(TA, z), phi, a, b);
+    return ok ? (polar ? 1 : 0) : 2;
+}
+template <bool LONLAT, bool DEGREES>
+HPGB_HD void hpgb_pix2ang_polar(const double *TQ, double z, double phi, double tcap, double &a, double &b) {
+    const double sth = sqrt(tcap * (2. - tcap));  // hpgeom/healpix_geom.c:317
+    hpgb_thetaphi_out<LONLAT, DEGREES>(hpgb_atan2_tab(TQ, sth, z), phi, a, b);
 }
 
 // pixel -> unit vector: hpgeom/healpix_geom.c:183-199

@@ -235,24 +235,26 @@ __global__ void __launch_bounds__(HPGB_BLOCK, Op::MINB) k_stream(const Op op, co
 int hpgb_sm_count();  // SMs of the current device (148 on B200)
 
 template <class K>
-static int hpgb_resident_ctas(K kernel) {
+static int hpgb_resident_ctas(K kernel, int dyn_smem = 0) {
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, HPGB_BLOCK, 0);
+    if (dyn_smem > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, HPGB_BLOCK, dyn_smem);
     return per_sm > 0 ? per_sm : 1;
 }
 
 static inline bool hpgb_aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
 
-// launch the scalar kernel (misaligned operands, per-element nside)
+// launch the scalar kernel (misaligned operands, per-element nside); dyn_smem = bytes of dynamic
+// shared memory the op's prologue() stages its tables into
 template <class Op>
-static int hpgb_launch_map1(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
+static int hpgb_launch_map1(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s, int dyn_smem = 0) {
     if (n <= 0) return HPGB_OK;
     static int occ1 = 0;
-    if (!occ1) occ1 = hpgb_resident_ctas(k_map1<Op>);
+    if (!occ1) occ1 = hpgb_resident_ctas(k_map1<Op>, dyn_smem);
     int64_t want = (n + HPGB_BLOCK - 1) / HPGB_BLOCK;
     int64_t grid = (int64_t)hpgb_sm_count() * occ1;
     if (want < grid) grid = want;
-    k_map1<Op><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(op, n, st);
+    k_map1<Op><<<(unsigned)grid, HPGB_BLOCK, dyn_smem, s>>>(op, n, st);
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
@@ -260,15 +262,15 @@ static int hpgb_launch_map1(const Op &op, int64_t n, hpgb_status_t *st, cudaStre
 
 // launch `op` over n elements; vec_ok = all operand pointers are 16-byte aligned
 template <class Op>
-static int hpgb_launch_map(const Op &op, int64_t n, bool vec_ok, hpgb_status_t *st, cudaStream_t s) {
+static int hpgb_launch_map(const Op &op, int64_t n, bool vec_ok, hpgb_status_t *st, cudaStream_t s, int dyn_smem = 0) {
     if (n <= 0) return HPGB_OK;
-    if (!vec_ok) return hpgb_launch_map1(op, n, st, s);
+    if (!vec_ok) return hpgb_launch_map1(op, n, st, s, dyn_smem);
     static int occ2 = 0;  // per instantiation, per process (one device kind per box)
-    if (!occ2) occ2 = hpgb_resident_ctas(k_map2<Op>);
+    if (!occ2) occ2 = hpgb_resident_ctas(k_map2<Op>, dyn_smem);
     int64_t want = ((n >> 1) + HPGB_BLOCK - 1) / HPGB_BLOCK;
     int64_t grid = (int64_t)hpgb_sm_count() * occ2;
     if (want < grid) grid = want > 0 ? want : 1;
-    k_map2<Op><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(op, n, st);
+    k_map2<Op><<<(unsigned)grid, HPGB_BLOCK, dyn_smem, s>>>(op, n, st);
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;

@@ -201,4 +201,115 @@ HPGB_HD double hpgb_atan2_any(const double *T, double y, double x) {
     return hpgb_atan2_cr(T, ys, xs);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Table-driven acos / atan2 for pixel centres (pixel_to_angle, interpolation ring colatitudes):
+// the same "correctly rounded in practice" contract as hpgb_acos_cr / hpgb_atan2_cr (result
+// returned as an unevaluated sum hi + lo good to ~2^-68 relative), at a quarter of the fp64
+// work -- no first guess, no double-double sin/cos, no division:
+//   acos(|z|) = sum_j a_j r^j around one of 897 cell centres zc (Taylor coefficients from mpmath,
+//   tools/gen_tables.py), r = |z| - zc EXACT; cells are uniform (2^-8) for |z| <= 1/2 and of
+//   relative width 2^-7 in u = 1 - |z| beyond, so |r| / (1 - |zc|) <= 2^-8 everywhere and ten terms
+//   reach 2^-70; a_0, a_1 are double-doubles, a_1 r is an exact two-product, the rest is Horner.
+//   z < 0 : pi - acos(|z|), with pi as a double-double.
+//   atan2(s, c), 0 <= s <= 0.156 c (the polar caps, |z| > 0.99): q = s/c as quotient + exact
+//   remainder correction, then the same scheme around q = k/512 with eight terms.
+// TA / TQ point at the tables (HPGB_ACOS_TABLE_INIT / HPGB_ATANQ_TABLE_INIT), staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+HPGB_HD uint32_t hpgb_math_hi32(double v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2hiint(v);
+#else
+    union {
+        double d;
+        uint64_t u;
+    } c;
+    c.d = v;
+    return (uint32_t)(c.u >> 32);
+#endif
+}
+
+// acos(z) as hi + lo, |z| <= 0.99
+HPGB_HD void hpgb_acos_tab_dd(const double *TA, double z, double &hi, double &lo) {
+    const double a = fabs(z);
+    const double u = 1.0 - a;  // exact for a >= 1/2
+    const int ia = (int)rint(a * 256.0);
+    const int ib = 129 + (int)(hpgb_math_hi32(u) >> 13) - 1016 * 128;
+    int idx = a <= 0.5 ? ia : ib;
+    idx = idx < 0 ? 0 : (idx > HPGB_ACOS_ROWS - 1 ? HPGB_ACOS_ROWS - 1 : idx);  // NaN / out-of-domain input: stay inside the table
+    const double *row = TA + idx * HPGB_ACOS_ROW_DOUBLES;
+    // cell centre, recomputed exactly from the index
+    const double uc_lo = ldexp(1.0 + (double)((idx - 129) & 127) * 0.0078125, ((idx - 129) >> 7) - 7);
+    const double zc = a <= 0.5 ? (double)idx * 0.00390625 : 1.0 - (uc_lo + ldexp(1.0, ((idx - 129) >> 7) - 15));
+    const double r = a - zc;  // exact (Sterbenz)
+    double s = fma(row[11], r, row[10]);
+    s = fma(s, r, row[9]);
+    s = fma(s, r, row[8]);
+    s = fma(s, r, row[7]);
+    s = fma(s, r, row[6]);
+    s = fma(s, r, row[5]);
+    s = fma(s, r, row[4]);
+    double p, pe, h, hl;
+    hpgb_two_prod(row[2], r, p, pe);
+    const double low = row[1] + (pe + fma(row[3], r, (r * r) * s));
+    hpgb_fast_two_sum(row[0], p, h, hl);  // |a1 r| < acos(zc)
+    const double l = hl + low;
+    // z < 0: pi - (h + l)
+    const bool neg = z < 0.0;
+    const double A = neg ? HPGB_PI_1 : 0.0, Al = neg ? HPGB_PI_2 : 0.0;
+    const double sh = neg ? -h : h, sl = neg ? -l : l;
+    double e;
+    hpgb_fast_two_sum(A, sh, hi, e);  // A = 0, or A = pi_1 > |sh|
+    hi = neg ? hi : sh;
+    e = neg ? e : 0.0;
+    lo = e + (Al + sl);
+}
+HPGB_HD double hpgb_acos_tab(const double *TA, double z) {
+    double hi, lo;
+    hpgb_acos_tab_dd(TA, z, hi, lo);
+    return hi + lo;
+}
+
+// atan2(s, c) as hi + lo for 0 <= s <= 0.156 |c| (result pi - atan2(s, |c|) when c < 0)
+HPGB_HD void hpgb_atan2_tab_dd(const double *TQ, double s, double c, double &hi, double &lo) {
+    const double ca = fabs(c);
+#if defined(__CUDA_ARCH__)
+    double ic;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ic) : "d"(ca));
+    const double ic2 = fma(ic, fma(-ca, ic, 1.0), ic);
+    const double qh = s * fma(ic2, fma(-ca, ic2, 1.0), ic2);
+#else
+    const double ic = 1.0 / ca;
+    const double qh = s * ic;
+#endif
+    const double ql = fma(-qh, ca, s) * ic;  // exact remainder, rough reciprocal: q = qh + ql to ~2^-75
+    int idx = (int)rint(qh * 512.0);
+    idx = idx < 0 ? 0 : (idx > HPGB_ATANQ_ROWS - 1 ? HPGB_ATANQ_ROWS - 1 : idx);
+    const double *row = TQ + idx * HPGB_ATANQ_ROW_DOUBLES;
+    const double r = qh - (double)idx * 0.001953125;  // exact
+    const double rt = r + ql;
+    double t = fma(row[9], rt, row[8]);
+    t = fma(t, rt, row[7]);
+    t = fma(t, rt, row[6]);
+    t = fma(t, rt, row[5]);
+    t = fma(t, rt, row[4]);
+    double p, pe, h, hl;
+    hpgb_two_prod(row[2], r, p, pe);
+    const double low = row[1] + (pe + fma(row[2], ql, fma(row[3], r, (rt * rt) * t)));
+    hpgb_two_sum(row[0], p, h, hl);  // atan(qc) may be 0 (first cell)
+    const double l = hl + low;
+    const bool neg = c < 0.0;
+    const double A = neg ? HPGB_PI_1 : 0.0, Al = neg ? HPGB_PI_2 : 0.0;
+    const double sh = neg ? -h : h, sl = neg ? -l : l;
+    double e;
+    hpgb_fast_two_sum(A, sh, hi, e);
+    hi = neg ? hi : sh;
+    e = neg ? e : 0.0;
+    lo = e + (Al + sl);
+}
+HPGB_HD double hpgb_atan2_tab(const double *TQ, double s, double c) {
+    double hi, lo;
+    hpgb_atan2_tab_dd(TQ, s, c, hi, lo);
+    return hi + lo;
+}
+
 #endif  // HPGB_MATH_H

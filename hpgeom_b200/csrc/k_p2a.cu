@@ -26,6 +26,11 @@ __device__ __forceinline__ bool var_geom(const int64_t *nside_v, int64_t i, int 
 // -------------------------------------------------------------------------------------------
 // pixel_to_angle   (reference loop: hpgeom/hpgeom.c:426-457)   8 B in + 16 B out per pixel
 // -------------------------------------------------------------------------------------------
+// acos / atan Taylor tables of hpgb_math.h (86 + 6.4 KB), staged into dynamic shared memory per CTA
+static __device__ const double g_hpgb_acos_tab[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES] = HPGB_ACOS_TABLE_INIT;
+static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES] = HPGB_ATANQ_TABLE_INIT;
+#define HPGB_P2A_TAB_DOUBLES (HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES + HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES)
+
 template <bool NEST, bool POW2, bool LONLAT, bool DEGREES, bool VAR>
 struct OpPix2Ang {
     const int64_t *pix;
@@ -33,13 +38,22 @@ struct OpPix2Ang {
     const int64_t *nside_v;
     int64_t base;
     hpgb_geom g;
+    hpgb_rk c;  // POW2 && !VAR: constants of the branch-free pix2loc
     typedef longlong2 In2;
-    typedef const double *Ctx;
-    HPGB_DEFAULT_RUN4
-    HPGB_STREAM_IN_I64(pix, 2)
+    typedef const double *Ctx;  // acos table; the atan table follows it
+    static constexpr int DYN_SMEM = HPGB_P2A_TAB_DOUBLES * 8;
+    static constexpr bool FAST = POW2 && !VAR;
 
-    __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
+    __device__ __forceinline__ Ctx prologue() const {
+        extern __shared__ __align__(16) double hpgb_p2a_tabs[];
+        for (int i = threadIdx.x; i < HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES; i += HPGB_BLOCK) hpgb_p2a_tabs[i] = g_hpgb_acos_tab[i];
+        for (int i = threadIdx.x; i < HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES; i += HPGB_BLOCK)
+            hpgb_p2a_tabs[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES + i] = g_hpgb_atanq_tab[i];
+        __syncthreads();
+        return hpgb_p2a_tabs;
+    }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
+    // general path (any nside, per-element nside): the reference's branches as they are
     __device__ __forceinline__ void conv(const hpgb_geom &gg, int64_t p, int64_t i, Ctx T, hpgb_bad_t &bad, double &va,
                                          double &vb) const {
         if (!hpgb_pixel_ok(gg, p)) {
@@ -47,14 +61,65 @@ struct OpPix2Ang {
             va = vb = 0.0;
             return;
         }
-        hpgb_pix2ang<NEST, POW2, LONLAT, DEGREES>(gg, T, p, va, vb);
+        hpgb_pix2ang<NEST, POW2, LONLAT, DEGREES>(gg, T, T + HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES, p, va, vb);
+    }
+    // power-of-two nside: straight-line hot part for every pixel, then the rare cases (out of range,
+    // |z| > 0.99, isqrt quirk) patched per element
+    struct Hot {
+        double va, vb, z, phi, tcap;
+        int code;
+    };
+    __device__ __forceinline__ Hot hot(int64_t p, Ctx T) const {
+        Hot h;
+        h.code = hpgb_pix2ang_k<NEST, LONLAT, DEGREES>(c, g, T, p, h.va, h.vb, h.z, h.phi, h.tcap);
+        if (!hpgb_pixel_ok(g, p)) h.code = 3;
+        return h;
+    }
+    __device__ __forceinline__ void fix(Hot &h, int64_t p, int64_t i, Ctx T, hpgb_bad_t &bad) const {
+        if (h.code == 1) {
+            hpgb_pix2ang_polar<LONLAT, DEGREES>(T + HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES, h.z, h.phi, h.tcap, h.va, h.vb);
+        } else if (h.code == 2) {
+            hpgb_pix2ang<NEST, POW2, LONLAT, DEGREES>(g, T, T + HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES, p, h.va, h.vb);
+        } else if (h.code == 3) {
+            bad.flag(base + i);
+            h.va = h.vb = 0.0;
+        }
     }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &bad) const {
-        double a0, b0, a1, b1;
-        conv(g, v.x, i, T, bad, a0, b0);
-        conv(g, v.y, i + 1, T, bad, a1, b1);
-        hpgb_st2(a + i, a0, a1);
-        hpgb_st2(b + i, b0, b1);
+        if (FAST) {
+            Hot h0 = hot(v.x, T), h1 = hot(v.y, T);
+            if (h0.code | h1.code) {
+                fix(h0, v.x, i, T, bad);
+                fix(h1, v.y, i + 1, T, bad);
+            }
+            hpgb_st2(a + i, h0.va, h1.va);
+            hpgb_st2(b + i, h0.vb, h1.vb);
+        } else {
+            double a0, b0, a1, b1;
+            conv(g, v.x, i, T, bad, a0, b0);
+            conv(g, v.y, i + 1, T, bad, a1, b1);
+            hpgb_st2(a + i, a0, a1);
+            hpgb_st2(b + i, b0, b1);
+        }
+    }
+    __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
+                                         hpgb_bad_t &bad) const {
+        if (FAST) {
+            Hot h0 = hot(v0.x, T), h1 = hot(v0.y, T), h2 = hot(v1.x, T), h3 = hot(v1.y, T);
+            if (h0.code | h1.code | h2.code | h3.code) {
+                fix(h0, v0.x, i0, T, bad);
+                fix(h1, v0.y, i0 + 1, T, bad);
+                fix(h2, v1.x, i1, T, bad);
+                fix(h3, v1.y, i1 + 1, T, bad);
+            }
+            hpgb_st2(a + i0, h0.va, h1.va);
+            hpgb_st2(b + i0, h0.vb, h1.vb);
+            hpgb_st2(a + i1, h2.va, h3.va);
+            hpgb_st2(b + i1, h2.vb, h3.vb);
+        } else {
+            run2(i0, v0, T, bad);
+            run2(i1, v1, T, bad);
+        }
     }
     __device__ __forceinline__ void run1(int64_t i, const Ctx &T, hpgb_bad_t &bad) const {
         double va = 0.0, vb = 0.0;
@@ -76,17 +141,17 @@ template <bool NEST, bool LONLAT, bool DEGREES>
 int launch_p2a_t(const int64_t *pix, double *a, double *b, int64_t n, int64_t nside, const int64_t *nside_v,
                  int64_t base, hpgb_status_t *st, cudaStream_t s) {
     if (nside_v) {  // per-element nside: the general-nside code path handles powers of two as well
-        OpPix2Ang<NEST, NEST, LONLAT, DEGREES, true> op{pix, a, b, nside_v, base, hpgb_geom()};
-        return hpgb_launch_map1(op, n, st, s);
+        OpPix2Ang<NEST, NEST, LONLAT, DEGREES, true> op{pix, a, b, nside_v, base, hpgb_geom(), hpgb_rk()};
+        return hpgb_launch_map1(op, n, st, s, decltype(op)::DYN_SMEM);
     }
     const hpgb_geom g = hpgb_make_geom(nside, NEST);
     const bool vec = hpgb_aligned16(pix) && hpgb_aligned16(a) && hpgb_aligned16(b);
     if (NEST || g.order >= 0) {
-        OpPix2Ang<NEST, true, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g};
-        return hpgb_launch_map(op, n, vec, st, s);
+        OpPix2Ang<NEST, true, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g, hpgb_make_rk(g)};
+        return hpgb_launch_map(op, n, vec, st, s, decltype(op)::DYN_SMEM);
     }
-    OpPix2Ang<false, false, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g};
-    return hpgb_launch_map(op, n, vec, st, s);
+    OpPix2Ang<false, false, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g, hpgb_rk()};
+    return hpgb_launch_map(op, n, vec, st, s, decltype(op)::DYN_SMEM);
 }
 
 }  // namespace

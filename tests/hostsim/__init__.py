@@ -17,7 +17,7 @@ class HostSim:
         self.lib = ctypes.CDLL(os.path.join(_HERE, "libhostsim.so"))
         for n in ("sim_nest_to_ring", "sim_ring_to_nest", "sim_ring_roundtrip_any", "sim_angle_to_pixel",
                   "sim_pixel_to_angle", "sim_pixel_to_vector", "sim_vector_to_pixel", "sim_neighbors", "sim_interp",
-                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k"):
+                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_pixel_to_angle_k"):
             getattr(self.lib, n).restype = ctypes.c_int64
         self.last_slow = 0
 
@@ -80,6 +80,17 @@ class HostSim:
         self._chk(self.lib.sim_pixel_to_angle(ctypes.c_int64(nside), pix.ctypes.data_as(_I), ctypes.c_int64(pix.size),
                                               int(nest), int(lonlat), int(degrees), a.ctypes.data_as(_D),
                                               b.ctypes.data_as(_D)))
+        return a, b
+
+    def pixel_to_angle_k(self, nside, pix, nest=True, lonlat=True, degrees=True):
+        """The branch-free power-of-two path of the kernels; self.last_slow = pixels that took a rare-case patch."""
+        pix = self._i(pix)
+        a, b = np.empty(pix.size), np.empty(pix.size)
+        r = self.lib.sim_pixel_to_angle_k(ctypes.c_int64(nside), pix.ctypes.data_as(_I), ctypes.c_int64(pix.size),
+                                          int(nest), int(lonlat), int(degrees), a.ctypes.data_as(_D), b.ctypes.data_as(_D))
+        if r < 0:
+            raise ValueError("bad element %d" % (-1 - r))
+        self.last_slow = r
         return a, b
 
     def pixel_to_vector(self, nside, pix, nest=True):

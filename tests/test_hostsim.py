@@ -225,6 +225,31 @@ def test_pixel_to_angle_golden(sim, nside, nest):
         assert not many or np.mean(lat != g["%s_b_%s" % (key, t)]) <= 0.01
 
 
+@pytest.mark.parametrize("nside", [1, 2, 8, 1024, 2 ** 16, 2 ** 29])
+def test_pixel_to_angle_branch_free_path(sim, nside):
+    """The straight-line power-of-two pixel_to_angle of the kernels (hpgb_pix2ang_k + rare-case
+    patches) is bit-identical to the reference-shaped hpgb_pix2ang on every zone boundary, in the
+    isqrt-quirk region and on random pixels, both schemes, all three angle conventions."""
+    rng = np.random.default_rng(nside + 5)
+    npix = 12 * nside * nside
+    ncap = 2 * nside * (nside - 1)
+    if npix < 100000:
+        pix = np.arange(npix)
+    else:
+        pix = np.concatenate([rng.integers(0, npix, 100000), np.arange(500), npix - 1 - np.arange(500),
+                              ncap + np.arange(-500, 500), npix - ncap + np.arange(-500, 500)])
+    if nside == 2 ** 29:
+        r = rng.integers(2 ** 26, nside, 5000)
+        pn = 2 * r * (r + 1) - 1 + rng.integers(-40, 41, r.size)
+        pix = np.concatenate([pix, pn, npix - 1 - pn])
+    for nest in (True, False):
+        for kw in ({}, {"degrees": False}, {"lonlat": False, "degrees": False}):
+            a0, b0 = sim.pixel_to_angle(nside, pix, nest=nest, **kw)
+            a1, b1 = sim.pixel_to_angle_k(nside, pix, nest=nest, **kw)
+            assert_bit_equal(a1, a0, "a")
+            assert_bit_equal(b1, b0, "b")
+
+
 @pytest.mark.parametrize("nside,nest", CASES)
 def test_pixel_to_vector_golden(sim, nside, nest):
     g = load_golden("pixel_to_vector")
@@ -284,8 +309,16 @@ def test_trig_correctly_rounded(sim):
     z = rng.uniform(-0.99, 0.99, n)
     exact = np.array([float(mp.acos(mp.mpf(float(v)))) for v in z])
     assert np.count_nonzero(call1("sim_acos_cr", z) != exact) <= 1
+    assert np.count_nonzero(call1("sim_acos_tab", z) != exact) <= 1
     y, xx = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
     out = np.empty(n)
     sim.lib.sim_atan2_cr(y.ctypes.data_as(D), xx.ctypes.data_as(D), ctypes.c_int64(n), out.ctypes.data_as(D))
     exact = np.array([float(mp.atan2(mp.mpf(float(a)), mp.mpf(float(b)))) for a, b in zip(y, xx)])
+    assert np.count_nonzero(out != exact) <= 1
+    # table-driven atan2 of the polar caps: s = sqrt(t (2 - t)), c = +-(1 - t), |c| > 0.99
+    t = 10 ** rng.uniform(-17, -2.0001, n)
+    c = (1 - t) * np.where(rng.uniform(size=n) < 0.5, -1.0, 1.0)
+    s = np.sqrt(t * (2 - t))
+    sim.lib.sim_atan2_tab(s.ctypes.data_as(D), c.ctypes.data_as(D), ctypes.c_int64(n), out.ctypes.data_as(D))
+    exact = np.array([float(mp.atan2(mp.mpf(float(a)), mp.mpf(float(b)))) for a, b in zip(s, c)])
     assert np.count_nonzero(out != exact) <= 1
