@@ -529,12 +529,12 @@ HPGB_HD bool hpgb_pix2loc_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, d
         const uint32_t t = (face >> 2) * c.ns + c.nsm1 - ix - iy;  // ring - nside (two's complement)
         north = (int32_t)t < 0;
         cap = t > c.ns2;  // jr > 3 nside, or jr < nside (wraps)
-        nr = cap ? (north ? t + c.ns : c.ns3 - t) : c.ns;
+        nr = hpgb_sel(cap, hpgb_sel(north, t + c.ns, c.ns3 - t), c.ns);
         zb = (int32_t)(c.ns - t);
         // jpll * nr + ix - iy, + 8 nr when negative (only face row 1, jpll = 0, can be negative)
         const uint32_t jp = 2u * (face & 3u) + 1u - ((face >> 2) & 1u);
         const uint32_t v = jp * nr + ix - iy;
-        tphi = (jp == 0u && ix < iy) ? v + 8u * nr : v;
+        tphi = hpgb_sel(jp == 0u && ix < iy, v + 8u * nr, v);
     } else {
         uint32_t ipb_lo;
         const uint32_t tmp = hpgb_r2n_zone(c, (uint64_t)pix, ipb_lo);  // ring - nside
@@ -551,10 +551,10 @@ HPGB_HD bool hpgb_pix2loc_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, d
         const uint32_t ir = (isq + 1u) >> 1;
         const uint32_t q0 = (uint32_t)ipm1 - ir * (2u * ir - 2u);  // 0-based in-ring index counted from the pole side
         ok = !cap || q0 < 4u * ir;
-        const uint32_t iphi_cap = north ? q0 + 1u : 4u * ir - q0;
-        nr = cap ? ir : c.ns;
+        const uint32_t iphi_cap = hpgb_sel(north, q0 + 1u, 4u * ir - q0);
+        nr = hpgb_sel(cap, ir, c.ns);
         zb = (int32_t)(c.ns - tmp);
-        tphi = cap ? iphi_cap : (ipb_lo & c.ns4m1) + 1u;
+        tphi = hpgb_sel(cap, iphi_cap, (ipb_lo & c.ns4m1) + 1u);
         phi_off = cap ? 0.5 : ((tmp & 1u) ? 1.0 : 0.5);  // belt: (iring + nside) & 1 ? 1 : 0.5, iring + nside = tmp + 2 nside
     }
     const double dnr = (double)nr;
@@ -565,12 +565,12 @@ HPGB_HD bool hpgb_pix2loc_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, d
     const double dt = (double)tphi;
     if (NEST) {
         const double pb = 0.75 * HPGB_HALFPI * dt * g.fact1;
-        const double pc = (0.5 * HPGB_HALFPI * dt) / dnr;
+        const double pc = hpgb_div_tame(0.5 * HPGB_HALFPI * dt, dnr);
         phi = cap ? pc : pb;
     } else {
         const double d = dt - phi_off;
         const double pb = d * HPGB_PI * 0.75 * g.fact1;
-        const double pc = d * HPGB_HALFPI / dnr;
+        const double pc = hpgb_div_tame(d * HPGB_HALFPI, dnr);
         phi = cap ? pc : pb;
     }
     return ok;
@@ -579,7 +579,7 @@ HPGB_HD bool hpgb_pix2loc_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, d
 // pixel -> angles: hpgeom/healpix_geom.c:172-181 + hpgeom/hpgeom_utils.c:145-165.
 // TA / TQ: the acos / atan tables of hpgb_math.h (table-driven, correctly rounded in practice).
 template <bool NEST, bool POW2, bool LONLAT, bool DEGREES>
-HPGB_HD void hpgb_pix2ang(const hpgb_geom &g, const double *TA, const double *TQ, int64_t pix, double &a, double &b) {
+HPGB_HD void hpgb_pix2ang(const hpgb_geom &g, const uint64_t *TA, const double *TQ, int64_t pix, double &a, double &b) {
     double z, phi, sth;
     bool have_sth;
     hpgb_pix2loc<NEST, POW2>(g, pix, z, phi, sth, have_sth);
@@ -622,7 +622,7 @@ HPGB_HD void hpgb_thetaphi_out(double theta, double phi, double &a, double &b) {
 // resolves afterwards (so that its pixels interleave): returns 0 = done, 1 = |z| > 0.99 (theta =
 // atan2(sth, z), hpgb_pix2ang_polar), 2 = isqrt quirk (hpgb_pix2ang).
 template <bool NEST, bool LONLAT, bool DEGREES>
-HPGB_HD int hpgb_pix2ang_k(const hpgb_rk &c, const hpgb_geom &g, const double *TA, int64_t pix, double &a, double &b,
+HPGB_HD int hpgb_pix2ang_k(const hpgb_rk &c, const hpgb_geom &g, const uint64_t *TA, int64_t pix, double &a, double &b,
                            double &z, double &phi, double &tcap) {
     bool polar;
     const bool ok = hpgb_pix2loc_k<NEST>(c, g, pix, z, phi, tcap, polar);

@@ -45,12 +45,12 @@ struct hpgb_bad_t {
 //   void run2(int64_t i, const In2&, const Ctx&, hpgb_bad_t&) const; // converts + stores i, i+1
 //   void run4(i0, v0, i1, v1, ctx, bad) const;                      // two pairs (ILP across both)
 //   void run1(int64_t i, const Ctx&, hpgb_bad_t&) const;            // scalar element
-template <class Op>
-__global__ void __launch_bounds__(HPGB_BLOCK) k_map2(const Op op, const int64_t n, hpgb_status_t *st) {
+template <class Op, int BLOCK = HPGB_BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_map2(const Op op, const int64_t n, hpgb_status_t *st) {
     const typename Op::Ctx ctx = op.prologue();
     const int64_t npair = n >> 1;
-    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
-    int64_t p = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * BLOCK;
+    int64_t p = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     hpgb_bad_t bad;
     for (; p + stride < npair; p += 2 * stride) {
         const typename Op::In2 v0 = op.load2(2 * p);
@@ -62,12 +62,12 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_map2(const Op op, const int64_t 
     bad.commit(st);
 }
 
-template <class Op>
-__global__ void __launch_bounds__(HPGB_BLOCK) k_map1(const Op op, const int64_t n, hpgb_status_t *st) {
+template <class Op, int BLOCK = HPGB_BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_map1(const Op op, const int64_t n, hpgb_status_t *st) {
     const typename Op::Ctx ctx = op.prologue();
-    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    const int64_t stride = (int64_t)gridDim.x * BLOCK;
     hpgb_bad_t bad;
-    for (int64_t i = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; i < n; i += stride) op.run1(i, ctx, bad);
+    for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride) op.run1(i, ctx, bad);
     bad.commit(st);
 }
 
@@ -235,42 +235,43 @@ __global__ void __launch_bounds__(HPGB_BLOCK, Op::MINB) k_stream(const Op op, co
 int hpgb_sm_count();  // SMs of the current device (148 on B200)
 
 template <class K>
-static int hpgb_resident_ctas(K kernel, int dyn_smem = 0) {
+static int hpgb_resident_ctas(K kernel, int dyn_smem = 0, int block = HPGB_BLOCK) {
     int per_sm = 0;
     if (dyn_smem > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, HPGB_BLOCK, dyn_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, dyn_smem);
     return per_sm > 0 ? per_sm : 1;
 }
 
 static inline bool hpgb_aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
 
 // launch the scalar kernel (misaligned operands, per-element nside); dyn_smem = bytes of dynamic
-// shared memory the op's prologue() stages its tables into
-template <class Op>
+// shared memory the op's prologue() stages its tables into; BLOCK = threads per CTA (ops with big
+// tables run ONE large CTA per SM so the table is staged once per SM)
+template <class Op, int BLOCK = HPGB_BLOCK>
 static int hpgb_launch_map1(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s, int dyn_smem = 0) {
     if (n <= 0) return HPGB_OK;
     static int occ1 = 0;
-    if (!occ1) occ1 = hpgb_resident_ctas(k_map1<Op>, dyn_smem);
-    int64_t want = (n + HPGB_BLOCK - 1) / HPGB_BLOCK;
+    if (!occ1) occ1 = hpgb_resident_ctas(k_map1<Op, BLOCK>, dyn_smem, BLOCK);
+    int64_t want = (n + BLOCK - 1) / BLOCK;
     int64_t grid = (int64_t)hpgb_sm_count() * occ1;
     if (want < grid) grid = want;
-    k_map1<Op><<<(unsigned)grid, HPGB_BLOCK, dyn_smem, s>>>(op, n, st);
+    k_map1<Op, BLOCK><<<(unsigned)grid, BLOCK, dyn_smem, s>>>(op, n, st);
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
 }
 
 // launch `op` over n elements; vec_ok = all operand pointers are 16-byte aligned
-template <class Op>
+template <class Op, int BLOCK = HPGB_BLOCK>
 static int hpgb_launch_map(const Op &op, int64_t n, bool vec_ok, hpgb_status_t *st, cudaStream_t s, int dyn_smem = 0) {
     if (n <= 0) return HPGB_OK;
-    if (!vec_ok) return hpgb_launch_map1(op, n, st, s, dyn_smem);
+    if (!vec_ok) return hpgb_launch_map1<Op, BLOCK>(op, n, st, s, dyn_smem);
     static int occ2 = 0;  // per instantiation, per process (one device kind per box)
-    if (!occ2) occ2 = hpgb_resident_ctas(k_map2<Op>, dyn_smem);
-    int64_t want = ((n >> 1) + HPGB_BLOCK - 1) / HPGB_BLOCK;
+    if (!occ2) occ2 = hpgb_resident_ctas(k_map2<Op, BLOCK>, dyn_smem, BLOCK);
+    int64_t want = ((n >> 1) + BLOCK - 1) / BLOCK;
     int64_t grid = (int64_t)hpgb_sm_count() * occ2;
     if (want < grid) grid = want > 0 ? want : 1;
-    k_map2<Op><<<(unsigned)grid, HPGB_BLOCK, dyn_smem, s>>>(op, n, st);
+    k_map2<Op, BLOCK><<<(unsigned)grid, BLOCK, dyn_smem, s>>>(op, n, st);
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;

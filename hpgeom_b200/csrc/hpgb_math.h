@@ -206,7 +206,8 @@ HPGB_HD double hpgb_atan2_any(const double *T, double y, double x) {
 // the same "correctly rounded in practice" contract as hpgb_acos_cr / hpgb_atan2_cr (result
 // returned as an unevaluated sum hi + lo good to ~2^-68 relative), at a quarter of the fp64
 // work -- no first guess, no double-double sin/cos, no division:
-//   acos(|z|) = sum_j a_j r^j around one of 897 cell centres zc (Taylor coefficients from mpmath,
+//   acos(|z|) = sum_j a_j r^j around one of 897 cell centres zc (Taylor coefficients from mpmath; a_6..a_9
+//   stored as floats: 80-byte rows, an odd number of 16-byte bank groups, so random gathers use every bank),
 //   tools/gen_tables.py), r = |z| - zc EXACT; cells are uniform (2^-8) for |z| <= 1/2 and of
 //   relative width 2^-7 in u = 1 - |z| beyond, so |r| / (1 - |zc|) <= 2^-8 everywhere and ten terms
 //   reach 2^-70; a_0, a_1 are double-doubles, a_1 r is an exact two-product, the rest is Horner.
@@ -228,19 +229,70 @@ HPGB_HD uint32_t hpgb_math_hi32(double v) {
 #endif
 }
 
-// acos(z) as hi + lo, |z| <= 0.99
-HPGB_HD void hpgb_acos_tab_dd(const double *TA, double z, double &hi, double &lo) {
+// a / b correctly rounded for "tame" operands (no overflow / underflow / subnormals anywhere near):
+// reciprocal approximation, two Newton steps, two residual corrections -- the sequence behind
+// div.rn.f64 without its special-case branch, so it stays straight-line code.  Validated against
+// operator / on 3e10 operand pairs of the domain it is used for (tools/ubench/divcheck.cu).
+HPGB_HD double hpgb_div_tame(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    y = fma(y, fma(-b, y, 1.0), y);
+    y = fma(y, fma(-b, y, 1.0), y);
+    double q = a * y;
+    q = fma(fma(-b, q, a), y, q);
+    q = fma(fma(-b, q, a), y, q);
+    return q;
+#else
+    return a / b;
+#endif
+}
+
+HPGB_HD double hpgb_w2d(uint64_t w) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)w);
+#else
+    union {
+        uint64_t b;
+        double d;
+    } cv;
+    cv.b = w;
+    return cv.d;
+#endif
+}
+HPGB_HD double hpgb_w2f(uint32_t w) {  // float bits -> double
+#if defined(__CUDA_ARCH__)
+    return (double)__uint_as_float(w);
+#else
+    union {
+        uint32_t b;
+        float f;
+    } cv;
+    cv.b = w;
+    return (double)cv.f;
+#endif
+}
+
+// acos(z) as hi + lo, |z| <= 0.99.  TA: rows of HPGB_ACOS_ROW_WORDS 64-bit words (see tools/gen_tables.py)
+HPGB_HD void hpgb_acos_tab_dd(const uint64_t *TA, double z, double &hi, double &lo) {
     const double a = fabs(z);
     const double u = 1.0 - a;  // exact for a >= 1/2
     const int ia = (int)rint(a * 256.0);
     const int ib = 129 + (int)(hpgb_math_hi32(u) >> 13) - 1016 * 128;
     int idx = a <= 0.5 ? ia : ib;
     idx = idx < 0 ? 0 : (idx > HPGB_ACOS_ROWS - 1 ? HPGB_ACOS_ROWS - 1 : idx);  // NaN / out-of-domain input: stay inside the table
-    const double *row = TA + idx * HPGB_ACOS_ROW_DOUBLES;
-    // cell centre, recomputed exactly from the index
-    const double uc_lo = ldexp(1.0 + (double)((idx - 129) & 127) * 0.0078125, ((idx - 129) >> 7) - 7);
-    const double zc = a <= 0.5 ? (double)idx * 0.00390625 : 1.0 - (uc_lo + ldexp(1.0, ((idx - 129) >> 7) - 15));
-    const double r = a - zc;  // exact (Sterbenz)
+    const uint64_t *roww = TA + idx * HPGB_ACOS_ROW_WORDS;
+    double row[12];
+#pragma unroll
+    for (int j = 0; j < 8; j++) row[j] = hpgb_w2d(roww[j]);
+    row[8] = hpgb_w2f((uint32_t)roww[8]);
+    row[9] = hpgb_w2f((uint32_t)(roww[8] >> 32));
+    row[10] = hpgb_w2f((uint32_t)roww[9]);
+    row[11] = hpgb_w2f((uint32_t)(roww[9] >> 32));
+    // r = |z| - zc, exact.  |z| <= 1/2: zc = idx / 256.  Beyond: zc = 1 - uc, uc = the cell's lower edge
+    // (u with all but 7 mantissa bits cleared) + half a cell (the next mantissa bit), so r = uc - u.
+    const double uc = hpgb_w2d((uint64_t)((hpgb_math_hi32(u) & 0xFFFFE000u) | 0x00001000u) << 32);
+    const double r = a <= 0.5 ? fma(-(double)idx, 0.00390625, a) : uc - u;
     double s = fma(row[11], r, row[10]);
     s = fma(s, r, row[9]);
     s = fma(s, r, row[8]);
@@ -253,17 +305,14 @@ HPGB_HD void hpgb_acos_tab_dd(const double *TA, double z, double &hi, double &lo
     const double low = row[1] + (pe + fma(row[3], r, (r * r) * s));
     hpgb_fast_two_sum(row[0], p, h, hl);  // |a1 r| < acos(zc)
     const double l = hl + low;
-    // z < 0: pi - (h + l)
+    // z < 0: pi - (h + l), pi as a double-double; both variants computed, two selects
+    double nh, ne;
+    hpgb_fast_two_sum(HPGB_PI_1, -h, nh, ne);  // pi_1 > h
     const bool neg = z < 0.0;
-    const double A = neg ? HPGB_PI_1 : 0.0, Al = neg ? HPGB_PI_2 : 0.0;
-    const double sh = neg ? -h : h, sl = neg ? -l : l;
-    double e;
-    hpgb_fast_two_sum(A, sh, hi, e);  // A = 0, or A = pi_1 > |sh|
-    hi = neg ? hi : sh;
-    e = neg ? e : 0.0;
-    lo = e + (Al + sl);
+    hi = neg ? nh : h;
+    lo = neg ? ne + (HPGB_PI_2 - l) : l;
 }
-HPGB_HD double hpgb_acos_tab(const double *TA, double z) {
+HPGB_HD double hpgb_acos_tab(const uint64_t *TA, double z) {
     double hi, lo;
     hpgb_acos_tab_dd(TA, z, hi, lo);
     return hi + lo;
@@ -297,14 +346,11 @@ HPGB_HD void hpgb_atan2_tab_dd(const double *TQ, double s, double c, double &hi,
     const double low = row[1] + (pe + fma(row[2], ql, fma(row[3], r, (rt * rt) * t)));
     hpgb_two_sum(row[0], p, h, hl);  // atan(qc) may be 0 (first cell)
     const double l = hl + low;
+    double nh, ne;
+    hpgb_fast_two_sum(HPGB_PI_1, -h, nh, ne);
     const bool neg = c < 0.0;
-    const double A = neg ? HPGB_PI_1 : 0.0, Al = neg ? HPGB_PI_2 : 0.0;
-    const double sh = neg ? -h : h, sl = neg ? -l : l;
-    double e;
-    hpgb_fast_two_sum(A, sh, hi, e);
-    hi = neg ? hi : sh;
-    e = neg ? e : 0.0;
-    lo = e + (Al + sl);
+    hi = neg ? nh : h;
+    lo = neg ? ne + (HPGB_PI_2 - l) : l;
 }
 HPGB_HD double hpgb_atan2_tab(const double *TQ, double s, double c) {
     double hi, lo;

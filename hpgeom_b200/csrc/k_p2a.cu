@@ -26,10 +26,14 @@ __device__ __forceinline__ bool var_geom(const int64_t *nside_v, int64_t i, int 
 // -------------------------------------------------------------------------------------------
 // pixel_to_angle   (reference loop: hpgeom/hpgeom.c:426-457)   8 B in + 16 B out per pixel
 // -------------------------------------------------------------------------------------------
-// acos / atan Taylor tables of hpgb_math.h (86 + 6.4 KB), staged into dynamic shared memory per CTA
-static __device__ const double g_hpgb_acos_tab[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES] = HPGB_ACOS_TABLE_INIT;
+// acos / atan Taylor tables of hpgb_math.h (72 + 6.4 KB), staged into dynamic shared memory per CTA
+static __device__ const unsigned long long g_hpgb_acos_tab[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS] = HPGB_ACOS_TABLE_INIT;
 static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES] = HPGB_ATANQ_TABLE_INIT;
-#define HPGB_P2A_TAB_DOUBLES (HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES + HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES)
+// one big CTA per SM: the 78 KB of tables are staged once per SM and 24 warps share them
+#ifndef HPGB_P2A_BLOCK
+#define HPGB_P2A_BLOCK 768
+#endif
+#define HPGB_P2A_TAB_DOUBLES (HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES)
 
 template <bool NEST, bool POW2, bool LONLAT, bool DEGREES, bool VAR>
 struct OpPix2Ang {
@@ -40,17 +44,20 @@ struct OpPix2Ang {
     hpgb_geom g;
     hpgb_rk c;  // POW2 && !VAR: constants of the branch-free pix2loc
     typedef longlong2 In2;
-    typedef const double *Ctx;  // acos table; the atan table follows it
+    typedef const uint64_t *Ctx;  // acos table (64-bit words); the atan table (doubles) follows it
     static constexpr int DYN_SMEM = HPGB_P2A_TAB_DOUBLES * 8;
     static constexpr bool FAST = POW2 && !VAR;
+    static __device__ __forceinline__ const double *atanq(Ctx T) {
+        return reinterpret_cast<const double *>(T + HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS);
+    }
 
     __device__ __forceinline__ Ctx prologue() const {
-        extern __shared__ __align__(16) double hpgb_p2a_tabs[];
-        for (int i = threadIdx.x; i < HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES; i += HPGB_BLOCK) hpgb_p2a_tabs[i] = g_hpgb_acos_tab[i];
-        for (int i = threadIdx.x; i < HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES; i += HPGB_BLOCK)
-            hpgb_p2a_tabs[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES + i] = g_hpgb_atanq_tab[i];
+        extern __shared__ __align__(16) unsigned long long hpgb_p2a_tabs[];
+        for (int i = threadIdx.x; i < HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS; i += blockDim.x) hpgb_p2a_tabs[i] = g_hpgb_acos_tab[i];
+        for (int i = threadIdx.x; i < HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES; i += blockDim.x)
+            hpgb_p2a_tabs[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + i] = (unsigned long long)__double_as_longlong(g_hpgb_atanq_tab[i]);
         __syncthreads();
-        return hpgb_p2a_tabs;
+        return reinterpret_cast<const uint64_t *>(hpgb_p2a_tabs);
     }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
     // general path (any nside, per-element nside): the reference's branches as they are
@@ -61,7 +68,7 @@ struct OpPix2Ang {
             va = vb = 0.0;
             return;
         }
-        hpgb_pix2ang<NEST, POW2, LONLAT, DEGREES>(gg, T, T + HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES, p, va, vb);
+        hpgb_pix2ang<NEST, POW2, LONLAT, DEGREES>(gg, T, atanq(T), p, va, vb);
     }
     // power-of-two nside: straight-line hot part for every pixel, then the rare cases (out of range,
     // |z| > 0.99, isqrt quirk) patched per element
@@ -77,9 +84,9 @@ struct OpPix2Ang {
     }
     __device__ __forceinline__ void fix(Hot &h, int64_t p, int64_t i, Ctx T, hpgb_bad_t &bad) const {
         if (h.code == 1) {
-            hpgb_pix2ang_polar<LONLAT, DEGREES>(T + HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES, h.z, h.phi, h.tcap, h.va, h.vb);
+            hpgb_pix2ang_polar<LONLAT, DEGREES>(atanq(T), h.z, h.phi, h.tcap, h.va, h.vb);
         } else if (h.code == 2) {
-            hpgb_pix2ang<NEST, POW2, LONLAT, DEGREES>(g, T, T + HPGB_ACOS_ROWS * HPGB_ACOS_ROW_DOUBLES, p, h.va, h.vb);
+            hpgb_pix2ang<NEST, POW2, LONLAT, DEGREES>(g, T, atanq(T), p, h.va, h.vb);
         } else if (h.code == 3) {
             bad.flag(base + i);
             h.va = h.vb = 0.0;
@@ -106,11 +113,19 @@ struct OpPix2Ang {
                                          hpgb_bad_t &bad) const {
         if (FAST) {
             Hot h0 = hot(v0.x, T), h1 = hot(v0.y, T), h2 = hot(v1.x, T), h3 = hot(v1.y, T);
-            if (h0.code | h1.code | h2.code | h3.code) {
-                fix(h0, v0.x, i0, T, bad);
-                fix(h1, v0.y, i0 + 1, T, bad);
-                fix(h2, v1.x, i1, T, bad);
-                fix(h3, v1.y, i1 + 1, T, bad);
+            // rare cases (1 % of the pixels are polar): one pixel per lane per pass, so a warp pays the
+            // long patch once per pass instead of once per pixel slot
+            unsigned pend = (h0.code ? 1u : 0u) | (h1.code ? 2u : 0u) | (h2.code ? 4u : 0u) | (h3.code ? 8u : 0u);
+            while (pend) {
+                const unsigned j = (unsigned)__ffs((int)pend) - 1u;
+                pend &= pend - 1u;
+                Hot h = j == 0u ? h0 : (j == 1u ? h1 : (j == 2u ? h2 : h3));
+                const int64_t p = j == 0u ? v0.x : (j == 1u ? v0.y : (j == 2u ? v1.x : v1.y));
+                fix(h, p, (j < 2u ? i0 : i1) + (j & 1u), T, bad);
+                if (j == 0u) h0.va = h.va, h0.vb = h.vb;
+                if (j == 1u) h1.va = h.va, h1.vb = h.vb;
+                if (j == 2u) h2.va = h.va, h2.vb = h.vb;
+                if (j == 3u) h3.va = h.va, h3.vb = h.vb;
             }
             hpgb_st2(a + i0, h0.va, h1.va);
             hpgb_st2(b + i0, h0.vb, h1.vb);
@@ -148,7 +163,7 @@ int launch_p2a_t(const int64_t *pix, double *a, double *b, int64_t n, int64_t ns
     const bool vec = hpgb_aligned16(pix) && hpgb_aligned16(a) && hpgb_aligned16(b);
     if (NEST || g.order >= 0) {
         OpPix2Ang<NEST, true, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g, hpgb_make_rk(g)};
-        return hpgb_launch_map(op, n, vec, st, s, decltype(op)::DYN_SMEM);
+        return hpgb_launch_map<decltype(op), HPGB_P2A_BLOCK>(op, n, vec, st, s, decltype(op)::DYN_SMEM);
     }
     OpPix2Ang<false, false, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g, hpgb_rk()};
     return hpgb_launch_map(op, n, vec, st, s, decltype(op)::DYN_SMEM);
