@@ -649,6 +649,24 @@ HPGB_HD void hpgb_pix2vec(const hpgb_geom &g, const double *T, int64_t pix, doub
     zz = z;
 }
 
+// pixel_to_vector for nside = 2^k, straight-line (see hpgb_pix2loc_k); false = isqrt quirk, use hpgb_pix2vec
+template <bool NEST>
+HPGB_HD bool hpgb_pix2vec_k(const hpgb_rk &c, const hpgb_geom &g, const double *T, int64_t pix, double &x, double &y,
+                            double &zz) {
+    double z, phi, tcap;
+    bool polar;
+    const bool ok = hpgb_pix2loc_k<NEST>(c, g, pix, z, phi, tcap, polar);
+    // sin(theta): hpgeom/healpix_geom.c:317 (polar, from tmp) or :193 (from z); the argument is never 0
+    // for a pixel centre, so the branch-free square root applies
+    const double sth = hpgb_sqrt_tame(polar ? tcap * (2. - tcap) : (1 - z) * (1 + z));
+    double s, co;
+    hpgb_sincos_cr(T, phi, s, co);
+    x = sth * co;
+    y = sth * s;
+    zz = z;
+    return ok;
+}
+
 // vector -> pixel: hpgeom/healpix_geom.c:161-170 (+ vec3_length, hpgeom/hpgeom_stack.c:396).
 // No validation, as in the reference.  phi = atan2(y, x) is the only libm call.
 template <bool NEST>

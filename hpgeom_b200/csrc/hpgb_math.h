@@ -273,6 +273,26 @@ HPGB_HD double hpgb_w2f(uint32_t w) {  // float bits -> double
 #endif
 }
 
+// sqrt(x) correctly rounded for tame x (normal, far from overflow): rsqrt approximation, two coupled
+// Newton steps, one residual correction (Markstein) -- sqrt.rn.f64 without its special-case branch.
+// Validated against sqrt() on 3e10 operands of the domain it is used for (tools/ubench/sqrtcheck.cu).
+HPGB_HD double hpgb_sqrt_tame(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    return fma(fma(-g, g, x), h, g);
+#else
+    return sqrt(x);
+#endif
+}
+
 // acos(z) as hi + lo, |z| <= 0.99.  TA: rows of HPGB_ACOS_ROW_WORDS 64-bit words (see tools/gen_tables.py)
 HPGB_HD void hpgb_acos_tab_dd(const uint64_t *TA, double z, double &hi, double &lo) {
     const double a = fabs(z);

@@ -301,12 +301,13 @@ struct OpPix2Vec {
     const int64_t *nside_v;
     int64_t base;
     hpgb_geom g;
+    hpgb_rk c;  // POW2 && !VAR
     typedef longlong2 In2;
     typedef const double *Ctx;
-    HPGB_DEFAULT_RUN4
-    HPGB_STREAM_IN_I64(pix, 2)
+    static constexpr bool FAST = POW2 && !VAR;
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
+    // general path: the reference's branches as they are
     __device__ __forceinline__ void conv(const hpgb_geom &gg, int64_t p, int64_t i, Ctx T, hpgb_bad_t &bad, double &vx,
                                          double &vy, double &vz) const {
         if (!hpgb_pixel_ok(gg, p)) {
@@ -316,13 +317,54 @@ struct OpPix2Vec {
         }
         hpgb_pix2vec<NEST, POW2>(gg, T, p, vx, vy, vz);
     }
+    // power-of-two nside: straight-line hot part, rare cases (out of range, isqrt quirk) patched afterwards
+    struct Hot {
+        double vx, vy, vz;
+        bool rare;
+    };
+    __device__ __forceinline__ Hot hot(int64_t p, Ctx T) const {
+        Hot h;
+        h.rare = !hpgb_pix2vec_k<NEST>(c, g, T, p, h.vx, h.vy, h.vz);
+        h.rare |= !hpgb_pixel_ok(g, p);
+        return h;
+    }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &bad) const {
         double x0, y0, z0, x1, y1, z1;
-        conv(g, v.x, i, T, bad, x0, y0, z0);
-        conv(g, v.y, i + 1, T, bad, x1, y1, z1);
+        if (FAST) {
+            Hot h0 = hot(v.x, T), h1 = hot(v.y, T);
+            if (h0.rare | h1.rare) {
+                if (h0.rare) conv(g, v.x, i, T, bad, h0.vx, h0.vy, h0.vz);
+                if (h1.rare) conv(g, v.y, i + 1, T, bad, h1.vx, h1.vy, h1.vz);
+            }
+            x0 = h0.vx, y0 = h0.vy, z0 = h0.vz, x1 = h1.vx, y1 = h1.vy, z1 = h1.vz;
+        } else {
+            conv(g, v.x, i, T, bad, x0, y0, z0);
+            conv(g, v.y, i + 1, T, bad, x1, y1, z1);
+        }
         hpgb_st2(x + i, x0, x1);
         hpgb_st2(y + i, y0, y1);
         hpgb_st2(z + i, z0, z1);
+    }
+    __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
+                                         hpgb_bad_t &bad) const {
+        if (FAST) {
+            Hot h0 = hot(v0.x, T), h1 = hot(v0.y, T), h2 = hot(v1.x, T), h3 = hot(v1.y, T);
+            if (h0.rare | h1.rare | h2.rare | h3.rare) {
+                if (h0.rare) conv(g, v0.x, i0, T, bad, h0.vx, h0.vy, h0.vz);
+                if (h1.rare) conv(g, v0.y, i0 + 1, T, bad, h1.vx, h1.vy, h1.vz);
+                if (h2.rare) conv(g, v1.x, i1, T, bad, h2.vx, h2.vy, h2.vz);
+                if (h3.rare) conv(g, v1.y, i1 + 1, T, bad, h3.vx, h3.vy, h3.vz);
+            }
+            hpgb_st2(x + i0, h0.vx, h1.vx);
+            hpgb_st2(y + i0, h0.vy, h1.vy);
+            hpgb_st2(z + i0, h0.vz, h1.vz);
+            hpgb_st2(x + i1, h2.vx, h3.vx);
+            hpgb_st2(y + i1, h2.vy, h3.vy);
+            hpgb_st2(z + i1, h2.vz, h3.vz);
+        } else {
+            run2(i0, v0, T, bad);
+            run2(i1, v1, T, bad);
+        }
     }
     __device__ __forceinline__ void run1(int64_t i, const Ctx &T, hpgb_bad_t &bad) const {
         double vx = 0.0, vy = 0.0, vz = 0.0;
@@ -345,10 +387,10 @@ int launch_p2v(const int64_t *pix, double *x, double *y, double *z, int64_t n, i
     if (n == 0) return HPGB_OK;
     if (nside_v) {
         if (nest) {
-            OpPix2Vec<true, true, true> op{pix, x, y, z, nside_v, base, hpgb_geom()};
+            OpPix2Vec<true, true, true> op{pix, x, y, z, nside_v, base, hpgb_geom(), hpgb_rk()};
             return hpgb_launch_map1(op, n, st, s);
         }
-        OpPix2Vec<false, false, true> op{pix, x, y, z, nside_v, base, hpgb_geom()};
+        OpPix2Vec<false, false, true> op{pix, x, y, z, nside_v, base, hpgb_geom(), hpgb_rk()};
         return hpgb_launch_map1(op, n, st, s);
     }
     int c = hpgb_check_nside(nside, nest);
@@ -356,14 +398,14 @@ int launch_p2v(const int64_t *pix, double *x, double *y, double *z, int64_t n, i
     const hpgb_geom g = hpgb_make_geom(nside, nest);
     const bool vec = hpgb_aligned16(pix) && hpgb_aligned16(x) && hpgb_aligned16(y) && hpgb_aligned16(z);
     if (nest) {
-        OpPix2Vec<true, true, false> op{pix, x, y, z, nullptr, base, g};
+        OpPix2Vec<true, true, false> op{pix, x, y, z, nullptr, base, g, hpgb_make_rk(g)};
         return hpgb_launch_map(op, n, vec, st, s);
     }
     if (g.order >= 0) {
-        OpPix2Vec<false, true, false> op{pix, x, y, z, nullptr, base, g};
+        OpPix2Vec<false, true, false> op{pix, x, y, z, nullptr, base, g, hpgb_make_rk(g)};
         return hpgb_launch_map(op, n, vec, st, s);
     }
-    OpPix2Vec<false, false, false> op{pix, x, y, z, nullptr, base, g};
+    OpPix2Vec<false, false, false> op{pix, x, y, z, nullptr, base, g, hpgb_rk()};
     return hpgb_launch_map(op, n, vec, st, s);
 }
 

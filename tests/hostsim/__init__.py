@@ -17,7 +17,7 @@ class HostSim:
         self.lib = ctypes.CDLL(os.path.join(_HERE, "libhostsim.so"))
         for n in ("sim_nest_to_ring", "sim_ring_to_nest", "sim_ring_roundtrip_any", "sim_angle_to_pixel",
                   "sim_pixel_to_angle", "sim_pixel_to_vector", "sim_vector_to_pixel", "sim_neighbors", "sim_interp",
-                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_pixel_to_angle_k"):
+                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_pixel_to_angle_k", "sim_pixel_to_vector_k"):
             getattr(self.lib, n).restype = ctypes.c_int64
         self.last_slow = 0
 
@@ -92,6 +92,16 @@ class HostSim:
             raise ValueError("bad element %d" % (-1 - r))
         self.last_slow = r
         return a, b
+
+    def pixel_to_vector_k(self, nside, pix, nest=True):
+        pix = self._i(pix)
+        x, y, z = np.empty(pix.size), np.empty(pix.size), np.empty(pix.size)
+        r = self.lib.sim_pixel_to_vector_k(ctypes.c_int64(nside), pix.ctypes.data_as(_I), ctypes.c_int64(pix.size), int(nest),
+                                           x.ctypes.data_as(_D), y.ctypes.data_as(_D), z.ctypes.data_as(_D))
+        if r < 0:
+            raise ValueError("bad element %d" % (-1 - r))
+        self.last_slow = r
+        return x, y, z
 
     def pixel_to_vector(self, nside, pix, nest=True):
         pix = self._i(pix)

@@ -248,6 +248,8 @@ def test_pixel_to_angle_branch_free_path(sim, nside):
             a1, b1 = sim.pixel_to_angle_k(nside, pix, nest=nest, **kw)
             assert_bit_equal(a1, a0, "a")
             assert_bit_equal(b1, b0, "b")
+        for got, ref in zip(sim.pixel_to_vector_k(nside, pix, nest=nest), sim.pixel_to_vector(nside, pix, nest=nest)):
+            assert_bit_equal(got, ref, "pixel_to_vector")
 
 
 @pytest.mark.parametrize("nside,nest", CASES)
