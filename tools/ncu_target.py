@@ -41,6 +41,15 @@ for _ in range(reps):
         assert L.hpgb_pixel_to_vector(pix.data_ptr(), a.data_ptr(), b.data_ptr(), c.data_ptr(), n, nside, None, 1, st.data_ptr(), s) == 0
     if which in ("all", "v2p"):
         assert L.hpgb_vector_to_pixel(a.data_ptr(), b.data_ptr(), c.data_ptr(), out.data_ptr(), n, nside, None, 1, st.data_ptr(), s) == 0
+    if which in ("all", "rest"):
+        m = n // 8
+        p4 = pix % (12 * 4096 * 4096 - 1)
+        o8 = out[: m * 8] if out.numel() >= m * 8 else torch.empty(m * 8, dtype=torch.int64, device="cuda")
+        for nest in (1, 0):
+            assert L.hpgb_neighbors(p4.data_ptr(), o8.data_ptr(), m, 4096, None, nest, st.data_ptr(), s) == 0
+            assert L.hpgb_interp_weights(lon.data_ptr(), lat.data_ptr(), o8.data_ptr(), a.data_ptr(), m, 4096, None, nest, 1, 1, st.data_ptr(), s) == 0
+            assert L.hpgb_upgrade_pixels(p4.data_ptr(), o8.data_ptr(), m, 4096, 8192, nest, st.data_ptr(), s) == 0
+        assert L.hpgb_lonlat_to_thetaphi(lon.data_ptr(), lat.data_ptr(), a.data_ptr(), b.data_ptr(), n, 1, st.data_ptr(), s) == 0
 torch.cuda.synchronize()
 assert st[0].item() == -1
 print("ok", n)
