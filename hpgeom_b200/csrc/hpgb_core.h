@@ -23,9 +23,11 @@
 
 #if defined(__CUDACC__)
 #define HPGB_HD __host__ __device__ __forceinline__
+#define HPGB_HDM __host__ __device__ __forceinline__  // member functions
 #define HPGB_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define HPGB_HD static inline
+#define HPGB_HDM inline
 #define HPGB_HD_NOINLINE static
 #endif
 

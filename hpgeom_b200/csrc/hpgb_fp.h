@@ -803,20 +803,41 @@ HPGB_HD int64_t hpgb_ring_above(const hpgb_geom &g, double z) {
     return (z > 0) ? ir : 4 * g.nside - ir - 1;
 }
 
-HPGB_HD void hpgb_ring_info2(const hpgb_geom &g, const double *T, int64_t ring, int64_t &startpix,
-                             int64_t &ringpix, double &theta, bool &shifted) {
+// The arithmetic the interpolation needs beyond + - *: two interchangeable providers.
+//   hpgb_mp_ref : IEEE / and sqrt, double-double acos / atan2 (any nside; the reference-shaped path)
+//   hpgb_mp_tab : the same values from the table-driven acos / atan2 of hpgb_math.h and the
+//                 branch-free division / square root (power-of-two nside kernels)
+struct hpgb_mp_ref {
+    const double *T;
+    HPGB_HDM double acos_(double z) const { return hpgb_acos_cr(T, z); }
+    HPGB_HDM double atan2_(double s, double c) const { return hpgb_atan2_cr(T, s, c); }
+    HPGB_HDM double div_(double a, double b) const { return a / b; }
+    HPGB_HDM double sqrt_(double x) const { return sqrt(x); }
+};
+struct hpgb_mp_tab {
+    const uint64_t *TA;
+    const double *TQ;
+    HPGB_HDM double acos_(double z) const { return hpgb_acos_tab(TA, z); }
+    HPGB_HDM double atan2_(double s, double c) const { return hpgb_atan2_tab(TQ, s, c, HPGB_ATANQ_ROWS); }
+    HPGB_HDM double div_(double a, double b) const { return hpgb_div_tame(a, b); }
+    HPGB_HDM double sqrt_(double x) const { return hpgb_sqrt_tame(x); }
+};
+
+template <class MP>
+HPGB_HD void hpgb_ring_info2(const hpgb_geom &g, const MP &mp, int64_t ring, int64_t &startpix, int64_t &ringpix,
+                             double &theta, bool &shifted) {
     const int64_t ns = g.nside;
     const int64_t nring = (ring > 2 * ns) ? 4 * ns - ring : ring;
     if (nring < ns) {
         const double t = (double)(nring * nring) * g.fact2;
         const double ct = 1 - t;
-        const double st = sqrt(t * (2 - t));
-        theta = hpgb_atan2_cr(T, st, ct);
+        const double st = mp.sqrt_(t * (2 - t));
+        theta = mp.atan2_(st, ct);
         ringpix = 4 * nring;
         shifted = true;
         startpix = 2 * nring * (nring - 1);
     } else {
-        theta = hpgb_acos_cr(T, (double)(2 * ns - nring) * g.fact1);
+        theta = mp.acos_((double)(2 * ns - nring) * g.fact1);
         ringpix = 4 * ns;
         shifted = ((nring - ns) & 1) == 0;
         startpix = g.ncap + (nring - ns) * ringpix;
@@ -828,16 +849,17 @@ HPGB_HD void hpgb_ring_info2(const hpgb_geom &g, const double *T, int64_t ring, 
 }
 
 // one ring: two pixels + phi weights (the twin blocks hpgeom/healpix_geom.c:1619-1636, :1637-1654)
-HPGB_HD void hpgb_ring_pair(const hpgb_geom &g, const double *T, int64_t ring, double phi, int64_t *p, double *w,
+template <class MP>
+HPGB_HD void hpgb_ring_pair(const hpgb_geom &g, const MP &mp, int64_t ring, double phi, int64_t *p, double *w,
                             double &theta) {
     int64_t sp, nr;
     bool shift;
-    hpgb_ring_info2(g, T, ring, sp, nr, theta, shift);
-    const double dphi = HPGB_TWOPI / (double)nr;
+    hpgb_ring_info2(g, mp, ring, sp, nr, theta, shift);
+    const double dphi = mp.div_(HPGB_TWOPI, (double)nr);
     const double hs = shift ? 0.5 : 0.0;
-    const double t = (phi / dphi - hs);
+    const double t = (mp.div_(phi, dphi) - hs);
     int64_t i1 = (t < 0) ? hpgb_d2ll(t) - 1 : hpgb_d2ll(t);
-    const double w1 = (phi - ((double)i1 + hs) * dphi) / dphi;
+    const double w1 = mp.div_(phi - ((double)i1 + hs) * dphi, dphi);
     int64_t i2 = i1 + 1;
     if (i1 < 0) i1 += nr;
     if (i2 >= nr) i2 -= nr;
@@ -847,18 +869,19 @@ HPGB_HD void hpgb_ring_pair(const hpgb_geom &g, const double *T, int64_t ring, d
     w[1] = w1;
 }
 
-template <bool NEST, bool POW2>
-HPGB_HD void hpgb_interpol(const hpgb_geom &g, const double *T, double theta, double phi, int64_t *p, double *w) {
-    const double z = hpgb_cos_cr(T, theta);
-    const int64_t ir1 = hpgb_ring_above(g, z);
+// everything after the choice of the ring pair (hpgeom/healpix_geom.c:1612-1690); ir1 = ring above the point.
+// rk: constants of the power-of-two RING -> NEST core (POW2 only)
+template <bool NEST, bool POW2, class MP>
+HPGB_HD void hpgb_interpol_rings(const hpgb_geom &g, const hpgb_rk &rk, const MP &mp, double theta, double phi,
+                                 int64_t ir1, int64_t *p, double *w) {
     const int64_t ir2 = ir1 + 1;
     double th1 = 0, th2 = 0;
     p[0] = p[1] = p[2] = p[3] = 0;
     w[0] = w[1] = w[2] = w[3] = 0;
-    if (ir1 > 0) hpgb_ring_pair(g, T, ir1, phi, p, w, th1);
-    if (ir2 < 4 * g.nside) hpgb_ring_pair(g, T, ir2, phi, p + 2, w + 2, th2);
+    if (ir1 > 0) hpgb_ring_pair(g, mp, ir1, phi, p, w, th1);
+    if (ir2 < 4 * g.nside) hpgb_ring_pair(g, mp, ir2, phi, p + 2, w + 2, th2);
     if (ir1 == 0) {
-        const double wt = theta / th2;
+        const double wt = mp.div_(theta, th2);
         w[2] *= wt;
         w[3] *= wt;
         const double fac = (1 - wt) * 0.25;
@@ -869,7 +892,7 @@ HPGB_HD void hpgb_interpol(const hpgb_geom &g, const double *T, double theta, do
         p[0] = (p[2] + 2) & 3;
         p[1] = (p[3] + 2) & 3;
     } else if (ir2 == 4 * g.nside) {
-        const double wt = (theta - th1) / (HPGB_PI - th1);
+        const double wt = mp.div_(theta - th1, HPGB_PI - th1);
         w[0] *= (1 - wt);
         w[1] *= (1 - wt);
         const double fac = wt * 0.25;
@@ -880,7 +903,7 @@ HPGB_HD void hpgb_interpol(const hpgb_geom &g, const double *T, double theta, do
         p[2] = ((p[0] + 2) & 3) + g.npix - 4;
         p[3] = ((p[1] + 2) & 3) + g.npix - 4;
     } else {
-        const double wt = (theta - th1) / (th2 - th1);
+        const double wt = mp.div_(theta - th1, th2 - th1);
         w[0] *= (1 - wt);
         w[1] *= (1 - wt);
         w[2] *= wt;
@@ -888,8 +911,40 @@ HPGB_HD void hpgb_interpol(const hpgb_geom &g, const double *T, double theta, do
     }
     if (NEST) {
 #pragma unroll
-        for (int m = 0; m < 4; m++) p[m] = hpgb_ring2nest(g, p[m]);
+        for (int m = 0; m < 4; m++) p[m] = POW2 ? hpgb_ring2nest_k<false>(rk, g, p[m]) : hpgb_ring2nest(g, p[m]);
     }
+}
+
+// reference-shaped: z = cos(theta) (correctly rounded), ring_above(z)
+template <bool NEST, bool POW2>
+HPGB_HD void hpgb_interpol(const hpgb_geom &g, const double *T, double theta, double phi, int64_t *p, double *w) {
+    const double z = hpgb_cos_cr(T, theta);
+    const hpgb_mp_ref mp{T};
+    hpgb_interpol_rings<NEST, false>(g, hpgb_rk(), mp, theta, phi, hpgb_ring_above(g, z), p, w);
+}
+
+// Fast choice of the ring pair for nside = 2^k: ring_above(cos theta) is a step function of theta, so
+// away from its steps a cheap cosine decides it (the polynomial sine of the angle_to_pixel fast path:
+// z = sin(pi/2 - theta) in the belt, nside sqrt(3 (1 - |z|)) = nside sqrt(6) sin(colat/2) in the caps).
+// Returns false -- the caller then runs hpgb_interpol -- when the value is within nside * 2^-44 of a
+// step, near the zone transition, or within 0.0102 rad of a pole (where the reference's own cos /
+// 1 - |z| is noisy, and where the two pole special cases live).
+HPGB_HD bool hpgb_ring_above_fast(const hpgb_geom &g, const hpgb_a2p_fast &f, double theta, int64_t &ir1) {
+    const double lat = (HPGB_PIO2_1 - theta) + HPGB_PIO2_2;
+    const bool north = theta < HPGB_PIO2_1;
+    const double colat = north ? theta : (HPGB_PI_1 - theta) + HPGB_PI_2;  // from the nearest pole
+    const double al = fabs(lat);
+    const bool eq = al <= f.asin23;
+    bool ok = (colat > 0.0102) & !(fabs(al - f.asin23) < 1e-11);
+    const double s = hpgb_sin_poly(f, eq ? lat : 0.5 * colat);
+    const double dns = (double)g.nside;
+    const double v = eq ? dns * (2.0 - 1.5 * s) : dns * (2.4494897427831780981972840747059 * s);
+    const double fl = floor(v);
+    const double fr = v - fl, m = dns * 5.6843418860808015e-14;  // 2^-44
+    ok &= (fr > m) & (fr < 1.0 - m);
+    const int64_t iv = (int64_t)fl;
+    ir1 = (eq | north) ? iv : 4 * g.nside - iv - 1;
+    return ok;
 }
 
 // lonlat_to_thetaphi with numpy's formulas (hpgeom/hpgeom.py:75-88): Python-style modulo,

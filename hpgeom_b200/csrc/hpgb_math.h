@@ -212,7 +212,8 @@ HPGB_HD double hpgb_atan2_any(const double *T, double y, double x) {
 //   relative width 2^-7 in u = 1 - |z| beyond, so |r| / (1 - |zc|) <= 2^-8 everywhere and ten terms
 //   reach 2^-70; a_0, a_1 are double-doubles, a_1 r is an exact two-product, the rest is Horner.
 //   z < 0 : pi - acos(|z|), with pi as a double-double.
-//   atan2(s, c), 0 <= s <= 0.156 c (the polar caps, |z| > 0.99): q = s/c as quotient + exact
+//   atan2(s, c), 0 <= s <= 1.13 |c| (polar-cap ring colatitudes; the first 80 rows, s <= 0.156 |c|, serve
+//   |z| > 0.99): q = s/c as quotient + exact
 //   remainder correction, then the same scheme around q = k/512 with eight terms.
 // TA / TQ point at the tables (HPGB_ACOS_TABLE_INIT / HPGB_ATANQ_TABLE_INIT), staged in shared memory.
 // ---------------------------------------------------------------------------------------------
@@ -339,7 +340,7 @@ HPGB_HD double hpgb_acos_tab(const uint64_t *TA, double z) {
 }
 
 // atan2(s, c) as hi + lo for 0 <= s <= 0.156 |c| (result pi - atan2(s, |c|) when c < 0)
-HPGB_HD void hpgb_atan2_tab_dd(const double *TQ, double s, double c, double &hi, double &lo) {
+HPGB_HD void hpgb_atan2_tab_dd(const double *TQ, double s, double c, double &hi, double &lo, int nrows = HPGB_ATANQ_ROWS_POLAR) {
     const double ca = fabs(c);
 #if defined(__CUDA_ARCH__)
     double ic;
@@ -352,7 +353,7 @@ HPGB_HD void hpgb_atan2_tab_dd(const double *TQ, double s, double c, double &hi,
 #endif
     const double ql = fma(-qh, ca, s) * ic;  // exact remainder, rough reciprocal: q = qh + ql to ~2^-75
     int idx = (int)rint(qh * 512.0);
-    idx = idx < 0 ? 0 : (idx > HPGB_ATANQ_ROWS - 1 ? HPGB_ATANQ_ROWS - 1 : idx);
+    idx = idx < 0 ? 0 : (idx > nrows - 1 ? nrows - 1 : idx);
     const double *row = TQ + idx * HPGB_ATANQ_ROW_DOUBLES;
     const double r = qh - (double)idx * 0.001953125;  // exact
     const double rt = r + ql;
@@ -372,9 +373,9 @@ HPGB_HD void hpgb_atan2_tab_dd(const double *TQ, double s, double c, double &hi,
     hi = neg ? nh : h;
     lo = neg ? ne + (HPGB_PI_2 - l) : l;
 }
-HPGB_HD double hpgb_atan2_tab(const double *TQ, double s, double c) {
+HPGB_HD double hpgb_atan2_tab(const double *TQ, double s, double c, int nrows = HPGB_ATANQ_ROWS_POLAR) {
     double hi, lo;
-    hpgb_atan2_tab_dd(TQ, s, c, hi, lo);
+    hpgb_atan2_tab_dd(TQ, s, c, hi, lo, nrows);
     return hi + lo;
 }
 

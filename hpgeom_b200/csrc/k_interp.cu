@@ -26,6 +26,15 @@ __device__ __forceinline__ bool var_geom(const int64_t *nside_v, int64_t i, int 
 // -------------------------------------------------------------------------------------------
 // get_interpolation_weights   (hpgeom/hpgeom.c:3491-3523)   16 B in + 64 B out per point
 // -------------------------------------------------------------------------------------------
+// acos / atan Taylor tables of hpgb_math.h (72 + 46 KB), staged into dynamic shared memory: ONE
+// 512-thread CTA per SM shares them.  The sin/cos table of the reference-shaped fallback is static.
+static __device__ const unsigned long long g_hpgb_acos_tab[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS] = HPGB_ACOS_TABLE_INIT;
+static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES] = HPGB_ATANQ_TABLE_INIT;
+#define HPGB_INTERP_TAB_WORDS (HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES)
+#ifndef HPGB_INTERP_BLOCK
+#define HPGB_INTERP_BLOCK 512
+#endif
+
 template <bool NEST, bool POW2, bool LONLAT, bool DEGREES, bool VAR>
 struct OpInterp {
     const double *a, *b;
@@ -34,32 +43,65 @@ struct OpInterp {
     const int64_t *nside_v;
     int64_t base;
     hpgb_geom g;
+    hpgb_rk rk;       // FAST: RING -> NEST constants
+    hpgb_a2p_fast f;  // FAST: polynomial of the cheap ring choice
     struct In2 {
         double2 a, b;
     };
-    typedef const double *Ctx;
+    struct Ctx {
+        const double *T;     // sin/cos rows (reference-shaped path)
+        const uint64_t *TA;  // acos rows
+        const double *TQ;    // atan rows
+    };
+    static constexpr bool FAST = POW2 && !VAR;
+    static constexpr int DYN_SMEM = FAST ? HPGB_INTERP_TAB_WORDS * 8 : 0;
     HPGB_DEFAULT_RUN4
-    HPGB_STREAM_IN_F64x2(a, b, 2)
-    __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
+    __device__ __forceinline__ Ctx prologue() const {
+        Ctx c{nullptr, nullptr, nullptr};
+        if (FAST) {
+            extern __shared__ __align__(16) unsigned long long hpgb_interp_tabs[];
+            for (int i = threadIdx.x; i < HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS; i += blockDim.x) hpgb_interp_tabs[i] = g_hpgb_acos_tab[i];
+            for (int i = threadIdx.x; i < HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES; i += blockDim.x)
+                hpgb_interp_tabs[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + i] = (unsigned long long)__double_as_longlong(g_hpgb_atanq_tab[i]);
+            c.TA = reinterpret_cast<const uint64_t *>(hpgb_interp_tabs);
+            c.TQ = reinterpret_cast<const double *>(hpgb_interp_tabs + HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS);
+        }
+        __shared__ double sT[4 * HPGB_SINCOS_ROWS];
+        for (int i = threadIdx.x; i < 4 * HPGB_SINCOS_ROWS; i += blockDim.x) sT[i] = g_hpgb_sincos[i];
+        __syncthreads();
+        c.T = sT;
+        return c;
+    }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(a + i), hpgb_ld2(b + i)}; }
-    __device__ __forceinline__ void row(const hpgb_geom &gg, double va, double vb, int64_t i, Ctx T, hpgb_bad_t &bad) const {
+    static __device__ __noinline__ void slow(const hpgb_geom &gg, const double *T, double theta, double phi, int64_t *p,
+                                             double *w) {
+        hpgb_interpol<NEST, POW2>(gg, T, theta, phi, p, w);
+    }
+    __device__ __forceinline__ void row(const hpgb_geom &gg, double va, double vb, int64_t i, const Ctx &c, hpgb_bad_t &bad) const {
         int64_t p[4] = {-1, -1, -1, -1};
         double w[4] = {0.0, 0.0, 0.0, 0.0};
         double theta, phi;
-        if (!hpgb_angles_exact<LONLAT, DEGREES>(va, vb, theta, phi))
+        if (!hpgb_angles_exact<LONLAT, DEGREES>(va, vb, theta, phi)) {
             bad.flag(base + i);
-        else
-            hpgb_interpol<NEST, POW2>(gg, T, theta, phi, p, w);
+        } else {
+            int64_t ir1;
+            if (FAST && hpgb_ring_above_fast(gg, f, theta, ir1)) {
+                const hpgb_mp_tab mp{c.TA, c.TQ};
+                hpgb_interpol_rings<NEST, true>(gg, rk, mp, theta, phi, ir1, p, w);
+            } else {
+                slow(gg, c.T, theta, phi, p, w);
+            }
+        }
         hpgb_st2(pix + 4 * i, p[0], p[1]);
         hpgb_st2(pix + 4 * i + 2, p[2], p[3]);
         hpgb_st2(wgt + 4 * i, w[0], w[1]);
         hpgb_st2(wgt + 4 * i + 2, w[2], w[3]);
     }
-    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &bad) const {
-        row(g, v.a.x, v.b.x, i, T, bad);
-        row(g, v.a.y, v.b.y, i + 1, T, bad);
+    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &c, hpgb_bad_t &bad) const {
+        row(g, v.a.x, v.b.x, i, c, bad);
+        row(g, v.a.y, v.b.y, i + 1, c, bad);
     }
-    __device__ __forceinline__ void run1(int64_t i, const Ctx &T, hpgb_bad_t &bad) const {
+    __device__ __forceinline__ void run1(int64_t i, const Ctx &c, hpgb_bad_t &bad) const {
         hpgb_geom gg = g;
         if (VAR && !var_geom(nside_v, i, NEST, gg)) {
             bad.flag(base + i);
@@ -69,7 +111,7 @@ struct OpInterp {
             }
             return;
         }
-        row(gg, hpgb_ld1(a + i), hpgb_ld1(b + i), i, T, bad);
+        row(gg, hpgb_ld1(a + i), hpgb_ld1(b + i), i, c, bad);
     }
 };
 
@@ -77,16 +119,16 @@ template <bool NEST, bool LONLAT, bool DEGREES>
 int launch_interp_t(const double *a, const double *b, int64_t *pix, double *wgt, int64_t n, int64_t nside,
                     const int64_t *nside_v, int64_t base, hpgb_status_t *st, cudaStream_t s) {
     if (nside_v) {
-        OpInterp<NEST, NEST, LONLAT, DEGREES, true> op{a, b, pix, wgt, nside_v, base, hpgb_geom()};
+        OpInterp<NEST, NEST, LONLAT, DEGREES, true> op{a, b, pix, wgt, nside_v, base, hpgb_geom(), hpgb_rk(), hpgb_a2p_fast()};
         return hpgb_launch_map1(op, n, st, s);
     }
     const hpgb_geom g = hpgb_make_geom(nside, NEST);
     const bool vec = hpgb_aligned16(a) && hpgb_aligned16(b);
     if (NEST || g.order >= 0) {
-        OpInterp<NEST, true, LONLAT, DEGREES, false> op{a, b, pix, wgt, nullptr, base, g};
-        return hpgb_launch_map(op, n, vec, st, s);
+        OpInterp<NEST, true, LONLAT, DEGREES, false> op{a, b, pix, wgt, nullptr, base, g, hpgb_make_rk(g), hpgb_make_a2p_fast<false, false>(g)};
+        return hpgb_launch_map<decltype(op), HPGB_INTERP_BLOCK>(op, n, vec, st, s, decltype(op)::DYN_SMEM);
     }
-    OpInterp<false, false, LONLAT, DEGREES, false> op{a, b, pix, wgt, nullptr, base, g};
+    OpInterp<false, false, LONLAT, DEGREES, false> op{a, b, pix, wgt, nullptr, base, g, hpgb_rk(), hpgb_a2p_fast()};
     return hpgb_launch_map(op, n, vec, st, s);
 }
 

@@ -17,7 +17,7 @@ class HostSim:
         self.lib = ctypes.CDLL(os.path.join(_HERE, "libhostsim.so"))
         for n in ("sim_nest_to_ring", "sim_ring_to_nest", "sim_ring_roundtrip_any", "sim_angle_to_pixel",
                   "sim_pixel_to_angle", "sim_pixel_to_vector", "sim_vector_to_pixel", "sim_neighbors", "sim_interp",
-                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_pixel_to_angle_k", "sim_pixel_to_vector_k"):
+                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_pixel_to_angle_k", "sim_pixel_to_vector_k", "sim_interp_k"):
             getattr(self.lib, n).restype = ctypes.c_int64
         self.last_slow = 0
 
@@ -133,6 +133,18 @@ class HostSim:
         self._chk(self.lib.sim_interp(ctypes.c_int64(nside), a.ctypes.data_as(_D), b.ctypes.data_as(_D),
                                       ctypes.c_int64(a.size), int(nest), int(lonlat), int(degrees),
                                       p.ctypes.data_as(_I), w.ctypes.data_as(_D)))
+        return p, w
+
+    def get_interpolation_weights_k(self, nside, a, b, nest=True, lonlat=True, degrees=True, exact_only=False):
+        """Power-of-two kernel path (fast ring choice + tables); self.last_slow = points that fell back."""
+        a, b = self._f(a), self._f(b)
+        p = np.empty((a.size, 4), dtype=np.int64)
+        w = np.empty((a.size, 4), dtype=np.float64)
+        ns = ctypes.c_int64(0)
+        self._chk(self.lib.sim_interp_k(ctypes.c_int64(nside), a.ctypes.data_as(_D), b.ctypes.data_as(_D),
+                                        ctypes.c_int64(a.size), int(nest), int(lonlat), int(degrees), int(exact_only),
+                                        p.ctypes.data_as(_I), w.ctypes.data_as(_D), ctypes.byref(ns)))
+        self.last_slow = ns.value
         return p, w
 
     def lonlat_to_thetaphi(self, lon, lat, degrees=True):

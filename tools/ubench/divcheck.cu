@@ -39,9 +39,15 @@ __global__ void k(unsigned long long *bad, unsigned long long *n, int iters, uin
         const double t3 = (double)(uint32_t)(r1 % (uint64_t)(8.0 * b));
         const double a3 = 0.5 * 1.570796326794896619231321691639751442099 * t3;
         if (div_fast(a3, b) != a3 / b) nb++;
+        // generic tame operands (interpolation weights): random mantissas, exponents within +-40
+        const uint64_t r3 = rng(s), r4 = rng(s);
+        const double ga = __longlong_as_double((long long)(((uint64_t)(1023 - 40 + (int)(r3 % 81)) << 52) | (r3 >> 12)));
+        const double gb = __longlong_as_double((long long)(((uint64_t)(1023 - 40 + (int)(r4 % 81)) << 52) | (r4 >> 12)));
+        if (div_fast(ga, gb) != ga / gb) nb++;
+        if (div_fast(-ga, gb) != -ga / gb) nb++;
     }
     atomicAdd(bad, nb);
-    atomicAdd(n, 3ull * iters);
+    atomicAdd(n, 5ull * iters);
 }
 
 int main() {
