@@ -848,10 +848,11 @@ HPGB_HD void hpgb_ring_info2(const hpgb_geom &g, const MP &mp, int64_t ring, int
     }
 }
 
-// one ring: two pixels + phi weights (the twin blocks hpgeom/healpix_geom.c:1619-1636, :1637-1654)
-template <class MP>
-HPGB_HD void hpgb_ring_pair(const hpgb_geom &g, const MP &mp, int64_t ring, double phi, int64_t *p, double *w,
-                            double &theta) {
+// one ring: two pixels + phi weights (the twin blocks hpgeom/healpix_geom.c:1619-1636, :1637-1654).
+// NESTK: write NEST pixel numbers straight from (ring, in-ring index) -- power-of-two nside only.
+template <bool NESTK, class MP>
+HPGB_HD void hpgb_ring_pair(const hpgb_geom &g, const hpgb_rk &rk, const MP &mp, int64_t ring, double phi, int64_t *p,
+                            double *w, double &theta) {
     int64_t sp, nr;
     bool shift;
     hpgb_ring_info2(g, mp, ring, sp, nr, theta, shift);
@@ -863,8 +864,13 @@ HPGB_HD void hpgb_ring_pair(const hpgb_geom &g, const MP &mp, int64_t ring, doub
     int64_t i2 = i1 + 1;
     if (i1 < 0) i1 += nr;
     if (i2 >= nr) i2 -= nr;
-    p[0] = sp + i1;
-    p[1] = sp + i2;
+    if (NESTK) {
+        p[0] = hpgb_ringidx2nest_k(rk, (uint32_t)ring, (uint32_t)i1);
+        p[1] = hpgb_ringidx2nest_k(rk, (uint32_t)ring, (uint32_t)i2);
+    } else {
+        p[0] = sp + i1;
+        p[1] = sp + i2;
+    }
     w[0] = 1 - w1;
     w[1] = w1;
 }
@@ -878,8 +884,18 @@ HPGB_HD void hpgb_interpol_rings(const hpgb_geom &g, const hpgb_rk &rk, const MP
     double th1 = 0, th2 = 0;
     p[0] = p[1] = p[2] = p[3] = 0;
     w[0] = w[1] = w[2] = w[3] = 0;
-    if (ir1 > 0) hpgb_ring_pair(g, mp, ir1, phi, p, w, th1);
-    if (ir2 < 4 * g.nside) hpgb_ring_pair(g, mp, ir2, phi, p + 2, w + 2, th2);
+    if (NEST && POW2 && ir1 > 0 && ir2 < 4 * g.nside) {  // the common case: NEST numbers straight from (ring, index)
+        hpgb_ring_pair<true>(g, rk, mp, ir1, phi, p, w, th1);
+        hpgb_ring_pair<true>(g, rk, mp, ir2, phi, p + 2, w + 2, th2);
+        const double wt = mp.div_(theta - th1, th2 - th1);
+        w[0] *= (1 - wt);
+        w[1] *= (1 - wt);
+        w[2] *= wt;
+        w[3] *= wt;
+        return;
+    }
+    if (ir1 > 0) hpgb_ring_pair<false>(g, rk, mp, ir1, phi, p, w, th1);
+    if (ir2 < 4 * g.nside) hpgb_ring_pair<false>(g, rk, mp, ir2, phi, p + 2, w + 2, th2);
     if (ir1 == 0) {
         const double wt = mp.div_(theta, th2);
         w[2] *= wt;

@@ -229,6 +229,35 @@ HPGB_HD int64_t hpgb_xyf2nest_k(const hpgb_rk &c, uint32_t ix, uint32_t iy, uint
     return (int64_t)((((uint64_t)hi << 32) | lo) + ((uint64_t)face << c.k2));
 }
 
+// (ring number 1..4 nside-1, 0-based in-ring index counted eastward) -> NEST pixel: ring2xyf without
+// the isqrt, for callers that already know the ring (interpolation): caps fc = q div nr (special_div),
+// belt the edge-line coordinates.  Branch-free.
+HPGB_HD int64_t hpgb_ringidx2nest_k(const hpgb_rk &c, uint32_t ring, uint32_t q) {
+    const bool south = ring > c.ns2;
+    const uint32_t nring = south ? c.ns4 - ring : ring;
+    const bool cap = nring < c.ns;
+    // caps
+    const uint32_t nr = cap ? nring : c.ns;
+    uint32_t r = q;
+    const uint32_t t1 = (r >= 2u * nr) ? 1u : 0u;
+    r -= t1 ? 2u * nr : 0u;
+    const uint32_t t2 = (r >= nr) ? 1u : 0u;
+    r -= t2 ? nr : 0u;
+    const uint32_t face_c = 2u * t1 + t2 + (south ? 8u : 0u);
+    const uint32_t ix_c = south ? r : c.ns - nr + r;
+    const uint32_t iy_c = south ? nr - 1u - r : c.nsm1 - r;
+    // belt
+    const uint32_t tmp = ring - c.ns;
+    const uint32_t jp = q + (tmp >> 1);
+    const uint32_t jm = jp + c.ns - tmp;
+    const uint32_t ifp = jp >> c.k, ifm = jm >> c.k;
+    const uint32_t face_b = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
+    const uint32_t ix = hpgb_sel(cap, ix_c, jm & c.nsm1);
+    const uint32_t iy = hpgb_sel(cap, iy_c, ~jp & c.nsm1);
+    const uint32_t face = hpgb_sel(cap, face_c, face_b);
+    return hpgb_xyf2nest_k<false>(c, ix, iy, face);
+}
+
 // RING pixel (must be < npix) -> NEST pixel.  HI: order >= 16.
 template <bool HI>
 HPGB_HD int64_t hpgb_ring2nest_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix) {

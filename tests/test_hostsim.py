@@ -278,6 +278,38 @@ def test_interp_golden(sim, nside, nest):
     assert np.abs(w - ref).max() <= 8 * np.spacing(np.pi) * nside
 
 
+@pytest.mark.parametrize("nside", [2 ** 29, 4096, 8, 1])
+def test_interp_fast_path(sim, oracle_port, nside):
+    """get_interpolation_weights the way the power-of-two kernels do it (cheap ring choice with guard,
+    table-driven ring colatitudes, branch-free division, NEST numbers straight from (ring, index))
+    against the oracle: pixels bit-exact; weights bit-exact except where a last-bit difference of a
+    ring colatitude (ours or glibc's, both ~1e-4..1e-3 of the calls) is amplified by the
+    theta-weight's cancellation -- bounded here in absolute terms."""
+    rng = np.random.default_rng(nside + 23)
+    n = 60_000
+    k = n // 6
+    lon = rng.uniform(0, 360, n)
+    lat = np.degrees(np.arcsin(rng.uniform(-1, 1, n)))
+    lat[:k] = np.sign(rng.uniform(-1, 1, k)) * (90 - 10 ** rng.uniform(-9, 1, k))
+    lat[k:2 * k] = np.sign(rng.uniform(-1, 1, k)) * (41.810314895778596 + rng.normal(0, 1, k) * 10 ** rng.uniform(-12, 0, k))
+    plon, plat = oracle_port.pixel_to_angle(nside, rng.integers(0, 12 * nside * nside, k), nest=False)
+    lat[2 * k:3 * k] = plat * (1 + rng.integers(-3, 4, k) * 2.0 ** -52)  # points sitting on ring colatitudes
+    lat = np.clip(lat, -90, 90)
+    for nest in (True, False):
+        p1, w1 = sim.get_interpolation_weights_k(nside, lon, lat, nest=nest)
+        p0, w0 = oracle_port.get_interpolation_weights(nside, lon, lat, nest=nest)
+        # points placed ON a ring colatitude: ring_above(cos theta) flips with the last bit of cos, and glibc's
+        # cos is mis-rounded for ~1.4e-3 of arguments -- those rows (and only those) may pick the other ring pair
+        flipped = (p1 != p0).any(axis=1)
+        assert flipped.mean() <= 1e-3
+        assert not flipped[: 2 * k].any() and not flipped[3 * k:].any()
+        same = ~flipped
+        assert np.mean((w1[same] != w0[same]).any(axis=1)) <= 5e-3
+        assert np.abs(w1[same] - w0[same]).max() <= 4 * np.spacing(np.pi) * nside  # one ulp of a ring theta / ring spacing
+        pe, we = sim.get_interpolation_weights_k(nside, lon, lat, nest=nest, exact_only=True)
+        assert_bit_equal(p1, pe, "fast vs reference-shaped pixels")
+
+
 def test_lonlat_golden(sim):
     g = load_golden("lonlat")
     th, ph = sim.lonlat_to_thetaphi(g["lon"], g["lat"])
