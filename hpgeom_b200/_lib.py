@@ -51,6 +51,11 @@ _SIGS = {
     "hpgb_host_upgrade_pixels": [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, ctypes.POINTER(c_i64)],
     "hpgb_lonlat_to_thetaphi": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp],
     "hpgb_host_lonlat_to_thetaphi": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, ctypes.POINTER(c_i64)],
+    "hpgb_boundaries": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp],
+    "hpgb_host_boundaries": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int,
+                             ctypes.POINTER(c_i64)],
+    "hpgb_max_pixel_radius": [c_vp, c_vp, c_i64, c_int, c_vp, c_vp],
+    "hpgb_host_max_pixel_radius": [c_vp, c_vp, c_i64, c_int, c_int, ctypes.POINTER(c_i64)],
     "hpgb_explain_nside": [c_i64, c_int, ctypes.c_char_p, c_int],
     "hpgb_explain_angle": [c_i64, c_int, c_dbl, c_dbl, c_int, c_int, ctypes.c_char_p, c_int],
     "hpgb_explain_pixel": [c_i64, c_int, c_i64, ctypes.c_char_p, c_int],

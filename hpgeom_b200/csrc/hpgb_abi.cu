@@ -60,6 +60,15 @@ int hpgb_lonlat_to_thetaphi(const double *d_lon, const double *d_lat, double *d_
     return launch_lonlat(d_lon, d_lat, d_theta, d_phi, n, degrees, 0, d_status, S(stream));
 }
 
+int hpgb_boundaries(const int64_t *d_pix, double *d_a, double *d_b, int64_t n, int64_t nside, const int64_t *d_nside_v,
+                    int64_t step, int nest, int lonlat, int degrees, hpgb_status_t *d_status, void *stream) {
+    return launch_boundaries(d_pix, d_a, d_b, n, nside, d_nside_v, step, nest, lonlat, degrees, 0, d_status, S(stream));
+}
+int hpgb_max_pixel_radius(const int64_t *d_nside, double *d_radius, int64_t n, int degrees, hpgb_status_t *d_status,
+                          void *stream) {
+    return launch_max_pixrad(d_nside, d_radius, n, degrees, 0, d_status, S(stream));
+}
+
 // ---- host-pointer entry points: operands in C-argument order, then the optional nside array ----
 #define IN(p, b) {(cc)(p), nullptr, (b)}
 #define OUT(p, b) {nullptr, (char *)(p), (b)}
@@ -127,6 +136,17 @@ int hpgb_host_lonlat_to_thetaphi(const double *lon, const double *lat, double *t
                                  int degrees, int device, int64_t *first_bad) {
     hpgb_pipe_arr arrs[4] = {IN(lon, 8), IN(lat, 8), OUT(theta, 8), OUT(phi, 8)};
     PIPE(arrs, 4, launch_lonlat((const double *)d[0], (const double *)d[1], (double *)d[2], (double *)d[3], cn, degrees, base, st, s));
+}
+int hpgb_host_boundaries(const int64_t *pix, double *a_n4s, double *b_n4s, int64_t n, int64_t nside, const int64_t *nside_v,
+                         int64_t step, int nest, int lonlat, int degrees, int device, int64_t *first_bad) {
+    if (step < 1) return HPGB_E_BAD_ARGUMENT;
+    hpgb_pipe_arr arrs[4] = {IN(pix, 8), OUT(a_n4s, 32 * step), OUT(b_n4s, 32 * step), IN(nside_v, 8)};
+    PIPE(arrs, nside_v ? 4 : 3,
+         launch_boundaries((const int64_t *)d[0], (double *)d[1], (double *)d[2], cn, nside, NSV(3), step, nest, lonlat, degrees, base, st, s));
+}
+int hpgb_host_max_pixel_radius(const int64_t *nside, double *radius, int64_t n, int degrees, int device, int64_t *first_bad) {
+    hpgb_pipe_arr arrs[2] = {IN(nside, 8), OUT(radius, 8)};
+    PIPE(arrs, 2, launch_max_pixrad((const int64_t *)d[0], (double *)d[1], cn, degrees, base, st, s));
 }
 
 }  // extern "C"

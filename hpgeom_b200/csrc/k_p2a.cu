@@ -33,7 +33,7 @@ static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW
 #ifndef HPGB_P2A_BLOCK
 #define HPGB_P2A_BLOCK 768
 #endif
-#define HPGB_P2A_TAB_DOUBLES (HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES)
+#define HPGB_P2A_TAB_DOUBLES (HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + HPGB_ATANQ_ROWS_POLAR * HPGB_ATANQ_ROW_DOUBLES)
 
 template <bool NEST, bool POW2, bool LONLAT, bool DEGREES, bool VAR>
 struct OpPix2Ang {
@@ -54,7 +54,7 @@ struct OpPix2Ang {
     __device__ __forceinline__ Ctx prologue() const {
         extern __shared__ __align__(16) unsigned long long hpgb_p2a_tabs[];
         for (int i = threadIdx.x; i < HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS; i += blockDim.x) hpgb_p2a_tabs[i] = g_hpgb_acos_tab[i];
-        for (int i = threadIdx.x; i < HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES; i += blockDim.x)
+        for (int i = threadIdx.x; i < HPGB_ATANQ_ROWS_POLAR * HPGB_ATANQ_ROW_DOUBLES; i += blockDim.x)
             hpgb_p2a_tabs[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + i] = (unsigned long long)__double_as_longlong(g_hpgb_atanq_tab[i]);
         __syncthreads();
         return reinterpret_cast<const uint64_t *>(hpgb_p2a_tabs);

@@ -19,6 +19,17 @@ from . import _lib
 from ._dispatch import F8, I8, set_default_device  # noqa: F401
 
 __all__ = [
+    'thetaphi_to_lonlat',
+    'npixel_to_nside',
+    'nside_to_pixel_area',
+    'nside_to_resolution',
+    'nside_to_order',
+    'order_to_nside',
+    'angle_to_vector',
+    'vector_to_angle',
+    'reorder',
+    'boundaries',
+    'max_pixel_radius',
     'angle_to_pixel',
     'pixel_to_angle',
     'lonlat_to_thetaphi',
@@ -121,6 +132,44 @@ def neighbors(nside, pix, nest=True, n_threads=1):
     return out
 
 
+def boundaries(nside, pix, step=1, lonlat=True, nest=True, degrees=True, n_threads=1):
+    """Positions along the boundary of each pixel (reference: hpgeom/hpgeom.c:2046-2278, core
+    hpgeom/healpix_geom.c:807-888): ``step`` points per edge, starting at the north corner.
+    Returns ``(a, b)`` of shape (4*step,) for a scalar pixel, else (N, 4*step)."""
+    lonlat, nest, degrees = bool(lonlat), bool(nest), bool(degrees)
+    step = int(step)
+    if step < 1:
+        raise ValueError("step must be positive.")
+
+    def dims(ns, arrs):
+        if len(arrs[0].shape) > 1:
+            raise ValueError("pix array must be at most 1D.")
+
+    a, b = _d.elementwise(
+        "boundaries", nside, [pix], [I8], [F8, F8], [step, int(nest), int(lonlat), int(degrees)], nest=nest,
+        out_cols=[4 * step, 4 * step], max_ndim=dims, bcast_msg="nside, pix arrays could not be broadcast together.",
+        explain=lambda ns, v: _lib.explain_pixel(ns, nest, v[0]))
+    return a, b
+
+
+def max_pixel_radius(nside, degrees=True, n_threads=1):
+    """Maximum angular distance between a pixel centre and its corners, per nside (reference:
+    hpgeom/hpgeom.c:3255-3440, core hpgeom/healpix_geom.c:480-502)."""
+    be = _d.pick_backend(nside)
+    ns = be.coerce(_d._np_view(nside) if be.name == "numpy" else nside, I8)
+    shape = be.shape(ns)
+    n = int(np.prod(shape, dtype=np.int64))
+    out = be.empty(shape, F8)
+    if n == 0:
+        return out
+    nsc = be.expand(ns, shape)
+    rc, bad = be.call("max_pixel_radius", [be.ptr(nsc), be.ptr(out)], [n, int(bool(degrees))])
+    _lib.check_rc(rc)
+    if bad >= 0:
+        raise ValueError(_lib.explain_nside(int(be.item(nsc, bad)), False))
+    return be.scalar(out) if len(shape) == 0 else out
+
+
 def get_interpolation_weights(nside, a, b, lonlat=True, nest=True, degrees=True, n_threads=1):
     """Bilinear interpolation pixels and weights (reference: hpgeom/hpgeom.c:3537-3777).
     Returns ``(pixels (N, 4) int64, weights (N, 4) float64)``, or (4,) each for scalar input."""
@@ -173,6 +222,133 @@ def lonlat_to_thetaphi(lon, lat, degrees=True):
     if len(be.shape(phi)) == 0:
         phi = be.scalar(phi)
     return theta, phi
+
+
+def thetaphi_to_lonlat(theta, phi, degrees=True):
+    """Convert theta/phi (radians) to longitude/latitude (reference: hpgeom/hpgeom.py:91-112).
+
+    One subtraction and one multiplication per element (numpy's ``rad2deg`` = ``x * (180/pi)``);
+    evaluated with numpy for numpy inputs and with torch on the device for CUDA tensors."""
+    if _d._is_torch(theta) or _d._is_torch(phi):
+        torch = _d.torch
+        theta, phi = torch.as_tensor(theta), torch.as_tensor(phi)
+        lon, lat = phi, -(theta - np.pi / 2.)
+        return (torch.rad2deg(lon), torch.rad2deg(lat)) if degrees else (lon, lat)
+    lon = phi
+    lat = -(theta - np.pi / 2.)
+    if degrees:
+        lon, lat = np.rad2deg(lon), np.rad2deg(lat)
+    return lon, lat
+
+
+def npixel_to_nside(npixel):
+    """nside for a number of pixels (reference: hpgeom/hpgeom.py:209-229)."""
+    if np.any(npixel <= 0):
+        raise ValueError("Illegal npixel (must be positive)")
+    nside = np.sqrt(np.atleast_1d(npixel) / 12.0)
+    if np.any(nside != np.floor(nside)):
+        raise ValueError("Illegal npixel (it must be 12*nside*nside)")
+    return int(nside[0]) if len(nside) == 1 else nside.astype(np.int64)
+
+
+def nside_to_pixel_area(nside, degrees=True):
+    """Pixel area in square degrees or steradians (reference: hpgeom/hpgeom.py:232-254)."""
+    area = 4 * np.pi / nside_to_npixel(nside)
+    return np.rad2deg(np.rad2deg(area)) if degrees else area
+
+
+def nside_to_resolution(nside, units='degrees'):
+    """sqrt(pixel area) in the requested units (reference: hpgeom/hpgeom.py:257-292)."""
+    res = np.sqrt(nside_to_pixel_area(nside, degrees=False))
+    if units == 'radians':
+        return res
+    scale = {'degrees': None, 'arcminutes': (60.,), 'arcseconds': (60., 60.)}
+    if units not in scale:
+        raise ValueError("Invalid units.  Must be radians, degrees, arcminutes, or arcseconds.")
+    value = np.rad2deg(res)
+    for f in scale[units] or ():
+        value = value * f
+    return value
+
+
+def nside_to_order(nside):
+    """log2(nside) (reference: hpgeom/hpgeom.py:295-318)."""
+    _nside = np.atleast_1d(nside)
+    if np.any((_nside <= 0) | (_nside > max_nside) | ((_nside & (_nside - 1)) != 0)):
+        raise ValueError("nside must be postive power of 2, and less than 2**30")
+    if hasattr(nside, '__len__'):
+        return np.round(np.log2(nside)).astype(np.int64)
+    return int(np.round(np.log2(nside)))
+
+
+def order_to_nside(order):
+    """2**order (reference: hpgeom/hpgeom.py:321-339)."""
+    if np.any((order != np.int64(order)) | (order < 0) | (order > 29)):
+        raise ValueError("Order must be integer, 0<=order<=29.")
+    return 2**order
+
+
+def _check_theta_phi(theta, phi):
+    # reference: hpgeom/hpgeom.py:342-361
+    _theta, _phi = np.atleast_1d(_d._np_view(theta)), np.atleast_1d(_d._np_view(phi))
+    if np.any((_theta < 0.0) | (_theta > np.pi)):
+        raise ValueError("Co-latitude (theta) out of range.")
+    if np.any((_phi < 0.0) | (_phi > 2 * np.pi)):
+        raise ValueError("Longitude (phi) out of range.")
+
+
+def angle_to_vector(a, b, lonlat=True, degrees=True):
+    """Angles to unit vectors, (N, 3) or (3,) (reference: hpgeom/hpgeom.py:364-393; a numpy helper
+    there too: sin/cos come from the host libm, or from torch for CUDA tensors)."""
+    if lonlat:
+        theta, phi = lonlat_to_thetaphi(a, b, degrees=degrees)
+    else:
+        _check_theta_phi(a, b)
+        theta, phi = a, b
+    if _d._is_torch(theta) or _d._is_torch(phi):
+        torch = _d.torch
+        theta, phi = torch.as_tensor(theta), torch.as_tensor(phi)
+        st = torch.sin(theta)
+        return torch.stack([st * torch.cos(phi), st * torch.sin(phi), torch.cos(theta)]).transpose(0, -1)
+    st = np.sin(theta)
+    return np.array([st * np.cos(phi), st * np.sin(phi), np.cos(theta)]).transpose()
+
+
+def vector_to_angle(vec, lonlat=True, degrees=True):
+    """(N, 3) or (3,) vectors to angles (reference: hpgeom/hpgeom.py:396-422)."""
+    if _d._is_torch(vec):
+        torch = _d.torch
+        v = vec.reshape(-1, 3)
+        theta = torch.acos(v[:, 2] / torch.sqrt(torch.sum(torch.square(v), dim=1)))
+        phi = torch.remainder(torch.atan2(v[:, 1], v[:, 0]), 2. * np.pi)
+    else:
+        v = np.atleast_1d(vec).reshape(-1, 3)
+        theta = np.arccos(v[:, 2] / np.sqrt(np.sum(np.square(v), axis=1)))
+        phi = np.arctan2(v[:, 1], v[:, 0]) % (2. * np.pi)
+    return thetaphi_to_lonlat(theta, phi, degrees=degrees) if lonlat else (theta, phi)
+
+
+def reorder(map_in, ring_to_nest=True):
+    """Reorder a full-sky map between RING and NEST (reference: hpgeom/hpgeom.py:425-462).
+
+    The permutation comes from the nest_to_ring / ring_to_nest kernels over ALL pixels at once (the
+    reference walks 24 groups to bound its temporaries); the scatter is numpy's / torch's, on the
+    device for CUDA tensors."""
+    npix = map_in.numel() if _d._is_torch(map_in) else map_in.size
+    nside = npixel_to_nside(npix)
+    nside_to_order(nside)  # ValueError unless nside is a legal NEST resolution
+    if _d._is_torch(map_in):
+        torch = _d.torch
+        pixels = torch.arange(npix, dtype=torch.int64, device=map_in.device)
+        target = globals()['ring_to_nest'](nside, pixels) if ring_to_nest else nest_to_ring(nside, pixels)
+        out = torch.zeros_like(map_in)
+        out[target] = map_in
+        return out
+    pixels = np.arange(npix, dtype=np.int64)
+    target = globals()['ring_to_nest'](nside, pixels) if ring_to_nest else nest_to_ring(nside, pixels)
+    out = np.zeros_like(map_in)
+    out[target] = map_in
+    return out
 
 
 def nside_to_npixel(nside):

@@ -141,6 +141,23 @@ int hpgb_lonlat_to_thetaphi(const double *d_lon, const double *d_lat, double *d_
 int hpgb_host_lonlat_to_thetaphi(const double *lon, const double *lat, double *theta, double *phi,
                                  int64_t n, int degrees, int device, int64_t *first_bad);
 
+/* ---- boundaries: hpgeom/hpgeom.c:1956-2278 (core hpgeom/healpix_geom.c:807-888); outputs are
+ * (n, 4*step) row-major: `step` points along each of the four edges, starting at the north corner
+ * and going N->W, W->S, S->E, E->N ---- */
+int hpgb_boundaries(const int64_t *d_pix, double *d_a_n4s, double *d_b_n4s, int64_t n, int64_t nside,
+                    const int64_t *d_nside_v, int64_t step, int nest, int lonlat, int degrees,
+                    hpgb_status_t *d_status, void *stream);
+int hpgb_host_boundaries(const int64_t *pix, double *a_n4s, double *b_n4s, int64_t n, int64_t nside,
+                         const int64_t *nside_v, int64_t step, int nest, int lonlat, int degrees,
+                         int device, int64_t *first_bad);
+
+/* ---- max_pixel_radius: hpgeom/hpgeom.c:3202-3440 (core hpgeom/healpix_geom.c:480-502); one value
+ * per nside (RING rules: any positive nside <= 2^29) ---- */
+int hpgb_max_pixel_radius(const int64_t *d_nside, double *d_radius, int64_t n, int degrees,
+                          hpgb_status_t *d_status, void *stream);
+int hpgb_host_max_pixel_radius(const int64_t *nside, double *radius, int64_t n, int degrees, int device,
+                               int64_t *first_bad);
+
 /* ---- error text for ONE element (host side, pure functions) -------------------------------
  * Re-evaluates the reference's checks in the reference's order for the element the kernel
  * flagged and writes the reference's message (at most `cap` bytes, NUL terminated).

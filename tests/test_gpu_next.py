@@ -1,0 +1,142 @@
+"""GPU parity of the rows next to the hot path: boundaries, max_pixel_radius,
+reorder, the helpers that run through the kernels, and the healpy_compat shims -- against golden
+vectors generated from the unmodified reference (tests/golden/make_golden_next.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN as GOLDEN_DIR, assert_bit_equal, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hpg():
+    import hpgeom_b200
+    return hpgeom_b200
+
+
+@pytest.fixture(scope="module")
+def hpc():
+    from hpgeom_b200 import healpy_compat
+    return healpy_compat
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLDEN_DIR, "golden_next.npz"))
+
+
+def close_angles(got, ref, scale=1.0, frac=0.01):
+    """theta-derived outputs: one ulp of theta (pi-sized), mostly bit-identical."""
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1.5 * np.spacing(np.pi) * scale
+    assert got.size < 500 or np.mean(got != ref) <= frac
+
+
+@pytest.mark.parametrize("nside", [1, 2, 32, 1024, 2 ** 20, 2 ** 29, 3, 924])
+def test_boundaries_golden(hpg, g, nside):
+    pix = g["bnd_pix_%d" % nside]
+    for nest in ([True, False] if nside & (nside - 1) == 0 else [False]):
+        for step in (1, 2, 5):
+            tag = "bnd_%d_%s_%d_" % (nside, "nest" if nest else "ring", step)
+            th, ph = hpg.boundaries(nside, pix, step=step, nest=nest, lonlat=False)
+            assert_bit_equal(ph, g[tag + "tp_b"], "phi")
+            close_angles(th, g[tag + "tp_a"])
+            lon, lat = hpg.boundaries(nside, pix, step=step, nest=nest)
+            assert_bit_equal(lon, g[tag + "deg_a"], "lon")
+            close_angles(lat, g[tag + "deg_b"], 180.0 / np.pi)
+            lon, lat = hpg.boundaries(nside, pix, step=step, nest=nest, degrees=False)
+            assert_bit_equal(lon, g[tag + "rad_a"], "lon")
+            close_angles(lat, g[tag + "rad_b"])
+
+
+def test_boundaries_shapes_errors_and_device_tensors(hpg, g):
+    import torch
+    a, b = hpg.boundaries(1024, 77, step=3)
+    assert a.shape == (12,) and b.shape == (12,)
+    assert_bit_equal(a, g["bnd_scalar_a"])
+    close_angles(b, g["bnd_scalar_b"], 180.0 / np.pi)
+    with open(os.path.join(GOLDEN_DIR, "golden_next_errors.json")) as f:
+        errs = json.load(f)
+    for name, fn in (("bnd_2d", lambda: hpg.boundaries(32, np.zeros((2, 2), dtype=np.int64))),
+                     ("bnd_badpix", lambda: hpg.boundaries(32, 12 * 32 * 32)),
+                     ("bnd_nest_nonpow2", lambda: hpg.boundaries(30, 1)),
+                     ("mpr_bad", lambda: hpg.max_pixel_radius(0)),
+                     ("mpr_big", lambda: hpg.max_pixel_radius(2 ** 30))):
+        with pytest.raises(ValueError) as e:
+            fn()
+        assert str(e.value) == errs[name][1], name
+    pix = g["bnd_pix_1024"]
+    ta, tb = hpg.boundaries(1024, torch.from_numpy(pix).cuda(), step=2)
+    na, nb = hpg.boundaries(1024, pix, step=2)
+    assert ta.is_cuda and np.array_equal(ta.cpu().numpy(), na) and np.array_equal(tb.cpu().numpy(), nb)
+    # first bad pixel wins, on a large array
+    big = np.zeros(500_000, dtype=np.int64)
+    big[400_000] = -5
+    big[450_000] = -6
+    with pytest.raises(ValueError, match=r"Pixel value -5 out of range"):
+        hpg.boundaries(64, big)
+
+
+def test_max_pixel_radius(hpg, g):
+    for key, kw in (("deg", {}), ("rad", {"degrees": False})):
+        got = hpg.max_pixel_radius(g["mpr_nside"], **kw)
+        assert ulp_diff(got, g["mpr_" + key]).max() <= 1.0
+        assert np.mean(got != g["mpr_" + key]) <= 0.1
+    assert isinstance(float(hpg.max_pixel_radius(64)), float) and np.ndim(hpg.max_pixel_radius(64)) == 0
+
+
+def test_reorder_and_helpers_through_the_kernels(hpg, g):
+    import torch
+    for nside in (1, 4, 32):
+        m = g["reorder_in_%d" % nside]
+        assert_bit_equal(hpg.reorder(m, ring_to_nest=True), g["reorder_r2n_%d" % nside])
+        assert_bit_equal(hpg.reorder(m, ring_to_nest=False), g["reorder_n2r_%d" % nside])
+        t = hpg.reorder(torch.from_numpy(m).cuda(), ring_to_nest=True)
+        assert t.is_cuda and np.array_equal(t.cpu().numpy(), g["reorder_r2n_%d" % nside])
+    assert_bit_equal(hpg.angle_to_vector(g["h_lon"], g["h_lat"]), g["h_a2v_ll"])
+    assert_bit_equal(hpg.angle_to_vector(10.0, 20.0), g["h_a2v_scalar"])
+    # a full-size map on the device: reorder there and back
+    nside = 2048
+    m = torch.arange(12 * nside * nside, dtype=torch.float64, device="cuda")
+    assert torch.equal(hpg.reorder(hpg.reorder(m, ring_to_nest=True), ring_to_nest=False), m)
+
+
+@pytest.mark.parametrize("nest", [True, False])
+def test_healpy_compat(hpc, g, nest):
+    nside = 256
+    t = "nest" if nest else "ring"
+    pix, theta, phi, lon, lat, vec = g["hp_pix"], g["h_theta"], g["h_phi"], g["h_lon"], g["h_lat"], g["h_vec"]
+    assert_bit_equal(hpc.ang2pix(nside, theta, phi, nest=nest), g["hp_ang2pix_" + t])
+    assert_bit_equal(hpc.ang2pix(nside, lon, lat, nest=nest, lonlat=True), g["hp_ang2pix_ll_" + t])
+    a, b = hpc.pix2ang(nside, pix, nest=nest)
+    close_angles(a, g["hp_pix2ang_a_" + t])
+    assert_bit_equal(b, g["hp_pix2ang_b_" + t])
+    a, b = hpc.pix2ang(nside, pix, nest=nest, lonlat=True)
+    assert_bit_equal(a, g["hp_pix2ang_ll_a_" + t])
+    close_angles(b, g["hp_pix2ang_ll_b_" + t], 180.0 / np.pi)
+    x, y, z = hpc.pix2vec(nside, pix, nest=nest)
+    ref = g["hp_pix2vec_" + t]
+    assert_bit_equal(z, ref[2])
+    assert ulp_diff(x, ref[0]).max() <= 2 and ulp_diff(y, ref[1]).max() <= 2
+    assert_bit_equal(hpc.vec2pix(nside, vec[:, 0], vec[:, 1], vec[:, 2], nest=nest), g["hp_vec2pix_" + t])
+    assert_bit_equal(hpc.get_all_neighbours(nside, pix, nest=nest), g["hp_neigh_pix_" + t])
+    assert_bit_equal(hpc.get_all_neighbours(nside, theta, phi, nest=nest), g["hp_neigh_ang_" + t])
+    assert_bit_equal(hpc.get_all_neighbours(nside, 100, nest=nest), g["hp_neigh_scalar_" + t])
+    p, w = hpc.get_interp_weights(nside, theta, phi, nest=nest)
+    assert_bit_equal(p, g["hp_interp_p_" + t])
+    assert np.abs(w - g["hp_interp_w_" + t]).max() <= 4 * np.spacing(np.pi) * nside
+    p, w = hpc.get_interp_weights(nside, pix, nest=nest)
+    assert p.shape == g["hp_interp_pix_p_" + t].shape and np.mean(p != g["hp_interp_pix_p_" + t]) <= 0.02
+    b3 = hpc.boundaries(nside, pix[:20], step=2, nest=nest)
+    assert b3.shape == g["hp_bnd_" + t].shape and np.abs(b3 - g["hp_bnd_" + t]).max() <= 4e-16
+    b1 = hpc.boundaries(nside, 5, step=1, nest=nest)
+    assert b1.shape == g["hp_bnd_scalar_" + t].shape and np.abs(b1 - g["hp_bnd_scalar_" + t]).max() <= 4e-16
+    if nest:
+        assert_bit_equal(hpc.nest2ring(nside, pix), g["hp_nest2ring"])
+        assert_bit_equal(hpc.ring2nest(nside, pix), g["hp_ring2nest"])
+        assert_bit_equal(hpc.ang2vec(lon, lat, lonlat=True), g["hp_ang2vec_ll"])
+        assert ulp_diff(np.array([hpc.max_pixrad(64), hpc.max_pixrad(64, degrees=True)]), g["hp_scalars"][8:]).max() <= 1
