@@ -56,13 +56,29 @@ _SIGS = {
                              ctypes.POINTER(c_i64)],
     "hpgb_max_pixel_radius": [c_vp, c_vp, c_i64, c_int, c_vp, c_vp],
     "hpgb_host_max_pixel_radius": [c_vp, c_vp, c_i64, c_int, c_int, ctypes.POINTER(c_i64)],
+    "hpgb_ranges_offsets": [c_vp, c_i64, c_int, c_vp, c_vp, c_vp],
+    "hpgb_ranges_expand": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp],
+    "hpgb_host_ranges_count": [c_vp, c_i64, c_int, c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],
+    "hpgb_host_ranges_expand": [c_vp, c_i64, c_int, c_vp, c_i64, c_int],
+    "hpgb_query_circle_ring_plan": [c_i64, c_dbl, c_dbl, c_dbl, c_int, c_i64, c_int, c_int, c_vp],
+    "hpgb_query_circle_ring_work_bytes": [c_vp],
+    "hpgb_query_circle_ring_ranges": [c_vp, c_vp, c_vp, c_vp],
+    "hpgb_host_query_circle_ring_count": [c_vp, c_int, ctypes.POINTER(c_i64)],
+    "hpgb_host_query_circle_ring_fill": [c_vp, c_vp, c_i64, c_int],
     "hpgb_explain_nside": [c_i64, c_int, ctypes.c_char_p, c_int],
     "hpgb_explain_angle": [c_i64, c_int, c_dbl, c_dbl, c_int, c_int, ctypes.c_char_p, c_int],
     "hpgb_explain_pixel": [c_i64, c_int, c_i64, ctypes.c_char_p, c_int],
 }
-_RESTYPES = {"hpgb_error_string": ctypes.c_char_p, "hpgb_launch_count": c_i64}
+_RESTYPES = {"hpgb_error_string": ctypes.c_char_p, "hpgb_launch_count": c_i64,
+             "hpgb_query_circle_ring_work_bytes": c_i64}
 
 EXPORTS = tuple(_SIGS)
+
+
+class Disc(ctypes.Structure):
+    """hpgb_disc_t of include/hpgb.h"""
+    _fields_ = [(n, c_i64) for n in ("nside", "fct", "whole_sphere", "irmin", "irmax", "north_hi", "south_lo", "cpix", "m")] \
+        + [(n, c_dbl) for n in ("phi", "z0", "xa", "cosrbig", "cosrsmall")]
 
 _lib = None
 

@@ -33,4 +33,8 @@ int launch_boundaries(const int64_t *pix, double *a, double *b, int64_t n, int64
                       int64_t step, int nest, int lonlat, int degrees, int64_t base, hpgb_status_t *st, cudaStream_t s);
 int launch_max_pixrad(const int64_t *nside, double *out, int64_t n, int degrees, int64_t base, hpgb_status_t *st,
                       cudaStream_t s);
+int launch_ranges_offsets(const int64_t *ranges, int64_t m, int inclusive, int64_t *offs, hpgb_status_t *st, cudaStream_t s);
+int launch_ranges_expand(const int64_t *ranges, const int64_t *offs, int64_t m, int64_t out_begin, int64_t out_count,
+                         int64_t *out, cudaStream_t s);
+int launch_qc_ring_ranges(const hpgb_disc_t *plan, int64_t *ranges, int64_t *work, cudaStream_t s);
 #endif

@@ -2,10 +2,12 @@
 
 Same signatures and defaults as the reference's shims -- RING ordering, theta/phi in radians,
 ``lonlat=True`` meaning degrees, (8, N) / (4, N) transposed outputs -- each one a call into
-``hpgeom_b200.hpgeom``, i.e. into the CUDA kernels.  The region queries (``query_disc``,
-``query_polygon``) are not on the elementwise path this package implements and raise
+``hpgeom_b200.hpgeom``, i.e. into the CUDA kernels.  ``query_disc`` runs the RING query_circle
+kernels (healpy's default ordering); ``query_polygon`` is not built and raises
 ``NotImplementedError``.
 """
+import warnings
+
 from .hpgeom import (
     UNSEEN,
     angle_to_pixel,
@@ -23,6 +25,7 @@ from .hpgeom import (
     order_to_nside,
     pixel_to_angle,
     pixel_to_vector,
+    query_circle_vec,
     ring_to_nest,
     vector_to_angle,
     vector_to_pixel,
@@ -46,7 +49,12 @@ def pix2ang(nside, pix, nest=False, lonlat=False):
 
 
 def query_disc(nside, vec, radius, inclusive=False, fact=4, nest=False, buff=None):
-    raise NotImplementedError("query_disc is a region query; hpgeom_b200 implements the elementwise conversion path only")
+    """reference: hpgeom/healpy_compat.py:103-142"""
+    pixels = query_circle_vec(nside, vec, radius, inclusive=inclusive, fact=fact, nest=nest)
+    if buff is not None:
+        warnings.warn("In hpgeom, setting buff is less performant than simply returning the pixels.")
+        buff[0: len(pixels)] = pixels
+    return pixels
 
 
 def query_polygon(nside, vertices, inclusive=False, fact=4, nest=False, buff=None):

@@ -10,6 +10,7 @@ Inputs may be numpy arrays / Python scalars (results are numpy, computed on the 
 ``set_default_device``) or device-resident ``torch`` CUDA tensors (results are CUDA tensors on
 the same device; the kernels run on the current torch stream).  There is no CPU fallback.
 """
+import ctypes
 import numbers
 
 import numpy as np
@@ -40,6 +41,8 @@ __all__ = [
     'neighbors',
     'get_interpolation_weights',
     'pixel_ranges_to_pixels',
+    'query_circle',
+    'query_circle_vec',
     'upgrade_pixels',
     'upgrade_pixel_ranges',
     'nside_to_npixel',
@@ -362,20 +365,113 @@ def nside_to_npixel(nside):
 def pixel_ranges_to_pixels(pixel_ranges, inclusive=False):
     """Expand an (M, 2) array of [lo, hi) ranges (reference: hpgeom/hpgeom.c:3795-3896).
 
-    Host-side helper kept for API completeness (variable-length expansion is not on the
-    accelerated path; upgrade_pixels below fuses its equal-length case into one kernel)."""
-    r = np.asarray(_d._np_view(pixel_ranges))
-    if r.dtype != np.int64:
-        r = r.astype(np.int64, casting="safe")
-    if r.ndim != 2 or r.shape[1] != 2:
+    Two passes like the reference's two loops, both on the GPU (csrc/k_ranges.cu): the count pass
+    validates the rows and prefix-sums their lengths, the expand pass writes the pixel list.
+    numpy in -> numpy out through the chunked D2H pipeline; a torch CUDA tensor stays resident.
+    """
+    be = _d.pick_backend(pixel_ranges)
+    inclusive = int(bool(inclusive))
+    if be.name == "numpy":
+        r = be.coerce(_d._np_view(pixel_ranges), I8)
+    else:
+        r = be.coerce(pixel_ranges, I8)
+    shape = be.shape(r)
+    if len(shape) != 2 or shape[1] != 2:
         raise ValueError("pixel_ranges must be 2D, with shape (M, 2).")
-    if r.size == 0:
-        return np.zeros(0, dtype=np.int64)
-    if np.any(r[:, 1] < r[:, 0]):
-        raise ValueError("pixel_ranges[:, 0] must all be <= pixel_ranges[:, 1]")
-    lens = r[:, 1] - r[:, 0] + int(bool(inclusive))
-    starts = np.repeat(r[:, 0] - np.concatenate(([0], np.cumsum(lens)[:-1])), lens)
-    return starts + np.arange(int(lens.sum()), dtype=np.int64)
+    m = int(shape[0])
+    if m == 0:
+        return be.empty((0,), I8)
+    r = be.expand(r, shape)  # C-contiguous rows = 16-byte (lo, hi) pairs
+    bad_msg = "pixel_ranges[:, 0] must all be <= pixel_ranges[:, 1]"
+    L = _lib.lib()
+    if be.name == "numpy":
+        total, first_bad = ctypes.c_int64(0), ctypes.c_int64(-1)
+        _lib.check_rc(L.hpgb_host_ranges_count(be.ptr(r), m, inclusive, be.device, ctypes.byref(total),
+                                               ctypes.byref(first_bad)))
+        if first_bad.value >= 0:
+            raise ValueError(bad_msg)
+        out = be.empty((total.value,), I8)
+        _lib.check_rc(L.hpgb_host_ranges_expand(be.ptr(r), m, inclusive, be.ptr(out), total.value, be.device))
+        return out
+    torch = _d.torch
+    with torch.cuda.device(be.device):
+        if r.data_ptr() % 16:
+            r = r.clone()
+        offs = torch.empty(m + 1, dtype=torch.int64, device=be.dev)
+        rc, first_bad = be.call("ranges_offsets", [be.ptr(r)], [m, inclusive, be.ptr(offs)])
+        _lib.check_rc(rc)
+        if first_bad >= 0:
+            raise ValueError(bad_msg)
+        total = int(offs[m].item())
+        out = torch.empty(total, dtype=torch.int64, device=be.dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(be.device).cuda_stream)
+        _lib.check_rc(L.hpgb_ranges_expand(be.ptr(r), be.ptr(offs), m, 0, total, be.ptr(out), stream))
+    return out
+
+
+def query_circle(nside, a, b, radius, inclusive=False, fact=4, nest=True, lonlat=True, degrees=True,
+                 return_pixel_ranges=False, device_resident=False):
+    """Pixels whose centres lie within (inclusive: which overlap) a circle
+    (reference: hpgeom/hpgeom.c:765-864 -> query_disc, hpgeom/healpix_geom.c:632-747).
+
+    RING scheme: the per-disc scalars are prepared on the host, every ring the disc touches is one
+    GPU thread (csrc/k_query.cu) and the resulting intervals are expanded by the
+    pixel_ranges_to_pixels kernels.  Same argument checks, order and messages as the reference.
+    ``device_resident=True`` (an extension) returns a torch CUDA tensor instead of a numpy array.
+    The NEST scheme (the reference's hierarchical search) is not built yet.
+    """
+    nside, a, b, radius = int(nside), float(a), float(b), float(radius)
+    inclusive, nest, lonlat, degrees = bool(inclusive), bool(nest), bool(lonlat), bool(degrees)
+    fact = int(fact)
+    if return_pixel_ranges and not nest:
+        raise RuntimeError("Can only use return_pixel_ranges with nest ordering.")
+    L = _lib.lib()
+    plan = _lib.Disc()
+    rc = L.hpgb_query_circle_ring_plan(nside, a, b, radius, int(inclusive), fact, int(lonlat), int(degrees),
+                                       ctypes.byref(plan))
+    if rc == 6:
+        raise ValueError(_lib.explain_angle(1, False, a, b, lonlat, degrees))
+    if rc == 7:
+        raise ValueError("Radius must be positive.")
+    if rc in (1, 2, 3) or (nest and _lib.explain_nside(nside, True)):
+        raise ValueError(_lib.explain_nside(nside, nest))
+    if inclusive:  # hpgeom/hpgeom_utils.c:73-87
+        if fact <= 0:
+            raise ValueError("Inclusive factor %d must be positive." % fact)
+        if fact * nside > max_nside:
+            raise ValueError("Inclusive factor * nside must be <= %d" % max_nside)
+        if nest and (fact & (fact - 1)) > 0:
+            raise ValueError("Inclusive factor %d must be power of 2 for nest." % fact)
+    _lib.check_rc(rc)
+    if nest:
+        raise NotImplementedError("query_circle: only the RING scheme (nest=False) runs on the GPU so far")
+    dev = _d.default_device()
+    if not device_resident:
+        total = ctypes.c_int64(0)
+        _lib.check_rc(L.hpgb_host_query_circle_ring_count(ctypes.byref(plan), dev, ctypes.byref(total)))
+        out = np.empty(total.value, dtype=np.int64)
+        _lib.check_rc(L.hpgb_host_query_circle_ring_fill(ctypes.byref(plan), ctypes.c_void_p(out.ctypes.data),
+                                                         total.value, dev))
+        return out
+    torch = _d.torch
+    with torch.cuda.device(dev):
+        m = int(plan.m)
+        table = torch.empty((m, 2), dtype=torch.int64, device="cuda:%d" % dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        wb = int(L.hpgb_query_circle_ring_work_bytes(ctypes.byref(plan)))
+        work = torch.empty(max(wb, 16) // 8, dtype=torch.int64, device="cuda:%d" % dev)
+        _lib.check_rc(L.hpgb_query_circle_ring_ranges(ctypes.byref(plan), ctypes.c_void_p(table.data_ptr()),
+                                                      ctypes.c_void_p(work.data_ptr()), stream))
+    return pixel_ranges_to_pixels(table)
+
+
+def query_circle_vec(nside, vec, radius, inclusive=False, fact=4, nest=True):
+    """query_circle for a centre given as a unit vector, radius in radians
+    (reference: hpgeom/hpgeom.py:115-160)."""
+    if len(vec) != 3:
+        raise ValueError("vec must be 3 elements.")
+    theta, phi = vector_to_angle(vec, lonlat=False)
+    return query_circle(nside, theta[0], phi[0], radius, inclusive=inclusive, fact=fact, nest=nest, lonlat=False)
 
 
 def _upgrade_scalar_checks(nside, nside_upgrade):

@@ -40,6 +40,9 @@ extern "C" {
 #define HPGB_E_NSIDE_TOO_LARGE 3    /* hpgeom/hpgeom_utils.c:40-44 */
 #define HPGB_E_BAD_ARGUMENT 4
 #define HPGB_E_NO_DEVICE 5
+#define HPGB_E_BAD_ANGLE 6  /* query plans: text from hpgb_explain_angle */
+#define HPGB_E_BAD_RADIUS 7 /* hpgeom/hpgeom_utils.c:89-98 */
+#define HPGB_E_BAD_FACT 8   /* hpgeom/hpgeom_utils.c:73-87 */
 #define HPGB_E_CUDA 1000 /* + cudaError_t */
 
 #define HPGB_NO_BAD_ELEMENT 0xFFFFFFFFFFFFFFFFull
@@ -157,6 +160,57 @@ int hpgb_max_pixel_radius(const int64_t *d_nside, double *d_radius, int64_t n, i
                           hpgb_status_t *d_status, void *stream);
 int hpgb_host_max_pixel_radius(const int64_t *nside, double *radius, int64_t n, int degrees, int device,
                                int64_t *first_bad);
+
+/* ---- pixel_ranges_to_pixels: hpgeom/hpgeom.c:3795-3896.  Ranges are (m,2) row-major [lo, hi) rows
+ * (16-byte aligned); `inclusive` adds 1 to every hi.  Like the reference's two loops, two calls:
+ *   hpgb_ranges_offsets : the count loop (:3843-3856).  Flags the first row with hi < lo in *d_status
+ *                         and writes the exclusive prefix sums of the lengths to d_offsets_mp1[0..m]
+ *                         (d_offsets_mp1[m] = number of output pixels; the caller reads it to allocate);
+ *   hpgb_ranges_expand  : the expand loop (:3868-3876) for the window [out_begin, out_begin+out_count)
+ *                         of the pixel list, written to d_out[0..out_count).
+ * Host forms: count returns the output size, expand fills `out` (total pixels) through the chunked
+ * D2H pipeline. ---- */
+int hpgb_ranges_offsets(const int64_t *d_ranges_m2, int64_t m, int inclusive, int64_t *d_offsets_mp1,
+                        hpgb_status_t *d_status, void *stream);
+int hpgb_ranges_expand(const int64_t *d_ranges_m2, const int64_t *d_offsets_mp1, int64_t m,
+                       int64_t out_begin, int64_t out_count, int64_t *d_out, void *stream);
+int hpgb_host_ranges_count(const int64_t *ranges_m2, int64_t m, int inclusive, int device,
+                           int64_t *total, int64_t *first_bad);
+int hpgb_host_ranges_expand(const int64_t *ranges_m2, int64_t m, int inclusive, int64_t *out,
+                            int64_t total, int device);
+
+/* ---- query_circle, RING scheme: hpgeom/hpgeom.c:765-864 -> query_disc, hpgeom/healpix_geom.c:632-747.
+ * The reference walks the rings the disc touches one by one; here every ring is one GPU thread.
+ *   hpgb_query_circle_ring_plan   : host only, O(1): the wrapper's argument checks in its order
+ *                                   (angles, radius, nside, fact: hpgeom/hpgeom.c:793-838; returns
+ *                                   HPGB_E_BAD_ANGLE / _RADIUS / nside codes / _FACT) and the per-disc
+ *                                   scalars of :638-674 and :737-743.  inclusive = 0 ignores fact.
+ *                                   plan->m = rows of the range table.
+ *   hpgb_query_circle_ring_ranges : fills the (m,2) table of [lo, hi) pixel intervals (ascending,
+ *                                   disjoint, unused rows (0,0)): row 0 = north polar range, rows
+ *                                   1+2j / 2+2j = ring irmin+j, last row = south polar range.
+ *                                   d_work = hpgb_query_circle_ring_work_bytes(plan) bytes of device
+ *                                   scratch (16-byte aligned; 0 bytes / NULL unless fact > 1): the
+ *                                   inclusive edge scans the reference does sequentially (:701-710)
+ *                                   are spread over the whole grid there.
+ * The pixel list is then hpgb_ranges_offsets + hpgb_ranges_expand on that table.
+ * Host forms: count returns the number of pixels, fill writes them (host buffer of `total`). ---- */
+typedef struct hpgb_disc {
+    int64_t nside, fct;        /* fct = max(fact, 1) */
+    int64_t whole_sphere;      /* 1: the disc covers every pixel; the table is the single row (0, npix) */
+    int64_t irmin, irmax;      /* rings scanned (irmin > irmax: none) */
+    int64_t north_hi;          /* > 0: the polar range [0, north_hi) */
+    int64_t south_lo;          /* >= 0: the polar range [south_lo, npix) */
+    int64_t cpix;              /* RING pixel holding the disc centre */
+    int64_t m;                 /* rows of the range table */
+    double phi, z0, xa, cosrbig, cosrsmall;
+} hpgb_disc_t;
+int hpgb_query_circle_ring_plan(int64_t nside, double a, double b, double radius, int inclusive,
+                                int64_t fact, int lonlat, int degrees, hpgb_disc_t *plan);
+int64_t hpgb_query_circle_ring_work_bytes(const hpgb_disc_t *plan);
+int hpgb_query_circle_ring_ranges(const hpgb_disc_t *plan, int64_t *d_ranges_m2, void *d_work, void *stream);
+int hpgb_host_query_circle_ring_count(const hpgb_disc_t *plan, int device, int64_t *total);
+int hpgb_host_query_circle_ring_fill(const hpgb_disc_t *plan, int64_t *out, int64_t total, int device);
 
 /* ---- error text for ONE element (host side, pure functions) -------------------------------
  * Re-evaluates the reference's checks in the reference's order for the element the kernel

@@ -77,8 +77,8 @@ def test_error_texts():
         assert kind == "ValueError" and str(e.value) == msg, name
 
 
-def test_region_queries_are_out_of_scope():
+def test_region_queries_not_built():
     with pytest.raises(NotImplementedError):
-        hpc.query_disc(32, [1, 0, 0], 0.1)
+        hpc.query_disc(32, [1, 0, 0], 0.1, nest=True)  # NEST query_circle: hierarchical search, not built
     with pytest.raises(NotImplementedError):
         hpc.query_polygon(32, np.eye(3))

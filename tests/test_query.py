@@ -1,0 +1,217 @@
+"""query_circle (RING) and pixel_ranges_to_pixels: SURVEY.md 8(a) row a18 and 8(f) row 4.
+
+CPU tier: the per-ring element function + host plan (compiled for the host, tests/hostsim) against
+golden vectors frozen from the unmodified reference (tests/golden/make_golden_query.py), and against
+the live reference where oracle/_ref is present.  GPU tier: the public API through the C ABI.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal, load_golden
+
+
+def cases():
+    g = load_golden("query")
+    ends = np.cumsum(g["qc_sizes"])
+    for k, p in enumerate(g["qc_params"]):
+        nside, a, b, radius, fact, lonlat, degrees = p
+        yield (int(nside), float(a), float(b), float(radius), int(fact), bool(lonlat), bool(degrees)), \
+            g["qc_pix"][ends[k] - g["qc_sizes"][k]:ends[k]]
+
+
+def expand(table):
+    parts = [np.arange(lo, hi, dtype=np.int64) for lo, hi in table if hi > lo]
+    return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+
+
+@pytest.fixture(scope="module")
+def sim():
+    from hostsim import HostSim
+    return HostSim()
+
+
+def test_hostsim_ring_tables_match_golden(sim):
+    """theta/phi cases only (the lonlat forms go through the C ABI plan, GPU tier)."""
+    n = 0
+    for (nside, a, b, radius, fact, lonlat, degrees), want in cases():
+        if lonlat:
+            continue
+        table = sim.query_circle_ring_ranges(nside, a, b, radius, fact)
+        assert np.all(table[:, 1] >= table[:, 0])
+        nz = table[table[:, 1] > table[:, 0]]
+        assert np.all(nz[1:, 0] >= nz[:-1, 1]), "rows must be ascending and disjoint"
+        assert_bit_equal(expand(table), want, "nside=%d fact=%d" % (nside, fact))
+        n += 1
+    assert n > 500
+
+
+def test_hostsim_ring_vs_live_reference(sim, oracle_ref):
+    if oracle_ref is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(5)
+    for nside in (4, 37, 512, 2 ** 14):
+        for _ in range(25):
+            theta, phi = float(np.arccos(rng.uniform(-1, 1))), float(rng.uniform(0, 2 * np.pi))
+            radius = float(10 ** rng.uniform(-3.5, 0.3)) if nside < 2 ** 12 else float(10 ** rng.uniform(-4, -2))
+            for fact in (0, 1, 4, 5):
+                want = oracle_ref.query_circle(nside, theta, phi, radius, inclusive=fact > 0, fact=max(fact, 1),
+                                               nest=False, lonlat=False)
+                assert_bit_equal(expand(sim.query_circle_ring_ranges(nside, theta, phi, radius, fact)), want)
+
+
+def test_plan_argument_checks():
+    """The plan is host-only code: the wrapper's checks, in its order (hpgeom/hpgeom.c:793-838)."""
+    import hpgeom_b200 as hpg
+    with pytest.raises(ValueError, match=r"lat = 100 out of range \[-90, 90\]"):
+        hpg.query_circle(1024, 0.0, 100.0, -1.0, nest=False)
+    with pytest.raises(ValueError, match=r"colatitude \(theta\) = -0.1 out of range"):
+        hpg.query_circle(1024, -0.1, 0.0, 1.0, nest=False, lonlat=False)
+    with pytest.raises(ValueError, match="Radius must be positive."):
+        hpg.query_circle(0, 0.0, 0.0, 0.0, nest=False)
+    with pytest.raises(ValueError, match="nside"):
+        hpg.query_circle(0, 0.0, 0.0, 1.0, nest=False)
+    with pytest.raises(ValueError, match="power of 2"):
+        hpg.query_circle(1000, 0.0, 0.0, 1.0, nest=True)
+    with pytest.raises(ValueError, match="Inclusive factor 0 must be positive."):
+        hpg.query_circle(1024, 0.0, 0.0, 1.0, inclusive=True, fact=0, nest=False)
+    with pytest.raises(ValueError, match=r"Inclusive factor \* nside must be <= 536870912"):
+        hpg.query_circle(2 ** 29, 0.0, 0.0, 1.0, inclusive=True, fact=2, nest=False)
+    with pytest.raises(ValueError, match="Inclusive factor 3 must be power of 2 for nest."):
+        hpg.query_circle(1024, 0.0, 0.0, 1.0, inclusive=True, fact=3, nest=True)
+    with pytest.raises(RuntimeError, match="return_pixel_ranges"):
+        hpg.query_circle(1024, 0.0, 0.0, 1.0, nest=False, return_pixel_ranges=True)
+    with pytest.raises(ValueError, match="vec must be 3 elements."):
+        hpg.query_circle_vec(1024, [1.0, 0.0], 0.1)
+    with pytest.raises(ValueError, match=r"pixel_ranges must be 2D, with shape \(M, 2\)."):
+        hpg.pixel_ranges_to_pixels(np.zeros(4, dtype=np.int64))
+    assert hpg.pixel_ranges_to_pixels(np.zeros((0, 2), dtype=np.int64)).shape == (0,)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU tier
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def hpg():
+    import hpgeom_b200
+    return hpgeom_b200
+
+
+@pytest.mark.gpu
+def test_query_circle_golden(hpg):
+    n = 0
+    for (nside, a, b, radius, fact, lonlat, degrees), want in cases():
+        got = hpg.query_circle(nside, a, b, radius, inclusive=fact > 0, fact=max(fact, 1), nest=False, lonlat=lonlat,
+                               degrees=degrees)
+        assert_bit_equal(got, want, "nside=%d fact=%d lonlat=%d" % (nside, fact, lonlat))
+        n += 1
+    assert n > 900
+
+
+@pytest.mark.gpu
+def test_query_circle_device_resident_vec_and_healpy(hpg):
+    import torch
+    from hpgeom_b200 import healpy_compat as hpc
+    k = 0
+    for (nside, a, b, radius, fact, lonlat, degrees), want in cases():
+        k += 1
+        if k % 25:
+            continue
+        t = hpg.query_circle(nside, a, b, radius, inclusive=fact > 0, fact=max(fact, 1), nest=False, lonlat=lonlat,
+                             degrees=degrees, device_resident=True)
+        assert isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.int64
+        assert_bit_equal(t.cpu().numpy(), want)
+    vec = hpg.angle_to_vector(1.1, 2.2, lonlat=False)
+    a = hpg.query_circle_vec(512, vec, 0.05, nest=False)
+    b = hpg.query_circle(512, 1.1, 2.2, 0.05, nest=False, lonlat=False)
+    c = hpc.query_disc(512, vec, 0.05)
+    assert a.size > 100 and np.array_equal(a, b) and np.array_equal(a, c)
+
+
+@pytest.mark.gpu
+def test_query_circle_big_disc_properties(hpg, oracle_ref):
+    """A disc of 2.1e8 pixels at nside 2^14: sorted, unique, complete against pixel_to_angle distances;
+    identical to the reference where it is present."""
+    nside, theta, phi, radius = 2 ** 14, 0.7, 4.0, 0.5
+    got = hpg.query_circle(nside, theta, phi, radius, nest=False, lonlat=False)
+    assert got.size > 1.9e8 and np.all(np.diff(got) > 0)
+    if oracle_ref is not None:
+        assert_bit_equal(got, oracle_ref.query_circle(nside, theta, phi, radius, nest=False, lonlat=False))
+    rng = np.random.default_rng(3)
+    samp = rng.integers(0, 12 * nside * nside, 2_000_000)
+    th, ph = hpg.pixel_to_angle(nside, samp, nest=False, lonlat=False)
+    cosd = np.cos(th) * np.cos(theta) + np.sin(th) * np.sin(theta) * np.cos(ph - phi)
+    inside = cosd > np.cos(radius) + 1e-9
+    outside = cosd < np.cos(radius) - 1e-9
+    member = np.isin(samp, got)
+    assert np.all(member[inside]) and not np.any(member[outside])
+
+
+@pytest.mark.gpu
+def test_pixel_ranges_to_pixels_golden_and_torch(hpg):
+    import torch
+    g = load_golden("query")
+    rr = g["pr_ranges"]
+    assert hpg.pixel_ranges_to_pixels(np.array([[0, 3], [10, 10], [20, 22]])).tolist() == [0, 1, 2, 20, 21]
+    assert hpg.pixel_ranges_to_pixels(np.array([[0, 3], [10, 10]]), inclusive=True).tolist() == [0, 1, 2, 3, 10]
+    with pytest.raises(ValueError, match=r"must all be <="):
+        hpg.pixel_ranges_to_pixels(np.array([[5, 3]]))
+    assert_bit_equal(hpg.pixel_ranges_to_pixels(rr), g["pr_excl"])
+    assert_bit_equal(hpg.pixel_ranges_to_pixels(rr, inclusive=True), g["pr_incl"])
+    r32 = (rr % 1000 + np.array([0, 1000])).astype(np.int32)  # safe cast int32 -> int64, like the reference
+    assert_bit_equal(hpg.pixel_ranges_to_pixels(r32), np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in r32]))
+    t = hpg.pixel_ranges_to_pixels(torch.from_numpy(rr).cuda(), inclusive=True)
+    assert t.is_cuda
+    assert_bit_equal(t.cpu().numpy(), g["pr_incl"])
+    bad = rr.copy()
+    bad[1234, 1] = bad[1234, 0] - 1
+    for x in (bad, torch.from_numpy(bad).cuda()):
+        with pytest.raises(ValueError, match=r"pixel_ranges\[:, 0\] must all be <= pixel_ranges\[:, 1\]"):
+            hpg.pixel_ranges_to_pixels(x)
+    with pytest.raises(TypeError):
+        hpg.pixel_ranges_to_pixels(rr.astype(np.float64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", ["long", "short", "mixed", "empties", "single"])
+def test_pixel_ranges_to_pixels_shapes(hpg, oracle_port, shape):
+    """Every regime of the expand kernel: one range per many tiles, many ranges per tile, more than
+    one 1024-offset window per tile (runs of empty rows), and a scan over several scan tiles."""
+    rng = np.random.default_rng(11)
+    if shape == "long":
+        m, ln = 37, rng.integers(1, 3_000_000, 37)
+    elif shape == "short":
+        m, ln = 700_001, rng.integers(0, 7, 700_001)
+    elif shape == "mixed":
+        m = 50_000
+        ln = np.where(rng.random(m) < 0.01, rng.integers(1000, 200_000, m), rng.integers(0, 4, m))
+    elif shape == "empties":
+        m = 300_000
+        ln = np.zeros(m, dtype=np.int64)
+        ln[rng.integers(0, m, 40)] = rng.integers(1, 5000, 40)
+        ln[0] = ln[-1] = 0
+    else:
+        m, ln = 1, np.array([12345])
+    lo = rng.integers(0, 2 ** 58, m)
+    rr = np.stack([lo, lo + ln], axis=1).astype(np.int64)
+    for incl in (False, True):
+        want = oracle_port.pixel_ranges_to_pixels(rr, inclusive=incl)
+        assert_bit_equal(hpg.pixel_ranges_to_pixels(rr, inclusive=incl), want, "%s incl=%d" % (shape, incl))
+    import torch
+    t = torch.from_numpy(rr).cuda()
+    assert_bit_equal(hpg.pixel_ranges_to_pixels(t).cpu().numpy(), oracle_port.pixel_ranges_to_pixels(rr))
+    # a misaligned output window (odd out_begin) through the raw C ABI
+    from hpgeom_b200 import _lib
+    import ctypes
+    L = _lib.lib()
+    offs = torch.empty(m + 1, dtype=torch.int64, device="cuda")
+    st = torch.full((2,), -1, dtype=torch.int64, device="cuda")
+    assert L.hpgb_ranges_offsets(t.data_ptr(), m, 0, offs.data_ptr(), st.data_ptr(), None) == 0
+    total = int(offs[m].item())
+    want = oracle_port.pixel_ranges_to_pixels(rr)
+    assert total == want.size
+    if total > 10:
+        begin, count = 3, total - 7
+        buf = torch.zeros(count + 1, dtype=torch.int64, device="cuda")
+        assert L.hpgb_ranges_expand(t.data_ptr(), offs.data_ptr(), m, begin, count, buf.data_ptr() + 8, None) == 0
+        torch.cuda.synchronize()
+        assert_bit_equal(buf[1:].cpu().numpy(), want[begin:begin + count])
