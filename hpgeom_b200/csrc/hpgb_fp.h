@@ -791,6 +791,54 @@ HPGB_HD void hpgb_neighbors(const hpgb_geom &g, int64_t pix, int64_t *out) {
     }
 }
 
+// RING neighbours for nside = 2^k (scalar-nside kernel).  A pixel strictly inside its base face has its
+// eight neighbours on five consecutive rings (N: ring-2; NW, NE: ring-1; W, E: same ring; SW, SE: ring+1;
+// S: ring+2), so the zone / multiplier work of xyf2ring (hpgb_xyf2ring_k, hpgb_reorder.h: pixel = A*B + C)
+// is done once per RING and only the in-ring offset once per neighbour; everything is selects.  Face-edge
+// pixels (4/nside of all) take the general routine out of line.  Same values as hpgb_neighbors<false, true>.
+HPGB_HD_NOINLINE void hpgb_neighbors_ring_edge(const hpgb_geom &g, int64_t pix, int64_t *out) {
+    hpgb_neighbors<false, true>(g, pix, out);
+}
+HPGB_HD void hpgb_neighbors_ring_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, int64_t *out) {
+    uint32_t ix, iy, face;
+    hpgb_ring2xyf_k(c, g, pix, ix, iy, face);
+    if (!(ix > 0u && ix < c.nsm1 && iy > 0u && iy < c.nsm1)) {
+        int64_t tmp[8];  // the out-of-line call gets its own (local-memory) row, so `out` stays in registers
+        hpgb_neighbors_ring_edge(g, pix, tmp);
+#pragma unroll
+        for (int m = 0; m < 8; m++) out[m] = tmp[m];
+        return;
+    }
+    const uint32_t fc = face & 3u, fr = face >> 2;
+    const uint32_t frns = fr * c.ns;
+    const uint32_t t0 = frns + c.nsm1 - ix - iy;                            // ring - nside of the centre
+    const uint32_t w0 = fc * c.ns2 + (ix - iy) + c.nsm1 - (frns & c.ns);    // jpll * nside + ix - iy - 1
+    const uint32_t fm2 = fc - 2u;
+    uint32_t A[5], B[5], Ch[5], zn[5], zs[5], ks[5];
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint32_t t = t0 + (uint32_t)(r - 2);
+        zn[r] = (int32_t)t < 0 ? 1u : 0u;
+        zs[r] = (int32_t)t >= (int32_t)c.ns2 ? 1u : 0u;
+        const uint32_t nr = hpgb_sel(zn[r], t + c.ns, c.ns3 - t);
+        A[r] = hpgb_sel(zn[r] | zs[r], nr, t + c.belt_a0);
+        B[r] = hpgb_sel(zn[r], 2u * nr + fm2, hpgb_sel(zs[r], fm2 - 2u * nr, c.ns4));
+        Ch[r] = hpgb_sel(zs[r], c.npix_hi - nr, 0u);
+        ks[r] = t & 1u;
+    }
+    // neighbour order SW, W, NW, N, NE, E, SE, S (hpgeom/hpgeom.c:2879); ring index = 2 - (dx + dy)
+    const int dx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+    const int dy[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const int r = 2 - (dx[m] + dy[m]);
+        const uint32_t X = ((w0 + (uint32_t)(dx[m] - dy[m]) + ks[r]) >> 1) & c.ns4m1;
+        const uint32_t cl = hpgb_sel(zn[r], ~(iy + (uint32_t)dy[m]) & c.nsm1,
+                                     hpgb_sel(zs[r], c.npix_lo | (ix + (uint32_t)dx[m]), X + c.belt_c0));
+        out[m] = (int64_t)((uint64_t)A[r] * (uint64_t)B[r] + (((uint64_t)Ch[r] << 32) | cl));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // bilinear interpolation: hpgeom/healpix_geom.c:504-510 (ring_above), :1585-1606
 // (get_ring_info2), :1608-1690 (get_interpol)

@@ -216,6 +216,35 @@ HPGB_HD void hpgb_r2n_cap(const hpgb_rk &c, const hpgb_geom &g, uint64_t up, boo
     iy = north ? c.nsm1 - q : ir - 1u - q;
 }
 
+// RING pixel (must be < npix) -> (ix, iy, face): ring2xyf of the reference (hpgeom/healpix_geom.c:410-454)
+// from the pieces above
+HPGB_HD void hpgb_ring2xyf_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, uint32_t &ix, uint32_t &iy, uint32_t &face) {
+    uint32_t ipb_lo;
+    const uint32_t tmp = hpgb_r2n_zone(c, (uint64_t)pix, ipb_lo);
+    if (hpgb_r2n_is_cap(c, tmp))
+        hpgb_r2n_cap(c, g, (uint64_t)pix, (int32_t)tmp < 0, ix, iy, face);
+    else
+        hpgb_r2n_belt(c, tmp, ipb_lo, ix, iy, face);
+}
+
+// upgrade_pixels in the RING scheme without any Morton code (reference chain: ring_to_nest -> children
+// p << 2k .. -> nest_to_ring, hpgeom/hpgeom.py:515-556): parent -> (ix, iy, face); its children are the
+// 2^k x 2^k block (ix << k | cx, iy << k | cy) of the same face, in nest order (child number =
+// interleave(cx, cy)); this converts the C consecutive children starting at child number `first`
+// (a multiple of C; C = 1 or 4).  `last` = the parent is nest pixel npix-1 (the reference refuses it).
+template <int C>
+HPGB_HD void hpgb_upgrade_ring_group(const hpgb_rk &c, const hpgb_rk &cu, const hpgb_geom &g, int64_t p, uint64_t first,
+                                     int64_t *r, bool &last) {
+    uint32_t ix, iy, face, gx, gy;
+    hpgb_ring2xyf_k(c, g, p, ix, iy, face);
+    last = face == 11u && ix == c.nsm1 && iy == c.nsm1;
+    const uint32_t kk = cu.k - c.k;
+    hpgb_deinterleave(first, gx, gy);
+    const uint32_t bx = (ix << kk) | gx, by = (iy << kk) | gy;
+#pragma unroll
+    for (int j = 0; j < C; j++) r[j] = hpgb_xyf2ring_k(cu, bx + (uint32_t)(j & 1), by + (uint32_t)(j >> 1), face);
+}
+
 template <bool HI>
 HPGB_HD int64_t hpgb_xyf2nest_k(const hpgb_rk &c, uint32_t ix, uint32_t iy, uint32_t face) {
     uint32_t lo = hpgb_prmt(ix, iy, 0x5140), hi = hpgb_prmt(ix, iy, 0x7362);

@@ -229,6 +229,7 @@ struct OpNeighbors {
     const int64_t *nside_v;
     int64_t base;
     hpgb_geom g;
+    hpgb_rk c;  // constants of the minimum-instruction RING core (scalar power-of-two nside)
     typedef longlong2 In2;
     typedef hpgb_no_ctx Ctx;
     HPGB_DEFAULT_RUN4
@@ -240,6 +241,8 @@ struct OpNeighbors {
             bad.flag(base + i);
 #pragma unroll
             for (int m = 0; m < 8; m++) r[m] = -1;
+        } else if (!NEST && POW2 && !VAR) {
+            hpgb_neighbors_ring_k(c, gg, p, r);
         } else {
             hpgb_neighbors<NEST, POW2>(gg, p, r);
         }
@@ -286,6 +289,65 @@ struct OpNeighbors {
     }
 };
 
+// RING neighbours, scalar nside = 2^k, 16-byte aligned operands.  The per-pixel body (ring -> xyf, five
+// ring set-ups, eight offsets: hpgb_neighbors_ring_k) is ~300 instructions; inlined four times by the
+// generic skeleton it overflowed the instruction cache (54 % of the stall samples were instruction
+// fetch).  Here it exists ONCE: a warp takes 64 consecutive pixels, every lane converts its two pixels in
+// a rolled loop and drops the rows into the XOR-swizzled staging buffer, then the warp writes the 4 KiB
+// of rows with fully coalesced 128-bit streaming stores.  The next chunk's pixels are loaded before the
+// current one is converted.
+__global__ void __launch_bounds__(HPGB_BLOCK) k_neighbors_ring(const int64_t *__restrict__ pix, int64_t *__restrict__ out,
+                                                               const int64_t n, const hpgb_geom g, const hpgb_rk c,
+                                                               const int64_t base, hpgb_status_t *st) {
+    __shared__ longlong2 sbuf[HPGB_BLOCK / 32][32 * 8];
+    const int lane = threadIdx.x & 31;
+    longlong2 *ws = sbuf[threadIdx.x >> 5];
+    const int64_t gw = (int64_t)blockIdx.x * (HPGB_BLOCK / 32) + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * (HPGB_BLOCK / 32);
+    const int64_t nchunk = n >> 6;
+    hpgb_bad_t bad;
+    auto convert = [&](int64_t p, int64_t i, int64_t *r) {
+        if (!hpgb_pixel_ok(g, p)) {
+            bad.flag(base + i);
+#pragma unroll
+            for (int m = 0; m < 8; m++) r[m] = -1;
+        } else {
+            hpgb_neighbors_ring_k(c, g, p, r);
+        }
+    };
+    int64_t ch = gw;
+    longlong2 v = make_longlong2(0, 0);
+    if (ch < nchunk) v = hpgb_ld2(pix + ch * 64 + 2 * lane);
+    for (; ch < nchunk; ch += nw) {
+        const longlong2 cur = v;
+        if (ch + nw < nchunk) v = hpgb_ld2(pix + (ch + nw) * 64 + 2 * lane);
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            int64_t r[8];
+            convert(q ? cur.y : cur.x, ch * 64 + 2 * lane + q, r);
+#pragma unroll
+            for (int j = 0; j < 4; j++) ws[lane * 8 + ((q * 4 + j) ^ (lane & 7))] = make_longlong2(r[2 * j], r[2 * j + 1]);
+        }
+        __syncwarp();
+        longlong2 *dst = reinterpret_cast<longlong2 *>(out + ch * 512);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int idx = k * 32 + lane, src = idx >> 3, j = idx & 7;
+            __stcs(dst + idx, ws[src * 8 + (j ^ (src & 7))]);
+        }
+        __syncwarp();
+    }
+    // tail (< 64 pixels): one pixel per thread, direct stores
+    const int64_t t = (nchunk << 6) + (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x;
+    if (t < n) {
+        int64_t r[8];
+        convert(hpgb_ld1(pix + t), t, r);
+#pragma unroll
+        for (int m = 0; m < 8; m += 2) hpgb_st2(out + 8 * t + m, r[m], r[m + 1]);
+    }
+    bad.commit(st);
+}
+
 }  // namespace
 
 int launch_neighbors(const int64_t *pix, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v, int nest,
@@ -295,10 +357,10 @@ int launch_neighbors(const int64_t *pix, int64_t *out, int64_t n, int64_t nside,
     if (!hpgb_aligned16(out)) return HPGB_E_BAD_ARGUMENT;  // rows are written with 128-bit stores
     if (nside_v) {
         if (nest) {
-            OpNeighbors<true, true, true> op{pix, out, nside_v, base, hpgb_geom()};
+            OpNeighbors<true, true, true> op{pix, out, nside_v, base, hpgb_geom(), hpgb_rk()};
             return hpgb_launch_map1(op, n, st, s);
         }
-        OpNeighbors<false, false, true> op{pix, out, nside_v, base, hpgb_geom()};
+        OpNeighbors<false, false, true> op{pix, out, nside_v, base, hpgb_geom(), hpgb_rk()};
         return hpgb_launch_map1(op, n, st, s);
     }
     int c = hpgb_check_nside(nside, nest);
@@ -306,14 +368,25 @@ int launch_neighbors(const int64_t *pix, int64_t *out, int64_t n, int64_t nside,
     const hpgb_geom g = hpgb_make_geom(nside, nest);
     const bool vec = hpgb_aligned16(pix);
     if (nest) {
-        OpNeighbors<true, true, false> op{pix, out, nullptr, base, g};
+        OpNeighbors<true, true, false> op{pix, out, nullptr, base, g, hpgb_rk()};
         return hpgb_launch_map(op, n, vec, st, s);
+    }
+    if (g.order >= 0 && vec) {
+        static int occ = 0;
+        if (!occ) occ = hpgb_resident_ctas(k_neighbors_ring, 0, HPGB_BLOCK);
+        int64_t grid = (int64_t)hpgb_sm_count() * occ;
+        const int64_t want = ((n >> 6) + HPGB_BLOCK / 32 - 1) / (HPGB_BLOCK / 32);
+        if (want < grid) grid = want > 0 ? want : 1;
+        k_neighbors_ring<<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n, g, hpgb_make_rk(g), base, st);
+        g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
     }
     if (g.order >= 0) {
-        OpNeighbors<false, true, false> op{pix, out, nullptr, base, g};
+        OpNeighbors<false, true, false> op{pix, out, nullptr, base, g, hpgb_make_rk(g)};
         return hpgb_launch_map(op, n, vec, st, s);
     }
-    OpNeighbors<false, false, false> op{pix, out, nullptr, base, g};
+    OpNeighbors<false, false, false> op{pix, out, nullptr, base, g, hpgb_rk()};
     return hpgb_launch_map(op, n, vec, st, s);
 }
 
@@ -347,14 +420,16 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_upgrade(const int64_t *__restric
 #pragma unroll
             for (int j = 0; j < C; j++) r[j] = -1;
         } else {
-            if (!NEST) p = hpgb_ring2nest_k<false>(c, g, p);
-            if (p == g.npix - 1) bad.flag(HPGB_UPGRADE_CLASS1 | (base + i));
-            // first child of the group: parent << 2k, plus C * (group index within the parent)
-            const int64_t first = (p << (gshift + (C == 4 ? 2 : (C == 2 ? 1 : 0)))) + ((w & (((int64_t)1 << gshift) - 1)) * C);
+            if (NEST) {
+                if (p == g.npix - 1) bad.flag(HPGB_UPGRADE_CLASS1 | (base + i));
+                // first child of the group: parent << 2k, plus C * (group index within the parent)
+                const int64_t first = (p << (gshift + (C == 4 ? 2 : (C == 2 ? 1 : 0)))) + ((w & (((int64_t)1 << gshift) - 1)) * C);
 #pragma unroll
-            for (int j = 0; j < C; j++) {
-                const uint64_t q = (uint64_t)(first + j);
-                r[j] = NEST ? (int64_t)q : hpgb_nest2ring_k<false>(cu, (uint32_t)q, (uint32_t)(q >> 32));
+                for (int j = 0; j < C; j++) r[j] = first + j;
+            } else {
+                bool last;
+                hpgb_upgrade_ring_group<C>(c, cu, g, p, (uint64_t)(w & (((int64_t)1 << gshift) - 1)) * C, r, last);
+                if (last) bad.flag(HPGB_UPGRADE_CLASS1 | (base + i));
             }
         }
         if (C == 4) {

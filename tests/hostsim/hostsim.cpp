@@ -75,3 +75,21 @@ int64_t sim_ring_roundtrip_any(int64_t nside, const int64_t *in, int64_t n, int6
 #ifdef HAVE_FP
 #include "hostsim_fp.inc"
 #endif
+
+// upgrade_pixels, RING scheme, as k_upgrade<false, C> does it (hpgb_upgrade_ring_group)
+extern "C" int64_t sim_upgrade_ring(int64_t nside, int64_t nside_up, const int64_t *pix, int64_t n, int group4, int64_t *out) {
+    const hpgb_geom g = hpgb_make_geom(nside, 1), gu = hpgb_make_geom(nside_up, 1);
+    const hpgb_rk c = hpgb_make_rk(g), cu = hpgb_make_rk(gu);
+    const int64_t ratio = (nside_up / nside) * (nside_up / nside);
+    for (int64_t i = 0; i < n; i++) {
+        if (!hpgb_pixel_ok(g, pix[i])) return i;
+        bool last;
+        if (group4 && ratio >= 4) {
+            for (int64_t f = 0; f < ratio; f += 4) hpgb_upgrade_ring_group<4>(c, cu, g, pix[i], (uint64_t)f, out + i * ratio + f, last);
+        } else {
+            for (int64_t f = 0; f < ratio; f++) hpgb_upgrade_ring_group<1>(c, cu, g, pix[i], (uint64_t)f, out + i * ratio + f, last);
+        }
+        if (last) return i;
+    }
+    return -1;
+}
