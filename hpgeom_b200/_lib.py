@@ -65,6 +65,12 @@ _SIGS = {
     "hpgb_query_circle_ring_ranges": [c_vp, c_vp, c_vp, c_vp],
     "hpgb_host_query_circle_ring_count": [c_vp, c_int, ctypes.POINTER(c_i64)],
     "hpgb_host_query_circle_ring_fill": [c_vp, c_vp, c_i64, c_int],
+    "hpgb_query_circle_nest_open": [c_i64, c_dbl, c_dbl, c_dbl, c_int, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_vp),
+                                    ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],
+    "hpgb_query_nest_ranges": [c_vp, c_vp, ctypes.POINTER(c_i64)],
+    "hpgb_query_nest_pixels_host": [c_vp, c_vp, c_i64],
+    "hpgb_query_nest_pixels_device": [c_vp, c_vp, c_i64, c_vp],
+    "hpgb_query_nest_close": [c_vp],
     "hpgb_explain_nside": [c_i64, c_int, ctypes.c_char_p, c_int],
     "hpgb_explain_angle": [c_i64, c_int, c_dbl, c_dbl, c_int, c_int, ctypes.c_char_p, c_int],
     "hpgb_explain_pixel": [c_i64, c_int, c_i64, ctypes.c_char_p, c_int],

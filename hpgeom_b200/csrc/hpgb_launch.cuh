@@ -367,6 +367,17 @@ __device__ __forceinline__ void hpgb_st1(double *p, double a) { __stcs(p, a); }
 // warp store touch 32 half-filled sectors; instead the units take a turn through shared memory
 // (XOR-swizzled, conflict-free both ways) so that each store instruction writes 512 contiguous
 // bytes.  Full warps only (callers fall back to direct stores otherwise).  NU = 4 or 8.
+// store policy of the coalesced row stores (A/B switch): 0 = streaming (evict-first), 1 = plain write-back
+#ifndef HPGB_ROW_ST
+#define HPGB_ROW_ST 0
+#endif
+__device__ __forceinline__ void hpgb_row_st(longlong2 *p, const longlong2 &v) {
+#if HPGB_ROW_ST == 1
+    *p = v;
+#else
+    __stcs(p, v);
+#endif
+}
 template <int NU>
 __device__ __forceinline__ void hpgb_warp_store_units(longlong2 *warp_dst, const longlong2 (&u)[NU], longlong2 *warp_smem) {
     const int lane = threadIdx.x & 31;
@@ -379,7 +390,7 @@ __device__ __forceinline__ void hpgb_warp_store_units(longlong2 *warp_dst, const
     for (int k = 0; k < NU; k++) {
         const int idx = k * 32 + lane, src = idx / NU, j = idx & M;
         const int ssw = NU == 8 ? (src & 7) : ((src >> 1) & 3);
-        __stcs(warp_dst + idx, warp_smem[src * NU + (j ^ ssw)]);
+        hpgb_row_st(warp_dst + idx, warp_smem[src * NU + (j ^ ssw)]);
     }
     __syncwarp();
 }

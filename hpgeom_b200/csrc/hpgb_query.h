@@ -236,4 +236,87 @@ static inline int hpgb_qc_plan(int64_t nside, double theta, double phi, double r
     return HPGB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// query_circle in the NEST scheme: the reference's hierarchical search (query_disc, NEST branch,
+// hpgeom/healpix_geom.c:748-800, and check_pixel_nest, :541-601).  The reference walks the pixel
+// tree depth first with an explicit stack; the verdict on a pixel (drop it / output it or its
+// order-`order` ancestor / look at its four children) only depends on the pixel itself, so here the
+// tree is walked breadth first, one kernel launch per order over the whole frontier (k_query.cu),
+// and the emitted [lo, hi) ranges are sorted afterwards.  The depth-first walk abandons the rest of a
+// sub-tree once its ancestor has been output ("unwind the stack"); breadth first that shows up as the
+// same single-pixel range emitted more than once, removed after the sort.
+// ---------------------------------------------------------------------------------------------
+#define HPGB_QN_MAX_ORDER 29
+struct hpgb_qn_plan {
+    int order, omax, inclusive, whole_sphere;
+    double ptg_z, ptg_phi, cosrad;
+    double crpdr[HPGB_QN_MAX_ORDER + 1], crmdr[HPGB_QN_MAX_ORDER + 1];
+};
+
+// hpgeom/healpix_geom.c:748-771 (host, libm); fact = 0: not inclusive
+static inline int hpgb_qn_make_plan(int64_t nside, double theta, double phi, double radius, int64_t fact, hpgb_qn_plan *p) {
+    const int c = hpgb_check_nside(nside, 1);
+    if (c) return c;
+    if (fact < 0 || (fact & (fact - 1)) || (fact > 0 && fact * nside > ((int64_t)1 << 29))) return HPGB_E_BAD_FACT;
+    *p = hpgb_qn_plan();
+    p->order = hpgb_ilog2_u64((uint64_t)nside);
+    p->inclusive = fact != 0;
+    p->omax = p->order + (p->inclusive ? hpgb_ilog2_u64((uint64_t)fact) : 0);
+    p->ptg_phi = phi;
+    if (radius >= HPGB_PI) {  // the disc covers the whole sphere
+        p->whole_sphere = 1;
+        return HPGB_OK;
+    }
+    p->ptg_z = cos(theta);
+    p->cosrad = cos(radius);
+    for (int o = 0; o <= p->omax; o++) {
+        const double dr = max_pixrad_host((int64_t)1 << o);  // safety distance
+        p->crpdr[o] = ((radius + dr) > HPGB_PI) ? -1. : cos(radius + dr);
+        p->crmdr[o] = ((radius - dr) < 0.) ? 1. : cos(radius - dr);
+    }
+    return HPGB_OK;
+}
+
+// Verdict on pixel `pix` of order o (g = geometry of nside 2^o, NEST): 0 = nothing, 1 = output the range
+// [lo, hi) at order `order`, 2 = visit the four children 4 pix .. 4 pix + 3 at order o + 1.
+// hpgeom/healpix_geom.c:784-796 + check_pixel_nest (:541-601).
+HPGB_HD int hpgb_qn_visit(const hpgb_qn_plan &P, const hpgb_geom &g, const double *T, int o, int64_t pix, int64_t &lo, int64_t &hi) {
+    double z, phi, sth;
+    bool hs;
+    hpgb_pix2loc<true, true>(g, pix, z, phi, sth, hs);
+    const double cang = hpgb_cosdist_zphi(T, P.ptg_z, P.ptg_phi, z, phi);
+    if (!(cang > P.crpdr[o])) return 0;
+    const int zone = (cang < P.cosrad) ? 1 : ((cang <= P.crmdr[o]) ? 2 : 3);
+    if (o < P.order) {
+        if (zone >= 3) {
+            const int sdist = 2 * (P.order - o);
+            lo = pix << sdist;
+            hi = (pix + 1) << sdist;
+            return 1;
+        }
+        return 2;
+    }
+    if (o > P.order) {  // implies inclusive
+        if (zone >= 2 || o >= P.omax) {
+            lo = pix >> (2 * (o - P.order));
+            hi = lo + 1;
+            return 1;
+        }
+        return 2;
+    }
+    if (zone >= 2) {
+        lo = pix;
+        hi = pix + 1;
+        return 1;
+    }
+    if (P.inclusive) {
+        if (P.order < P.omax) return 2;
+        lo = pix;
+        hi = pix + 1;
+        return 1;
+    }
+    return 0;
+}
+
 #endif  // HPGB_QUERY_H

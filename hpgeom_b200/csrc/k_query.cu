@@ -6,6 +6,9 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "hpgb_core.h"
 #include "hpgb_fp.h"
@@ -268,6 +271,281 @@ int hpgb_host_query_circle_ring_fill(const hpgb_disc_t *plan, int64_t *out, int6
                                   return launch_ranges_expand(d.ranges, d.offs, m, base, cn, (int64_t *)dp[0], s);
                               },
                               nullptr);
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// NEST scheme: breadth-first hierarchical search (hpgb_qn_visit, hpgb_query.h), one launch per order.
+// =============================================================================================
+namespace {
+
+// one order of the walk: verdict per frontier pixel, warp-aggregated appends to the next frontier
+// (4 children per kept pixel) and to this order's range list.  cnt[0] = children written, cnt[1] = ranges.
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qn_level(const hpgb_qn_plan P, const hpgb_geom g, const int o,
+                                                         const int64_t *__restrict__ frontier, const int64_t n,
+                                                         int64_t *__restrict__ next, int64_t *__restrict__ rlo,
+                                                         int64_t *__restrict__ rhi, unsigned long long *cnt) {
+    const double *T = hpgb_stage_table();
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    const int64_t rounds = (n + stride - 1) / stride;
+    for (int64_t k = 0; k < rounds; k++) {
+        const int64_t i = k * stride + (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x;
+        int v = 0;
+        int64_t pix = 0, lo = 0, hi = 0;
+        if (i < n) {
+            pix = frontier[i];
+            v = hpgb_qn_visit(P, g, T, o, pix, lo, hi);
+        }
+        const unsigned m1 = __ballot_sync(0xFFFFFFFFu, v == 1), m2 = __ballot_sync(0xFFFFFFFFu, v == 2);
+        unsigned long long b1 = 0, b2 = 0;
+        if (lane == 0) {
+            if (m1) b1 = atomicAdd(cnt + 1, (unsigned long long)__popc(m1));
+            if (m2) b2 = atomicAdd(cnt, 4ull * (unsigned long long)__popc(m2));
+        }
+        b1 = __shfl_sync(0xFFFFFFFFu, b1, 0);
+        b2 = __shfl_sync(0xFFFFFFFFu, b2, 0);
+        if (v == 1) {
+            const unsigned long long r = b1 + (unsigned long long)__popc(m1 & lt);
+            rlo[r] = lo;
+            rhi[r] = hi;
+        } else if (v == 2) {
+            longlong2 *c = reinterpret_cast<longlong2 *>(next + b2 + 4ull * (unsigned long long)__popc(m2 & lt));
+            c[0] = make_longlong2(4 * pix, 4 * pix + 1);
+            c[1] = make_longlong2(4 * pix + 2, 4 * pix + 3);
+        }
+    }
+}
+
+// sorted (lo, hi) -> (m,2) table; a repeated single pixel (see hpgb_query.h) becomes an empty row
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qn_table(const int64_t *__restrict__ lo, const int64_t *__restrict__ hi, int64_t m,
+                                                         longlong2 *__restrict__ table) {
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; i < m; i += stride) {
+        const int64_t a = lo[i];
+        const bool dup = i > 0 && lo[i - 1] == a;
+        table[i] = make_longlong2(a, dup ? a : hi[i]);
+    }
+}
+
+struct QnHandle {
+    int device = 0;
+    int64_t m = 0, total = 0;
+    int64_t *ranges = nullptr, *offs = nullptr;
+};
+
+struct DevBuf {  // frees on scope exit
+    std::vector<void *> ptrs;
+    ~DevBuf() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    template <class Tp>
+    cudaError_t alloc(Tp **p, size_t bytes) {
+        cudaError_t e = cudaMalloc((void **)p, bytes ? bytes : 16);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+    void release(void *p) {
+        for (auto &q : ptrs)
+            if (q == p) q = nullptr;
+    }
+};
+
+int qn_build(const hpgb_qn_plan &P, int64_t nside, QnHandle *h) {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CKQ(cudaSetDevice(h->device));
+    DevBuf pool;
+    const int64_t npix = 12 * nside * nside;
+    int64_t *keys = nullptr, *vals = nullptr;  // unsorted ranges
+    int64_t R = 0;
+    if (P.whole_sphere) {
+        R = 1;
+        CKQ(pool.alloc(&keys, 8));
+        CKQ(pool.alloc(&vals, 8));
+        const int64_t z = 0;
+        CKQ(cudaMemcpy(keys, &z, 8, cudaMemcpyHostToDevice));
+        CKQ(cudaMemcpy(vals, &npix, 8, cudaMemcpyHostToDevice));
+    } else {
+        unsigned long long *cnt = nullptr;
+        CKQ(pool.alloc(&cnt, 16));
+        int64_t *cur = nullptr;
+        int64_t n = 12;
+        CKQ(pool.alloc(&cur, 12 * 8));
+        const int64_t base12[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+        CKQ(cudaMemcpy(cur, base12, sizeof base12, cudaMemcpyHostToDevice));
+        std::vector<int64_t *> lvl_lo, lvl_hi;
+        std::vector<int64_t> lvl_n;
+        for (int o = 0; o <= P.omax && n > 0; o++) {
+            int64_t *next = nullptr, *rlo = nullptr, *rhi = nullptr;
+            CKQ(pool.alloc(&next, (size_t)n * 32));
+            CKQ(pool.alloc(&rlo, (size_t)n * 8));
+            CKQ(pool.alloc(&rhi, (size_t)n * 8));
+            CKQ(cudaMemsetAsync(cnt, 0, 16, 0));
+            const hpgb_geom g = hpgb_make_geom((int64_t)1 << o, 1);
+            int64_t grid = (n + HPGB_BLOCK - 1) / HPGB_BLOCK;
+            const int64_t cap = (int64_t)hpgb_sm_count() * 8;
+            if (grid > cap) grid = cap;
+            k_qn_level<<<(unsigned)grid, HPGB_BLOCK, 0, 0>>>(P, g, o, cur, n, next, rlo, rhi, cnt);
+            g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+            unsigned long long hc[2];
+            CKQ(cudaMemcpy(hc, cnt, 16, cudaMemcpyDeviceToHost));
+            lvl_lo.push_back(rlo);
+            lvl_hi.push_back(rhi);
+            lvl_n.push_back((int64_t)hc[1]);
+            R += (int64_t)hc[1];
+            cudaFree(cur);
+            pool.release(cur);
+            cur = next;
+            n = (int64_t)hc[0];
+        }
+        CKQ(pool.alloc(&keys, (size_t)R * 8));
+        CKQ(pool.alloc(&vals, (size_t)R * 8));
+        int64_t at = 0;
+        for (size_t l = 0; l < lvl_n.size(); l++) {
+            if (lvl_n[l] > 0) {
+                CKQ(cudaMemcpyAsync(keys + at, lvl_lo[l], (size_t)lvl_n[l] * 8, cudaMemcpyDeviceToDevice, 0));
+                CKQ(cudaMemcpyAsync(vals + at, lvl_hi[l], (size_t)lvl_n[l] * 8, cudaMemcpyDeviceToDevice, 0));
+            }
+            at += lvl_n[l];
+        }
+    }
+    h->m = R;
+    h->total = 0;
+    if (R > 0) {
+        int64_t *skeys = nullptr, *svals = nullptr;
+        void *tmp = nullptr;
+        size_t tmp_bytes = 0;
+        CKQ(pool.alloc(&skeys, (size_t)R * 8));
+        CKQ(pool.alloc(&svals, (size_t)R * 8));
+        CKQ(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, skeys, vals, svals, R, 0, 62, (cudaStream_t)0));
+        CKQ(pool.alloc(&tmp, tmp_bytes));
+        CKQ(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, skeys, vals, svals, R, 0, 62, (cudaStream_t)0));
+        CKQ(cudaMalloc(&h->ranges, (size_t)R * 16));
+        CKQ(cudaMalloc(&h->offs, (size_t)(R + 1) * 8));
+        int64_t grid = (R + HPGB_BLOCK - 1) / HPGB_BLOCK;
+        const int64_t cap = (int64_t)hpgb_sm_count() * 8;
+        if (grid > cap) grid = cap;
+        k_qn_table<<<(unsigned)grid, HPGB_BLOCK, 0, 0>>>(skeys, svals, R, reinterpret_cast<longlong2 *>(h->ranges));
+        g_hpgb_launches.fetch_add(2, std::memory_order_relaxed);
+        hpgb_status_t *st = nullptr;
+        CKQ(pool.alloc(&st, sizeof(hpgb_status_t)));
+        CKQ(cudaMemsetAsync(st, 0xFF, sizeof(hpgb_status_t), 0));
+        const int rc = launch_ranges_offsets(h->ranges, R, 0, h->offs, st, 0);
+        if (rc != HPGB_OK) {
+            cudaSetDevice(prev);
+            return rc;
+        }
+        CKQ(cudaMemcpy(&h->total, h->offs + R, 8, cudaMemcpyDeviceToHost));
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaSetDevice(prev);
+    return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hpgb_query_circle_nest_open(int64_t nside, double a, double b, double radius, int inclusive, int64_t fact, int lonlat,
+                                int degrees, int device, void **handle, int64_t *m, int64_t *total) {
+    if (!handle || !m || !total) return HPGB_E_BAD_ARGUMENT;
+    *handle = nullptr;
+    // argument checks in the wrapper's order: hpgeom/hpgeom.c:793-838
+    double theta, phi;
+    bool ok;
+    if (lonlat) {
+        ok = degrees ? hpgb_angles_exact<true, true>(a, b, theta, phi) : hpgb_angles_exact<true, false>(a, b, theta, phi);
+        if (ok && degrees) radius *= HPGB_PI / 180.0;
+    } else {
+        ok = hpgb_angles_exact<false, false>(a, b, theta, phi);
+    }
+    if (!ok) return HPGB_E_BAD_ANGLE;
+    if (radius <= 0) return HPGB_E_BAD_RADIUS;
+    const int c = hpgb_check_nside(nside, 1);
+    if (c) return c;
+    if (!inclusive) fact = 0;
+    else if (fact <= 0 || fact * nside > ((int64_t)1 << 29) || (fact & (fact - 1))) return HPGB_E_BAD_FACT;
+    hpgb_qn_plan P;
+    int rc = hpgb_qn_make_plan(nside, theta, phi, radius, fact, &P);
+    if (rc != HPGB_OK) return rc;
+    const int ndev = hpgb_device_count();
+    if (ndev <= 0) return HPGB_E_NO_DEVICE;
+    if (device < 0 || device >= ndev) return HPGB_E_BAD_ARGUMENT;
+    QnHandle *h = new QnHandle();
+    h->device = device;
+    rc = qn_build(P, nside, h);
+    if (rc != HPGB_OK) {
+        if (h->ranges) cudaFree(h->ranges);
+        if (h->offs) cudaFree(h->offs);
+        delete h;
+        return rc;
+    }
+    *handle = h;
+    *m = h->m;
+    *total = h->total;
+    return HPGB_OK;
+}
+
+int hpgb_query_nest_close(void *handle) {
+    QnHandle *h = (QnHandle *)handle;
+    if (!h) return HPGB_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->device);
+    if (h->ranges) cudaFree(h->ranges);
+    if (h->offs) cudaFree(h->offs);
+    cudaSetDevice(prev);
+    delete h;
+    return HPGB_OK;
+}
+
+// merged [lo, hi) ranges as the reference's range set holds them (touching ranges fused,
+// hpgeom/hpgeom_stack.c:231-250): out_m2 has room for m rows, *n_merged rows are written
+int hpgb_query_nest_ranges(void *handle, int64_t *out_m2, int64_t *n_merged) {
+    QnHandle *h = (QnHandle *)handle;
+    if (!h || !n_merged || (h->m > 0 && !out_m2)) return HPGB_E_BAD_ARGUMENT;
+    *n_merged = 0;
+    if (h->m == 0) return HPGB_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CKQ(cudaSetDevice(h->device));
+    CKQ(cudaMemcpy(out_m2, h->ranges, (size_t)h->m * 16, cudaMemcpyDeviceToHost));
+    cudaSetDevice(prev);
+    int64_t k = 0;  // in place: rows are sorted and disjoint; drop empty rows, fuse touching ones
+    for (int64_t i = 0; i < h->m; i++) {
+        const int64_t lo = out_m2[2 * i], hi = out_m2[2 * i + 1];
+        if (hi <= lo) continue;
+        if (k > 0 && lo <= out_m2[2 * k - 1]) {
+            if (hi > out_m2[2 * k - 1]) out_m2[2 * k - 1] = hi;
+        } else {
+            out_m2[2 * k] = lo;
+            out_m2[2 * k + 1] = hi;
+            k++;
+        }
+    }
+    *n_merged = k;
+    return HPGB_OK;
+}
+
+int hpgb_query_nest_pixels_host(void *handle, int64_t *out, int64_t total) {
+    QnHandle *h = (QnHandle *)handle;
+    if (!h || total != h->total || (total > 0 && !out)) return HPGB_E_BAD_ARGUMENT;
+    if (total == 0) return HPGB_OK;
+    hpgb_pipe_arr arrs[1] = {{nullptr, (char *)out, 8}};
+    return hpgb_host_pipeline(h->device, total, arrs, 1,
+                              [&](void **dp, int64_t base, int64_t cn, hpgb_status_t *, cudaStream_t s) {
+                                  return launch_ranges_expand(h->ranges, h->offs, h->m, base, cn, (int64_t *)dp[0], s);
+                              },
+                              nullptr);
+}
+
+int hpgb_query_nest_pixels_device(void *handle, int64_t *d_out, int64_t total, void *stream) {
+    QnHandle *h = (QnHandle *)handle;
+    if (!h || total != h->total || (total > 0 && !d_out)) return HPGB_E_BAD_ARGUMENT;
+    return launch_ranges_expand(h->ranges, h->offs, h->m, 0, total, d_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -135,12 +135,24 @@ __device__ __forceinline__ int window_find(const int64_t *soff, int64_t o) {
     return idx;
 }
 
+// store policy of the pixel list (A/B switch): 0 = streaming (evict-first), 1 = plain write-back
+#ifndef RG_ST
+#define RG_ST 0
+#endif
+__device__ __forceinline__ void rg_st2(int64_t *p, int64_t a, int64_t b) {
+#if RG_ST == 1
+    *reinterpret_cast<longlong2 *>(p) = make_longlong2(a, b);
+#else
+    __stcs(reinterpret_cast<longlong2 *>(p), make_longlong2(a, b));
+#endif
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(RG_BLOCK) k_ranges_expand(const longlong2 *__restrict__ ranges, const int64_t *__restrict__ offs,
                                                             int64_t m, int64_t out_begin, int64_t out_count,
                                                             int64_t *__restrict__ out, int64_t tiles_per_cta) {
-    __shared__ int64_t soff[RG_CH + 1];
-    __shared__ int64_t slo[RG_CH];
+    __shared__ int64_t soff[RG_CH + 1];  // offs[wbase .. wbase + RG_CH] (entries past m hold offs[m] = total)
+    __shared__ int64_t slo[RG_CH];       // start of ranges wbase .. wbase + RG_CH - 1
     __shared__ int64_t s_cur;
     const int tid = threadIdx.x;
     const int64_t ntiles = (out_count + RG_TILE - 1) / RG_TILE;
@@ -157,80 +169,90 @@ __global__ void __launch_bounds__(RG_BLOCK) k_ranges_expand(const longlong2 *__r
         s_cur = lo;
     }
     __syncthreads();
-    int64_t cur = s_cur;
+    int64_t wbase = s_cur;
+    auto load_window = [&]() {
+        for (int i = tid; i <= RG_CH; i += RG_BLOCK) {
+            const int64_t r = wbase + i;
+            soff[i] = offs[r < m ? r : m];
+            if (i < RG_CH) slo[i] = r < m ? ranges[r].x : 0;
+        }
+        __syncthreads();
+    };
+    load_window();
+    // The window is kept across tiles and only moves on when a tile reaches past it, so between moves
+    // the warps run without any barrier (long ranges: the kernel is a plain fill).
+    int idx_prev = 0;  // window slot of the range that held this thread's previous output
     for (int64_t t = t0; t < t1; t++) {
         const int64_t e0 = t * RG_TILE;                      // tile start, relative to out
         const int64_t o0 = out_begin + e0;                   // ... as a global output index
         const int64_t o_end = (e0 + RG_TILE < out_count ? e0 + RG_TILE : out_count) + out_begin;
+        // Common case, decided uniformly: a full tile that the current window covers.  No pending mask,
+        // no window moves; a thread whose eight outputs fall into one range (long ranges: always, and
+        // usually the range of its previous tile) just adds.
+        if (VEC && o_end - o0 == RG_TILE && (wbase + RG_CH >= m || soff[RG_CH] >= o_end)) {
+            const int64_t of = o0 + 2 * tid, ol = of + 3 * (2 * RG_BLOCK) + 1;
+            int idx = idx_prev;
+            if (!(soff[idx] <= of && soff[idx + 1] > of)) idx = window_find(soff, of);
+            int64_t v[RG_TILE / RG_BLOCK];
+            if (soff[idx + 1] > ol) {
+                const int64_t b = slo[idx] - soff[idx] + of;
+#pragma unroll
+                for (int k = 0; k < RG_TILE / RG_BLOCK; k++) v[k] = b + ((k >> 1) * (2 * RG_BLOCK) + (k & 1));
+            } else {
+#pragma unroll
+                for (int k = 0; k < RG_TILE / RG_BLOCK; k++) {
+                    const int64_t o = of + ((k >> 1) * (2 * RG_BLOCK) + (k & 1));
+                    if (soff[idx + 1] <= o) {
+                        if (k & 1) {
+                            while (soff[idx + 1] <= o) idx++;  // next output: usually one step (more over empty rows)
+                        } else {
+                            idx = window_find(soff, o);
+                        }
+                    }
+                    v[k] = slo[idx] + (o - soff[idx]);
+                }
+            }
+            idx_prev = idx;
+#pragma unroll
+            for (int k = 0; k < RG_TILE / RG_BLOCK; k += 2) rg_st2(out + e0 + (k >> 1) * (2 * RG_BLOCK) + 2 * tid, v[k], v[k + 1]);
+            continue;
+        }
         int64_t val[RG_TILE / RG_BLOCK];
         unsigned pending = 0;
 #pragma unroll
         for (int k = 0; k < RG_TILE / RG_BLOCK; k++)
             if (o0 + (k >> 1) * (2 * RG_BLOCK) + 2 * tid + (k & 1) < o_end) pending |= 1u << k;
-        for (;;) {  // rounds: uniform over the CTA
-            __syncthreads();  // the previous window (and s_cur) has been consumed
-            for (int i = tid; i <= RG_CH; i += RG_BLOCK) {
-                const int64_t r = cur + i;
-                soff[i] = offs[r < m ? r : m];
-                if (i < RG_CH) slo[i] = r < m ? ranges[r].x : 0;
-            }
-            __syncthreads();
-            // outputs below `cover` belong to ranges inside the window
-            const bool last_window = cur + RG_CH >= m;
-            const int64_t cover = soff[RG_CH];
-            if (soff[1] >= o_end) {  // whole tile inside range `cur`
-                const int64_t b = slo[0] - soff[0];
+        for (;;) {  // uniform over the CTA: wbase, cover, o_end are
+            const bool last_window = wbase + RG_CH >= m;
+            const int64_t cover = soff[RG_CH];  // outputs below it belong to ranges inside the window
+            int idx = -1;
 #pragma unroll
-                for (int k = 0; k < RG_TILE / RG_BLOCK; k++)
-                    val[k] = b + (o0 + (k >> 1) * (2 * RG_BLOCK) + 2 * tid + (k & 1));
-                pending = 0;
-            } else {
-#pragma unroll
-                for (int k = 0; k < RG_TILE / RG_BLOCK; k += 2) {
-                    const int64_t o = o0 + (k >> 1) * (2 * RG_BLOCK) + 2 * tid;
-                    if ((pending >> k) & 1u) {
-                        if (last_window || o < cover) {
-                            int idx = window_find(soff, o);
-                            val[k] = slo[idx] + (o - soff[idx]);
-                            pending &= ~(1u << k);
-                            if ((pending >> (k + 1)) & 1u) {
-                                if (last_window || o + 1 < cover) {
-                                    while (idx + 1 < RG_CH && soff[idx + 1] <= o + 1) idx++;  // zero-length ranges: may skip several
-                                    val[k + 1] = slo[idx] + (o + 1 - soff[idx]);
-                                    pending &= ~(1u << (k + 1));
-                                }
-                            }
-                        }
-                    } else if ((pending >> (k + 1)) & 1u) {  // first of the pair was resolved in an earlier round
-                        if (last_window || o + 1 < cover) {
-                            const int idx = window_find(soff, o + 1);
-                            val[k + 1] = slo[idx] + (o + 1 - soff[idx]);
-                            pending &= ~(1u << (k + 1));
+            for (int k = 0; k < RG_TILE / RG_BLOCK; k++) {
+                const int64_t o = o0 + (k >> 1) * (2 * RG_BLOCK) + 2 * tid + (k & 1);
+                if (((pending >> k) & 1u) && (last_window || o < cover)) {
+                    if (idx < 0 || soff[idx + 1] <= o) {
+                        if ((k & 1) && idx >= 0) {
+                            while (idx + 1 < RG_CH && soff[idx + 1] <= o) idx++;  // next output: usually one step (more over empty rows)
+                        } else {
+                            idx = window_find(soff, o);
                         }
                     }
+                    val[k] = slo[idx] + (o - soff[idx]);
+                    pending &= ~(1u << k);
                 }
             }
-            const bool done = last_window || cover >= o_end;
-            if (tid == 0) {
-                if (done) {  // window slot of the range holding the next tile's first output
-                    int idx = (soff[RG_CH] <= o_end) ? RG_CH : window_find(soff, o_end);
-                    int64_t nc = cur + idx;
-                    if (nc > m - 1) nc = m - 1;
-                    s_cur = nc;
-                } else {
-                    s_cur = cur + RG_CH;
-                }
-            }
-            __syncthreads();
-            cur = s_cur;
-            if (done) break;
+            if (last_window || cover >= o_end) break;
+            __syncthreads();  // everybody is done with this window
+            wbase += RG_CH;
+            load_window();
+            idx_prev = 0;
         }
 #pragma unroll
         for (int k = 0; k < RG_TILE / RG_BLOCK; k += 2) {
             const int64_t e = e0 + (k >> 1) * (2 * RG_BLOCK) + 2 * tid;
             const bool a = e + out_begin < o_end, b = e + 1 + out_begin < o_end;
             if (VEC && b) {
-                hpgb_st2(out + e, val[k], val[k + 1]);
+                rg_st2(out + e, val[k], val[k + 1]);
             } else {
                 if (a) hpgb_st1(out + e, val[k]);
                 if (b) hpgb_st1(out + e + 1, val[k + 1]);

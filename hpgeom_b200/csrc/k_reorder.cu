@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_neighbors_ring(const int64_t *__
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int idx = k * 32 + lane, src = idx >> 3, j = idx & 7;
-            __stcs(dst + idx, ws[src * 8 + (j ^ (src & 7))]);
+            hpgb_row_st(dst + idx, ws[src * 8 + (j ^ (src & 7))]);
         }
         __syncwarp();
     }

@@ -415,10 +415,11 @@ def query_circle(nside, a, b, radius, inclusive=False, fact=4, nest=True, lonlat
     (reference: hpgeom/hpgeom.c:765-864 -> query_disc, hpgeom/healpix_geom.c:632-747).
 
     RING scheme: the per-disc scalars are prepared on the host, every ring the disc touches is one
-    GPU thread (csrc/k_query.cu) and the resulting intervals are expanded by the
-    pixel_ranges_to_pixels kernels.  Same argument checks, order and messages as the reference.
-    ``device_resident=True`` (an extension) returns a torch CUDA tensor instead of a numpy array.
-    The NEST scheme (the reference's hierarchical search) is not built yet.
+    GPU thread (csrc/k_query.cu).  NEST scheme: the reference's hierarchical search walked breadth
+    first, one kernel launch per order over the whole frontier, ranges sorted on the device.  Either
+    way the resulting intervals are expanded by the pixel_ranges_to_pixels kernels.  Same argument
+    checks, order and messages as the reference.  ``device_resident=True`` (an extension) returns a
+    torch CUDA tensor instead of a numpy array.
     """
     nside, a, b, radius = int(nside), float(a), float(b), float(radius)
     inclusive, nest, lonlat, degrees = bool(inclusive), bool(nest), bool(lonlat), bool(degrees)
@@ -443,9 +444,10 @@ def query_circle(nside, a, b, radius, inclusive=False, fact=4, nest=True, lonlat
         if nest and (fact & (fact - 1)) > 0:
             raise ValueError("Inclusive factor %d must be power of 2 for nest." % fact)
     _lib.check_rc(rc)
-    if nest:
-        raise NotImplementedError("query_circle: only the RING scheme (nest=False) runs on the GPU so far")
     dev = _d.default_device()
+    if nest:
+        return _query_circle_nest(L, nside, a, b, radius, inclusive, fact, lonlat, degrees, return_pixel_ranges,
+                                  device_resident, dev)
     if not device_resident:
         total = ctypes.c_int64(0)
         _lib.check_rc(L.hpgb_host_query_circle_ring_count(ctypes.byref(plan), dev, ctypes.byref(total)))
@@ -463,6 +465,32 @@ def query_circle(nside, a, b, radius, inclusive=False, fact=4, nest=True, lonlat
         _lib.check_rc(L.hpgb_query_circle_ring_ranges(ctypes.byref(plan), ctypes.c_void_p(table.data_ptr()),
                                                       ctypes.c_void_p(work.data_ptr()), stream))
     return pixel_ranges_to_pixels(table)
+
+
+def _query_circle_nest(L, nside, a, b, radius, inclusive, fact, lonlat, degrees, return_pixel_ranges, device_resident, dev):
+    handle, m, total = ctypes.c_void_p(), ctypes.c_int64(0), ctypes.c_int64(0)
+    _lib.check_rc(L.hpgb_query_circle_nest_open(nside, a, b, radius, int(inclusive), fact, int(lonlat), int(degrees), dev,
+                                                ctypes.byref(handle), ctypes.byref(m), ctypes.byref(total)))
+    try:
+        if return_pixel_ranges:
+            table = np.empty((m.value, 2), dtype=np.int64)
+            k = ctypes.c_int64(0)
+            _lib.check_rc(L.hpgb_query_nest_ranges(handle, ctypes.c_void_p(table.ctypes.data), ctypes.byref(k)))
+            table = np.ascontiguousarray(table[:k.value])
+            return _d.torch.from_numpy(table).to("cuda:%d" % dev) if device_resident else table
+        if not device_resident:
+            out = np.empty(total.value, dtype=np.int64)
+            _lib.check_rc(L.hpgb_query_nest_pixels_host(handle, ctypes.c_void_p(out.ctypes.data), total.value))
+            return out
+        torch = _d.torch
+        with torch.cuda.device(dev):
+            out = torch.empty(total.value, dtype=torch.int64, device="cuda:%d" % dev)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check_rc(L.hpgb_query_nest_pixels_device(handle, ctypes.c_void_p(out.data_ptr()), total.value, stream))
+            torch.cuda.current_stream(dev).synchronize()  # the handle (range table) is freed below
+        return out
+    finally:
+        L.hpgb_query_nest_close(handle)
 
 
 def query_circle_vec(nside, vec, radius, inclusive=False, fact=4, nest=True):

@@ -212,6 +212,20 @@ int hpgb_query_circle_ring_ranges(const hpgb_disc_t *plan, int64_t *d_ranges_m2,
 int hpgb_host_query_circle_ring_count(const hpgb_disc_t *plan, int device, int64_t *total);
 int hpgb_host_query_circle_ring_fill(const hpgb_disc_t *plan, int64_t *out, int64_t total, int device);
 
+/* ---- query_circle, NEST scheme: the hierarchical search of query_disc (hpgeom/healpix_geom.c:748-800,
+ * check_pixel_nest :541-601), walked breadth first: one kernel launch per order over the whole frontier,
+ * the emitted ranges sorted on the device.  Frontier sizes are data dependent, so this entry point owns its
+ * device memory: open() runs the search on `device` (same argument checks and return codes as the RING
+ * plan; fact must be a power of two) and keeps the sorted range table + offsets in an opaque handle;
+ * m = table rows, total = pixels.  Then: the merged range list (return_pixel_ranges=True), the pixel
+ * list into a host buffer (chunked D2H pipeline) or into a device buffer on `stream`; close() frees. ---- */
+int hpgb_query_circle_nest_open(int64_t nside, double a, double b, double radius, int inclusive, int64_t fact,
+                                int lonlat, int degrees, int device, void **handle, int64_t *m, int64_t *total);
+int hpgb_query_nest_ranges(void *handle, int64_t *out_m2, int64_t *n_merged);
+int hpgb_query_nest_pixels_host(void *handle, int64_t *out, int64_t total);
+int hpgb_query_nest_pixels_device(void *handle, int64_t *d_out, int64_t total, void *stream);
+int hpgb_query_nest_close(void *handle);
+
 /* ---- error text for ONE element (host side, pure functions) -------------------------------
  * Re-evaluates the reference's checks in the reference's order for the element the kernel
  * flagged and writes the reference's message (at most `cap` bytes, NUL terminated).

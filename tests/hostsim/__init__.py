@@ -17,7 +17,7 @@ class HostSim:
         self.lib = ctypes.CDLL(os.path.join(_HERE, "libhostsim.so"))
         for n in ("sim_nest_to_ring", "sim_ring_to_nest", "sim_ring_roundtrip_any", "sim_angle_to_pixel",
                   "sim_pixel_to_angle", "sim_pixel_to_vector", "sim_vector_to_pixel", "sim_neighbors", "sim_interp",
-                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_pixel_to_angle_k", "sim_pixel_to_vector_k", "sim_interp_k", "sim_query_circle_ring"):
+                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_pixel_to_angle_k", "sim_pixel_to_vector_k", "sim_interp_k", "sim_query_circle_ring", "sim_query_circle_nest"):
             getattr(self.lib, n).restype = ctypes.c_int64
         self.last_slow = 0
 
@@ -166,4 +166,15 @@ class HostSim:
             raise ValueError("plan failed: %d" % -m)
         r = np.zeros((m, 2), dtype=np.int64)
         self.lib.sim_query_circle_ring(*args, r.ctypes.data_as(_I), ctypes.c_int64(m))
+        return r
+
+    def query_circle_nest_ranges(self, nside, theta, phi, radius, fact=0):
+        """merged (m, 2) range list of the NEST query_circle walk (radians; fact=0: non-inclusive)."""
+        args = (ctypes.c_int64(nside), ctypes.c_double(theta), ctypes.c_double(phi), ctypes.c_double(radius),
+                ctypes.c_int64(fact))
+        m = self.lib.sim_query_circle_nest(*args, None, ctypes.c_int64(0))
+        if m < 0:
+            raise ValueError("plan failed: %d" % -m)
+        r = np.zeros((m, 2), dtype=np.int64)
+        self.lib.sim_query_circle_nest(*args, r.ctypes.data_as(_I), ctypes.c_int64(m))
         return r

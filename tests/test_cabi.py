@@ -136,3 +136,5 @@ def test_no_cpu_fallback_without_device():
         hpg.pixel_ranges_to_pixels(np.array([[0, 3], [10, 10], [20, 22]]))
     with pytest.raises(RuntimeError, match="no CUDA device"):
         hpg.query_circle(1024, 10.0, 20.0, 1.0, nest=False)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hpg.query_circle(1024, 10.0, 20.0, 1.0)

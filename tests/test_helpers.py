@@ -79,6 +79,4 @@ def test_error_texts():
 
 def test_region_queries_not_built():
     with pytest.raises(NotImplementedError):
-        hpc.query_disc(32, [1, 0, 0], 0.1, nest=True)  # NEST query_circle: hierarchical search, not built
-    with pytest.raises(NotImplementedError):
         hpc.query_polygon(32, np.eye(3))

@@ -19,6 +19,15 @@ def cases():
             g["qc_pix"][ends[k] - g["qc_sizes"][k]:ends[k]]
 
 
+def nest_cases():
+    g = load_golden("query")
+    pe, re_ = np.cumsum(g["qn_sizes"]), np.cumsum(g["qn_rsizes"])
+    for k, p in enumerate(g["qn_params"]):
+        nside, theta, phi, radius, fact = p
+        yield (int(nside), float(theta), float(phi), float(radius), int(fact)), \
+            g["qn_pix"][pe[k] - g["qn_sizes"][k]:pe[k]], g["qn_ranges"][re_[k] - g["qn_rsizes"][k]:re_[k]]
+
+
 def expand(table):
     parts = [np.arange(lo, hi, dtype=np.int64) for lo, hi in table if hi > lo]
     return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
@@ -57,6 +66,17 @@ def test_hostsim_ring_vs_live_reference(sim, oracle_ref):
                 want = oracle_ref.query_circle(nside, theta, phi, radius, inclusive=fact > 0, fact=max(fact, 1),
                                                nest=False, lonlat=False)
                 assert_bit_equal(expand(sim.query_circle_ring_ranges(nside, theta, phi, radius, fact)), want)
+
+
+def test_hostsim_nest_walk_matches_golden(sim):
+    """The breadth-first walk with hpgb_qn_visit gives the reference's (depth-first) range set."""
+    n = 0
+    for (nside, theta, phi, radius, fact), pix, ranges in nest_cases():
+        got = sim.query_circle_nest_ranges(nside, theta, phi, radius, fact)
+        assert_bit_equal(got, ranges, "nside=%d fact=%d" % (nside, fact))
+        assert_bit_equal(expand(got), pix)
+        n += 1
+    assert n > 400
 
 
 def test_plan_argument_checks():
@@ -125,6 +145,43 @@ def test_query_circle_device_resident_vec_and_healpy(hpg):
     b = hpg.query_circle(512, 1.1, 2.2, 0.05, nest=False, lonlat=False)
     c = hpc.query_disc(512, vec, 0.05)
     assert a.size > 100 and np.array_equal(a, b) and np.array_equal(a, c)
+
+
+@pytest.mark.gpu
+def test_query_circle_nest_golden(hpg):
+    import torch
+    n = 0
+    for (nside, theta, phi, radius, fact), pix, ranges in nest_cases():
+        kw = dict(inclusive=fact > 0, fact=max(fact, 1), nest=True, lonlat=False)
+        assert_bit_equal(hpg.query_circle(nside, theta, phi, radius, **kw), pix, "nside=%d fact=%d" % (nside, fact))
+        n += 1
+        if n % 5 == 0:
+            assert_bit_equal(hpg.query_circle(nside, theta, phi, radius, return_pixel_ranges=True, **kw), ranges)
+        if n % 40 == 0:
+            t = hpg.query_circle(nside, theta, phi, radius, device_resident=True, **kw)
+            assert isinstance(t, torch.Tensor) and t.is_cuda
+            assert_bit_equal(t.cpu().numpy(), pix)
+            assert_bit_equal(hpg.query_circle(np.int64(nside), np.degrees(phi), 90.0 - np.degrees(theta), np.degrees(radius),
+                                              inclusive=fact > 0, fact=max(fact, 1)).shape, pix.shape)
+    assert n > 400
+
+
+@pytest.mark.gpu
+def test_query_circle_nest_big_and_whole_sphere(hpg, oracle_ref):
+    """2e8 pixels at nside 2^14 (same set as the RING query, up to pixel-centre round-off), default
+    arguments = NEST, a whole-sphere disc, and the live reference where present."""
+    nside, theta, phi, radius = 2 ** 14, 0.7, 4.0, 0.5
+    got = hpg.query_circle(nside, theta, phi, radius, lonlat=False)
+    assert got.size > 1.9e8 and np.all(np.diff(got) > 0)
+    ring = np.sort(hpg.ring_to_nest(nside, hpg.query_circle(nside, theta, phi, radius, nest=False, lonlat=False)))
+    assert abs(ring.size - got.size) < 50 and np.setxor1d(ring, got, assume_unique=True).size < 50
+    if oracle_ref is not None:
+        assert_bit_equal(got, oracle_ref.query_circle(nside, theta, phi, radius, lonlat=False))
+        for args in ((2 ** 20, 33.0, -41.0, 0.02), (2 ** 12, 200.0, 89.9, 3.0), (64, 0.0, 0.0, 200.0), (2 ** 25, 10.0, 10.0, 1e-4)):
+            for kw in (dict(), dict(inclusive=True), dict(inclusive=True, fact=16), dict(return_pixel_ranges=True)):
+                assert_bit_equal(hpg.query_circle(*args, **kw), oracle_ref.query_circle(*args, **kw), "%r %r" % (args, kw))
+    assert hpg.query_circle(8, 0.0, 0.0, 3.2, lonlat=False).tolist() == list(range(768))
+    assert hpg.query_circle(8, 0.0, 0.0, 3.2, lonlat=False, return_pixel_ranges=True).tolist() == [[0, 768]]
 
 
 @pytest.mark.gpu
