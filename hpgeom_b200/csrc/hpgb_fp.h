@@ -799,6 +799,17 @@ HPGB_HD void hpgb_neighbors(const hpgb_geom &g, int64_t pix, int64_t *out) {
 HPGB_HD_NOINLINE void hpgb_neighbors_ring_edge(const hpgb_geom &g, int64_t pix, int64_t *out) {
     hpgb_neighbors<false, true>(g, pix, out);
 }
+// NEST: Morton-plane arithmetic for face-interior pixels, the general routine out of line for the rest
+HPGB_HD_NOINLINE void hpgb_neighbors_nest_edge(const hpgb_geom &g, int64_t pix, int64_t *out) {
+    hpgb_neighbors<true, true>(g, pix, out);
+}
+HPGB_HD void hpgb_neighbors_nest_k(const hpgb_geom &g, int64_t pix, int64_t *out) {
+    if (hpgb_neighbors_nest_interior(g, pix, out)) return;
+    int64_t tmp[8];
+    hpgb_neighbors_nest_edge(g, pix, tmp);
+#pragma unroll
+    for (int m = 0; m < 8; m++) out[m] = tmp[m];
+}
 HPGB_HD void hpgb_neighbors_ring_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, int64_t *out) {
     uint32_t ix, iy, face;
     hpgb_ring2xyf_k(c, g, pix, ix, iy, face);

@@ -33,6 +33,14 @@ static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW
 #ifndef HPGB_P2A_BLOCK
 #define HPGB_P2A_BLOCK 768
 #endif
+// vector_to_pixel on the streaming skeleton: ring depth / sub-blocks per tile (three float64 inputs:
+// 24 KiB per sub-block and stage)
+#ifndef HPGB_V2P_ST
+#define HPGB_V2P_ST 2
+#endif
+#ifndef HPGB_V2P_H
+#define HPGB_V2P_H 2
+#endif
 #define HPGB_P2A_TAB_DOUBLES (HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + HPGB_ATANQ_ROWS_POLAR * HPGB_ATANQ_ROW_DOUBLES)
 
 template <bool NEST, bool POW2, bool LONLAT, bool DEGREES, bool VAR>
@@ -272,10 +280,10 @@ int launch_v2p_t(const double *x, const double *y, const double *z, int64_t *out
     const bool vec = hpgb_aligned16(x) && hpgb_aligned16(y) && hpgb_aligned16(z) && hpgb_aligned16(out);
     if (NEST && g.order >= 16) {
         OpVec2Pix<NEST, false, NEST> op{x, y, z, out, nullptr, base, g, hpgb_make_a2p_fast<true, true>(g), hpgb_make_rk(g)};
-        return hpgb_launch_auto(op, n, vec, st, s);
+        return hpgb_launch_auto<decltype(op), HPGB_V2P_ST, HPGB_V2P_H>(op, n, vec, st, s);
     }
     OpVec2Pix<NEST, false, false> op{x, y, z, out, nullptr, base, g, hpgb_make_a2p_fast<true, true>(g), hpgb_make_rk(g)};
-    return hpgb_launch_auto(op, n, vec, st, s);
+    return hpgb_launch_auto<decltype(op), HPGB_V2P_ST, HPGB_V2P_H>(op, n, vec, st, s);
 }
 
 }  // namespace

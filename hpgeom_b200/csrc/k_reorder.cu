@@ -289,14 +289,15 @@ struct OpNeighbors {
     }
 };
 
-// RING neighbours, scalar nside = 2^k, 16-byte aligned operands.  The per-pixel body (ring -> xyf, five
-// ring set-ups, eight offsets: hpgb_neighbors_ring_k) is ~300 instructions; inlined four times by the
-// generic skeleton it overflowed the instruction cache (54 % of the stall samples were instruction
-// fetch).  Here it exists ONCE: a warp takes 64 consecutive pixels, every lane converts its two pixels in
+// neighbours, scalar nside = 2^k, 16-byte aligned operands.  The per-pixel body (RING: ring -> xyf, five
+// ring set-ups, eight offsets, hpgb_neighbors_ring_k, ~300 instructions; NEST: Morton-plane arithmetic)
+// was inlined four times by the generic skeleton and overflowed the instruction cache (RING: 54 %, NEST:
+// 39 % of the stall samples were instruction fetch).  Here it exists ONCE: a warp takes 64 consecutive pixels, every lane converts its two pixels in
 // a rolled loop and drops the rows into the XOR-swizzled staging buffer, then the warp writes the 4 KiB
 // of rows with fully coalesced 128-bit streaming stores.  The next chunk's pixels are loaded before the
 // current one is converted.
-__global__ void __launch_bounds__(HPGB_BLOCK) k_neighbors_ring(const int64_t *__restrict__ pix, int64_t *__restrict__ out,
+template <bool NEST>
+__global__ void __launch_bounds__(HPGB_BLOCK) k_neighbors_rows(const int64_t *__restrict__ pix, int64_t *__restrict__ out,
                                                                const int64_t n, const hpgb_geom g, const hpgb_rk c,
                                                                const int64_t base, hpgb_status_t *st) {
     __shared__ longlong2 sbuf[HPGB_BLOCK / 32][32 * 8];
@@ -311,6 +312,8 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_neighbors_ring(const int64_t *__
             bad.flag(base + i);
 #pragma unroll
             for (int m = 0; m < 8; m++) r[m] = -1;
+        } else if (NEST) {
+            hpgb_neighbors_nest_k(g, p, r);
         } else {
             hpgb_neighbors_ring_k(c, g, p, r);
         }
@@ -367,20 +370,24 @@ int launch_neighbors(const int64_t *pix, int64_t *out, int64_t n, int64_t nside,
     if (c) return c;
     const hpgb_geom g = hpgb_make_geom(nside, nest);
     const bool vec = hpgb_aligned16(pix);
-    if (nest) {
-        OpNeighbors<true, true, false> op{pix, out, nullptr, base, g, hpgb_rk()};
-        return hpgb_launch_map(op, n, vec, st, s);
-    }
     if (g.order >= 0 && vec) {
-        static int occ = 0;
-        if (!occ) occ = hpgb_resident_ctas(k_neighbors_ring, 0, HPGB_BLOCK);
-        int64_t grid = (int64_t)hpgb_sm_count() * occ;
+        static int occ[2] = {0, 0};
+        if (!occ[nest ? 1 : 0])
+            occ[nest ? 1 : 0] = nest ? hpgb_resident_ctas(k_neighbors_rows<true>, 0, HPGB_BLOCK) : hpgb_resident_ctas(k_neighbors_rows<false>, 0, HPGB_BLOCK);
+        int64_t grid = (int64_t)hpgb_sm_count() * occ[nest ? 1 : 0];
         const int64_t want = ((n >> 6) + HPGB_BLOCK / 32 - 1) / (HPGB_BLOCK / 32);
         if (want < grid) grid = want > 0 ? want : 1;
-        k_neighbors_ring<<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n, g, hpgb_make_rk(g), base, st);
+        if (nest)
+            k_neighbors_rows<true><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n, g, hpgb_rk(), base, st);
+        else
+            k_neighbors_rows<false><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n, g, hpgb_make_rk(g), base, st);
         g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+    }
+    if (nest) {
+        OpNeighbors<true, true, false> op{pix, out, nullptr, base, g, hpgb_rk()};
+        return hpgb_launch_map(op, n, vec, st, s);
     }
     if (g.order >= 0) {
         OpNeighbors<false, true, false> op{pix, out, nullptr, base, g, hpgb_make_rk(g)};
