@@ -386,3 +386,71 @@ def test_config5_round_trip_property(hpg, oracle_port):
             assert np.abs(lat[bad].cpu().numpy() - olat).max() < 1e-13
             assert np.array_equal(oracle_port.angle_to_pixel(nside, olon, olat, nest=nest), back[bad].cpu().numpy())
         del lon, lat, back
+
+
+@pytest.mark.parametrize("nest", [True, False])
+def test_config2_full_size_properties(hpg, oracle_port, nest):
+    """config 2 at its stated size: 100M random pixels, nside=2^20, device resident.  Size-independent
+    properties: pixel -> angle -> pixel and pixel -> vector -> pixel are the identity, the vectors are unit
+    vectors to a few ulp, and a strided sample agrees with the oracle."""
+    import torch
+    nside, n = 2 ** 20, 100_000_000
+    g = torch.Generator(device="cuda").manual_seed(12345)
+    pix = torch.randint(0, 12 * nside * nside, (n,), dtype=torch.int64, device="cuda", generator=g)
+    lon, lat = hpg.pixel_to_angle(nside, pix, nest=nest)
+    assert torch.equal(hpg.angle_to_pixel(nside, lon, lat, nest=nest), pix)
+    x, y, z = hpg.pixel_to_vector(nside, pix, nest=nest)
+    assert torch.equal(hpg.vector_to_pixel(nside, x, y, z, nest=nest), pix)
+    assert float((x * x + y * y + z * z - 1.0).abs().max()) < 1e-15
+    s = slice(None, None, 977)
+    p = pix[s].cpu().numpy()
+    rlon, rlat = oracle_port.pixel_to_angle(nside, p, nest=nest)
+    assert np.array_equal(lon[s].cpu().numpy(), rlon)
+    assert np.abs(lat[s].cpu().numpy() - rlat).max() <= 1.5 * np.spacing(np.pi) * 180 / np.pi
+    rx, ry, rz = oracle_port.pixel_to_vector(nside, p, nest=nest)
+    assert np.array_equal(z[s].cpu().numpy(), rz)
+    assert ulp_diff(x[s].cpu().numpy(), rx).max() <= 2.0 and ulp_diff(y[s].cpu().numpy(), ry).max() <= 2.0
+
+
+@pytest.mark.parametrize("nest", [True, False])
+def test_config4_full_size_properties(hpg, oracle_port, nest):
+    """config 4 at its stated size: 200M elements, nside=4096, device resident, in 50M-element slabs.
+    neighbours: adjacency is symmetric (p is among the neighbours of each of its neighbours; checked on a
+    10M subsample through a second launch); interpolation: the weights are
+    non-negative and sum to 1, the four pixels are valid; upgrade: children >> 2 (nest) give back the
+    parent; strided samples of all three against the oracle."""
+    import torch
+    nside, n, slab = 4096, 200_000_000, 50_000_000
+    npix = 12 * nside * nside
+    g = torch.Generator(device="cuda").manual_seed(4096)
+    for s0 in range(0, n, slab):
+        pix = torch.randint(0, npix - 1, (slab,), dtype=torch.int64, device="cuda", generator=g)
+        nb = hpg.neighbors(nside, pix, nest=nest)
+        assert nb.shape == (slab, 8) and int(nb.min()) >= -1 and int(nb.max()) < npix
+        sub = slice(None, 10_000_000)
+        for d in range(8):
+            q = nb[sub, d]
+            ok = q >= 0
+            back = hpg.neighbors(nside, q[ok], nest=nest)
+            assert bool((back == pix[sub][ok][:, None]).any(dim=1).all()), "adjacency must be symmetric"
+            del back
+        st = slice(None, None, 4999)
+        assert np.array_equal(nb[st].cpu().numpy(), oracle_port.neighbors(nside, pix[st].cpu().numpy(), nest=nest))
+        del nb
+        up = hpg.upgrade_pixels(nside, pix, 2 * nside, nest=nest)
+        assert up.shape == (4 * slab,)
+        if nest:
+            assert torch.equal(up.view(slab, 4) >> 2, pix[:, None].expand(slab, 4))
+        else:
+            assert torch.equal(hpg.ring_to_nest(2 * nside, up).view(slab, 4) >> 2, hpg.ring_to_nest(nside, pix)[:, None].expand(slab, 4))
+        assert np.array_equal(up.view(slab, 4)[st].cpu().numpy().ravel(),
+                              oracle_port.upgrade_pixels(nside, pix[st].cpu().numpy(), 2 * nside, nest=nest))
+        del up
+        lon = torch.rand(slab, dtype=torch.float64, device="cuda", generator=g) * 360.0
+        lat = torch.rad2deg(torch.asin(torch.rand(slab, dtype=torch.float64, device="cuda", generator=g) * 2 - 1))
+        p4, w4 = hpg.get_interpolation_weights(nside, lon, lat, nest=nest)
+        assert int(p4.min()) >= 0 and int(p4.max()) < npix
+        assert float(w4.min()) >= 0.0 and float((w4.sum(dim=1) - 1.0).abs().max()) < 1e-12
+        rp, rw = oracle_port.get_interpolation_weights(nside, lon[st].cpu().numpy(), lat[st].cpu().numpy(), nest=nest)
+        assert np.array_equal(p4[st].cpu().numpy(), rp) and np.abs(w4[st].cpu().numpy() - rw).max() < 1e-10
+        del p4, w4, lon, lat, pix
