@@ -295,6 +295,48 @@ def main():
     ms_n2r, _ = timed(step_n2r, args.steps, max(args.warmup, 3))
     ms_n2r /= args.steps
     n2r_value = world * n / (ms_n2r * 1e-3) / 1e9
+    # ---- the other kernels of the path, same protocol (device resident, CUDA events, max over ranks), smaller
+    # batches: 2^27 elements at nside 2^29 (configs 2/3), 2^24 at nside 4096 (config 4).  Reported under "also".
+    also = {}
+
+    def add_also(name, step, elems, bytes_per_elem, workload):
+        ms_k, _ = timed(step, 5, 3)
+        ms_k /= 5
+        also[name] = {"value": world * elems / (ms_k * 1e-3) / 1e9, "unit": "Gelements/s", "ms_per_step": ms_k,
+                      "bytes_per_element": bytes_per_elem, "workload": workload}
+
+    def ck(rc):
+        assert rc == 0, _lib.error_string(rc)
+
+    m = min(n, 1 << 27)
+    ms8 = min(n, 1 << 24)
+    add_also("ring_to_nest", lambda: ck(L.hpgb_ring_to_nest(ring.data_ptr(), pix.data_ptr(), m, NSIDE, None, stp, sp)), m, 16,
+             "ring_to_nest nside=2^29 on 2^%d pixels per GPU (round trip of the nest_to_ring output)" % (m.bit_length() - 1))
+    f1, f2, f3 = (torch.empty(m, dtype=torch.float64, device=dev) for _ in range(3))
+    i1 = torch.empty(m, dtype=torch.int64, device=dev)
+    add_also("pixel_to_angle", lambda: ck(L.hpgb_pixel_to_angle(pix.data_ptr(), f1.data_ptr(), f2.data_ptr(), m, NSIDE, None, 1, 1, 1, stp, sp)),
+             m, 24, "pixel_to_angle nside=2^29 nest lonlat degrees, 2^%d pixels per GPU" % (m.bit_length() - 1))
+    add_also("pixel_to_vector", lambda: ck(L.hpgb_pixel_to_vector(pix.data_ptr(), f1.data_ptr(), f2.data_ptr(), f3.data_ptr(), m, NSIDE, None, 1, stp, sp)),
+             m, 32, "pixel_to_vector nside=2^29 nest, 2^%d pixels per GPU" % (m.bit_length() - 1))
+    add_also("vector_to_pixel", lambda: ck(L.hpgb_vector_to_pixel(f1.data_ptr(), f2.data_ptr(), f3.data_ptr(), i1.data_ptr(), m, NSIDE, None, 1, stp, sp)),
+             m, 32, "vector_to_pixel nside=2^29 nest on the vectors just produced, 2^%d per GPU" % (m.bit_length() - 1))
+    assert torch.equal(i1[:1 << 20], pix[:1 << 20]), "vector_to_pixel(pixel_to_vector(p)) != p"
+    p4 = pix[:ms8] % (12 * 4096 * 4096 - 1)
+    reps4 = (ms8 + lon_keep.numel() - 1) // lon_keep.numel()
+    lon4, lat4 = lon_keep.repeat(reps4)[:ms8].contiguous(), lat_keep.repeat(reps4)[:ms8].contiguous()
+    o8 = i1[:8 * ms8] if 8 * ms8 <= m else torch.empty(8 * ms8, dtype=torch.int64, device=dev)
+    w4 = f1[:4 * ms8] if 4 * ms8 <= m else torch.empty(4 * ms8, dtype=torch.float64, device=dev)
+    for nest_flag, tag in ((1, "nest"), (0, "ring")):
+        add_also("neighbors_" + tag, lambda nf=nest_flag: ck(L.hpgb_neighbors(p4.data_ptr(), o8.data_ptr(), ms8, 4096, None, nf, stp, sp)),
+                 ms8, 72, "neighbors nside=4096 %s, 2^%d pixels per GPU" % (tag, ms8.bit_length() - 1))
+        add_also("interpolation_weights_" + tag,
+                 lambda nf=nest_flag: ck(L.hpgb_interp_weights(lon4.data_ptr(), lat4.data_ptr(), o8.data_ptr(), w4.data_ptr(), ms8, 4096, None, nf, 1, 1, stp, sp)),
+                 ms8, 80, "get_interpolation_weights nside=4096 %s lonlat degrees, 2^%d points per GPU" % (tag, ms8.bit_length() - 1))
+        add_also("upgrade_pixels_" + tag,
+                 lambda nf=nest_flag: ck(L.hpgb_upgrade_pixels(p4.data_ptr(), o8.data_ptr(), ms8, 4096, 8192, nf, stp, sp)),
+                 ms8, 40, "upgrade_pixels nside=4096 -> 8192 %s, 2^%d input pixels per GPU" % (tag, ms8.bit_length() - 1))
+    assert int(status[0].item()) == -1, "a kernel flagged a bad element in valid synthetic input"
+    del f1, f2, f3, i1, o8, w4, p4, lon4, lat4
     # parity spot check (outside every timed region): the first 2^20 points of this rank against the oracle
     parity = None
     if rank == 0:
@@ -369,6 +411,9 @@ def main():
                                       "roofline_frac": 16 * n / (ms_n2r * 1e-3) / 1e9 / peak,
                                       "workload": "nest_to_ring nside=2^29 on the 2^%d pixels per GPU" % args.log2_points}},
         }
+        for name, rec in also.items():  # whole-job rate -> per-GPU algorithmic GB/s -> fraction of the measured peak
+            rec["roofline_frac"] = rec["value"] / world * rec["bytes_per_element"] / peak
+            line["also"][name] = rec
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             probe, kind, cores, _ = cpu_reference_rate(1 << 22, threads)
