@@ -318,12 +318,23 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_neighbors_rows(const int64_t *__
             hpgb_neighbors_ring_k(c, g, p, r);
         }
     };
+    // the pixels of the next chunk(s) are in flight while one is converted (measured: two ahead is best for
+    // NEST, +3 %; the RING body needs the registers more)
+#ifndef HPGB_NB_AHEAD
+#define HPGB_NB_AHEAD (NEST ? 2 : 1)
+#endif
     int64_t ch = gw;
-    longlong2 v = make_longlong2(0, 0);
-    if (ch < nchunk) v = hpgb_ld2(pix + ch * 64 + 2 * lane);
+    longlong2 v[HPGB_NB_AHEAD];
+#pragma unroll
+    for (int a = 0; a < HPGB_NB_AHEAD; a++) {
+        v[a] = make_longlong2(0, 0);
+        if (ch + a * nw < nchunk) v[a] = hpgb_ld2(pix + (ch + a * nw) * 64 + 2 * lane);
+    }
     for (; ch < nchunk; ch += nw) {
-        const longlong2 cur = v;
-        if (ch + nw < nchunk) v = hpgb_ld2(pix + (ch + nw) * 64 + 2 * lane);
+        const longlong2 cur = v[0];
+#pragma unroll
+        for (int a = 0; a + 1 < HPGB_NB_AHEAD; a++) v[a] = v[a + 1];
+        if (ch + HPGB_NB_AHEAD * nw < nchunk) v[HPGB_NB_AHEAD - 1] = hpgb_ld2(pix + (ch + HPGB_NB_AHEAD * nw) * 64 + 2 * lane);
 #pragma unroll 1
         for (int q = 0; q < 2; q++) {
             int64_t r[8];
