@@ -14,7 +14,10 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "hpgb_core.h"
 #include "hpgb_host.h"
@@ -86,6 +89,9 @@ struct HostCtx {
     cudaStream_t stream[HPGB_PIPE_SLOTS];
     char *dbuf[HPGB_PIPE_SLOTS] = {nullptr, nullptr, nullptr};
     size_t dbytes[HPGB_PIPE_SLOTS] = {0, 0, 0};
+    char *hbuf[HPGB_PIPE_SLOTS] = {nullptr, nullptr, nullptr};  // pinned staging for pageable caller buffers
+    size_t hbytes[HPGB_PIPE_SLOTS] = {0, 0, 0};
+    cudaEvent_t done[HPGB_PIPE_SLOTS];
     hpgb_status_t *d_status = nullptr;
     hpgb_status_t *h_status = nullptr;
 };
@@ -102,6 +108,82 @@ int64_t chunk_points() {
         v &= ~(int64_t)1;
     }
     return v;
+}
+
+// Plain numpy arrays are pageable: cudaMemcpyAsync then goes through the driver's single-threaded
+// staging (~8 GB/s measured: the drop-in ran no faster than the 16-thread reference).  For such operands
+// the pipeline stages through its own pinned buffers, filled / drained by a small pool of host threads
+// (parallel memcpy), so the PCIe engines see pinned memory and the host copies of chunk i+1 overlap the
+// DMA of chunk i.
+class CopyPool {
+  public:
+    static CopyPool &get() {
+        static CopyPool *p = new CopyPool;  // never destroyed: its threads sleep on the condition variable at exit
+        return *p;
+    }
+    // dst[0..bytes) = src[0..bytes), split over the pool (the caller takes the first share).  One job at a
+    // time: the pipeline calls it under g_ctx_mutex.
+    void copy(char *dst, const char *src, size_t bytes) {
+        const size_t min_part = (size_t)1 << 20;
+        int parts = (int)((bytes + min_part - 1) / min_part);
+        if (parts > nworkers_ + 1) parts = nworkers_ + 1;
+        if (parts <= 1) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        const size_t per = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            dst_ = dst, src_ = src, bytes_ = bytes, per_ = per;
+            next_ = 1, parts_ = parts, pending_ = parts - 1;
+        }
+        cv_.notify_all();
+        memcpy(dst, src, per < bytes ? per : bytes);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        parts_ = 0, next_ = 0;
+    }
+
+  private:
+    CopyPool() {
+        const char *e = getenv("HPGB_HOST_THREADS");
+        int n = e ? atoi(e) : (int)std::thread::hardware_concurrency();  // HPGB_HOST_THREADS overrides
+        if (!e && n > 16) n = 16;
+        if (n < 1) n = 1;
+        nworkers_ = n - 1;  // the caller is one of the copiers
+        for (int i = 0; i < nworkers_; i++) std::thread([this] { worker(); }).detach();
+    }
+    void worker() {
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            cv_.wait(lk, [&] { return next_ < parts_; });
+            const int part = next_++;
+            char *d = dst_;
+            const char *s = src_;
+            const size_t per = per_, bytes = bytes_;
+            lk.unlock();
+            const size_t off = (size_t)part * per;
+            if (off < bytes) memcpy(d + off, s + off, (off + per <= bytes) ? per : bytes - off);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    char *dst_ = nullptr;
+    const char *src_ = nullptr;
+    size_t bytes_ = 0, per_ = 0;
+    int next_ = 0, parts_ = 0, pending_ = 0, nworkers_ = 0;
+};
+
+bool is_pageable(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
 }
 
 #define CK(call)                                            \
@@ -126,7 +208,10 @@ int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int nar
     CK(cudaSetDevice(device));
     HostCtx &c = g_ctx[device];
     if (!c.ready) {
-        for (int s = 0; s < HPGB_PIPE_SLOTS; s++) CK(cudaStreamCreateWithFlags(&c.stream[s], cudaStreamNonBlocking));
+        for (int s = 0; s < HPGB_PIPE_SLOTS; s++) {
+            CK(cudaStreamCreateWithFlags(&c.stream[s], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c.done[s], cudaEventDisableTiming));
+        }
         CK(cudaMalloc(&c.d_status, sizeof(hpgb_status_t)));
         CK(cudaHostAlloc(&c.h_status, sizeof(hpgb_status_t), cudaHostAllocDefault));
         c.ready = true;
@@ -135,9 +220,13 @@ int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int nar
     const int64_t cp = chunk_points() < n ? chunk_points() : ((n + 1) & ~(int64_t)1);
     size_t off[HPGB_PIPE_MAX_ARR + 1];
     size_t total = 0;
+    bool stage[HPGB_PIPE_MAX_ARR];
+    bool any_stage = false;
     for (int a = 0; a < narr; a++) {
         off[a] = total;
         total += (((size_t)cp * (size_t)arrs[a].bytes_per_point) + 255) & ~(size_t)255;
+        stage[a] = is_pageable(arrs[a].h_in ? (const void *)arrs[a].h_in : (const void *)arrs[a].h_out);
+        any_stage |= stage[a];
     }
     for (int s = 0; s < HPGB_PIPE_SLOTS; s++) {
         if (c.dbytes[s] < total) {
@@ -147,29 +236,71 @@ int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int nar
             CK(cudaMalloc(&c.dbuf[s], total));
             c.dbytes[s] = total;
         }
+        if (any_stage && c.hbytes[s] < total) {
+            if (c.hbuf[s]) CK(cudaFreeHost(c.hbuf[s]));
+            c.hbuf[s] = nullptr;
+            c.hbytes[s] = 0;
+            CK(cudaHostAlloc(&c.hbuf[s], total, cudaHostAllocDefault));
+            c.hbytes[s] = total;
+        }
     }
     CK(cudaMemsetAsync(c.d_status, 0xFF, sizeof(hpgb_status_t), c.stream[0]));
     CK(cudaStreamSynchronize(c.stream[0]));
 
+    // chunk i's copy-out, chunk i+1's kernel and chunk i+2's copy-in overlap (one stream per slot).  Pageable
+    // operands pass through the slot's pinned staging buffer: filled by the copy pool before the H2D is
+    // queued, drained (after the slot's event) when the slot comes round again or at the end.
     int rc = HPGB_OK;
     int slot = 0;
+    int64_t slot_base[HPGB_PIPE_SLOTS], slot_n[HPGB_PIPE_SLOTS];
+    for (int s = 0; s < HPGB_PIPE_SLOTS; s++) slot_n[s] = 0;
+    auto drain = [&](int s) -> int {  // copy the staged outputs of the chunk in slot s to the caller
+        if (slot_n[s] == 0) return HPGB_OK;
+        cudaError_t e = cudaEventSynchronize(c.done[s]);
+        if (e != cudaSuccess) return HPGB_E_CUDA + (int)e;
+        for (int a = 0; a < narr; a++)
+            if (arrs[a].h_out && stage[a])
+                CopyPool::get().copy(arrs[a].h_out + (size_t)slot_base[s] * arrs[a].bytes_per_point, c.hbuf[s] + off[a],
+                                     (size_t)slot_n[s] * arrs[a].bytes_per_point);
+        slot_n[s] = 0;
+        return HPGB_OK;
+    };
     for (int64_t base = 0; base < n && rc == HPGB_OK; base += cp, slot = (slot + 1) % HPGB_PIPE_SLOTS) {
         const int64_t cn = (n - base) < cp ? (n - base) : cp;
         cudaStream_t st = c.stream[slot];
+        if (any_stage) {
+            rc = drain(slot);
+            if (rc != HPGB_OK) break;
+        }
         void *dptr[HPGB_PIPE_MAX_ARR];
         for (int a = 0; a < narr; a++) {
             dptr[a] = c.dbuf[slot] + off[a];
-            if (arrs[a].h_in)
-                CK(cudaMemcpyAsync(dptr[a], arrs[a].h_in + (size_t)base * arrs[a].bytes_per_point,
-                                   (size_t)cn * arrs[a].bytes_per_point, cudaMemcpyHostToDevice, st));
+            if (arrs[a].h_in) {
+                const char *src = arrs[a].h_in + (size_t)base * arrs[a].bytes_per_point;
+                const size_t bytes = (size_t)cn * arrs[a].bytes_per_point;
+                if (stage[a]) {
+                    CopyPool::get().copy(c.hbuf[slot] + off[a], src, bytes);
+                    src = c.hbuf[slot] + off[a];
+                }
+                CK(cudaMemcpyAsync(dptr[a], src, bytes, cudaMemcpyHostToDevice, st));
+            }
         }
         rc = launch(dptr, base, cn, c.d_status, st);
         if (rc != HPGB_OK) break;
         for (int a = 0; a < narr; a++) {
-            if (arrs[a].h_out)
-                CK(cudaMemcpyAsync(arrs[a].h_out + (size_t)base * arrs[a].bytes_per_point, dptr[a],
-                                   (size_t)cn * arrs[a].bytes_per_point, cudaMemcpyDeviceToHost, st));
+            if (arrs[a].h_out) {
+                char *dst = stage[a] ? c.hbuf[slot] + off[a] : arrs[a].h_out + (size_t)base * arrs[a].bytes_per_point;
+                CK(cudaMemcpyAsync(dst, dptr[a], (size_t)cn * arrs[a].bytes_per_point, cudaMemcpyDeviceToHost, st));
+            }
         }
+        if (any_stage) {
+            CK(cudaEventRecord(c.done[slot], st));
+            slot_base[slot] = base;
+            slot_n[slot] = cn;
+        }
+    }
+    if (any_stage && rc == HPGB_OK) {
+        for (int k = 0; k < HPGB_PIPE_SLOTS && rc == HPGB_OK; k++) rc = drain((slot + k) % HPGB_PIPE_SLOTS);
     }
     for (int s = 0; s < HPGB_PIPE_SLOTS; s++) {
         cudaError_t e = cudaStreamSynchronize(c.stream[s]);
@@ -193,9 +324,13 @@ extern "C" int hpgb_host_release(void) {
         cudaSetDevice(d);
         for (int s = 0; s < HPGB_PIPE_SLOTS; s++) {
             cudaStreamDestroy(c.stream[s]);
+            cudaEventDestroy(c.done[s]);
             if (c.dbuf[s]) cudaFree(c.dbuf[s]);
             c.dbuf[s] = nullptr;
             c.dbytes[s] = 0;
+            if (c.hbuf[s]) cudaFreeHost(c.hbuf[s]);
+            c.hbuf[s] = nullptr;
+            c.hbytes[s] = 0;
         }
         cudaFree(c.d_status);
         cudaFreeHost(c.h_status);

@@ -239,7 +239,8 @@ HPGB_HD void hpgb_upgrade_ring_group(const hpgb_rk &c, const hpgb_rk &cu, const 
     hpgb_ring2xyf_k(c, g, p, ix, iy, face);
     last = face == 11u && ix == c.nsm1 && iy == c.nsm1;
     const uint32_t kk = cu.k - c.k;
-    hpgb_deinterleave(first, gx, gy);
+    gx = gy = 0u;
+    if (first != 0) hpgb_deinterleave(first, gx, gy);  // nside_upgrade = 2 nside: always the first (only) group
     const uint32_t bx = (ix << kk) | gx, by = (iy << kk) | gy;
 #pragma unroll
     for (int j = 0; j < C; j++) r[j] = hpgb_xyf2ring_k(cu, bx + (uint32_t)(j & 1), by + (uint32_t)(j >> 1), face);
