@@ -37,6 +37,33 @@ int hpgb_sm_count() {
     return sms[dev];
 }
 
+cudaError_t hpgb_dev_alloc(void **p, size_t bytes) {
+    static bool tuned[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !tuned[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        tuned[dev] = true;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 16, (cudaStream_t)0);
+}
+void hpgb_dev_free(void *p) {
+    if (!p) return;
+    int prev = 0, dev = 0;
+    cudaGetDevice(&prev);
+    dev = prev;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) dev = a.device;
+    if (dev != prev) cudaSetDevice(dev);  // the legacy stream is per device
+    cudaFreeAsync(p, (cudaStream_t)0);
+    if (dev != prev) cudaSetDevice(prev);
+}
+
 extern "C" int hpgb_version(void) { return 100; }
 
 extern "C" int hpgb_device_count(void) {

@@ -25,6 +25,13 @@ struct hpgb_pipe_arr {
 // the chunk, device status, stream) -> HPGB_* code
 typedef std::function<int(void **, int64_t, int64_t, hpgb_status_t *, cudaStream_t)> hpgb_pipe_launch;
 
+// device scratch of the variable-length entry points (range tables, search frontiers): stream-ordered
+// allocations on the legacy stream from the device's default memory pool, whose release threshold is
+// raised once so that freed blocks are kept for the next call (a cudaMalloc / cudaFree pair costs more
+// than a small query)
+cudaError_t hpgb_dev_alloc(void **p, size_t bytes);
+void hpgb_dev_free(void *p);
+
 int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int narr,
                        const hpgb_pipe_launch &launch, int64_t *first_bad);
 

@@ -211,10 +211,10 @@ struct DevTable {
     int64_t *ranges = nullptr, *offs = nullptr, *work = nullptr;
     hpgb_status_t *st = nullptr;
     ~DevTable() {
-        if (work) cudaFree(work);
-        if (ranges) cudaFree(ranges);
-        if (offs) cudaFree(offs);
-        if (st) cudaFree(st);
+        if (work) hpgb_dev_free(work);
+        if (ranges) hpgb_dev_free(ranges);
+        if (offs) hpgb_dev_free(offs);
+        if (st) hpgb_dev_free(st);
     }
 };
 #define CKQ(call)                                                                      \
@@ -232,11 +232,11 @@ int build_table(const hpgb_disc_t *plan, int device, DevTable &d, int64_t *total
     int prev = 0;
     cudaGetDevice(&prev);
     CKQ(cudaSetDevice(device));
-    CKQ(cudaMalloc(&d.ranges, (size_t)plan->m * 16));
-    CKQ(cudaMalloc(&d.offs, (size_t)(plan->m + 1) * 8));
-    CKQ(cudaMalloc(&d.st, sizeof(hpgb_status_t)));
+    CKQ(hpgb_dev_alloc((void **)&d.ranges, (size_t)plan->m * 16));
+    CKQ(hpgb_dev_alloc((void **)&d.offs, (size_t)(plan->m + 1) * 8));
+    CKQ(hpgb_dev_alloc((void **)&d.st, sizeof(hpgb_status_t)));
     CKQ(cudaMemsetAsync(d.st, 0xFF, sizeof(hpgb_status_t), 0));
-    if (qc_work_bytes(plan) > 0) CKQ(cudaMalloc(&d.work, (size_t)qc_work_bytes(plan)));
+    if (qc_work_bytes(plan) > 0) CKQ(hpgb_dev_alloc((void **)&d.work, (size_t)qc_work_bytes(plan)));
     int rc = launch_qc_ring_ranges(plan, d.ranges, d.work, 0);
     if (rc == HPGB_OK) rc = launch_ranges_offsets(d.ranges, plan->m, 0, d.offs, d.st, 0);
     if (rc != HPGB_OK) {
@@ -339,11 +339,11 @@ struct QnHandle {
 struct DevBuf {  // frees on scope exit
     std::vector<void *> ptrs;
     ~DevBuf() {
-        for (void *p : ptrs) cudaFree(p);
+        for (void *p : ptrs) hpgb_dev_free(p);
     }
     template <class Tp>
     cudaError_t alloc(Tp **p, size_t bytes) {
-        cudaError_t e = cudaMalloc((void **)p, bytes ? bytes : 16);
+        cudaError_t e = hpgb_dev_alloc((void **)p, bytes);
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
@@ -396,7 +396,7 @@ int qn_build(const hpgb_qn_plan &P, int64_t nside, QnHandle *h) {
             lvl_hi.push_back(rhi);
             lvl_n.push_back((int64_t)hc[1]);
             R += (int64_t)hc[1];
-            cudaFree(cur);
+            hpgb_dev_free(cur);
             pool.release(cur);
             cur = next;
             n = (int64_t)hc[0];
@@ -423,8 +423,8 @@ int qn_build(const hpgb_qn_plan &P, int64_t nside, QnHandle *h) {
         CKQ(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, skeys, vals, svals, R, 0, 62, (cudaStream_t)0));
         CKQ(pool.alloc(&tmp, tmp_bytes));
         CKQ(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, skeys, vals, svals, R, 0, 62, (cudaStream_t)0));
-        CKQ(cudaMalloc(&h->ranges, (size_t)R * 16));
-        CKQ(cudaMalloc(&h->offs, (size_t)(R + 1) * 8));
+        CKQ(hpgb_dev_alloc((void **)&h->ranges, (size_t)R * 16));
+        CKQ(hpgb_dev_alloc((void **)&h->offs, (size_t)(R + 1) * 8));
         int64_t grid = (R + HPGB_BLOCK - 1) / HPGB_BLOCK;
         const int64_t cap = (int64_t)hpgb_sm_count() * 8;
         if (grid > cap) grid = cap;
@@ -478,8 +478,8 @@ int hpgb_query_circle_nest_open(int64_t nside, double a, double b, double radius
     h->device = device;
     rc = qn_build(P, nside, h);
     if (rc != HPGB_OK) {
-        if (h->ranges) cudaFree(h->ranges);
-        if (h->offs) cudaFree(h->offs);
+        if (h->ranges) hpgb_dev_free(h->ranges);
+        if (h->offs) hpgb_dev_free(h->offs);
         delete h;
         return rc;
     }
@@ -495,8 +495,8 @@ int hpgb_query_nest_close(void *handle) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(h->device);
-    if (h->ranges) cudaFree(h->ranges);
-    if (h->offs) cudaFree(h->offs);
+    if (h->ranges) hpgb_dev_free(h->ranges);
+    if (h->offs) hpgb_dev_free(h->offs);
     cudaSetDevice(prev);
     delete h;
     return HPGB_OK;

@@ -312,9 +312,9 @@ struct DevRanges {
     int64_t *ranges = nullptr, *offs = nullptr;
     hpgb_status_t *st = nullptr;
     ~DevRanges() {
-        if (ranges) cudaFree(ranges);
-        if (offs) cudaFree(offs);
-        if (st) cudaFree(st);
+        if (ranges) hpgb_dev_free(ranges);
+        if (offs) hpgb_dev_free(offs);
+        if (st) hpgb_dev_free(st);
     }
 };
 #define CKR(call)                                            \
@@ -334,9 +334,9 @@ int stage_ranges(const int64_t *ranges, int64_t m, int inclusive, int device, De
     int prev = 0;
     cudaGetDevice(&prev);
     CKR(cudaSetDevice(device));
-    CKR(cudaMalloc(&d.ranges, (size_t)m * 16));
-    CKR(cudaMalloc(&d.offs, (size_t)(m + 1) * 8));
-    CKR(cudaMalloc(&d.st, sizeof(hpgb_status_t)));
+    CKR(hpgb_dev_alloc((void **)&d.ranges, (size_t)m * 16));
+    CKR(hpgb_dev_alloc((void **)&d.offs, (size_t)(m + 1) * 8));
+    CKR(hpgb_dev_alloc((void **)&d.st, sizeof(hpgb_status_t)));
     CKR(cudaMemcpyAsync(d.ranges, ranges, (size_t)m * 16, cudaMemcpyHostToDevice, 0));
     CKR(cudaMemsetAsync(d.st, 0xFF, sizeof(hpgb_status_t), 0));
     const int rc = launch_ranges_offsets(d.ranges, m, inclusive, d.offs, d.st, 0);
