@@ -65,6 +65,11 @@ _SIGS = {
     "hpgb_query_circle_ring_ranges": [c_vp, c_vp, c_vp, c_vp],
     "hpgb_host_query_circle_ring_count": [c_vp, c_int, ctypes.POINTER(c_i64)],
     "hpgb_host_query_circle_ring_fill": [c_vp, c_vp, c_i64, c_int],
+    "hpgb_query_circle_ring_plan_many": [c_i64, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_vp,
+                                         ctypes.POINTER(c_i64)],
+    "hpgb_query_circle_ring_batch_prepare": [c_vp, c_i64, c_vp],
+    "hpgb_query_circle_ring_batch_ranges": [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp],
+    "hpgb_host_query_circle_ring_batch": [c_vp, c_i64, c_int, c_vp, ctypes.POINTER(c_i64), c_vp, c_i64],
     "hpgb_query_circle_nest_open": [c_i64, c_dbl, c_dbl, c_dbl, c_int, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_vp),
                                     ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],
     "hpgb_query_nest_ranges": [c_vp, c_vp, ctypes.POINTER(c_i64)],
@@ -76,7 +81,7 @@ _SIGS = {
     "hpgb_explain_pixel": [c_i64, c_int, c_i64, ctypes.c_char_p, c_int],
 }
 _RESTYPES = {"hpgb_error_string": ctypes.c_char_p, "hpgb_launch_count": c_i64,
-             "hpgb_query_circle_ring_work_bytes": c_i64}
+             "hpgb_query_circle_ring_work_bytes": c_i64, "hpgb_query_circle_ring_batch_prepare": c_i64}
 
 EXPORTS = tuple(_SIGS)
 

@@ -549,3 +549,272 @@ int hpgb_query_nest_pixels_device(void *handle, int64_t *d_out, int64_t total, v
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// Many discs at once, RING scheme ("a batched many-discs kernel").  One small disc
+// is launch-latency bound on a GPU; a batch is not: the D per-disc plans (same nside and fact) go to the
+// device, ONE launch runs every (disc, ring) pair -- a thread finds its disc by binary search over the
+// prefix sums of the ring counts -- and one offsets + expand pass writes all pixel lists back to back.
+// Row layout: disc d owns rows [2 ring_start[d] + 2 d, 2 ring_start[d+1] + 2 (d+1)): north polar row, two
+// rows per ring, south polar row -- i.e. D single-disc tables concatenated.
+// =============================================================================================
+namespace {
+
+__device__ __forceinline__ int64_t qb_find_disc(const int64_t *__restrict__ ring_start, int64_t D, int64_t j) {
+    int64_t lo = 0, hi = D;  // largest d < D with ring_start[d] <= j
+    while (hi - lo > 1) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (ring_start[mid] <= j) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qb_ring_ranges(const hpgb_disc_t *__restrict__ plans,
+                                                               const int64_t *__restrict__ ring_start, const int64_t D,
+                                                               const hpgb_geom g, const hpgb_geom g2,
+                                                               int64_t *__restrict__ ranges, int64_t *__restrict__ work) {
+    const double *T = hpgb_stage_table();
+    const int64_t nring = ring_start[D];
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    const int64_t t0 = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x;
+    for (int64_t j = t0; j < nring; j += stride) {
+        const int64_t dsc = qb_find_disc(ring_start, D, j);
+        const hpgb_disc_t d = plans[dsc];
+        int64_t row[4] = {0, 0, 0, 0};
+        int64_t ip_lo, ip_hi, nr, ipix1;
+        if (hpgb_qc_ring_raw(d, g, T, d.irmin + (j - ring_start[dsc]), ip_lo, ip_hi, nr, ipix1)) {
+            unsigned mask = 0u;
+            if (d.fct > 1) mask = hpgb_qc_ring_trim(d, g, g2, T, nr, ipix1, ip_lo, ip_hi, QC_SEQ_STEPS);
+            if (mask) {
+                const unsigned long long k = atomicAdd(reinterpret_cast<unsigned long long *>(work), 1ull);
+                int64_t *it = QC_ITEM(work, (int64_t)k);
+                it[0] = j;
+                it[1] = ip_lo;
+                it[2] = ip_hi;
+                it[3] = (int64_t)mask;
+                it[4] = it[5] = INT64_MAX;
+                it[6] = it[7] = 0;
+            } else {
+                hpgb_qc_ring_rows(ip_lo, ip_hi, nr, ipix1, row);
+            }
+        }
+        longlong2 *o = reinterpret_cast<longlong2 *>(ranges) + 2 * j + 2 * dsc + 1;
+        o[0] = make_longlong2(row[0], row[1]);
+        o[1] = make_longlong2(row[2], row[3]);
+    }
+    for (int64_t dsc = t0; dsc < D; dsc += stride) {
+        const hpgb_disc_t d = plans[dsc];
+        longlong2 *o = reinterpret_cast<longlong2 *>(ranges);
+        o[2 * ring_start[dsc] + 2 * dsc] = make_longlong2(0, d.north_hi > 0 ? d.north_hi : 0);
+        o[2 * ring_start[dsc + 1] + 2 * dsc + 1] = d.south_lo >= 0 ? make_longlong2(d.south_lo, g.npix) : make_longlong2(0, 0);
+    }
+}
+
+template <int END>
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qb_scan(const hpgb_disc_t *__restrict__ plans, const int64_t *__restrict__ ring_start,
+                                                        const int64_t D, const hpgb_geom g, const hpgb_geom g2,
+                                                        int64_t *__restrict__ work) {
+    const double *T = hpgb_stage_table();
+    __shared__ int64_t s_ticket, s_found;
+    const int64_t nitems = work[0];
+    for (int64_t k = 0; k < nitems; k++) {
+        int64_t *it = QC_ITEM(work, k);
+        const unsigned mask = (unsigned)it[3];
+        if (!(mask & (1u << END))) continue;
+        int64_t lo = it[1];
+        const int64_t hi = it[2];
+        if (END == 1 && (mask & 1u)) {
+            if (it[4] == INT64_MAX) continue;
+            lo += it[4];
+        }
+        const int64_t len = hi - lo + 1;
+        const int64_t dsc = qb_find_disc(ring_start, D, it[0]);
+        const hpgb_disc_t d = plans[dsc];
+        int64_t nr, ipix1;
+        bool shifted;
+        hpgb_ring_info_small(g, d.irmin + (it[0] - ring_start[dsc]), ipix1, nr, shifted);
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_ticket = (int64_t)atomicAdd(reinterpret_cast<unsigned long long *>(it + 6 + END), 1ull);
+                s_found = *reinterpret_cast<volatile int64_t *>(it + 4 + END);
+            }
+            __syncthreads();
+            const int64_t dist0 = s_ticket * HPGB_BLOCK;
+            if (dist0 >= len || dist0 > s_found) break;
+            const int64_t dist = dist0 + threadIdx.x;
+            if (dist < len) {
+                const int64_t ip = END ? hi - dist : lo + dist;
+                if (!hpgb_check_pixel_ring(g, g2, T, ip, nr, ipix1, d.fct, d.z0, d.phi, d.cosrsmall, d.cpix))
+                    atomicMin(reinterpret_cast<long long *>(it + 4 + END), (long long)dist);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qb_finish(const hpgb_disc_t *__restrict__ plans, const int64_t *__restrict__ ring_start,
+                                                          const int64_t D, const hpgb_geom g, const int64_t *__restrict__ work,
+                                                          int64_t *__restrict__ ranges) {
+    const int64_t nitems = work[0];
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    for (int64_t k = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; k < nitems; k += stride) {
+        const int64_t *it = QC_ITEM(work, k);
+        const unsigned mask = (unsigned)it[3];
+        int64_t ip_lo = it[1], ip_hi = it[2];
+        if (mask & 1u) ip_lo = it[4] == INT64_MAX ? ip_hi + 1 : ip_lo + it[4];
+        if (ip_lo <= ip_hi) ip_hi = it[5] == INT64_MAX ? ip_lo : ip_hi - it[5];
+        const int64_t dsc = qb_find_disc(ring_start, D, it[0]);
+        int64_t nr, ipix1, row[4];
+        bool shifted;
+        hpgb_ring_info_small(g, plans[dsc].irmin + (it[0] - ring_start[dsc]), ipix1, nr, shifted);
+        hpgb_qc_ring_rows(ip_lo, ip_hi, nr, ipix1, row);
+        longlong2 *o = reinterpret_cast<longlong2 *>(ranges) + 2 * it[0] + 2 * dsc + 1;
+        o[0] = make_longlong2(row[0], row[1]);
+        o[1] = make_longlong2(row[2], row[3]);
+    }
+}
+
+// pixels of disc d = offs[row_start[d+1]] - offs[row_start[d]]: the D + 1 list boundaries
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qb_disc_offsets(const int64_t *__restrict__ ring_start, const int64_t D,
+                                                                const int64_t *__restrict__ offs, int64_t *__restrict__ disc_offs) {
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    for (int64_t d = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; d <= D; d += stride) disc_offs[d] = offs[2 * ring_start[d] + 2 * d];
+}
+
+}  // namespace
+
+extern "C" {
+
+// d_plans: D plans of hpgb_query_circle_ring_plan (same nside and fct) copied to the device; d_ring_start:
+// D + 1 prefix sums of max(irmax - irmin + 1, 0) (whole-sphere plans count 0 rings and carry north_hi = npix:
+// hpgb_query_circle_ring_batch_prepare does both).  d_ranges: 2 * ring_start[D] + 2 * D rows.  d_work:
+// 64 * (ring_start[D] + 1) bytes when fct > 1, else NULL.
+int hpgb_query_circle_ring_batch_ranges(const hpgb_disc_t *d_plans, const int64_t *d_ring_start, int64_t D, int64_t total_rings,
+                                        int64_t nside, int64_t fct, int64_t *d_ranges_m2, void *d_work, void *stream) {
+    if (D < 0 || total_rings < 0 || (D > 0 && (!d_plans || !d_ring_start || !d_ranges_m2))) return HPGB_E_BAD_ARGUMENT;
+    if (D == 0) return HPGB_OK;
+    const int c = hpgb_check_nside(nside, 0);
+    if (c) return c;
+    if (fct < 1 || fct * nside > ((int64_t)1 << 29) || !hpgb_aligned16(d_ranges_m2)) return HPGB_E_BAD_ARGUMENT;
+    const bool trim = fct > 1;
+    if (trim && (!d_work || !hpgb_aligned16(d_work))) return HPGB_E_BAD_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    const hpgb_geom g = hpgb_make_geom(nside, 0), g2 = hpgb_make_geom(nside * fct, 0);
+    const int64_t nthreads = total_rings > D ? total_rings : D;
+    int64_t grid = (nthreads + HPGB_BLOCK - 1) / HPGB_BLOCK;
+    const int64_t cap = (int64_t)hpgb_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    if (trim) {
+        cudaError_t e = cudaMemsetAsync(d_work, 0, 64, s);
+        if (e != cudaSuccess) return HPGB_E_CUDA + (int)e;
+    }
+    k_qb_ring_ranges<<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(d_plans, d_ring_start, D, g, g2, d_ranges_m2, (int64_t *)d_work);
+    int launches = 1;
+    if (trim && total_rings > 0) {
+        const unsigned wide = (unsigned)hpgb_sm_count() * 4u;
+        k_qb_scan<0><<<wide, HPGB_BLOCK, 0, s>>>(d_plans, d_ring_start, D, g, g2, (int64_t *)d_work);
+        k_qb_scan<1><<<wide, HPGB_BLOCK, 0, s>>>(d_plans, d_ring_start, D, g, g2, (int64_t *)d_work);
+        k_qb_finish<<<(unsigned)(grid < 64 ? grid : 64), HPGB_BLOCK, 0, s>>>(d_plans, d_ring_start, D, g, (const int64_t *)d_work, d_ranges_m2);
+        launches += 3;
+    }
+    g_hpgb_launches.fetch_add(launches, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+}
+
+// plans for D discs in one call (host); stops at the first disc whose arguments the reference would reject:
+// returns its code and index
+int hpgb_query_circle_ring_plan_many(int64_t nside, const double *a, const double *b, const double *radius, int64_t D,
+                                     int inclusive, int64_t fact, int lonlat, int degrees, hpgb_disc_t *plans, int64_t *first_bad) {
+    if (first_bad) *first_bad = -1;
+    if (D < 0 || (D > 0 && (!a || !b || !radius || !plans))) return HPGB_E_BAD_ARGUMENT;
+    for (int64_t d = 0; d < D; d++) {
+        const int rc = hpgb_query_circle_ring_plan(nside, a[d], b[d], radius[d], inclusive, fact, lonlat, degrees, plans + d);
+        if (rc != HPGB_OK) {
+            if (first_bad) *first_bad = d;
+            return rc;
+        }
+    }
+    return HPGB_OK;
+}
+
+// host side of a batch: normalises the plans (whole-sphere discs become "no rings + north polar range
+// (0, npix)") and fills ring_start[0..D]; returns the total number of rings
+int64_t hpgb_query_circle_ring_batch_prepare(hpgb_disc_t *plans, int64_t D, int64_t *ring_start) {
+    int64_t acc = 0;
+    for (int64_t d = 0; d < D; d++) {
+        hpgb_disc_t &p = plans[d];
+        if (p.whole_sphere) {
+            p.irmin = 1;
+            p.irmax = 0;
+            p.north_hi = 12 * p.nside * p.nside;
+            p.south_lo = -1;
+        }
+        ring_start[d] = acc;
+        acc += p.irmax >= p.irmin ? p.irmax - p.irmin + 1 : 0;
+    }
+    ring_start[D] = acc;
+    return acc;
+}
+
+// Host form: every pixel list back to back in `out` (cap pixels), list d = out[disc_offsets[d] .. disc_offsets[d+1]).
+// Call with out = NULL to learn the sizes (disc_offsets is filled, *total set), then with the buffer.
+int hpgb_host_query_circle_ring_batch(hpgb_disc_t *plans, int64_t D, int device, int64_t *disc_offsets, int64_t *total,
+                                      int64_t *out, int64_t cap) {
+    if (D < 0 || !total || (D > 0 && (!plans || !disc_offsets))) return HPGB_E_BAD_ARGUMENT;
+    *total = 0;
+    if (D == 0) {
+        if (disc_offsets) disc_offsets[0] = 0;
+        return HPGB_OK;
+    }
+    for (int64_t d = 1; d < D; d++)
+        if (plans[d].nside != plans[0].nside || plans[d].fct != plans[0].fct) return HPGB_E_BAD_ARGUMENT;
+    const int ndev = hpgb_device_count();
+    if (ndev <= 0) return HPGB_E_NO_DEVICE;
+    if (device < 0 || device >= ndev) return HPGB_E_BAD_ARGUMENT;
+    std::vector<int64_t> ring_start((size_t)D + 1);
+    const int64_t nring = hpgb_query_circle_ring_batch_prepare(plans, D, ring_start.data());
+    const int64_t m = 2 * nring + 2 * D;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CKQ(cudaSetDevice(device));
+    DevBuf pool;
+    hpgb_disc_t *d_plans = nullptr;
+    int64_t *d_rs = nullptr, *d_ranges = nullptr, *d_offs = nullptr, *d_work = nullptr, *d_do = nullptr;
+    hpgb_status_t *st = nullptr;
+    CKQ(pool.alloc(&d_plans, (size_t)D * sizeof(hpgb_disc_t)));
+    CKQ(pool.alloc(&d_rs, (size_t)(D + 1) * 8));
+    CKQ(pool.alloc(&d_ranges, (size_t)m * 16));
+    CKQ(pool.alloc(&d_offs, (size_t)(m + 1) * 8));
+    CKQ(pool.alloc(&d_do, (size_t)(D + 1) * 8));
+    CKQ(pool.alloc(&st, sizeof(hpgb_status_t)));
+    if (plans[0].fct > 1) CKQ(pool.alloc(&d_work, (size_t)64 * (size_t)(nring + 1)));
+    CKQ(cudaMemcpyAsync(d_plans, plans, (size_t)D * sizeof(hpgb_disc_t), cudaMemcpyHostToDevice, 0));
+    CKQ(cudaMemcpyAsync(d_rs, ring_start.data(), (size_t)(D + 1) * 8, cudaMemcpyHostToDevice, 0));
+    CKQ(cudaMemsetAsync(st, 0xFF, sizeof(hpgb_status_t), 0));
+    int rc = hpgb_query_circle_ring_batch_ranges(d_plans, d_rs, D, nring, plans[0].nside, plans[0].fct, d_ranges, d_work, nullptr);
+    if (rc == HPGB_OK) rc = launch_ranges_offsets(d_ranges, m, 0, d_offs, st, 0);
+    if (rc != HPGB_OK) {
+        cudaSetDevice(prev);
+        return rc;
+    }
+    int64_t grid = (D + 1 + HPGB_BLOCK - 1) / HPGB_BLOCK;
+    if (grid > 1024) grid = 1024;
+    k_qb_disc_offsets<<<(unsigned)grid, HPGB_BLOCK, 0, 0>>>(d_rs, D, d_offs, d_do);
+    g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+    CKQ(cudaMemcpy(disc_offsets, d_do, (size_t)(D + 1) * 8, cudaMemcpyDeviceToHost));
+    *total = disc_offsets[D];
+    cudaSetDevice(prev);
+    if (!out) return HPGB_OK;
+    if (cap < *total) return HPGB_E_BAD_ARGUMENT;
+    if (*total == 0) return HPGB_OK;
+    hpgb_pipe_arr arrs[1] = {{nullptr, (char *)out, 8}};
+    return hpgb_host_pipeline(device, *total, arrs, 1,
+                              [&](void **dp, int64_t base, int64_t cn, hpgb_status_t *, cudaStream_t s) {
+                                  return launch_ranges_expand(d_ranges, d_offs, m, base, cn, (int64_t *)dp[0], s);
+                              },
+                              nullptr);
+}
+
+}  // extern "C"

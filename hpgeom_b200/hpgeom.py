@@ -43,6 +43,7 @@ __all__ = [
     'pixel_ranges_to_pixels',
     'query_circle',
     'query_circle_vec',
+    'query_circle_batch',
     'upgrade_pixels',
     'upgrade_pixel_ranges',
     'nside_to_npixel',
@@ -465,6 +466,66 @@ def query_circle(nside, a, b, radius, inclusive=False, fact=4, nest=True, lonlat
         _lib.check_rc(L.hpgb_query_circle_ring_ranges(ctypes.byref(plan), ctypes.c_void_p(table.data_ptr()),
                                                       ctypes.c_void_p(work.data_ptr()), stream))
     return pixel_ranges_to_pixels(table)
+
+
+def query_circle_batch(nside, a, b, radius, inclusive=False, fact=4, lonlat=True, degrees=True, device_resident=False):
+    """Many RING-scheme query_circle calls at once (an extension: the reference has no batched form).
+
+    ``a``, ``b``, ``radius`` are 1-D arrays of D discs (``radius`` may be a scalar); returns
+    ``(pixels, offsets)``: the D pixel lists back to back and the D + 1 list boundaries, list d =
+    ``pixels[offsets[d]:offsets[d+1]]``, each identical to ``query_circle(nside, a[d], b[d], radius[d],
+    nest=False, ...)``.  One small disc is launch-latency bound on a GPU; a batch runs every (disc, ring)
+    pair in one launch (csrc/k_query.cu).  Argument errors are reported for the first offending disc with
+    the reference's messages.
+    """
+    nside, fact, inclusive, lonlat, degrees = int(nside), int(fact), bool(inclusive), bool(lonlat), bool(degrees)
+    av = np.ascontiguousarray(np.atleast_1d(_d._np_view(a)), dtype=np.float64)
+    bv = np.ascontiguousarray(np.atleast_1d(_d._np_view(b)), dtype=np.float64)
+    if av.ndim != 1 or av.shape != bv.shape:
+        raise ValueError("a and b must be 1-D arrays of the same length")
+    rv = np.ascontiguousarray(np.broadcast_to(np.asarray(_d._np_view(radius), dtype=np.float64), av.shape))
+    D = int(av.size)
+    L = _lib.lib()
+    plans = (_lib.Disc * max(D, 1))()
+    bad = ctypes.c_int64(-1)
+    rc = L.hpgb_query_circle_ring_plan_many(nside, av.ctypes.data, bv.ctypes.data, rv.ctypes.data, D, int(inclusive), fact,
+                                            int(lonlat), int(degrees), plans, ctypes.byref(bad))
+    if rc != 0 and bad.value >= 0:
+        k = bad.value  # same checks, order and messages as the single call
+        query_circle(nside, float(av[k]), float(bv[k]), float(rv[k]), inclusive=inclusive, fact=fact, nest=False,
+                     lonlat=lonlat, degrees=degrees)
+    _lib.check_rc(rc)
+    dev = _d.default_device()
+    if not device_resident:
+        offsets = np.zeros(D + 1, dtype=np.int64)
+        total = ctypes.c_int64(0)
+        _lib.check_rc(L.hpgb_host_query_circle_ring_batch(plans, D, dev, offsets.ctypes.data, ctypes.byref(total), None, 0))
+        out = np.empty(total.value, dtype=np.int64)
+        if total.value:
+            _lib.check_rc(L.hpgb_host_query_circle_ring_batch(plans, D, dev, offsets.ctypes.data, ctypes.byref(total),
+                                                              out.ctypes.data, total.value))
+        return out, offsets
+    torch = _d.torch
+    ring_start = np.zeros(D + 1, dtype=np.int64)
+    nring = int(L.hpgb_query_circle_ring_batch_prepare(plans, D, ring_start.ctypes.data))
+    m = 2 * nring + 2 * D
+    with torch.cuda.device(dev):
+        cuda = "cuda:%d" % dev
+        d_plans = torch.from_numpy(np.frombuffer(plans, dtype=np.uint8, count=D * ctypes.sizeof(_lib.Disc)).copy()).to(cuda)
+        d_rs = torch.from_numpy(ring_start).to(cuda)
+        table = torch.empty((max(m, 1), 2), dtype=torch.int64, device=cuda)
+        fct = fact if inclusive else 1
+        work = torch.empty(8 * (nring + 1) if fct > 1 else 2, dtype=torch.int64, device=cuda)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if D:
+            _lib.check_rc(L.hpgb_query_circle_ring_batch_ranges(d_plans.data_ptr(), d_rs.data_ptr(), D, nring, nside, fct,
+                                                                table.data_ptr(), work.data_ptr(), stream))
+        table = table[:m]
+        pixels = pixel_ranges_to_pixels(table) if m else torch.empty(0, dtype=torch.int64, device=cuda)
+        lens = (table[:, 1] - table[:, 0]).clamp_(min=0)
+        csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=cuda), torch.cumsum(lens, 0)])
+        offsets = csum[2 * d_rs + 2 * torch.arange(D + 1, device=cuda)]
+    return pixels, offsets
 
 
 def _query_circle_nest(L, nside, a, b, radius, inclusive, fact, lonlat, degrees, return_pixel_ranges, device_resident, dev):

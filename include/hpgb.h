@@ -212,6 +212,22 @@ int hpgb_query_circle_ring_ranges(const hpgb_disc_t *plan, int64_t *d_ranges_m2,
 int hpgb_host_query_circle_ring_count(const hpgb_disc_t *plan, int device, int64_t *total);
 int hpgb_host_query_circle_ring_fill(const hpgb_disc_t *plan, int64_t *out, int64_t total, int device);
 
+/* ---- many discs at once, RING scheme (an extension: the reference has no batched call).  One small disc is
+ * launch-latency bound on a GPU, a batch is not: D plans of hpgb_query_circle_ring_plan (same nside and fact)
+ * are prepared on the host, ONE launch runs every (disc, ring) pair and one offsets + expand pass writes the
+ * D pixel lists back to back.  prepare: normalises the plans and fills ring_start[0..D] (returns the total ring
+ * count); batch_ranges: device form, table of 2 * rings + 2 * D rows = the D single-disc tables concatenated;
+ * host form: call with out = NULL for disc_offsets[0..D] and *total, then again with the buffer. ---- */
+int hpgb_query_circle_ring_plan_many(int64_t nside, const double *a, const double *b, const double *radius,
+                                     int64_t n_discs, int inclusive, int64_t fact, int lonlat, int degrees,
+                                     hpgb_disc_t *plans, int64_t *first_bad);
+int64_t hpgb_query_circle_ring_batch_prepare(hpgb_disc_t *plans, int64_t n_discs, int64_t *ring_start);
+int hpgb_query_circle_ring_batch_ranges(const hpgb_disc_t *d_plans, const int64_t *d_ring_start, int64_t n_discs,
+                                        int64_t total_rings, int64_t nside, int64_t fct, int64_t *d_ranges_m2,
+                                        void *d_work, void *stream);
+int hpgb_host_query_circle_ring_batch(hpgb_disc_t *plans, int64_t n_discs, int device, int64_t *disc_offsets,
+                                      int64_t *total, int64_t *out, int64_t cap);
+
 /* ---- query_circle, NEST scheme: the hierarchical search of query_disc (hpgeom/healpix_geom.c:748-800,
  * check_pixel_nest :541-601), walked breadth first: one kernel launch per order over the whole frontier,
  * the emitted ranges sorted on the device.  Frontier sizes are data dependent, so this entry point owns its

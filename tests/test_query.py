@@ -272,3 +272,38 @@ def test_pixel_ranges_to_pixels_shapes(hpg, oracle_port, shape):
         assert L.hpgb_ranges_expand(t.data_ptr(), offs.data_ptr(), m, begin, count, buf.data_ptr() + 8, None) == 0
         torch.cuda.synchronize()
         assert_bit_equal(buf[1:].cpu().numpy(), want[begin:begin + count])
+
+
+@pytest.mark.gpu
+def test_query_circle_batch_matches_single_goldens(hpg):
+    """Batched RING query: every list of a batch equals the golden single-disc result (batches = the golden
+    cases grouped by nside and fact), host and device-resident forms; an empty batch; error reporting."""
+    import collections
+    import torch
+    groups = collections.defaultdict(list)
+    for (nside, a, b, radius, fact, lonlat, degrees), want in cases():
+        if not lonlat:
+            groups[(nside, fact)].append((a, b, radius, want))
+    assert len(groups) > 30
+    for k, ((nside, fact), items) in enumerate(sorted(groups.items())):
+        a = np.array([it[0] for it in items]); b = np.array([it[1] for it in items]); r = np.array([it[2] for it in items])
+        kw = dict(inclusive=fact > 0, fact=max(fact, 1), lonlat=False)
+        pix, offs = hpg.query_circle_batch(nside, a, b, r, **kw)
+        assert offs.shape == (len(items) + 1,) and offs[0] == 0 and offs[-1] == pix.size
+        for d, it in enumerate(items):
+            assert_bit_equal(pix[offs[d]:offs[d + 1]], it[3], "nside=%d fact=%d disc %d" % (nside, fact, d))
+        if k % 4 == 0:
+            tp, to = hpg.query_circle_batch(nside, a, b, r, device_resident=True, **kw)
+            assert isinstance(tp, torch.Tensor) and tp.is_cuda
+            assert_bit_equal(tp.cpu().numpy(), pix)
+            assert_bit_equal(to.cpu().numpy(), offs)
+    pix, offs = hpg.query_circle_batch(64, np.zeros(0), np.zeros(0), 0.1)
+    assert pix.shape == (0,) and offs.tolist() == [0]
+    with pytest.raises(ValueError, match=r"lat = 95 out of range \[-90, 90\]"):
+        hpg.query_circle_batch(1024, [10.0, 20.0], [5.0, 95.0], 1.0)
+    # scalar radius broadcast, many small discs, against the single call
+    rng = np.random.default_rng(8)
+    lon, lat = 360 * rng.random(2000), np.degrees(np.arcsin(2 * rng.random(2000) - 1))
+    pix, offs = hpg.query_circle_batch(2048, lon, lat, 0.2)
+    for d in (0, 17, 1999):
+        assert_bit_equal(pix[offs[d]:offs[d + 1]], hpg.query_circle(2048, lon[d], lat[d], 0.2, nest=False))
