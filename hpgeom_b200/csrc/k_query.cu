@@ -319,6 +319,53 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_qn_level(const hpgb_qn_plan P, c
     }
 }
 
+// The first orders of the walk have a handful of pixels (12, then at most 4x per order): one launch + one
+// host round trip per order costs more than the work.  This single-CTA kernel walks orders 0, 1, ... for as long
+// as the next frontier is sure to fit QN_SMALL_CAP entries (and the ranges QN_SMALL_RCAP), ping-ponging between
+// two global buffers; it leaves the frontier in bufA and {next order, frontier size, ranges} in state[0..2].
+// A small query (a few thousand pixels) finishes here.
+#define QN_SMALL_CAP 16384
+#define QN_SMALL_RCAP 32768
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qn_small(const hpgb_qn_plan P, int64_t *__restrict__ bufA, int64_t *__restrict__ bufB,
+                                                         int64_t *__restrict__ rlo, int64_t *__restrict__ rhi, int64_t *__restrict__ state) {
+    const double *T = hpgb_stage_table();
+    __shared__ int s_next, s_r;
+    int64_t *src = bufA, *dst = bufB;
+    if (threadIdx.x < 12) src[threadIdx.x] = threadIdx.x;
+    if (threadIdx.x == 0) s_next = 0, s_r = 0;
+    __syncthreads();
+    int n = 12, o = 0, r = 0;
+    while (o <= P.omax && n > 0 && 4 * n <= QN_SMALL_CAP && r + n <= QN_SMALL_RCAP) {
+        const hpgb_geom g = hpgb_make_geom((int64_t)1 << o, 1);
+        for (int i = threadIdx.x; i < n; i += HPGB_BLOCK) {
+            const int64_t pix = src[i];
+            int64_t lo, hi;
+            const int v = hpgb_qn_visit(P, g, T, o, pix, lo, hi);
+            if (v == 1) {
+                const int k = atomicAdd(&s_r, 1);
+                rlo[k] = lo;
+                rhi[k] = hi;
+            } else if (v == 2) {
+                const int k = atomicAdd(&s_next, 4);
+                dst[k] = 4 * pix, dst[k + 1] = 4 * pix + 1, dst[k + 2] = 4 * pix + 2, dst[k + 3] = 4 * pix + 3;
+            }
+        }
+        __syncthreads();
+        n = s_next;
+        r = s_r;
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = 0;
+        int64_t *t = src;
+        src = dst;
+        dst = t;
+        o++;
+        __syncthreads();
+    }
+    if (src != bufA)
+        for (int i = threadIdx.x; i < n; i += HPGB_BLOCK) bufA[i] = src[i];
+    if (threadIdx.x == 0) state[0] = o, state[1] = n, state[2] = r;
+}
+
 // sorted (lo, hi) -> (m,2) table; a repeated single pixel (see hpgb_query.h) becomes an empty row
 __global__ void __launch_bounds__(HPGB_BLOCK) k_qn_table(const int64_t *__restrict__ lo, const int64_t *__restrict__ hi, int64_t m,
                                                          longlong2 *__restrict__ table) {
@@ -371,14 +418,25 @@ int qn_build(const hpgb_qn_plan &P, int64_t nside, QnHandle *h) {
     } else {
         unsigned long long *cnt = nullptr;
         CKQ(pool.alloc(&cnt, 16));
-        int64_t *cur = nullptr;
-        int64_t n = 12;
-        CKQ(pool.alloc(&cur, 12 * 8));
-        const int64_t base12[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
-        CKQ(cudaMemcpy(cur, base12, sizeof base12, cudaMemcpyHostToDevice));
+        // orders with small frontiers: one single-CTA launch (k_qn_small)
+        int64_t *cur = nullptr, *bufB = nullptr, *rlo0 = nullptr, *rhi0 = nullptr, *state = nullptr;
+        CKQ(pool.alloc(&cur, (size_t)QN_SMALL_CAP * 8));
+        CKQ(pool.alloc(&bufB, (size_t)QN_SMALL_CAP * 8));
+        CKQ(pool.alloc(&rlo0, (size_t)QN_SMALL_RCAP * 8));
+        CKQ(pool.alloc(&rhi0, (size_t)QN_SMALL_RCAP * 8));
+        CKQ(pool.alloc(&state, 32));
+        k_qn_small<<<1, HPGB_BLOCK, 0, 0>>>(P, cur, bufB, rlo0, rhi0, state);
+        g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+        int64_t hs[3];
+        CKQ(cudaMemcpy(hs, state, 24, cudaMemcpyDeviceToHost));
+        int64_t n = hs[1];
         std::vector<int64_t *> lvl_lo, lvl_hi;
         std::vector<int64_t> lvl_n;
-        for (int o = 0; o <= P.omax && n > 0; o++) {
+        lvl_lo.push_back(rlo0);
+        lvl_hi.push_back(rhi0);
+        lvl_n.push_back(hs[2]);
+        R += hs[2];
+        for (int o = (int)hs[0]; o <= P.omax && n > 0; o++) {
             int64_t *next = nullptr, *rlo = nullptr, *rhi = nullptr;
             CKQ(pool.alloc(&next, (size_t)n * 32));
             CKQ(pool.alloc(&rlo, (size_t)n * 8));
