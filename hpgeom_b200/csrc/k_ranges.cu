@@ -10,12 +10,14 @@
 //   hpgb_ranges_expand   writes any window [out_begin, out_begin + out_count) of the pixel list.
 //                        Each CTA owns a contiguous run of 2048-pixel output tiles, finds its first
 //                        range with ONE binary search and then walks forward: a window of 1024
-//                        offsets + range starts is staged in shared memory, every thread resolves its
-//                        8 outputs against it (nothing to search when the tile lies inside one range,
-//                        the common case for query results) and stores them as 128-bit streaming
-//                        stores.  8 B written per pixel: HBM-write bound.
+//                        offsets + range starts is staged in shared memory and KEPT across tiles
+//                        (it only moves on when a tile reaches past it).  A full tile inside the
+//                        window runs without any barrier: a thread whose eight outputs fall into
+//                        one range (long ranges: always, usually the range of its previous tile)
+//                        just adds; otherwise it searches the window per 16-byte unit.  128-bit
+//                        streaming stores, 8 B written per pixel: 5.95 TB/s on long ranges.
 //
-// The same pair expands the ring ranges of query_circle (k_query.cu).
+// The same pair expands the range tables of query_circle (k_query.cu), single and batched.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
