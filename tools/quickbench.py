@@ -53,7 +53,7 @@ if "n2r" in which:
 if "r2n" in which:
     bench("r2n", lambda: L.hpgb_ring_to_nest(P(pix), P(out), n, nside, None, P(st), s), 16)
 a = b = c = None
-if any(w in which for w in ("p2a", "p2v", "v2p")):
+if any(w in which for w in ("p2a", "p2v", "v2p", "lonlat")):
     a = torch.empty(n, dtype=torch.float64, device="cuda")
     b = torch.empty(n, dtype=torch.float64, device="cuda")
     c = torch.empty(n, dtype=torch.float64, device="cuda")
@@ -95,3 +95,16 @@ if "upgrade" in which:
     bench("upgrade nest 4096->8192", lambda: L.hpgb_upgrade_pixels(P(p4), P(out), m, 4096, 8192, 1, P(st), s), 40)
     bench("upgrade ring 4096->8192", lambda: L.hpgb_upgrade_pixels(P(p4), P(out), m, 4096, 8192, 0, P(st), s), 40)
     n = n_save
+if "bounds" in which:
+    m = n // 8
+    p4 = pix[:m] % (12 * 4096 * 4096)
+    ba = torch.empty((m, 4), dtype=torch.float64, device="cuda")
+    bb = torch.empty((m, 4), dtype=torch.float64, device="cuda")
+    n_save = n
+    n = m
+    bench("boundaries nest 4096 step 1", lambda: L.hpgb_boundaries(P(p4), P(ba), P(bb), m, 4096, None, 1, 1, 1, 1, P(st), s), 72)
+    bench("boundaries ring 4096 step 1", lambda: L.hpgb_boundaries(P(p4), P(ba), P(bb), m, 4096, None, 1, 0, 1, 1, P(st), s), 72)
+    n = n_save
+    del ba, bb
+if "lonlat" in which:
+    bench("lonlat_to_thetaphi deg", lambda: L.hpgb_lonlat_to_thetaphi(P(lon), P(lat), P(a), P(b), n, 1, P(st), s), 32)
