@@ -27,12 +27,12 @@ __device__ __forceinline__ bool var_geom(const int64_t *nside_v, int64_t i, int 
 // get_interpolation_weights   (hpgeom/hpgeom.c:3491-3523)   16 B in + 64 B out per point
 // -------------------------------------------------------------------------------------------
 // acos / atan Taylor tables of hpgb_math.h (72 + 46 KB), staged into dynamic shared memory: ONE
-// 512-thread CTA per SM shares them.  The sin/cos table of the reference-shaped fallback is static.
+// 640-thread CTA per SM shares them.  The sin/cos table of the reference-shaped fallback is static.
 static __device__ const unsigned long long g_hpgb_acos_tab[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS] = HPGB_ACOS_TABLE_INIT;
 static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES] = HPGB_ATANQ_TABLE_INIT;
 #define HPGB_INTERP_TAB_WORDS (HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES)
 #ifndef HPGB_INTERP_BLOCK
-#define HPGB_INTERP_BLOCK 512
+#define HPGB_INTERP_BLOCK 640
 #endif
 
 template <bool NEST, bool POW2, bool LONLAT, bool DEGREES, bool VAR>
@@ -77,9 +77,11 @@ struct OpInterp {
                                              double *w) {
         hpgb_interpol<NEST, POW2>(gg, T, theta, phi, p, w);
     }
-    __device__ __forceinline__ void row(const hpgb_geom &gg, double va, double vb, int64_t i, const Ctx &c, hpgb_bad_t &bad) const {
-        int64_t p[4] = {-1, -1, -1, -1};
-        double w[4] = {0.0, 0.0, 0.0, 0.0};
+    // the four pixels and weights of one point (the reference's loop body, hpgeom/hpgeom.c:3491-3523)
+    __device__ __forceinline__ void values(const hpgb_geom &gg, double va, double vb, int64_t i, const Ctx &c, hpgb_bad_t &bad,
+                                           int64_t *p, double *w) const {
+        p[0] = p[1] = p[2] = p[3] = -1;
+        w[0] = w[1] = w[2] = w[3] = 0.0;
         double theta, phi;
         if (!hpgb_angles_exact<LONLAT, DEGREES>(va, vb, theta, phi)) {
             bad.flag(base + i);
@@ -89,9 +91,18 @@ struct OpInterp {
                 const hpgb_mp_tab mp{c.TA, c.TQ};
                 hpgb_interpol_rings<NEST, true>(gg, rk, mp, theta, phi, ir1, p, w);
             } else {
-                slow(gg, c.T, theta, phi, p, w);
+                int64_t tp[4];  // the out-of-line call gets its own row, so p / w stay in registers
+                double tw[4];
+                slow(gg, c.T, theta, phi, tp, tw);
+#pragma unroll
+                for (int m = 0; m < 4; m++) p[m] = tp[m], w[m] = tw[m];
             }
         }
+    }
+    __device__ __forceinline__ void row(const hpgb_geom &gg, double va, double vb, int64_t i, const Ctx &c, hpgb_bad_t &bad) const {
+        int64_t p[4];
+        double w[4];
+        values(gg, va, vb, i, c, bad, p, w);
         hpgb_st2(pix + 4 * i, p[0], p[1]);
         hpgb_st2(pix + 4 * i + 2, p[2], p[3]);
         hpgb_st2(wgt + 4 * i, w[0], w[1]);
@@ -115,6 +126,85 @@ struct OpInterp {
     }
 };
 
+// Scalar power-of-two nside, aligned operands.  The body of one point is ~1000 instructions; the generic
+// skeleton inlined it four times (k_map2: two pairs in flight), 19 000 SASS instructions = 300 KB of code that
+// no instruction cache holds.  Here it exists ONCE: a warp takes 64 consecutive points, every lane converts its
+// two points in a rolled loop and drops the two (4,) rows into XOR-swizzled staging buffers, then the warp
+// writes 2 KiB of pixels and 2 KiB of weights with fully coalesced 128-bit streaming stores.  The next chunk's
+// angles are loaded before the current one is converted.
+template <class Op>
+__global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_rows(const Op op, const int64_t n, hpgb_status_t *st) {
+    extern __shared__ __align__(16) unsigned long long hpgb_interp_tabs[];
+    const typename Op::Ctx ctx = op.prologue();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    longlong2 *wp = reinterpret_cast<longlong2 *>(hpgb_interp_tabs + HPGB_INTERP_TAB_WORDS) + warp * 256;  // 128 units pixels,
+    longlong2 *ww = wp + 128;                                                                                // 128 units weights
+    const int64_t gw = (int64_t)blockIdx.x * (HPGB_INTERP_BLOCK / 32) + warp;
+    const int64_t nw = (int64_t)gridDim.x * (HPGB_INTERP_BLOCK / 32);
+    const int64_t nfull = n >> 6, nchunk = (n + 63) >> 6;  // the last chunk may be partial: same code, guarded
+    hpgb_bad_t bad;
+    const int sw = (lane >> 1) & 3;
+    auto fetch = [&](int64_t c) {
+        typename Op::In2 r;
+        const int64_t i = c * 64 + 2 * lane;
+        if (c < nfull) return op.load2(i);
+        r.a.x = i < n ? hpgb_ld1(op.a + i) : 0.0;  // past the end: a valid dummy point, never stored
+        r.b.x = i < n ? hpgb_ld1(op.b + i) : 0.0;
+        r.a.y = i + 1 < n ? hpgb_ld1(op.a + i + 1) : 0.0;
+        r.b.y = i + 1 < n ? hpgb_ld1(op.b + i + 1) : 0.0;
+        return r;
+    };
+    int64_t ch = gw;
+    typename Op::In2 v = typename Op::In2();
+    if (ch < nchunk) v = fetch(ch);
+    for (; ch < nchunk; ch += nw) {
+        const typename Op::In2 cur = v;
+        if (ch + nw < nchunk) v = fetch(ch + nw);
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            int64_t p[4];
+            double w[4];
+            op.values(op.g, q ? cur.a.y : cur.a.x, q ? cur.b.y : cur.b.x, ch * 64 + 2 * lane + q, ctx, bad, p, w);
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                wp[lane * 4 + ((q * 2 + j) ^ sw)] = make_longlong2(p[2 * j], p[2 * j + 1]);
+                ww[lane * 4 + ((q * 2 + j) ^ sw)] = make_longlong2(__double_as_longlong(w[2 * j]), __double_as_longlong(w[2 * j + 1]));
+            }
+        }
+        __syncwarp();
+        longlong2 *dp = reinterpret_cast<longlong2 *>(op.pix + ch * 256);
+        longlong2 *dw = reinterpret_cast<longlong2 *>(op.wgt + ch * 256);
+        const int64_t units = ch < nfull ? 128 : 2 * (n - ch * 64);  // two 16-byte units per point
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int idx = k * 32 + lane, src = idx >> 2, j = idx & 3, ssw = (src >> 1) & 3;
+            if (idx < units) {
+                hpgb_row_st(dp + idx, wp[src * 4 + (j ^ ssw)]);
+                hpgb_row_st(dw + idx, ww[src * 4 + (j ^ ssw)]);
+            }
+        }
+        __syncwarp();
+    }
+    bad.commit(st);
+}
+
+template <class Op>
+int launch_interp_rows(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
+    const int smem = Op::DYN_SMEM + (HPGB_INTERP_BLOCK / 32) * 256 * 16;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_interp_rows<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr = true;
+    }
+    int64_t grid = hpgb_sm_count();
+    const int64_t want = (((n + 63) >> 6) + HPGB_INTERP_BLOCK / 32 - 1) / (HPGB_INTERP_BLOCK / 32);
+    if (want < grid) grid = want > 0 ? want : 1;
+    k_interp_rows<Op><<<(unsigned)grid, HPGB_INTERP_BLOCK, smem, s>>>(op, n, st);
+    g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+}
+
 template <bool NEST, bool LONLAT, bool DEGREES>
 int launch_interp_t(const double *a, const double *b, int64_t *pix, double *wgt, int64_t n, int64_t nside,
                     const int64_t *nside_v, int64_t base, hpgb_status_t *st, cudaStream_t s) {
@@ -126,6 +216,7 @@ int launch_interp_t(const double *a, const double *b, int64_t *pix, double *wgt,
     const bool vec = hpgb_aligned16(a) && hpgb_aligned16(b);
     if (NEST || g.order >= 0) {
         OpInterp<NEST, true, LONLAT, DEGREES, false> op{a, b, pix, wgt, nullptr, base, g, hpgb_make_rk(g), hpgb_make_a2p_fast<false, false>(g)};
+        if (vec) return launch_interp_rows(op, n, st, s);
         return hpgb_launch_map<decltype(op), HPGB_INTERP_BLOCK>(op, n, vec, st, s, decltype(op)::DYN_SMEM);
     }
     OpInterp<false, false, LONLAT, DEGREES, false> op{a, b, pix, wgt, nullptr, base, g, hpgb_rk(), hpgb_a2p_fast()};
