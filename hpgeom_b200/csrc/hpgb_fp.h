@@ -947,8 +947,7 @@ HPGB_HD void hpgb_ring_pair(const hpgb_geom &g, const hpgb_rk &rk, const MP &mp,
     if (i1 < 0) i1 += nr;
     if (i2 >= nr) i2 -= nr;
     if (NESTK) {
-        p[0] = hpgb_ringidx2nest_k(rk, (uint32_t)ring, (uint32_t)i1);
-        p[1] = hpgb_ringidx2nest_k(rk, (uint32_t)ring, (uint32_t)i2);
+        hpgb_ringidx2nest_pair_k(rk, (uint32_t)ring, (uint32_t)i1, (uint32_t)i2, p[0], p[1]);
     } else {
         p[0] = sp + i1;
         p[1] = sp + i2;

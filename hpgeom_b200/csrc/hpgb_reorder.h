@@ -262,7 +262,7 @@ HPGB_HD int64_t hpgb_xyf2nest_k(const hpgb_rk &c, uint32_t ix, uint32_t iy, uint
 // (ring number 1..4 nside-1, 0-based in-ring index counted eastward) -> NEST pixel: ring2xyf without
 // the isqrt, for callers that already know the ring (interpolation): caps fc = q div nr (special_div),
 // belt the edge-line coordinates.  Branch-free.
-HPGB_HD int64_t hpgb_ringidx2nest_k(const hpgb_rk &c, uint32_t ring, uint32_t q) {
+HPGB_HD void hpgb_ringidx2xyf_k(const hpgb_rk &c, uint32_t ring, uint32_t q, uint32_t &ix, uint32_t &iy, uint32_t &face) {
     const bool south = ring > c.ns2;
     const uint32_t nring = south ? c.ns4 - ring : ring;
     const bool cap = nring < c.ns;
@@ -282,10 +282,37 @@ HPGB_HD int64_t hpgb_ringidx2nest_k(const hpgb_rk &c, uint32_t ring, uint32_t q)
     const uint32_t jm = jp + c.ns - tmp;
     const uint32_t ifp = jp >> c.k, ifm = jm >> c.k;
     const uint32_t face_b = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
-    const uint32_t ix = hpgb_sel(cap, ix_c, jm & c.nsm1);
-    const uint32_t iy = hpgb_sel(cap, iy_c, ~jp & c.nsm1);
-    const uint32_t face = hpgb_sel(cap, face_c, face_b);
+    ix = hpgb_sel(cap, ix_c, jm & c.nsm1);
+    iy = hpgb_sel(cap, iy_c, ~jp & c.nsm1);
+    face = hpgb_sel(cap, face_c, face_b);
+}
+HPGB_HD int64_t hpgb_ringidx2nest_k(const hpgb_rk &c, uint32_t ring, uint32_t q) {
+    uint32_t ix, iy, face;
+    hpgb_ringidx2xyf_k(c, ring, q, ix, iy, face);
     return hpgb_xyf2nest_k<false>(c, ix, iy, face);
+}
+
+// Two pixels of one ring (the interpolation pair): q2 is normally q1 + 1, the EAST neighbour, which inside
+// a base face is (ix + 1, iy - 1) -- one step on the even and one on the odd bit plane of the first
+// pixel's Morton code (dilated-integer arithmetic, a dozen instructions instead of a second conversion).
+// Pairs that straddle a face edge or wrap around the ring take the plain conversion (out of line).
+HPGB_HD_NOINLINE int64_t hpgb_ringidx2nest_far(const hpgb_rk &c, uint32_t ring, uint32_t q) {
+    return hpgb_ringidx2nest_k(c, ring, q);
+}
+HPGB_HD void hpgb_ringidx2nest_pair_k(const hpgb_rk &c, uint32_t ring, uint32_t q1, uint32_t q2, int64_t &p1, int64_t &p2) {
+    uint32_t ix, iy, face;
+    hpgb_ringidx2xyf_k(c, ring, q1, ix, iy, face);
+    p1 = hpgb_xyf2nest_k<false>(c, ix, iy, face);
+    if (q2 == q1 + 1u && ix < c.nsm1 && iy > 0u) {
+        const uint64_t m = (((uint64_t)c.hmask << 32) | c.lmask);  // nside^2 - 1
+        const uint64_t EV = 0x5555555555555555ull & m, OD = 0xAAAAAAAAAAAAAAAAull & m;
+        const uint64_t v = (uint64_t)p1 & m, fb = (uint64_t)p1 - v;
+        const uint64_t xp = (((v & EV) | OD) + 1) & EV;  // ix + 1: the carry rides over the odd plane
+        const uint64_t ym = ((v & OD) - 2) & OD;         // iy - 1: the borrow rides over the (zero) even plane
+        p2 = (int64_t)(fb + (xp | ym));
+    } else {
+        p2 = hpgb_ringidx2nest_far(c, ring, q2);
+    }
 }
 
 // RING pixel (must be < npix) -> NEST pixel.  HI: order >= 16.
