@@ -35,6 +35,9 @@ static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW
 #endif
 // vector_to_pixel on the streaming skeleton: ring depth / sub-blocks per tile (three float64 inputs:
 // 24 KiB per sub-block and stage)
+#ifndef HPGB_P2V_BLOCK
+#define HPGB_P2V_BLOCK 640
+#endif
 #ifndef HPGB_V2P_ST
 #define HPGB_V2P_ST 2
 #endif
@@ -407,11 +410,11 @@ int launch_p2v(const int64_t *pix, double *x, double *y, double *z, int64_t n, i
     const bool vec = hpgb_aligned16(pix) && hpgb_aligned16(x) && hpgb_aligned16(y) && hpgb_aligned16(z);
     if (nest) {
         OpPix2Vec<true, true, false> op{pix, x, y, z, nullptr, base, g, hpgb_make_rk(g)};
-        return hpgb_launch_map(op, n, vec, st, s);
+        return hpgb_launch_map<decltype(op), HPGB_P2V_BLOCK>(op, n, vec, st, s);
     }
     if (g.order >= 0) {
         OpPix2Vec<false, true, false> op{pix, x, y, z, nullptr, base, g, hpgb_make_rk(g)};
-        return hpgb_launch_map(op, n, vec, st, s);
+        return hpgb_launch_map<decltype(op), HPGB_P2V_BLOCK>(op, n, vec, st, s);
     }
     OpPix2Vec<false, false, false> op{pix, x, y, z, nullptr, base, g, hpgb_rk()};
     return hpgb_launch_map(op, n, vec, st, s);
