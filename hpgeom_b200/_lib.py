@@ -72,6 +72,10 @@ _SIGS = {
     "hpgb_host_query_circle_ring_batch": [c_vp, c_i64, c_int, c_vp, ctypes.POINTER(c_i64), c_vp, c_i64],
     "hpgb_query_circle_nest_open": [c_i64, c_dbl, c_dbl, c_dbl, c_int, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_vp),
                                     ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],
+    "hpgb_query_circle_nest_batch_open": [c_i64, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_int,
+                                          ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
+                                          ctypes.POINTER(c_i64)],
+    "hpgb_query_nest_batch_offsets": [c_vp, c_vp],
     "hpgb_query_nest_ranges": [c_vp, c_vp, ctypes.POINTER(c_i64)],
     "hpgb_query_nest_pixels_host": [c_vp, c_vp, c_i64],
     "hpgb_query_nest_pixels_device": [c_vp, c_vp, c_i64, c_vp],

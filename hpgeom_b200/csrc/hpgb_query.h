@@ -255,7 +255,10 @@ struct hpgb_qn_plan {
 };
 
 // hpgeom/healpix_geom.c:748-771 (host, libm); fact = 0: not inclusive
-static inline int hpgb_qn_make_plan(int64_t nside, double theta, double phi, double radius, int64_t fact, hpgb_qn_plan *p) {
+// dr_cache: optional array of HPGB_QN_MAX_ORDER + 1 doubles, all < 0 before the first call -- the safety distance
+// max_pixrad(order) does not depend on the disc, so a batch computes it once
+static inline int hpgb_qn_make_plan(int64_t nside, double theta, double phi, double radius, int64_t fact, hpgb_qn_plan *p,
+                                    double *dr_cache = nullptr) {
     const int c = hpgb_check_nside(nside, 1);
     if (c) return c;
     if (fact < 0 || (fact & (fact - 1)) || (fact > 0 && fact * nside > ((int64_t)1 << 29))) return HPGB_E_BAD_FACT;
@@ -271,7 +274,13 @@ static inline int hpgb_qn_make_plan(int64_t nside, double theta, double phi, dou
     p->ptg_z = cos(theta);
     p->cosrad = cos(radius);
     for (int o = 0; o <= p->omax; o++) {
-        const double dr = max_pixrad_host((int64_t)1 << o);  // safety distance
+        double dr;  // safety distance
+        if (dr_cache) {
+            if (dr_cache[o] < 0) dr_cache[o] = max_pixrad_host((int64_t)1 << o);
+            dr = dr_cache[o];
+        } else {
+            dr = max_pixrad_host((int64_t)1 << o);
+        }
         p->crpdr[o] = ((radius + dr) > HPGB_PI) ? -1. : cos(radius + dr);
         p->crmdr[o] = ((radius - dr) < 0.) ? 1. : cos(radius - dr);
     }

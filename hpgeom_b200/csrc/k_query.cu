@@ -381,6 +381,8 @@ struct QnHandle {
     int device = 0;
     int64_t m = 0, total = 0;
     int64_t *ranges = nullptr, *offs = nullptr;
+    int64_t n_discs = 0;            // batched search: number of discs and
+    int64_t *disc_offs = nullptr;   // the n_discs + 1 boundaries of their pixel lists (device)
 };
 
 struct DevBuf {  // frees on scope exit
@@ -555,6 +557,7 @@ int hpgb_query_nest_close(void *handle) {
     cudaSetDevice(h->device);
     if (h->ranges) hpgb_dev_free(h->ranges);
     if (h->offs) hpgb_dev_free(h->offs);
+    if (h->disc_offs) hpgb_dev_free(h->disc_offs);
     cudaSetDevice(prev);
     delete h;
     return HPGB_OK;
@@ -873,6 +876,324 @@ int hpgb_host_query_circle_ring_batch(hpgb_disc_t *plans, int64_t D, int device,
                                   return launch_ranges_expand(d_ranges, d_offs, m, base, cn, (int64_t *)dp[0], s);
                               },
                               nullptr);
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// Many discs at once, NEST scheme (extension): the breadth-first search of k_qn_level over a frontier of
+// (disc, pixel) pairs -- every order is ONE launch for the whole batch -- then the ranges are ordered by
+// (disc, lo) with two stable radix sorts and expanded in one pass.  All discs share nside and fact.
+// =============================================================================================
+namespace {
+
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qnb_seed(int64_t *__restrict__ fpix, int32_t *__restrict__ fdisc,
+                                                         const int32_t *__restrict__ active, int64_t nactive) {
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; i < 12 * nactive; i += stride) {
+        fpix[i] = i % 12;
+        fdisc[i] = active[i / 12];
+    }
+}
+
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qnb_level(const hpgb_qn_plan *__restrict__ plans, const hpgb_geom g, const int o,
+                                                          const int64_t *__restrict__ fpix, const int32_t *__restrict__ fdisc,
+                                                          const int64_t n, int64_t *__restrict__ npix, int32_t *__restrict__ ndisc,
+                                                          int64_t *__restrict__ rlo, int64_t *__restrict__ rhi,
+                                                          int32_t *__restrict__ rdisc, unsigned long long *cnt) {
+    const double *T = hpgb_stage_table();
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    const int64_t rounds = (n + stride - 1) / stride;
+    for (int64_t k = 0; k < rounds; k++) {
+        const int64_t i = k * stride + (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x;
+        int v = 0;
+        int32_t d = 0;
+        int64_t pix = 0, lo = 0, hi = 0;
+        if (i < n) {
+            pix = fpix[i];
+            d = fdisc[i];
+            const hpgb_qn_plan *P = plans + d;
+            // the fields of the plan this order needs, read through the pointer (520-byte plans stay in L2)
+            hpgb_qn_plan q;
+            q.order = P->order, q.omax = P->omax, q.inclusive = P->inclusive, q.whole_sphere = 0;
+            q.ptg_z = P->ptg_z, q.ptg_phi = P->ptg_phi, q.cosrad = P->cosrad;
+            q.crpdr[o] = P->crpdr[o], q.crmdr[o] = P->crmdr[o];
+            v = hpgb_qn_visit(q, g, T, o, pix, lo, hi);
+        }
+        const unsigned m1 = __ballot_sync(0xFFFFFFFFu, v == 1), m2 = __ballot_sync(0xFFFFFFFFu, v == 2);
+        unsigned long long b1 = 0, b2 = 0;
+        if (lane == 0) {
+            if (m1) b1 = atomicAdd(cnt + 1, (unsigned long long)__popc(m1));
+            if (m2) b2 = atomicAdd(cnt, 4ull * (unsigned long long)__popc(m2));
+        }
+        b1 = __shfl_sync(0xFFFFFFFFu, b1, 0);
+        b2 = __shfl_sync(0xFFFFFFFFu, b2, 0);
+        if (v == 1) {
+            const unsigned long long r = b1 + (unsigned long long)__popc(m1 & lt);
+            rlo[r] = lo;
+            rhi[r] = hi;
+            rdisc[r] = d;
+        } else if (v == 2) {
+            const unsigned long long c0 = b2 + 4ull * (unsigned long long)__popc(m2 & lt);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                npix[c0 + j] = 4 * pix + j;
+                ndisc[c0 + j] = d;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qnb_iota(int32_t *p, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; i < n; i += stride) p[i] = (int32_t)i;
+}
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qnb_gather_disc(const int32_t *__restrict__ disc, const int32_t *__restrict__ perm,
+                                                                int64_t n, int32_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; i < n; i += stride) out[i] = disc[perm[i]];
+}
+// rows in (disc, lo) order; a repeated (disc, lo) -- the breadth-first stand-in for "unwind the stack" -- is emptied
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qnb_table(const int64_t *__restrict__ lo, const int64_t *__restrict__ hi,
+                                                          const int32_t *__restrict__ perm, const int32_t *__restrict__ sdisc,
+                                                          int64_t m, longlong2 *__restrict__ table) {
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; i < m; i += stride) {
+        const int32_t p = perm[i];
+        const int64_t a = lo[p];
+        const bool dup = i > 0 && sdisc[i - 1] == sdisc[i] && lo[perm[i - 1]] == a;
+        table[i] = make_longlong2(a, dup ? a : hi[p]);
+    }
+}
+// disc_offs[d] = first output pixel of disc d = offs[first row whose disc >= d]
+__global__ void __launch_bounds__(HPGB_BLOCK) k_qnb_disc_offsets(const int32_t *__restrict__ sdisc, int64_t m, const int64_t *__restrict__ offs,
+                                                                 int64_t D, int64_t *__restrict__ disc_offs) {
+    const int64_t stride = (int64_t)gridDim.x * HPGB_BLOCK;
+    for (int64_t d = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x; d <= D; d += stride) {
+        int64_t lo = 0, hi = m;  // lower bound of d in sdisc[0..m)
+        while (lo < hi) {
+            const int64_t mid = lo + ((hi - lo) >> 1);
+            if ((int64_t)sdisc[mid] < d) lo = mid + 1; else hi = mid;
+        }
+        disc_offs[d] = offs[lo];
+    }
+}
+
+inline int64_t grid_for(int64_t n) {
+    int64_t grid = (n + HPGB_BLOCK - 1) / HPGB_BLOCK;
+    const int64_t cap = (int64_t)hpgb_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    return grid < 1 ? 1 : grid;
+}
+
+int qnb_build(const std::vector<hpgb_qn_plan> &plans, int64_t nside, QnHandle *h) {
+    const int64_t D = (int64_t)plans.size();
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CKQ(cudaSetDevice(h->device));
+    DevBuf pool;
+    const int64_t npix = 12 * nside * nside;
+    const int omax = plans[0].omax;
+    hpgb_qn_plan *d_plans = nullptr;
+    CKQ(pool.alloc(&d_plans, (size_t)D * sizeof(hpgb_qn_plan)));
+    CKQ(cudaMemcpyAsync(d_plans, plans.data(), (size_t)D * sizeof(hpgb_qn_plan), cudaMemcpyHostToDevice, 0));
+    // whole-sphere discs skip the search: their single range goes straight into the list
+    std::vector<int32_t> active;
+    std::vector<int64_t> w_lo, w_hi;
+    std::vector<int32_t> w_disc;
+    for (int64_t d = 0; d < D; d++) {
+        if (plans[d].whole_sphere) {
+            w_lo.push_back(0), w_hi.push_back(npix), w_disc.push_back((int32_t)d);
+        } else {
+            active.push_back((int32_t)d);
+        }
+    }
+    std::vector<int64_t *> lvl_lo, lvl_hi;
+    std::vector<int32_t *> lvl_disc;
+    std::vector<int64_t> lvl_n;
+    int64_t R = 0;
+    if (!w_lo.empty()) {
+        int64_t *a = nullptr, *b = nullptr;
+        int32_t *c = nullptr;
+        const size_t k = w_lo.size();
+        CKQ(pool.alloc(&a, k * 8));
+        CKQ(pool.alloc(&b, k * 8));
+        CKQ(pool.alloc(&c, k * 4));
+        CKQ(cudaMemcpyAsync(a, w_lo.data(), k * 8, cudaMemcpyHostToDevice, 0));
+        CKQ(cudaMemcpyAsync(b, w_hi.data(), k * 8, cudaMemcpyHostToDevice, 0));
+        CKQ(cudaMemcpyAsync(c, w_disc.data(), k * 4, cudaMemcpyHostToDevice, 0));
+        lvl_lo.push_back(a), lvl_hi.push_back(b), lvl_disc.push_back(c), lvl_n.push_back((int64_t)k);
+        R += (int64_t)k;
+    }
+    int64_t n = 12 * (int64_t)active.size();
+    if (n > 0) {
+        unsigned long long *cnt = nullptr;
+        int32_t *d_active = nullptr, *cdisc = nullptr;
+        int64_t *cpix = nullptr;
+        CKQ(pool.alloc(&cnt, 16));
+        CKQ(pool.alloc(&d_active, active.size() * 4));
+        CKQ(cudaMemcpyAsync(d_active, active.data(), active.size() * 4, cudaMemcpyHostToDevice, 0));
+        CKQ(pool.alloc(&cpix, (size_t)n * 8));
+        CKQ(pool.alloc(&cdisc, (size_t)n * 4));
+        k_qnb_seed<<<(unsigned)grid_for(n), HPGB_BLOCK, 0, 0>>>(cpix, cdisc, d_active, (int64_t)active.size());
+        int launches = 1;
+        for (int o = 0; o <= omax && n > 0; o++) {
+            int64_t *np_ = nullptr, *rlo = nullptr, *rhi = nullptr;
+            int32_t *nd_ = nullptr, *rdisc = nullptr;
+            CKQ(pool.alloc(&np_, (size_t)n * 32));
+            CKQ(pool.alloc(&nd_, (size_t)n * 16));
+            CKQ(pool.alloc(&rlo, (size_t)n * 8));
+            CKQ(pool.alloc(&rhi, (size_t)n * 8));
+            CKQ(pool.alloc(&rdisc, (size_t)n * 4));
+            CKQ(cudaMemsetAsync(cnt, 0, 16, 0));
+            const hpgb_geom g = hpgb_make_geom((int64_t)1 << o, 1);
+            k_qnb_level<<<(unsigned)grid_for(n), HPGB_BLOCK, 0, 0>>>(d_plans, g, o, cpix, cdisc, n, np_, nd_, rlo, rhi, rdisc, cnt);
+            launches++;
+            unsigned long long hc[2];
+            CKQ(cudaMemcpy(hc, cnt, 16, cudaMemcpyDeviceToHost));
+            lvl_lo.push_back(rlo), lvl_hi.push_back(rhi), lvl_disc.push_back(rdisc), lvl_n.push_back((int64_t)hc[1]);
+            R += (int64_t)hc[1];
+            hpgb_dev_free(cpix), pool.release(cpix);
+            hpgb_dev_free(cdisc), pool.release(cdisc);
+            cpix = np_, cdisc = nd_;
+            n = (int64_t)hc[0];
+        }
+        g_hpgb_launches.fetch_add(launches, std::memory_order_relaxed);
+    }
+    h->m = R;
+    h->total = 0;
+    h->n_discs = D;
+    CKQ(hpgb_dev_alloc((void **)&h->disc_offs, (size_t)(D + 1) * 8));
+    if (R == 0) {
+        CKQ(cudaMemsetAsync(h->disc_offs, 0, (size_t)(D + 1) * 8, 0));
+    } else {
+        if (R > 0x7FFFFFFF) {
+            cudaSetDevice(prev);
+            return HPGB_E_BAD_ARGUMENT;  // 32-bit row permutation
+        }
+        int64_t *lo = nullptr, *hi = nullptr, *slo = nullptr;
+        int32_t *disc = nullptr, *perm0 = nullptr, *perm1 = nullptr, *perm2 = nullptr, *kd = nullptr, *sd = nullptr;
+        CKQ(pool.alloc(&lo, (size_t)R * 8));
+        CKQ(pool.alloc(&hi, (size_t)R * 8));
+        CKQ(pool.alloc(&slo, (size_t)R * 8));
+        CKQ(pool.alloc(&disc, (size_t)R * 4));
+        CKQ(pool.alloc(&perm0, (size_t)R * 4));
+        CKQ(pool.alloc(&perm1, (size_t)R * 4));
+        CKQ(pool.alloc(&perm2, (size_t)R * 4));
+        CKQ(pool.alloc(&kd, (size_t)R * 4));
+        CKQ(pool.alloc(&sd, (size_t)R * 4));
+        int64_t at = 0;
+        for (size_t l = 0; l < lvl_n.size(); l++) {
+            if (lvl_n[l] > 0) {
+                CKQ(cudaMemcpyAsync(lo + at, lvl_lo[l], (size_t)lvl_n[l] * 8, cudaMemcpyDeviceToDevice, 0));
+                CKQ(cudaMemcpyAsync(hi + at, lvl_hi[l], (size_t)lvl_n[l] * 8, cudaMemcpyDeviceToDevice, 0));
+                CKQ(cudaMemcpyAsync(disc + at, lvl_disc[l], (size_t)lvl_n[l] * 4, cudaMemcpyDeviceToDevice, 0));
+            }
+            at += lvl_n[l];
+        }
+        const unsigned gr = (unsigned)grid_for(R);
+        k_qnb_iota<<<gr, HPGB_BLOCK, 0, 0>>>(perm0, R);
+        void *tmp = nullptr;
+        size_t t1 = 0, t2 = 0;
+        CKQ(cub::DeviceRadixSort::SortPairs(nullptr, t1, lo, slo, perm0, perm1, R, 0, 62, (cudaStream_t)0));
+        CKQ(cub::DeviceRadixSort::SortPairs(nullptr, t2, kd, sd, perm1, perm2, R, 0, 31, (cudaStream_t)0));
+        const size_t tb = t1 > t2 ? t1 : t2;
+        CKQ(pool.alloc(&tmp, tb));
+        size_t tt = tb;
+        CKQ(cub::DeviceRadixSort::SortPairs(tmp, tt, lo, slo, perm0, perm1, R, 0, 62, (cudaStream_t)0));  // by lo
+        k_qnb_gather_disc<<<gr, HPGB_BLOCK, 0, 0>>>(disc, perm1, R, kd);
+        tt = tb;
+        CKQ(cub::DeviceRadixSort::SortPairs(tmp, tt, kd, sd, perm1, perm2, R, 0, 31, (cudaStream_t)0));    // then (stable) by disc
+        CKQ(hpgb_dev_alloc((void **)&h->ranges, (size_t)R * 16));
+        CKQ(hpgb_dev_alloc((void **)&h->offs, (size_t)(R + 1) * 8));
+        k_qnb_table<<<gr, HPGB_BLOCK, 0, 0>>>(lo, hi, perm2, sd, R, reinterpret_cast<longlong2 *>(h->ranges));
+        hpgb_status_t *st = nullptr;
+        CKQ(pool.alloc(&st, sizeof(hpgb_status_t)));
+        CKQ(cudaMemsetAsync(st, 0xFF, sizeof(hpgb_status_t), 0));
+        const int rc = launch_ranges_offsets(h->ranges, R, 0, h->offs, st, 0);
+        if (rc != HPGB_OK) {
+            cudaSetDevice(prev);
+            return rc;
+        }
+        k_qnb_disc_offsets<<<(unsigned)grid_for(D + 1), HPGB_BLOCK, 0, 0>>>(sd, R, h->offs, D, h->disc_offs);
+        g_hpgb_launches.fetch_add(6, std::memory_order_relaxed);
+        CKQ(cudaMemcpy(&h->total, h->offs + R, 8, cudaMemcpyDeviceToHost));
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaSetDevice(prev);
+    return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hpgb_query_circle_nest_batch_open(int64_t nside, const double *a, const double *b, const double *radius, int64_t D,
+                                      int inclusive, int64_t fact, int lonlat, int degrees, int device, void **handle,
+                                      int64_t *m, int64_t *total, int64_t *first_bad) {
+    if (!handle || !m || !total || D < 0 || (D > 0 && (!a || !b || !radius))) return HPGB_E_BAD_ARGUMENT;
+    *handle = nullptr;
+    if (first_bad) *first_bad = -1;
+    if (D > 0x7FFFFFFF) return HPGB_E_BAD_ARGUMENT;
+    std::vector<hpgb_qn_plan> plans((size_t)D);
+    double dr_cache[HPGB_QN_MAX_ORDER + 1];
+    for (int o = 0; o <= HPGB_QN_MAX_ORDER; o++) dr_cache[o] = -1.0;
+    for (int64_t d = 0; d < D; d++) {  // argument checks per disc, in the wrapper's order (hpgeom/hpgeom.c:793-838)
+        double theta, phi, r = radius[d];
+        bool ok;
+        if (lonlat) {
+            ok = degrees ? hpgb_angles_exact<true, true>(a[d], b[d], theta, phi) : hpgb_angles_exact<true, false>(a[d], b[d], theta, phi);
+            if (ok && degrees) r *= HPGB_PI / 180.0;
+        } else {
+            ok = hpgb_angles_exact<false, false>(a[d], b[d], theta, phi);
+        }
+        int rc = HPGB_OK;
+        if (!ok) rc = HPGB_E_BAD_ANGLE;
+        else if (r <= 0) rc = HPGB_E_BAD_RADIUS;
+        else if ((rc = hpgb_check_nside(nside, 1)) != 0) {
+        } else if (inclusive && (fact <= 0 || fact * nside > ((int64_t)1 << 29) || (fact & (fact - 1)))) rc = HPGB_E_BAD_FACT;
+        else rc = hpgb_qn_make_plan(nside, theta, phi, r, inclusive ? fact : 0, &plans[(size_t)d], dr_cache);
+        if (rc != HPGB_OK) {
+            if (first_bad) *first_bad = d;
+            return rc;
+        }
+    }
+    const int ndev = hpgb_device_count();
+    if (ndev <= 0) return HPGB_E_NO_DEVICE;
+    if (device < 0 || device >= ndev) return HPGB_E_BAD_ARGUMENT;
+    QnHandle *h = new QnHandle();
+    h->device = device;
+    int rc = HPGB_OK;
+    if (D > 0) rc = qnb_build(plans, nside, h);
+    else {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device);
+        if (hpgb_dev_alloc((void **)&h->disc_offs, 8) != cudaSuccess || cudaMemset(h->disc_offs, 0, 8) != cudaSuccess) rc = HPGB_E_CUDA;
+        cudaSetDevice(prev);
+    }
+    if (rc != HPGB_OK) {
+        hpgb_query_nest_close(h);
+        return rc;
+    }
+    *handle = h;
+    *m = h->m;
+    *total = h->total;
+    return HPGB_OK;
+}
+
+// the n_discs + 1 boundaries of the pixel lists of a batched handle (host buffer)
+int hpgb_query_nest_batch_offsets(void *handle, int64_t *disc_offsets) {
+    QnHandle *h = (QnHandle *)handle;
+    if (!h || !h->disc_offs || !disc_offsets) return HPGB_E_BAD_ARGUMENT;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CKQ(cudaSetDevice(h->device));
+    CKQ(cudaMemcpy(disc_offsets, h->disc_offs, (size_t)(h->n_discs + 1) * 8, cudaMemcpyDeviceToHost));
+    cudaSetDevice(prev);
+    return HPGB_OK;
 }
 
 }  // extern "C"

@@ -468,17 +468,21 @@ def query_circle(nside, a, b, radius, inclusive=False, fact=4, nest=True, lonlat
     return pixel_ranges_to_pixels(table)
 
 
-def query_circle_batch(nside, a, b, radius, inclusive=False, fact=4, lonlat=True, degrees=True, device_resident=False):
-    """Many RING-scheme query_circle calls at once (an extension: the reference has no batched form).
+def query_circle_batch(nside, a, b, radius, inclusive=False, fact=4, nest=False, lonlat=True, degrees=True,
+                       device_resident=False):
+    """Many query_circle calls at once (an extension: the reference has no batched form).
 
     ``a``, ``b``, ``radius`` are 1-D arrays of D discs (``radius`` may be a scalar); returns
     ``(pixels, offsets)``: the D pixel lists back to back and the D + 1 list boundaries, list d =
     ``pixels[offsets[d]:offsets[d+1]]``, each identical to ``query_circle(nside, a[d], b[d], radius[d],
-    nest=False, ...)``.  One small disc is launch-latency bound on a GPU; a batch runs every (disc, ring)
-    pair in one launch (csrc/k_query.cu).  Argument errors are reported for the first offending disc with
-    the reference's messages.
+    nest=nest, ...)``.  One small disc is launch-latency bound on a GPU; a batch runs every (disc, ring)
+    pair (RING) or every order of the hierarchical search over all discs (NEST) in one launch
+    (csrc/k_query.cu).  Argument errors are reported for the first offending disc with the reference's
+    messages.  Note the default here is RING (the cheaper scheme for small discs).
     """
     nside, fact, inclusive, lonlat, degrees = int(nside), int(fact), bool(inclusive), bool(lonlat), bool(degrees)
+    if nest:
+        return _query_circle_batch_nest(nside, a, b, radius, inclusive, fact, lonlat, degrees, device_resident)
     av = np.ascontiguousarray(np.atleast_1d(_d._np_view(a)), dtype=np.float64)
     bv = np.ascontiguousarray(np.atleast_1d(_d._np_view(b)), dtype=np.float64)
     if av.ndim != 1 or av.shape != bv.shape:
@@ -526,6 +530,42 @@ def query_circle_batch(nside, a, b, radius, inclusive=False, fact=4, lonlat=True
         csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=cuda), torch.cumsum(lens, 0)])
         offsets = csum[2 * d_rs + 2 * torch.arange(D + 1, device=cuda)]
     return pixels, offsets
+
+
+def _query_circle_batch_nest(nside, a, b, radius, inclusive, fact, lonlat, degrees, device_resident):
+    av = np.ascontiguousarray(np.atleast_1d(_d._np_view(a)), dtype=np.float64)
+    bv = np.ascontiguousarray(np.atleast_1d(_d._np_view(b)), dtype=np.float64)
+    if av.ndim != 1 or av.shape != bv.shape:
+        raise ValueError("a and b must be 1-D arrays of the same length")
+    rv = np.ascontiguousarray(np.broadcast_to(np.asarray(_d._np_view(radius), dtype=np.float64), av.shape))
+    D = int(av.size)
+    L = _lib.lib()
+    dev = _d.default_device()
+    handle, m, total, bad = ctypes.c_void_p(), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(-1)
+    rc = L.hpgb_query_circle_nest_batch_open(nside, av.ctypes.data, bv.ctypes.data, rv.ctypes.data, D, int(inclusive), fact,
+                                             int(lonlat), int(degrees), dev, ctypes.byref(handle), ctypes.byref(m),
+                                             ctypes.byref(total), ctypes.byref(bad))
+    if rc != 0 and bad.value >= 0:
+        k = bad.value  # same checks, order and messages as the single call
+        query_circle(nside, float(av[k]), float(bv[k]), float(rv[k]), inclusive=inclusive, fact=fact, nest=True,
+                     lonlat=lonlat, degrees=degrees)
+    _lib.check_rc(rc)
+    try:
+        offsets = np.zeros(D + 1, dtype=np.int64)
+        _lib.check_rc(L.hpgb_query_nest_batch_offsets(handle, offsets.ctypes.data))
+        if not device_resident:
+            out = np.empty(total.value, dtype=np.int64)
+            _lib.check_rc(L.hpgb_query_nest_pixels_host(handle, ctypes.c_void_p(out.ctypes.data), total.value))
+            return out, offsets
+        torch = _d.torch
+        with torch.cuda.device(dev):
+            out = torch.empty(total.value, dtype=torch.int64, device="cuda:%d" % dev)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check_rc(L.hpgb_query_nest_pixels_device(handle, ctypes.c_void_p(out.data_ptr()), total.value, stream))
+            torch.cuda.current_stream(dev).synchronize()
+            return out, torch.from_numpy(offsets).to("cuda:%d" % dev)
+    finally:
+        L.hpgb_query_nest_close(handle)
 
 
 def _query_circle_nest(L, nside, a, b, radius, inclusive, fact, lonlat, degrees, return_pixel_ranges, device_resident, dev):

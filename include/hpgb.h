@@ -242,6 +242,16 @@ int hpgb_query_nest_pixels_host(void *handle, int64_t *out, int64_t total);
 int hpgb_query_nest_pixels_device(void *handle, int64_t *d_out, int64_t total, void *stream);
 int hpgb_query_nest_close(void *handle);
 
+/* ---- many discs at once, NEST scheme (extension): the same search over a frontier of (disc, pixel) pairs, every
+ * order ONE launch for the whole batch, ranges ordered by (disc, lo) with two stable radix sorts.  The handle is
+ * used like a single-disc one (hpgb_query_nest_pixels_host / _device, hpgb_query_nest_close); the D + 1
+ * boundaries of the pixel lists come from hpgb_query_nest_batch_offsets.  first_bad = the first disc whose
+ * arguments the reference would reject (the return code says why). ---- */
+int hpgb_query_circle_nest_batch_open(int64_t nside, const double *a, const double *b, const double *radius,
+                                      int64_t n_discs, int inclusive, int64_t fact, int lonlat, int degrees,
+                                      int device, void **handle, int64_t *m, int64_t *total, int64_t *first_bad);
+int hpgb_query_nest_batch_offsets(void *handle, int64_t *disc_offsets);
+
 /* ---- error text for ONE element (host side, pure functions) -------------------------------
  * Re-evaluates the reference's checks in the reference's order for the element the kernel
  * flagged and writes the reference's message (at most `cap` bytes, NUL terminated).

@@ -307,3 +307,37 @@ def test_query_circle_batch_matches_single_goldens(hpg):
     pix, offs = hpg.query_circle_batch(2048, lon, lat, 0.2)
     for d in (0, 17, 1999):
         assert_bit_equal(pix[offs[d]:offs[d + 1]], hpg.query_circle(2048, lon[d], lat[d], 0.2, nest=False))
+
+
+@pytest.mark.gpu
+def test_query_circle_batch_nest_matches_single_goldens(hpg):
+    """Batched NEST search: every list of a batch equals the golden single-disc result."""
+    import collections
+    import torch
+    groups = collections.defaultdict(list)
+    for (nside, theta, phi, radius, fact), pix, ranges in nest_cases():
+        groups[(nside, fact)].append((theta, phi, radius, pix))
+    assert len(groups) > 30
+    for k, ((nside, fact), items) in enumerate(sorted(groups.items())):
+        a = np.array([it[0] for it in items]); b = np.array([it[1] for it in items]); r = np.array([it[2] for it in items])
+        kw = dict(inclusive=fact > 0, fact=max(fact, 1), nest=True, lonlat=False)
+        pix, offs = hpg.query_circle_batch(nside, a, b, r, **kw)
+        assert offs.shape == (len(items) + 1,) and offs[0] == 0 and offs[-1] == pix.size
+        for d, it in enumerate(items):
+            assert_bit_equal(pix[offs[d]:offs[d + 1]], it[3], "nside=%d fact=%d disc %d" % (nside, fact, d))
+        if k % 5 == 0:
+            tp, to = hpg.query_circle_batch(nside, a, b, r, device_resident=True, **kw)
+            assert isinstance(tp, torch.Tensor) and tp.is_cuda
+            assert_bit_equal(tp.cpu().numpy(), pix)
+            assert_bit_equal(to.cpu().numpy(), offs)
+    pix, offs = hpg.query_circle_batch(64, np.zeros(0), np.zeros(0), 0.1, nest=True)
+    assert pix.shape == (0,) and offs.tolist() == [0]
+    with pytest.raises(ValueError, match=r"power of 2"):
+        hpg.query_circle_batch(1000, [10.0], [5.0], 1.0, nest=True)
+    with pytest.raises(ValueError, match=r"Radius must be positive."):
+        hpg.query_circle_batch(1024, [10.0, 20.0], [5.0, 5.0], [1.0, 0.0], nest=True)
+    # whole-sphere discs mixed with small ones, default-argument single calls as the check
+    lon, lat, rad = np.array([10.0, 200.0, 33.0, 300.0]), np.array([5.0, -60.0, 89.0, 0.0]), np.array([1.0, 190.0, 0.5, 181.0])
+    pix, offs = hpg.query_circle_batch(32, lon, lat, rad, nest=True)
+    for d in range(4):
+        assert_bit_equal(pix[offs[d]:offs[d + 1]], hpg.query_circle(32, lon[d], lat[d], rad[d]))

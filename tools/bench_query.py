@@ -56,3 +56,17 @@ for D, nside, rdeg in ((20000, 2048, 0.2), (200000, 2048, 0.2), (20000, 2 ** 16,
         assert np.array_equal(r, pix[offs[nref - 1]:offs[nref]])
         line += "  reference loop %9.2f ms (x%.1f)" % (tr * 1e3, tr / t)
     print(line, flush=True)
+
+for D, nside, rdeg in ((20000, 2048, 0.2), (200000, 2048, 0.2)):
+    lon, lat = 360 * rng.random(D), np.degrees(np.arcsin(2 * rng.random(D) - 1))
+    t, (pix, offs) = best(lambda: hpg.query_circle_batch(nside, lon, lat, rdeg, nest=True))
+    line = "NEST batch of %6d discs nside=%d r=%g deg: %10d pix  ours %8.2f ms (%.2f Mdiscs/s)" % (D, nside, rdeg, pix.size, t * 1e3, D / t / 1e6)
+    if ref is not None:
+        nref = min(D, 20000)
+        t0 = time.perf_counter()
+        for d in range(nref):
+            r = ref.query_circle(nside, lon[d], lat[d], rdeg)
+        tr = (time.perf_counter() - t0) * D / nref
+        assert np.array_equal(r, pix[offs[nref - 1]:offs[nref]])
+        line += "  reference loop %9.2f ms (x%.1f)" % (tr * 1e3, tr / t)
+    print(line, flush=True)
