@@ -1,6 +1,13 @@
-// k_query.cu -- query_circle in the RING scheme (reference: hpgeom/hpgeom.c:765-864 and query_disc,
-// hpgeom/healpix_geom.c:632-747): per-disc plan on the host, one GPU thread per ring for the pixel
-// intervals (hpgb_query.h), expansion by the kernels of k_ranges.cu.  See include/hpgb.h.
+// k_query.cu -- query_circle (reference: hpgeom/hpgeom.c:765-864 and query_disc, hpgeom/healpix_geom.c:541-800).
+// The element functions (one ring, one pixel of the search tree) are in hpgb_query.h; every variant ends in
+// an (M,2) table of [lo, hi) pixel ranges that the kernels of k_ranges.cu expand.  Four parts:
+//   1. RING, one disc   : per-disc plan on the host, one GPU thread per ring, grid-wide ticket scan for the
+//                         inclusive edge trimming;
+//   2. NEST, one disc   : the hierarchical search walked breadth first, one launch per order (the small
+//                         orders in one single-CTA launch), device radix sort of the ranges (cub: plumbing);
+//   3. RING, many discs : one launch over all (disc, ring) pairs;
+//   4. NEST, many discs : the search over (disc, pixel) frontiers, ranges ordered by (disc, lo).
+// See include/hpgb.h for the C ABI.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
