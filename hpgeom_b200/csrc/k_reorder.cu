@@ -461,7 +461,10 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_upgrade(const int64_t *__restric
     };
     // four parent loads in flight per thread: each warp-wide load only brings in 8..32 distinct
     // parents, so without this the kernel is bound by load latency, not bandwidth
-    constexpr int U = NEST ? 4 : 2;
+#ifndef HPGB_UPG_RING_U
+#define HPGB_UPG_RING_U 4
+#endif
+    constexpr int U = NEST ? 4 : HPGB_UPG_RING_U;
     int64_t w = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x;
     for (; w + (U - 1) * stride < n_groups; w += U * stride) {
         int64_t p[U];
