@@ -20,39 +20,29 @@ namespace {
 static __device__ const unsigned long long g_hpgb_acos_tab[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS] = HPGB_ACOS_TABLE_INIT;
 static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW_DOUBLES] = HPGB_ATANQ_TABLE_INIT;  // first 80 rows staged
 #define HPGB_BND_TAB_WORDS (HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + HPGB_ATANQ_ROWS_POLAR * HPGB_ATANQ_ROW_DOUBLES)
-#define HPGB_BND_BLOCK 512
+#ifndef HPGB_BND_BLOCK
+#define HPGB_BND_BLOCK 1024
+#endif
 
 // hpgeom/healpix_geom.c:807-841 + :857-865, then hpgeom/hpgeom_utils.c:145-165
 template <bool LONLAT, bool DEGREES>
 __device__ __forceinline__ void boundary_point(const uint64_t *TA, const double *TQ, double x, double y, uint32_t face,
                                                double &a, double &b) {
     const double jr = (double)(int)hpgb_jrll(face) - x - y;
-    double nr, z, sth = 0.0;
-    bool have_sth = false;
-    if (jr < 1) {
-        nr = jr;
-        const double tmp = hpgb_div_tame(nr * nr, 3.);
-        z = 1 - tmp;
-        if (z > 0.99) {
-            sth = sqrt(tmp * (2.0 - tmp));
-            have_sth = true;
-        }
-    } else if (jr > 3) {
-        nr = 4 - jr;
-        const double tmp = hpgb_div_tame(nr * nr, 3.);
-        z = tmp - 1;
-        if (z < -0.99) {
-            sth = sqrt(tmp * (2. - tmp));
-            have_sth = true;
-        }
-    } else {
-        nr = 1;
-        z = hpgb_div_tame((2 - jr) * 2., 3.);
-    }
+    // the three zones of xyf2loc with ONE division: the numerator is selected, not the branch (a warp of
+    // random pixels would otherwise run all three); same operations per zone as the reference
+    const bool north = jr < 1, south = jr > 3;
+    const double nr = north ? jr : (south ? 4 - jr : 1.0);
+    const double q = hpgb_div_tame((north | south) ? nr * nr : (2 - jr) * 2., 3.);
+    const double z = north ? 1 - q : (south ? q - 1 : q);
+    double sth = 0.0;
+    const bool have_sth = (north && z > 0.99) || (south && z < -0.99);
+    if (have_sth) sth = sqrt(q * (2.0 - q));
     double tmp = (double)(int)hpgb_jpll(face) * nr + x - y;
     if (tmp < 0) tmp += 8;
     if (tmp >= 8) tmp -= 8;
-    const double phi = (nr < 1e-15) ? 0 : (0.5 * HPGB_HALFPI * tmp) / nr;
+    // nr >= 1e-15 here: tame operands, the branch-free division gives the IEEE quotient
+    const double phi = (nr < 1e-15) ? 0 : hpgb_div_tame(0.5 * HPGB_HALFPI * tmp, nr < 1e-15 ? 1.0 : nr);
     const double theta = have_sth ? hpgb_atan2_tab(TQ, sth, z) : hpgb_acos_tab(TA, z);
     hpgb_thetaphi_out<LONLAT, DEGREES>(theta, phi, a, b);
 }
@@ -74,7 +64,7 @@ __global__ void __launch_bounds__(HPGB_BND_BLOCK) k_boundaries(const int64_t *__
     const int64_t stride = (int64_t)gridDim.x * HPGB_BND_BLOCK;
     hpgb_bad_t bad;
     for (int64_t w = (int64_t)blockIdx.x * HPGB_BND_BLOCK + threadIdx.x; w < total; w += stride) {
-        const int64_t e = w / step, i = w - e * step;
+        const int64_t e = step == 1 ? w : w / step, i = w - e * step;
         hpgb_geom gg = g;
         const int64_t p = __ldg(pix + e);
         double *ra = oa + e * 4 * step, *rb = ob + e * 4 * step;
@@ -103,10 +93,11 @@ __global__ void __launch_bounds__(HPGB_BND_BLOCK) k_boundaries(const int64_t *__
         }
         // hpgeom/healpix_geom.c:867-888
         const double dns = (double)gg.nside;
-        const double dc = 0.5 / dns;
-        const double xc = ((double)ix + 0.5) / dns;
-        const double yc = ((double)iy + 0.5) / dns;
-        const double d = 1.0 / ((double)(step * gg.nside));
+        // nside and step * nside are integers in [1, 2^40]: tame operands, IEEE quotients without the slow path
+        const double dc = hpgb_div_tame(0.5, dns);
+        const double xc = hpgb_div_tame((double)ix + 0.5, dns);
+        const double yc = hpgb_div_tame((double)iy + 0.5, dns);
+        const double d = hpgb_div_tame(1.0, (double)(step * gg.nside));
         const double id = (double)i * d;
         boundary_point<LONLAT, DEGREES>(TA, TQ, xc + dc - id, yc + dc, face, ra[i], rb[i]);
         boundary_point<LONLAT, DEGREES>(TA, TQ, xc - dc, yc + dc - id, face, ra[i + step], rb[i + step]);
