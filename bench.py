@@ -302,6 +302,8 @@ def main():
     def add_also(name, step, elems, bytes_per_elem, workload):
         ms_k, _ = timed(step, 5, 3)
         ms_k /= 5
+        assert int(status[0].item()) == -1, "%s flagged element %d of valid synthetic input (rank %d)" % (
+            name, int(status[0].item()), rank)
         also[name] = {"value": world * elems / (ms_k * 1e-3) / 1e9, "unit": "Gelements/s", "ms_per_step": ms_k,
                       "bytes_per_element": bytes_per_elem, "workload": workload}
 
@@ -310,10 +312,13 @@ def main():
 
     m = min(n, 1 << 27)
     ms8 = min(n, 1 << 24)
-    add_also("ring_to_nest", lambda: ck(L.hpgb_ring_to_nest(ring.data_ptr(), pix.data_ptr(), m, NSIDE, None, stp, sp)), m, 16,
-             "ring_to_nest nside=2^29 on 2^%d pixels per GPU (round trip of the nest_to_ring output)" % (m.bit_length() - 1))
     f1, f2, f3 = (torch.empty(m, dtype=torch.float64, device=dev) for _ in range(3))
     i1 = torch.empty(m, dtype=torch.int64, device=dev)
+    # ring_to_nest writes to a scratch array: it is NOT the inverse of nest_to_ring for every pixel at nside 2^29 --
+    # the reference's uncorrected isqrt (hpgeom/healpix_geom.c:60) sends ~1e-8 of the RING pixels of the largest cap
+    # rings to garbage, which the kernel reproduces bit for bit; `pix` must stay valid for the kernels below
+    add_also("ring_to_nest", lambda: ck(L.hpgb_ring_to_nest(ring.data_ptr(), i1.data_ptr(), m, NSIDE, None, stp, sp)), m, 16,
+             "ring_to_nest nside=2^29 on 2^%d pixels per GPU (the nest_to_ring output)" % (m.bit_length() - 1))
     add_also("pixel_to_angle", lambda: ck(L.hpgb_pixel_to_angle(pix.data_ptr(), f1.data_ptr(), f2.data_ptr(), m, NSIDE, None, 1, 1, 1, stp, sp)),
              m, 24, "pixel_to_angle nside=2^29 nest lonlat degrees, 2^%d pixels per GPU" % (m.bit_length() - 1))
     add_also("pixel_to_vector", lambda: ck(L.hpgb_pixel_to_vector(pix.data_ptr(), f1.data_ptr(), f2.data_ptr(), f3.data_ptr(), m, NSIDE, None, 1, stp, sp)),
@@ -322,6 +327,11 @@ def main():
              m, 32, "vector_to_pixel nside=2^29 nest on the vectors just produced, 2^%d per GPU" % (m.bit_length() - 1))
     assert torch.equal(i1[:1 << 20], pix[:1 << 20]), "vector_to_pixel(pixel_to_vector(p)) != p"
     p4 = pix[:ms8] % (12 * 4096 * 4096 - 1)
+    # upgrade_pixels refuses the LAST NEST pixel like the reference (hpgeom/hpgeom.py:505); in the RING scheme that
+    # is one particular pixel inside the range: keep it out of the RING batch (p4 never holds npix-1 itself)
+    import hpgeom_b200
+    last_ring = hpgeom_b200.nest_to_ring(4096, torch.tensor([12 * 4096 * 4096 - 1], device=dev))
+    p4r = torch.where(p4 == last_ring, p4 - 1, p4)
     reps4 = (ms8 + lon_keep.numel() - 1) // lon_keep.numel()
     lon4, lat4 = lon_keep.repeat(reps4)[:ms8].contiguous(), lat_keep.repeat(reps4)[:ms8].contiguous()
     o8 = i1[:8 * ms8] if 8 * ms8 <= m else torch.empty(8 * ms8, dtype=torch.int64, device=dev)
@@ -333,10 +343,10 @@ def main():
                  lambda nf=nest_flag: ck(L.hpgb_interp_weights(lon4.data_ptr(), lat4.data_ptr(), o8.data_ptr(), w4.data_ptr(), ms8, 4096, None, nf, 1, 1, stp, sp)),
                  ms8, 80, "get_interpolation_weights nside=4096 %s lonlat degrees, 2^%d points per GPU" % (tag, ms8.bit_length() - 1))
         add_also("upgrade_pixels_" + tag,
-                 lambda nf=nest_flag: ck(L.hpgb_upgrade_pixels(p4.data_ptr(), o8.data_ptr(), ms8, 4096, 8192, nf, stp, sp)),
+                 lambda nf=nest_flag: ck(L.hpgb_upgrade_pixels((p4 if nf else p4r).data_ptr(), o8.data_ptr(), ms8, 4096, 8192, nf, stp, sp)),
                  ms8, 40, "upgrade_pixels nside=4096 -> 8192 %s, 2^%d input pixels per GPU" % (tag, ms8.bit_length() - 1))
     assert int(status[0].item()) == -1, "a kernel flagged a bad element in valid synthetic input"
-    del f1, f2, f3, i1, o8, w4, p4, lon4, lat4
+    del f1, f2, f3, i1, o8, w4, p4, p4r, lon4, lat4
     # parity spot check (outside every timed region): the first 2^20 points of this rank against the oracle
     parity = None
     if rank == 0:
