@@ -158,3 +158,16 @@ def test_full_size_round_trip(hpg, oracle_port):
     del back, ring
     nest = hpg.ring_to_nest(nside, pix)
     assert np.array_equal(nest[:m].cpu().numpy(), oracle_port.ring_to_nest(nside, sample))
+
+
+def test_reference_isqrt_quirk_known_pixel(hpg, oracle_port):
+    """A concrete pixel met by bench.py on rank 1: at nside 2^29 the reference's uncorrected isqrt
+    (hpgeom/healpix_geom.c:60) sends RING pixel 3094394892722022934 to a negative 'NEST pixel'; the kernel
+    must return the same value, and nest_to_ring of the original stays correct."""
+    nside = 2 ** 29
+    ring = np.array([3094394892722022934, 3094394892722022933, 3094394892722022935], dtype=np.int64)
+    want = oracle_port.ring_to_nest(nside, ring)
+    assert want[0] == -2888003994884788701
+    assert_bit_equal(hpg.ring_to_nest(nside, ring), want)
+    nest = np.array([2486596126579491022], dtype=np.int64)
+    assert hpg.nest_to_ring(nside, nest)[0] == ring[0]
