@@ -58,7 +58,7 @@ def query_disc(nside, vec, radius, inclusive=False, fact=4, nest=False, buff=Non
 
 
 def query_polygon(nside, vertices, inclusive=False, fact=4, nest=False, buff=None):
-    raise NotImplementedError("query_polygon is a region query; hpgeom_b200 implements the elementwise conversion path only")
+    raise NotImplementedError("query_polygon is not built: hpgeom_b200 covers the elementwise conversion path and query_circle")
 
 
 def nest2ring(nside, pix):
