@@ -38,6 +38,9 @@ static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW
 #ifndef HPGB_P2V_BLOCK
 #define HPGB_P2V_BLOCK 640
 #endif
+#ifndef HPGB_V2P_MINB
+#define HPGB_V2P_MINB 2
+#endif
 #ifndef HPGB_V2P_ST
 #define HPGB_V2P_ST 2
 #endif
@@ -226,7 +229,7 @@ struct OpVec2Pix {
         double2 x, y, z;
     };
     typedef const double *Ctx;
-    HPGB_STREAM_IN_F64x3(x, y, z, 2)
+    HPGB_STREAM_IN_F64x3(x, y, z, HPGB_V2P_MINB)
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(x + i), hpgb_ld2(y + i), hpgb_ld2(z + i)}; }
     static __device__ __noinline__ int64_t slow(const hpgb_geom &gg, Ctx T, double vx, double vy, double vz) {
