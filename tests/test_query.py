@@ -107,6 +107,43 @@ def test_plan_argument_checks():
     assert hpg.pixel_ranges_to_pixels(np.zeros((0, 2), dtype=np.int64)).shape == (0,)
 
 
+def test_batch_planning_is_host_only():
+    """hpgb_query_circle_ring_plan_many / _batch_prepare run on the host: per-disc plans equal the single-disc
+    plan, the first rejected disc is reported, whole-sphere discs are normalised, ring_start is the prefix sum."""
+    import ctypes
+    from hpgeom_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(4)
+    D, nside = 50, 256
+    a, b = 360 * rng.random(D), np.degrees(np.arcsin(2 * rng.random(D) - 1))
+    r = 10 ** rng.uniform(-1, 1.5, D)
+    r[7] = 200.0  # degrees: covers the sphere
+    plans = (_lib.Disc * D)()
+    bad = ctypes.c_int64(-1)
+    assert L.hpgb_query_circle_ring_plan_many(nside, a.ctypes.data, b.ctypes.data, r.ctypes.data, D, 1, 2, 1, 1, plans,
+                                              ctypes.byref(bad)) == 0 and bad.value == -1
+    one = _lib.Disc()
+    for d in (0, 7, 31):
+        assert L.hpgb_query_circle_ring_plan(nside, a[d], b[d], r[d], 1, 2, 1, 1, ctypes.byref(one)) == 0
+        assert bytes(one) == bytes(plans[d])
+    assert plans[7].whole_sphere == 1 and plans[7].m == 1
+    ring_start = np.zeros(D + 1, dtype=np.int64)
+    total = L.hpgb_query_circle_ring_batch_prepare(plans, D, ring_start.ctypes.data)
+    counts = [max(p.irmax - p.irmin + 1, 0) for p in plans]
+    assert counts[7] == 0 and plans[7].north_hi == 12 * nside * nside and plans[7].south_lo == -1
+    assert ring_start.tolist() == [0] + np.cumsum(counts).tolist() and total == sum(counts)
+    # the first offending disc and the reference's error class for it
+    b2 = b.copy()
+    b2[13] = 91.0
+    r2 = r.copy()
+    r2[5] = -1.0
+    assert L.hpgb_query_circle_ring_plan_many(nside, a.ctypes.data, b2.ctypes.data, r2.ctypes.data, D, 0, 4, 1, 1, plans,
+                                              ctypes.byref(bad)) == 7 and bad.value == 5   # radius
+    r2[5] = 1.0
+    assert L.hpgb_query_circle_ring_plan_many(nside, a.ctypes.data, b2.ctypes.data, r2.ctypes.data, D, 0, 4, 1, 1, plans,
+                                              ctypes.byref(bad)) == 6 and bad.value == 13  # latitude
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU tier
 # ------------------------------------------------------------------------------------------------
