@@ -464,7 +464,10 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_upgrade(const int64_t *__restric
 #ifndef HPGB_UPG_RING_U
 #define HPGB_UPG_RING_U 4
 #endif
-    constexpr int U = NEST ? 4 : HPGB_UPG_RING_U;
+#ifndef HPGB_UPG_NEST_U
+#define HPGB_UPG_NEST_U 16
+#endif
+    constexpr int U = NEST ? HPGB_UPG_NEST_U : HPGB_UPG_RING_U;
     int64_t w = (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x;
     for (; w + (U - 1) * stride < n_groups; w += U * stride) {
         int64_t p[U];
