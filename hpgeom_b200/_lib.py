@@ -26,6 +26,8 @@ _SIGS = {
     "hpgb_status_reset": [c_vp, c_vp],
     "hpgb_launch_count": [],
     "hpgb_host_release": [],
+    "hpgb_host_set_devices": [ctypes.POINTER(c_int), c_int],
+    "hpgb_host_get_devices": [ctypes.POINTER(c_int), c_int],
     "hpgb_pinned_alloc": [ctypes.POINTER(c_vp), c_i64],
     "hpgb_pinned_free": [c_vp],
     "hpgb_nest_to_ring": [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],

@@ -199,6 +199,27 @@ HPGB_HD uint32_t hpgb_hi32(double v) {
 #endif
 }
 
+HPGB_HD uint32_t hpgb_lo32(double v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(v);
+#else
+    union {
+        double d;
+        uint64_t u;
+    } c;
+    c.d = v;
+    return (uint32_t)c.u;
+#endif
+}
+// low 32 bits of (hi:lo) >> s, 0 < s < 32 (SHF.R.U64 on the device)
+HPGB_HD uint32_t hpgb_funnel_r(uint32_t lo, uint32_t hi, int s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return (lo >> s) | (hi << (32 - s));
+#endif
+}
+
 // Per-nside constants of the fast path, host-computed and passed by value with the geometry.
 // The polynomial coefficients and unit factors travel here too: kernel parameters live in the
 // constant bank, so fp64 instructions read them as operands instead of materialising 64-bit
@@ -217,6 +238,8 @@ struct hpgb_a2p_fast {
     uint32_t mask_hi, pad2_;      // fraction bits at or above 2 * margin
     uint32_t face_shift_hi;       // 2*order - 32 when order >= 16 (face bits live in the high word)
     uint32_t ord;                 // order, 0 when nside is not a power of two (fast path disabled then)
+    double ns_s_magic;            // ns_s + 2^52 (HPGB_A2P_MAGIC: the edge-line coordinates are read off the mantissa)
+    uint32_t margin2, pad3_;      // 2 * margin (HPGB_A2P_MAGIC: any value, not only powers of two)
 };
 
 template <bool LONLAT, bool DEGREES>
@@ -224,11 +247,22 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
     hpgb_a2p_fast f;
     const double dns = (double)g.nside;
     const int order = g.order < 0 ? 0 : g.order;
+#if !defined(HPGB_A2P_V1)
+    // F = 20 fraction bits for every order: coordinate * 2^20 < 6 * 2^29 * 2^20 < 2^52, so  value + 2^52  lies in
+    // [2^52, 2^53) and its mantissa IS the coordinate in fixed point, rounded to the nearest unit (no F2I).  margin =
+    // nside * 2^-44 in these units (32 at order 29), never below 16 units (2^-16 pixel: the fast path's error is a few
+    // 2^-52 of a value < 2^32), plus 2 units for the two roundings to the unit grid (S + 2^52, then +- D).
+    f.fbits = 20u;
+    f.fmask = 0xFFFFFu;
+    f.margin = (order >= 25 ? (1u << (order - 24)) : 1u);
+    f.margin = (f.margin < 16u ? 16u : f.margin) + 2u;
+#else
     // F fraction bits, always inside the low 32-bit word; margin = nside * 2^-44 in fixed-point
     // units (never below 16 units), see the derivation above hpgb_angle_to_pixel_nest_fast
     f.fbits = order >= 27 ? (uint32_t)(58 - order) : 32u;
     f.fmask = f.fbits >= 32 ? 0xFFFFFFFFu : ((1u << f.fbits) - 1u);
     f.margin = order >= 26 ? (1u << 14) : (order >= 16 ? (1u << (order - 12)) : 16u);
+#endif
     const double scale = ldexp(1.0, (int)f.fbits);
     f.ns_s = dns * scale;
     f.ns_half_s = 0.5 * dns * scale;
@@ -265,6 +299,9 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
     f.ord = (uint32_t)order;
     f.mask_hi = f.fmask & ~(2u * f.margin - 1u);
     f.pad2_ = 0;
+    f.ns_s_magic = f.ns_s + 4503599627370496.0;  // exact: ns_s is an integer < 2^50
+    f.margin2 = 2u * f.margin;
+    f.pad3_ = 0;
     return f;
 }
 
@@ -289,19 +326,31 @@ HPGB_HD double hpgb_sin_poly(const hpgb_a2p_fast &f, double a) {  // |a| <= 0.74
 // (1 - tp) * tmp are at least `margin` away from integers (a convex-combination argument:
 // frac(tp * ir) lies between frac(tp * tmp) and 1 - frac((1 - tp) * tmp)), i.e. whenever the
 // fast result is kept.  rk is only read for RING.
+#if defined(HPGB_A2P_V1)
 template <bool NEST, bool HI>
 HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, double nttd, double tq,
                                 double e, double v, double hemi, int64_t &pix) {
     // ---- edge-line coordinates, already scaled to fixed point with F fraction bits ----
     const double W = fma(e, f.ns_s - v, v);
-    const double S = fma(tq, W, fma(nttd, f.ns_s, f.ns_s));
     const double Dp = hpgb_copysign_xor(fma(0.5, v, -f.ns_s), hemi);  // +-(w/2 - nside)
     const double D = fma(e, -v - Dp, Dp);
+#if 0
+    // S carries 2^52: S +- D lands in [2^52, 2^53), where one ulp is one fixed-point unit -- the sum's mantissa is
+    // the coordinate (20 fraction bits), its integer part one funnel shift away.  The exponent field (0x433) sits
+    // above bit 51 and falls off the 32-bit result of the shift.
+    const double S = fma(tq, W, fma(nttd, f.ns_s, f.ns_s_magic));
+    const double r1 = S + D, r2 = S - D;
+    const uint32_t l1 = hpgb_lo32(r1), l2 = hpgb_lo32(r2);
+    const unsigned guard = (unsigned)(((l1 + f.margin) & 0xFFFFFu) < f.margin2) | (unsigned)(((l2 + f.margin) & 0xFFFFFu) < f.margin2);
+    const uint32_t j1 = hpgb_funnel_r(l1, hpgb_hi32(r1), 20), j2 = hpgb_funnel_r(l2, hpgb_hi32(r2), 20);
+#else
+    const double S = fma(tq, W, fma(nttd, f.ns_s, f.ns_s));
     const uint64_t x1 = (uint64_t)hpgb_d2ll(S + D);
     const uint64_t x2 = (uint64_t)hpgb_d2ll(S - D);
     // within `margin` of an integer?  (the fraction sits in the low word; 2 * margin is a power of two)
     const unsigned guard = (unsigned)((((uint32_t)x1 + f.margin) & f.mask_hi) == 0u) | (unsigned)((((uint32_t)x2 + f.margin) & f.mask_hi) == 0u);
     const uint32_t j1 = (uint32_t)(x1 >> f.fbits), j2 = (uint32_t)(x2 >> f.fbits);
+#endif
     const uint32_t nsm1 = (uint32_t)g.nside - 1u;
     const uint32_t ifp = j1 >> f.ord, ifm = j2 >> f.ord;
     const uint32_t face = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
@@ -318,10 +367,53 @@ HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, cons
     return guard;
 }
 
+#else
+// The fp64 pipe of sm_100a does not run beside the integer pipes: a DFMA / DADD / DSETP costs the warp scheduler
+// two issue cycles, any 32-bit instruction one, and nothing overlaps them (tools/ubench/pipes2.cu: 2 DFMA + 2 LOP3
+// = 0.71 instructions / clock / scheduler, the angle_to_pixel mix 0.73 -- the kernel runs at 0.67).  So the tail
+// below spends 32-bit selects, not fp64 blends, on the equatorial / polar split, never forms floor() or a
+// float -> int conversion (XU pipe, 9 cycles a warp), and adds the quarter-turn count in the integer domain:
+//   ntt : quarter turns of the longitude, floor(tt) mod 4;   tq = frac(tt) - 1/2;   eq : |z| <= 2/3
+//   v   : (3/4) nside z (equatorial) or w = nside sqrt(3 (1 - |z|)) (polar), scaled by 2^20
+//   x1 = S + D, x2 = S - D,  S = nside + tq W + 2^52  (W = nside / w),  D = -v (equatorial) or +-(w/2 - nside)
+// S +- D lands in [2^52, 2^53), where one ulp is one fixed-point unit: the sum's mantissa IS the coordinate (20
+// fraction bits, rounded to nearest), its integer part one funnel shift away -- the exponent field sits above
+// bit 51 and falls off the 32-bit result of the shift.  ntt * nside is added to both integer parts afterwards.
+template <bool NEST, bool HI>
+HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, uint32_t ntt, double tq,
+                                bool eq, double v, double hemi, int64_t &pix) {
+    const double W = eq ? f.ns_s : v;
+    const double S = fma(tq, W, f.ns_s_magic);
+    const double Dp = hpgb_copysign_xor(fma(0.5, v, -f.ns_s), hemi);  // +-(w/2 - nside)
+    const double D = eq ? -v : Dp;
+    const double r1 = S + D, r2 = S - D;
+    const uint32_t l1 = hpgb_lo32(r1), l2 = hpgb_lo32(r2);
+    // within `margin` units of an integer?
+    const unsigned guard = (unsigned)(((l1 + f.margin) & 0xFFFFFu) < f.margin2) | (unsigned)(((l2 + f.margin) & 0xFFFFFu) < f.margin2);
+    const uint32_t turn = ntt << f.ord;  // ntt * nside
+    const uint32_t j1 = hpgb_funnel_r(l1, hpgb_hi32(r1), 20) + turn, j2 = hpgb_funnel_r(l2, hpgb_hi32(r2), 20) + turn;
+    const uint32_t nsm1 = (uint32_t)g.nside - 1u;
+    const uint32_t ifp = j1 >> f.ord, ifm = j2 >> f.ord;
+    const uint32_t face = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
+    const uint32_t ix = j2 & nsm1;
+    const uint32_t iy = ~j1 & nsm1;  // nside - 1 - (j1 mod nside)
+    if (!NEST) {
+        pix = hpgb_xyf2ring_k(rk, ix, iy, face);
+    } else if (HI) {
+        const uint64_t m = hpgb_interleave(ix, iy);
+        pix = (int64_t)(m + ((uint64_t)(face << f.face_shift_hi) << 32));
+    } else {
+        pix = hpgb_xyf2nest((int)f.ord, ix, iy, face);
+    }
+    return guard;
+}
+#endif
+
 // Fast path for one point: candidate pixel + whether it can be trusted (false -> the caller runs
 // the exact path).  Branch-free apart from the equatorial/polar integer tail; the guard
 // conditions are accumulated bitwise so no short-circuit branches appear in the hot loop.
 // HI: nside >= 2^16, i.e. the face number only touches the high word of the pixel.
+#if defined(HPGB_A2P_V1)
 template <bool NEST, bool LONLAT, bool DEGREES, bool HI>
 HPGB_HD uint32_t hpgb_angle_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, double a,
                                             double b, int64_t &pix) {
@@ -366,7 +458,44 @@ HPGB_HD uint32_t hpgb_angle_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_f
     guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, nttd, tq, e, v, lat, pix);
     return guard | (f.enabled ^ 1u);
 }
-
+#else
+// 1.5 * 2^52: adding it rounds a double of magnitude < 2^51 to the nearest integer, which then sits in the low
+// mantissa bits (two's complement for negative values)
+#define HPGB_RND_MAGIC 6755399441055744.0
+template <bool NEST, bool LONLAT, bool DEGREES, bool HI>
+HPGB_HD uint32_t hpgb_angle_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, double a,
+                                            double b, int64_t &pix) {
+    // ---- latitude (radians, signed), half colatitude from the nearest pole, tt - 1/2 ----
+    double lat, hcth, u;
+    unsigned guard;
+    if (LONLAT) {
+        lat = DEGREES ? b * f.k_lat : b;
+        hcth = DEGREES ? (f.pole - fabs(b)) * f.k_hcth : ((f.pole - fabs(b)) + f.pole_lo) * 0.5;
+        u = fma(a, f.k_lon, -0.5);  // lon/90 - 1/2 or lon*2/pi - 1/2: one rounding
+        guard = (unsigned)!(fabs(b) < f.lat_max) | (unsigned)!(fabs(a) <= f.lon_max);
+    } else {
+        lat = (f.pole - a) + f.pole_lo;  // pi/2 - theta, accurate also near the equator
+        hcth = 0.5 * ((a < f.pole) ? a : (HPGB_PI_1 - a) + HPGB_PI_2);
+        u = fma(b, f.k_lon, -0.5);
+        guard = (unsigned)!(a > 0.0102) | (unsigned)!(a < 3.1313) | (unsigned)!(b >= 0.0) | (unsigned)!(b < 6.2831853);
+    }
+    const double al = fabs(lat);
+    const bool eq = al <= f.asin23;
+    guard |= (unsigned)(fabs(al - f.asin23) < 1e-11);
+    // floor(tt) = RN(tt - 1/2) unless tt is (nearly) an integer -- and then the point is on a face edge / the wrap
+    // and goes to the exact path anyway (|tq| guard).  The rounding is one addition of 1.5 * 2^52; the integer is
+    // read off the sum's low word, so a negative or wrapped longitude needs nothing extra: ntt = floor(tt) mod 4.
+    const double r = u + HPGB_RND_MAGIC;
+    const double tq = u - (r - HPGB_RND_MAGIC);  // frac(tt) - 1/2, exact
+    const uint32_t ntt = hpgb_lo32(r) & 3u;
+    guard |= (unsigned)!(fabs(tq) < 0.5 - 3.8146972656250000e-06);  // tt within 2^-18 of an integer
+    // ---- one sine for both zones: z = sin(lat) (equatorial), w = sqrt(6) nside sin(colat / 2) (polar) ----
+    const double s = hpgb_sin_poly(f, eq ? lat : hcth);
+    const double v = (eq ? f.ns_075_s : f.ns_sqrt6_s) * s;  // (3/4) nside z   or   w
+    guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, ntt, tq, eq, v, lat, pix);
+    return guard | (f.enabled ^ 1u);
+}
+#endif
 
 
 // ---------------------------------------------------------------------------------------------
@@ -426,10 +555,14 @@ HPGB_HD uint32_t hpgb_vector_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_
     const double s2 = (r2 * il) * il;  // sin^2(theta)
     const bool eq = za <= 2.0 / 3.0;
     guard |= (unsigned)(fabs(za - 2.0 / 3.0) < 1e-11);
-    const double e = eq ? 1.0 : 0.0;
     const double q = (3.0 * s2) * hpgb_rcp_fast(1.0 + za);  // 3 (1 - |z|)
     const double w = f.ns_s * (q * hpgb_rsqrt_fast(q));      // nside sqrt(3 (1 - |z|))
+#if defined(HPGB_A2P_V1)
+    const double e = eq ? 1.0 : 0.0;
     const double v = fma(e, f.ns_075_s * nz - w, w);
+#else
+    const double v = eq ? f.ns_075_s * nz : w;
+#endif
     // ---- phi ----
     const double ax = fabs(x), ay = fabs(y);
     const bool swap = ay > ax;
@@ -447,12 +580,16 @@ HPGB_HD uint32_t hpgb_vector_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_
     const double u = at * HPGB_INV_HALFPI;                                    // in quarter turns, [0, 1/2]
     // quadrant: floor(tt) from the signs alone; tp = u or 1 - u by the parity of (swap, x < 0, y < 0)
     const uint32_t xs = hpgb_hi32(x) >> 31, ys = hpgb_hi32(y) >> 31;
-    const double xn = xs ? 1.0 : 0.0;
-    const double nttd = ys ? 3.0 - xn : xn;
     const bool flip = ((uint32_t)swap ^ xs ^ ys) != 0u;
     const double tq = flip ? 0.5 - u : u - 0.5;  // tp - 1/2
     guard |= (unsigned)!(fabs(tq) < 0.5 - 3.8146972656250000e-06);  // tt within 2^-18 of an integer (face edge / wrap)
+#if defined(HPGB_A2P_V1)
+    const double xn = xs ? 1.0 : 0.0;
+    const double nttd = ys ? 3.0 - xn : xn;
     guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, nttd, tq, e, v, nz, pix);
+#else
+    guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, ys ? 3u - xs : xs, tq, eq, v, nz, pix);
+#endif
     return guard | (f.enabled ^ 1u);
 }
 
@@ -676,8 +813,14 @@ HPGB_HD bool hpgb_pix2vec_k(const hpgb_rk &c, const hpgb_geom &g, const double *
     // sin(theta): hpgeom/healpix_geom.c:317 (polar, from tmp) or :193 (from z); the argument is never 0
     // for a pixel centre, so the branch-free square root applies
     const double sth = hpgb_sqrt_tame(polar ? tcap * (2. - tcap) : (1 - z) * (1 + z));
+    // cos(phi), sin(phi) to <= 0.51 ulp in plain doubles: x, y end up within 2 ulp of the reference's (which
+    // multiplies glibc's correctly rounded values by the same sth), bit-identical for ~98 % of the pixels
     double s, co;
+#if defined(HPGB_P2V_DD)
     hpgb_sincos_cr(T, phi, s, co);
+#else
+    hpgb_sincos_sd(T, phi, s, co);
+#endif
     x = sth * co;
     y = sth * s;
     zz = z;

@@ -124,17 +124,27 @@ struct HostCtx {
 };
 
 HostCtx g_ctx[64];
-std::mutex g_ctx_mutex;
+std::mutex g_ctx_mutex[64];  // one pipeline per device at a time; different devices run concurrently (hpgb_host_*_multi)
 
-int64_t chunk_points() {
-    static int64_t v = 0;
-    if (!v) {
+// Chunk size of the pipeline, in points.  The slots are sized in BYTES, not points: row-valued operands
+// (upgrade_pixels: 8 * 4^k bytes per point, boundaries: 64 * step) would otherwise ask for 3 device + 3 pinned
+// buffers of many GB each where the reference only needs the output array.  A slot holds at most
+// HPGB_HOST_SLOT_BYTES (default 96 MiB, the size the 2^22-point chunks of angle_to_pixel use: large enough to run
+// PCIe at full rate, small enough that three slots overlap on a 10M-point call); HPGB_HOST_CHUNK caps the points.
+int64_t chunk_points(size_t bytes_per_point) {
+    static int64_t cap = 0, budget = 0;
+    if (!cap) {
         const char *e = getenv("HPGB_HOST_CHUNK");
-        v = e ? atoll(e) : ((int64_t)1 << 22);
-        if (v < 2) v = 2;
-        v &= ~(int64_t)1;
+        int64_t v = e ? atoll(e) : ((int64_t)1 << 22);
+        const char *b = getenv("HPGB_HOST_SLOT_BYTES");
+        int64_t w = b ? atoll(b) : ((int64_t)96 << 20);
+        budget = w < 4096 ? 4096 : w;
+        cap = v < 2 ? 2 : v;
     }
-    return v;
+    int64_t v = cap;
+    if (bytes_per_point > 0 && (int64_t)bytes_per_point * v > budget) v = budget / (int64_t)bytes_per_point;
+    if (v < 2) v = 2;
+    return v & ~(int64_t)1;
 }
 
 // Plain numpy arrays are pageable: cudaMemcpyAsync then goes through the driver's single-threaded
@@ -149,8 +159,9 @@ class CopyPool {
         return *p;
     }
     // dst[0..bytes) = src[0..bytes), split over the pool (the caller takes the first share).  One job at a
-    // time: the pipeline calls it under g_ctx_mutex.
+    // time (submit_): pipelines of different devices take turns, each job uses the whole pool.
     void copy(char *dst, const char *src, size_t bytes) {
+        std::lock_guard<std::mutex> job(submit_);
         const size_t min_part = (size_t)1 << 20;
         int parts = (int)((bytes + min_part - 1) / min_part);
         if (parts > nworkers_ + 1) parts = nworkers_ + 1;
@@ -195,7 +206,7 @@ class CopyPool {
             if (--pending_ == 0) done_.notify_all();
         }
     }
-    std::mutex m_;
+    std::mutex m_, submit_;
     std::condition_variable cv_, done_;
     char *dst_ = nullptr;
     const char *src_ = nullptr;
@@ -221,18 +232,21 @@ bool is_pageable(const void *p) {
 
 }  // namespace
 
-int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int narr,
-                       const hpgb_pipe_launch &launch, int64_t *first_bad) {
+static int pipeline_one(int device, int64_t n, const hpgb_pipe_arr *arrs, int narr, const hpgb_pipe_launch &launch,
+                        int64_t *first_bad) {
     if (first_bad) *first_bad = -1;
     if (n <= 0) return HPGB_OK;
     int ndev = hpgb_device_count();
     if (ndev <= 0) return HPGB_E_NO_DEVICE;
     if (device < 0 || device >= ndev || device >= 64 || narr > HPGB_PIPE_MAX_ARR) return HPGB_E_BAD_ARGUMENT;
 
-    std::lock_guard<std::mutex> lock(g_ctx_mutex);
-    int prev = 0;
-    cudaGetDevice(&prev);
-    CK(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lock(g_ctx_mutex[device]);
+    struct DeviceGuard {  // every return path restores the caller's current device
+        int prev = 0;
+        DeviceGuard() { cudaGetDevice(&prev); }
+        ~DeviceGuard() { cudaSetDevice(prev); }
+    } guard;
+    CK(cudaSetDevice(device));  // the CK() returns below happen before any asynchronous work is queued
     HostCtx &c = g_ctx[device];
     if (!c.ready) {
         for (int s = 0; s < HPGB_PIPE_SLOTS; s++) {
@@ -244,7 +258,12 @@ int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int nar
         c.ready = true;
     }
 
-    const int64_t cp = chunk_points() < n ? chunk_points() : ((n + 1) & ~(int64_t)1);
+    size_t bpp = 0;
+    for (int a = 0; a < narr; a++) bpp += (size_t)arrs[a].bytes_per_point;
+    const int64_t cpb = chunk_points(bpp);
+    const int64_t cp = cpb < n ? cpb : ((n + 1) & ~(int64_t)1);
+    const int64_t nchunks = (n + cp - 1) / cp;
+    const int nslots = nchunks < HPGB_PIPE_SLOTS ? (int)nchunks : HPGB_PIPE_SLOTS;  // no more slots than chunks
     size_t off[HPGB_PIPE_MAX_ARR + 1];
     size_t total = 0;
     bool stage[HPGB_PIPE_MAX_ARR];
@@ -255,7 +274,7 @@ int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int nar
         stage[a] = is_pageable(arrs[a].h_in ? (const void *)arrs[a].h_in : (const void *)arrs[a].h_out);
         any_stage |= stage[a];
     }
-    for (int s = 0; s < HPGB_PIPE_SLOTS; s++) {
+    for (int s = 0; s < nslots; s++) {
         if (c.dbytes[s] < total) {
             if (c.dbuf[s]) CK(cudaFree(c.dbuf[s]));
             c.dbuf[s] = nullptr;
@@ -292,7 +311,17 @@ int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int nar
         slot_n[s] = 0;
         return HPGB_OK;
     };
-    for (int64_t base = 0; base < n && rc == HPGB_OK; base += cp, slot = (slot + 1) % HPGB_PIPE_SLOTS) {
+#define CKB(call)                                  \
+    {                                              \
+        cudaError_t e_ = (call);                   \
+        if (e_ != cudaSuccess) {                   \
+            rc = HPGB_E_CUDA + (int)e_;            \
+            break;                                 \
+        }                                          \
+    }
+    // every exit from here on goes through the common tail (synchronise the slot streams, restore the device):
+    // an early return would leave kernels / copies in flight on the caller's buffers
+    for (int64_t base = 0; base < n && rc == HPGB_OK; base += cp, slot = (slot + 1) % nslots) {
         const int64_t cn = (n - base) < cp ? (n - base) : cp;
         cudaStream_t st = c.stream[slot];
         if (any_stage) {
@@ -309,43 +338,138 @@ int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int nar
                     CopyPool::get().copy(c.hbuf[slot] + off[a], src, bytes);
                     src = c.hbuf[slot] + off[a];
                 }
-                CK(cudaMemcpyAsync(dptr[a], src, bytes, cudaMemcpyHostToDevice, st));
+                cudaError_t e_ = cudaMemcpyAsync(dptr[a], src, bytes, cudaMemcpyHostToDevice, st);
+                if (e_ != cudaSuccess) {
+                    rc = HPGB_E_CUDA + (int)e_;
+                    break;
+                }
             }
         }
+        if (rc != HPGB_OK) break;
         rc = launch(dptr, base, cn, c.d_status, st);
         if (rc != HPGB_OK) break;
-        for (int a = 0; a < narr; a++) {
+        for (int a = 0; a < narr && rc == HPGB_OK; a++) {
             if (arrs[a].h_out) {
                 char *dst = stage[a] ? c.hbuf[slot] + off[a] : arrs[a].h_out + (size_t)base * arrs[a].bytes_per_point;
-                CK(cudaMemcpyAsync(dst, dptr[a], (size_t)cn * arrs[a].bytes_per_point, cudaMemcpyDeviceToHost, st));
+                cudaError_t e_ = cudaMemcpyAsync(dst, dptr[a], (size_t)cn * arrs[a].bytes_per_point, cudaMemcpyDeviceToHost, st);
+                if (e_ != cudaSuccess) rc = HPGB_E_CUDA + (int)e_;
             }
         }
+        if (rc != HPGB_OK) break;
         if (any_stage) {
-            CK(cudaEventRecord(c.done[slot], st));
+            CKB(cudaEventRecord(c.done[slot], st));
             slot_base[slot] = base;
             slot_n[slot] = cn;
         }
     }
+#undef CKB
     if (any_stage && rc == HPGB_OK) {
-        for (int k = 0; k < HPGB_PIPE_SLOTS && rc == HPGB_OK; k++) rc = drain((slot + k) % HPGB_PIPE_SLOTS);
+        for (int k = 0; k < nslots && rc == HPGB_OK; k++) rc = drain((slot + k) % nslots);
     }
     for (int s = 0; s < HPGB_PIPE_SLOTS; s++) {
         cudaError_t e = cudaStreamSynchronize(c.stream[s]);
         if (e != cudaSuccess && rc == HPGB_OK) rc = HPGB_E_CUDA + (int)e;
     }
     if (rc == HPGB_OK) {
-        CK(cudaMemcpy(c.h_status, c.d_status, sizeof(hpgb_status_t), cudaMemcpyDeviceToHost));
-        if (first_bad && c.h_status->first_bad != HPGB_NO_BAD_ELEMENT) *first_bad = (int64_t)c.h_status->first_bad;
+        cudaError_t e = cudaMemcpy(c.h_status, c.d_status, sizeof(hpgb_status_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess)
+            rc = HPGB_E_CUDA + (int)e;
+        else if (first_bad && c.h_status->first_bad != HPGB_NO_BAD_ELEMENT)
+            *first_bad = (int64_t)c.h_status->first_bad;
     }
-    cudaSetDevice(prev);
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// One host array over several GPUs from ONE process (device == HPGB_DEVICE_ALL): the flat index range is cut
+// into contiguous shards exactly like the reference cuts it over its worker threads (hpgeom/hpgeom.c:272-279:
+// chunk = n / T, the first n % T workers take one extra element), one host thread per GPU runs the ordinary
+// single-device pipeline on its shard, results land in the caller's output arrays.  No collective: shards are
+// independent.  Element errors keep their meaning: every shard reports GLOBAL indices, the smallest wins.
+// ---------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_devset_mutex;
+std::vector<int> g_devset;  // empty = every visible device
+const int64_t kMinShardPoints = (int64_t)1 << 18;  // below this a second GPU costs more (launch + copy latency) than it brings
+}  // namespace
+
+extern "C" int hpgb_host_set_devices(const int *devices, int n_dev) {
+    const int ndev = hpgb_device_count();
+    if (n_dev < 0 || n_dev > 64 || (n_dev > 0 && !devices)) return HPGB_E_BAD_ARGUMENT;
+    for (int i = 0; i < n_dev; i++) {
+        if (devices[i] < 0 || devices[i] >= ndev) return HPGB_E_BAD_ARGUMENT;
+        for (int j = 0; j < i; j++)
+            if (devices[j] == devices[i]) return HPGB_E_BAD_ARGUMENT;
+    }
+    std::lock_guard<std::mutex> lock(g_devset_mutex);
+    g_devset.assign(devices, devices + n_dev);
+    return HPGB_OK;
+}
+
+extern "C" int hpgb_host_get_devices(int *devices, int cap) {
+    std::vector<int> set;
+    {
+        std::lock_guard<std::mutex> lock(g_devset_mutex);
+        set = g_devset;
+    }
+    if (set.empty())
+        for (int d = 0; d < hpgb_device_count() && d < 64; d++) set.push_back(d);
+    for (int i = 0; i < (int)set.size() && i < cap; i++) devices[i] = set[i];
+    return (int)set.size();
+}
+
+int hpgb_host_first_device(int device) {
+    if (device != HPGB_DEVICE_ALL) return device;
+    int d[64];
+    return hpgb_host_get_devices(d, 64) > 0 ? d[0] : 0;
+}
+
+int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int narr, const hpgb_pipe_launch &launch,
+                       int64_t *first_bad) {
+    if (device != HPGB_DEVICE_ALL) return pipeline_one(device, n, arrs, narr, launch, first_bad);
+    if (first_bad) *first_bad = -1;
+    if (n <= 0) return HPGB_OK;
+    int devs[64];
+    int G = hpgb_host_get_devices(devs, 64);
+    if (G <= 0) return HPGB_E_NO_DEVICE;
+    if ((int64_t)G > (n + kMinShardPoints - 1) / kMinShardPoints) G = (int)((n + kMinShardPoints - 1) / kMinShardPoints);
+    if (G <= 1) return pipeline_one(devs[0], n, arrs, narr, launch, first_bad);
+    std::vector<int> rc(G, HPGB_OK);
+    std::vector<int64_t> fb(G, -1);
+    const int64_t chunk = n / G, rem = n % G;
+    auto shard = [&](int r) {
+        const int64_t lo = r * chunk + (r < rem ? r : rem), cn = chunk + (r < rem ? 1 : 0);
+        hpgb_pipe_arr sub[HPGB_PIPE_MAX_ARR];
+        for (int a = 0; a < narr; a++) {
+            sub[a] = arrs[a];
+            if (sub[a].h_in) sub[a].h_in += (size_t)lo * (size_t)arrs[a].bytes_per_point;
+            if (sub[a].h_out) sub[a].h_out += (size_t)lo * (size_t)arrs[a].bytes_per_point;
+        }
+        rc[r] = pipeline_one(devs[r], cn, sub, narr,
+                             [&launch, lo](void **d, int64_t base, int64_t c, hpgb_status_t *st, cudaStream_t s) {
+                                 return launch(d, lo + base, c, st, s);
+                             },
+                             &fb[r]);
+    };
+    std::vector<std::thread> workers;
+    for (int r = 1; r < G; r++) workers.emplace_back(shard, r);
+    shard(0);
+    for (auto &w : workers) w.join();
+    int out_rc = HPGB_OK;
+    int64_t best = -1;
+    for (int r = 0; r < G; r++) {
+        if (rc[r] != HPGB_OK && out_rc == HPGB_OK) out_rc = rc[r];
+        if (fb[r] >= 0 && (best < 0 || fb[r] < best)) best = fb[r];
+    }
+    if (first_bad) *first_bad = best;
+    return out_rc;
+}
+
 extern "C" int hpgb_host_release(void) {
-    std::lock_guard<std::mutex> lock(g_ctx_mutex);
     int prev = 0;
     cudaGetDevice(&prev);
     for (int d = 0; d < 64; d++) {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex[d]);
         HostCtx &c = g_ctx[d];
         if (!c.ready) continue;
         cudaSetDevice(d);

@@ -32,7 +32,11 @@ typedef std::function<int(void **, int64_t, int64_t, hpgb_status_t *, cudaStream
 cudaError_t hpgb_dev_alloc(void **p, size_t bytes);
 void hpgb_dev_free(void *p);
 
+// device >= 0: that GPU; device == HPGB_DEVICE_ALL: contiguous shards over the device set (hpgb_host_set_devices),
+// one host thread per GPU
 int hpgb_host_pipeline(int device, int64_t n, const hpgb_pipe_arr *arrs, int narr,
                        const hpgb_pipe_launch &launch, int64_t *first_bad);
+// entry points whose device scratch lives on ONE GPU (range tables, query plans): HPGB_DEVICE_ALL -> first of the set
+int hpgb_host_first_device(int device);
 
 #endif

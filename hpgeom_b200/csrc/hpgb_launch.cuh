@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <type_traits>
 
 #include "../../include/hpgb.h"
 #include "hpgb_tables.h"
@@ -28,9 +29,18 @@
 
 extern std::atomic<int64_t> g_hpgb_launches;
 
+// ops that defer work to the end of the streaming kernel (e.g. a queue of rare elements) declare
+// `static constexpr bool HAS_EPILOGUE = true` and provide run4u(...) -- run4 for a converged CTA, may use
+// warp collectives -- and epilogue(ctx, bad); k_map2 / k_map1 keep calling run4 / run2 / run1
+template <class T, class = void>
+struct hpgb_has_epilogue : std::false_type {};
+template <class T>
+struct hpgb_has_epilogue<T, std::void_t<decltype(T::HAS_EPILOGUE)>> : std::bool_constant<T::HAS_EPILOGUE> {};
+
 struct hpgb_bad_t {
     unsigned long long idx;
-    __device__ __forceinline__ hpgb_bad_t() : idx(HPGB_NO_BAD_ELEMENT) {}
+    int aux;  // per-thread scratch an op may carry through the kernel (e.g. the length of its warp's queue)
+    __device__ __forceinline__ hpgb_bad_t() : idx(HPGB_NO_BAD_ELEMENT), aux(0) {}
     __device__ __forceinline__ void flag(int64_t i) {
         if ((unsigned long long)i < idx) idx = (unsigned long long)i;
     }
@@ -87,8 +97,8 @@ struct hpgb_no_ctx {};
     }
 __device__ __forceinline__ const double *hpgb_stage_table() {
     __shared__ double sT[HPGB_TABLE_DOUBLES];
-    for (int i = threadIdx.x; i < 4 * HPGB_SINCOS_ROWS; i += HPGB_BLOCK) sT[i] = g_hpgb_sincos[i];
-    for (int i = threadIdx.x; i < HPGB_ATAN16_ROWS; i += HPGB_BLOCK) sT[4 * HPGB_SINCOS_ROWS + i] = g_hpgb_atan16[i];
+    for (int i = threadIdx.x; i < 4 * HPGB_SINCOS_ROWS; i += blockDim.x) sT[i] = g_hpgb_sincos[i];
+    for (int i = threadIdx.x; i < HPGB_ATAN16_ROWS; i += blockDim.x) sT[4 * HPGB_SINCOS_ROWS + i] = g_hpgb_atan16[i];
     __syncthreads();
     return sT;
 }
@@ -118,7 +128,6 @@ __device__ __forceinline__ const double *hpgb_stage_table() {
 //   TILE_HOOK ops replace the per-thread run4 calls by  tile<TILE>(stage, extra_smem, first_element,
 //   tid, ctx, bad, empty_barrier)  and may rewrite the stage in place (see OpReorder, ring -> nest).
 // -------------------------------------------------------------------------------------------
-#define HPGB_SUB 1024  // elements per sub-block (4 per thread)
 
 __device__ __forceinline__ uint32_t hpgb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void hpgb_mbar_init(uint64_t *bar, uint32_t count) {
@@ -159,20 +168,37 @@ __device__ __forceinline__ void hpgb_mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
-template <class Op, int STAGES, int H>
-__global__ void __launch_bounds__(HPGB_BLOCK, Op::MINB) k_stream(const Op op, const int64_t n, hpgb_status_t *st) {
+// BLOCK = threads per CTA (a sub-block is 4 * BLOCK elements: thread t owns {2t, 2t+1} and {2 BLOCK + 2t, + 1});
+// MINB = min resident CTAs/SM (register cap); CONTIG = false: tiles are dealt round-robin to the CTAs (the grid
+// sweeps the arrays as one moving window), true: every CTA owns one contiguous run of tiles.
+template <class Op, int STAGES, int H, int BLOCK = HPGB_BLOCK, int MINB = Op::MINB, bool CONTIG = false>
+__global__ void __launch_bounds__(BLOCK, MINB) k_stream(const Op op, const int64_t n, hpgb_status_t *st) {
     constexpr int NIN = Op::NIN;
-    constexpr int TILE = HPGB_SUB * H;
+    constexpr int SUB = 4 * BLOCK;
+    constexpr int TILE = SUB * H;
     constexpr uint32_t ARR_BYTES = TILE * 8;
+    static_assert(!Op::TILE_HOOK || BLOCK == HPGB_BLOCK, "tile-hook ops are written for HPGB_BLOCK threads");
     extern __shared__ __align__(128) unsigned char hpgb_stage_smem[];
     __shared__ uint64_t full[STAGES], empty[STAGES];
     const typename Op::Ctx ctx = op.prologue();
     const int tid = threadIdx.x;
     const int64_t ntiles = n / TILE;
+    // this CTA's tiles: t0, t0 + tstep, ... < tend
+    int64_t t0, tend, tstep;
+    if (CONTIG) {
+        const int64_t per = ntiles / gridDim.x, rem = ntiles % gridDim.x;
+        t0 = (int64_t)blockIdx.x * per + ((int64_t)blockIdx.x < rem ? (int64_t)blockIdx.x : rem);
+        tend = t0 + per + ((int64_t)blockIdx.x < rem ? 1 : 0);
+        tstep = 1;
+    } else {
+        t0 = blockIdx.x;
+        tend = ntiles;
+        tstep = gridDim.x;
+    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
             hpgb_mbar_init(&full[s], 1);
-            hpgb_mbar_init(&empty[s], HPGB_BLOCK / 32);
+            hpgb_mbar_init(&empty[s], BLOCK / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -185,22 +211,31 @@ __global__ void __launch_bounds__(HPGB_BLOCK, Op::MINB) k_stream(const Op op, co
                           (const unsigned char *)op.src(k) + (size_t)tile * ARR_BYTES, ARR_BYTES, &full[s]);
     };
     if (tid == 0) {
-        int64_t t = blockIdx.x;
-        for (int s = 0; s < STAGES && t < ntiles; s++, t += gridDim.x) issue(s, t);
+        int64_t t = t0;
+        for (int s = 0; s < STAGES && t < tend; s++, t += tstep) issue(s, t);
     }
     hpgb_bad_t bad;
     int s = 0, sprev = STAGES - 1;
     uint32_t phase = 0, phase_prev = 1;  // parity of full[s] now / of empty[sprev] for the refill
     bool first = true;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int64_t t = t0; t < tend; t += tstep) {
         if (tid == 0 && !first) {  // refill the stage every warp left one iteration ago
-            const int64_t tn = t + (int64_t)(STAGES - 1) * gridDim.x;
-            if (tn < ntiles) {
+            const int64_t tn = t + (int64_t)(STAGES - 1) * tstep;
+#if defined(HPGB_STREAM_NOMEM)
+            // compute ceiling of an op (never built into the library): the ring is filled ONCE, every later iteration
+            // converts the same resident tiles again and stores into this CTA's own window of `out` (L2 resident)
+            if (false) {
+#else
+            if (tn < tend) {
+#endif
                 hpgb_mbar_wait(&empty[sprev], phase_prev);
                 issue(sprev, tn);
             }
         }
         first = false;
+#if defined(HPGB_STREAM_NOMEM)  // tools/ubench/a2p_sweep.cu only: compute ceiling, see below
+        if (t < t0 + (int64_t)STAGES * tstep)
+#endif
         hpgb_mbar_wait(&full[s], phase);
         const unsigned char *stage = hpgb_stage_smem + (size_t)s * NIN * ARR_BYTES;
         if constexpr (Op::TILE_HOOK) {
@@ -210,14 +245,21 @@ __global__ void __launch_bounds__(HPGB_BLOCK, Op::MINB) k_stream(const Op op, co
         } else {
 #pragma unroll
             for (int h = 0; h < H; h++) {
-                const typename Op::In2 v0 = op.load2s(stage, TILE, h * HPGB_SUB + 2 * tid);
-                const typename Op::In2 v1 = op.load2s(stage, TILE, h * HPGB_SUB + HPGB_SUB / 2 + 2 * tid);
+                const typename Op::In2 v0 = op.load2s(stage, TILE, h * SUB + 2 * tid);
+                const typename Op::In2 v1 = op.load2s(stage, TILE, h * SUB + SUB / 2 + 2 * tid);
                 if (h == H - 1) {  // this warp is done with the stage
                     __syncwarp();
                     if ((tid & 31) == 0) hpgb_mbar_arrive(&empty[s]);
                 }
-                const int64_t e0 = t * TILE + h * HPGB_SUB + 2 * tid;
-                op.run4(e0, v0, e0 + HPGB_SUB / 2, v1, ctx, bad);
+#if defined(HPGB_STREAM_NOMEM)
+                const int64_t e0 = ((int64_t)blockIdx.x * STAGES + s) * TILE + h * SUB + 2 * tid;
+#else
+                const int64_t e0 = t * TILE + h * SUB + 2 * tid;
+#endif
+                if constexpr (hpgb_has_epilogue<Op>::value)
+                    op.run4u(e0, v0, e0 + SUB / 2, v1, ctx, bad);  // every thread of the CTA is here: warp collectives allowed
+                else
+                    op.run4(e0, v0, e0 + SUB / 2, v1, ctx, bad);
             }
         }
         sprev = s;
@@ -227,19 +269,46 @@ __global__ void __launch_bounds__(HPGB_BLOCK, Op::MINB) k_stream(const Op op, co
             phase ^= 1u;
         }
     }
+    if constexpr (hpgb_has_epilogue<Op>::value) op.epilogue(ctx, bad);  // e.g. drain a queue of deferred elements
     if (blockIdx.x == 0)  // fewer than TILE leftover elements
-        for (int64_t i = ntiles * TILE + tid; i < n; i += HPGB_BLOCK) op.run1(i, ctx, bad);
+        for (int64_t i = ntiles * TILE + tid; i < n; i += BLOCK) op.run1(i, ctx, bad);
     bad.commit(st);
 }
 
 int hpgb_sm_count();  // SMs of the current device (148 on B200)
 
+// Launch configuration cached PER DEVICE: the opt-in for more than 48 KB of dynamic shared memory
+// (cudaFuncAttributeMaxDynamicSharedMemorySize) is a per-device attribute of the function, so a process
+// that uses cuda:0 and then cuda:1 must set it on each.  Slot = current device; 0 = not set up yet.
+// (Relaxed atomics: two threads racing on the first call compute and store the same value.)
+struct hpgb_occ_cache {
+    std::atomic<int> v[64];
+    hpgb_occ_cache() {
+        for (auto &x : v) x.store(0, std::memory_order_relaxed);
+    }
+};
+static inline int hpgb_current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d < 0 || d >= 64) ? 0 : d;
+}
+// resident CTAs/SM of `kernel` on the current device (sets the dynamic-smem opt-in first); >= 1
 template <class K>
 static int hpgb_resident_ctas(K kernel, int dyn_smem = 0, int block = HPGB_BLOCK) {
     int per_sm = 0;
     if (dyn_smem > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, dyn_smem);
     return per_sm > 0 ? per_sm : 1;
+}
+template <class K>
+static int hpgb_resident_ctas_cached(hpgb_occ_cache &cache, K kernel, int dyn_smem = 0, int block = HPGB_BLOCK) {
+    const int dev = hpgb_current_device();
+    int occ = cache.v[dev].load(std::memory_order_relaxed);
+    if (!occ) {
+        occ = hpgb_resident_ctas(kernel, dyn_smem, block);
+        cache.v[dev].store(occ, std::memory_order_relaxed);
+    }
+    return occ;
 }
 
 static inline bool hpgb_aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
@@ -250,8 +319,8 @@ static inline bool hpgb_aligned16(const void *p) { return (((uintptr_t)p) & 15u)
 template <class Op, int BLOCK = HPGB_BLOCK>
 static int hpgb_launch_map1(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s, int dyn_smem = 0) {
     if (n <= 0) return HPGB_OK;
-    static int occ1 = 0;
-    if (!occ1) occ1 = hpgb_resident_ctas(k_map1<Op, BLOCK>, dyn_smem, BLOCK);
+    static hpgb_occ_cache cache;  // per instantiation
+    const int occ1 = hpgb_resident_ctas_cached(cache, k_map1<Op, BLOCK>, dyn_smem, BLOCK);
     int64_t want = (n + BLOCK - 1) / BLOCK;
     int64_t grid = (int64_t)hpgb_sm_count() * occ1;
     if (want < grid) grid = want;
@@ -266,8 +335,8 @@ template <class Op, int BLOCK = HPGB_BLOCK>
 static int hpgb_launch_map(const Op &op, int64_t n, bool vec_ok, hpgb_status_t *st, cudaStream_t s, int dyn_smem = 0) {
     if (n <= 0) return HPGB_OK;
     if (!vec_ok) return hpgb_launch_map1<Op, BLOCK>(op, n, st, s, dyn_smem);
-    static int occ2 = 0;  // per instantiation, per process (one device kind per box)
-    if (!occ2) occ2 = hpgb_resident_ctas(k_map2<Op, BLOCK>, dyn_smem, BLOCK);
+    static hpgb_occ_cache cache;
+    const int occ2 = hpgb_resident_ctas_cached(cache, k_map2<Op, BLOCK>, dyn_smem, BLOCK);
     int64_t want = ((n >> 1) + BLOCK - 1) / BLOCK;
     int64_t grid = (int64_t)hpgb_sm_count() * occ2;
     if (want < grid) grid = want > 0 ? want : 1;
@@ -278,22 +347,17 @@ static int hpgb_launch_map(const Op &op, int64_t n, bool vec_ok, hpgb_status_t *
 }
 
 // launch the TMA streaming kernel (operands 16-byte aligned); falls back to k_map2 for small n
-template <class Op, int STAGES, int H = 1>
+template <class Op, int STAGES, int H = 1, int BLOCK = HPGB_BLOCK, int MINB = Op::MINB, bool CONTIG = false>
 static int hpgb_launch_stream(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
-    constexpr int TILE = HPGB_SUB * H;
+    constexpr int TILE = 4 * BLOCK * H;
     if (n < 4 * TILE) return hpgb_launch_map(op, n, true, st, s);
     const int smem = STAGES * Op::NIN * TILE * 8 + Op::EXTRA_SMEM;
-    static int occ = 0;
-    if (!occ) {
-        cudaFuncSetAttribute(k_stream<Op, STAGES, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream<Op, STAGES, H>, HPGB_BLOCK, smem);
-        occ = per_sm > 0 ? per_sm : 1;
-    }
+    static hpgb_occ_cache cache;
+    const int occ = hpgb_resident_ctas_cached(cache, k_stream<Op, STAGES, H, BLOCK, MINB, CONTIG>, smem, BLOCK);
     int64_t grid = (int64_t)hpgb_sm_count() * occ;
     const int64_t ntiles = n / TILE;
     if (ntiles < grid) grid = ntiles;
-    k_stream<Op, STAGES, H><<<(unsigned)grid, HPGB_BLOCK, smem, s>>>(op, n, st);
+    k_stream<Op, STAGES, H, BLOCK, MINB, CONTIG><<<(unsigned)grid, BLOCK, smem, s>>>(op, n, st);
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;

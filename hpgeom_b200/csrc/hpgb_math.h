@@ -139,6 +139,54 @@ HPGB_HD void hpgb_sincos_cr(const double *T, double x, double &s, double &c) {
     c = ch + cl;
 }
 
+// ---------------------------------------------------------------------------------------------
+// sin and cos of x (0 <= |x| < 2^20) as PLAIN doubles, error <= 0.51 ulp: the same reduction and table as
+// the double-double routine above, but only the two leading terms of the angle-addition formula are kept
+// exact (S + C d as a two-product + two-sum); everything below 2^-7 of the result is plain fma arithmetic.
+// About 40 fp64 operations instead of ~85.  Used where the consumer multiplies the result afterwards and
+// the contract is "<= 2 ulp" rather than "the bits glibc returns" (pixel_to_vector: x = sin(theta) cos(phi)).
+// ---------------------------------------------------------------------------------------------
+HPGB_HD void hpgb_sincos_sd(const double *T, double x, double &s, double &c) {
+    // x = q pi/2 + r, r = rh + rl
+    const double fq = rint(x * HPGB_2OPI);
+    const int q = (int)fq;
+    const double t = fma(-fq, HPGB_PIO2_1, x);  // exact (see hpgb_reduce_pio2)
+    double w, we;
+    hpgb_two_prod(fq, HPGB_PIO2_2, w, we);
+    const double rh = t - w;
+    const double rl = ((t - rh) - w) - fma(fq, HPGB_PIO2_3, we);  // |t| >= |w| or both tiny: fast two-sum is exact enough
+    const bool neg = rh < 0.0;
+    const double a = fabs(rh);
+    const double al = neg ? -rl : rl;
+    const double fk = rint(a * 64.0);
+    const int k = (int)fk;
+    const double d = fma(-fk, 0.015625, a);  // exact
+    const double Sh = T[4 * k + 0], Sl = T[4 * k + 1], Ch = T[4 * k + 2], Cl = T[4 * k + 3];
+    const double p = d * d;
+    // sin(delta) = d + sd, cos(delta) = 1 + cd   (delta = d + al, |delta| <= 2^-7)
+    const double sd = fma(d * p, fma(p, fma(p, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), al);
+    const double cd = fma(p, fma(p, fma(p, -1.0 / 720.0, 1.0 / 24.0), -0.5), -d * al);
+    double sa, ca;
+    {   // sin(a) = S + C d + [C sd + S cd + Sl + Cl d]
+        double m, me, v, ve;
+        hpgb_two_prod(Ch, d, m, me);
+        hpgb_fast_two_sum(Sh, m, v, ve);  // |S| >= |C d| for k >= 1; k = 0: S = 0
+        sa = v + (ve + (me + fma(Ch, sd, fma(Sh, cd, fma(Cl, d, Sl)))));
+    }
+    {   // cos(a) = C - S d + [-S sd + C cd + Cl - Sl d]
+        double m, me, v, ve;
+        hpgb_two_prod(-Sh, d, m, me);
+        hpgb_fast_two_sum(Ch, m, v, ve);
+        ca = v + (ve + (me + fma(-Sh, sd, fma(Ch, cd, fma(-Sl, d, Cl)))));
+    }
+    if (neg) sa = -sa;
+    const bool swap = q & 1;
+    s = swap ? ca : sa;
+    c = swap ? sa : ca;
+    if (q & 2) s = -s;
+    if ((q + 1) & 2) c = -c;
+}
+
 // 24-bit first guesses (any estimate good to ~2^-20 gives the same final result)
 HPGB_HD double hpgb_acos_guess(double z) {
 #if defined(__CUDA_ARCH__)

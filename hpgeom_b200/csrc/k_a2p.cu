@@ -22,6 +22,9 @@
 #ifndef HPGB_A2P_MINB
 #define HPGB_A2P_MINB 2
 #endif
+#ifndef HPGB_A2P_QBLOCK
+#define HPGB_A2P_QBLOCK HPGB_BLOCK  // threads per CTA of the kernels that use the deferred-exact-path queue
+#endif
 
 namespace {
 
@@ -79,6 +82,64 @@ struct OpAng2Pix {
         if (g1) p1 = slow(g, v.a.y, v.b.y, i + 1, T, bad);
         hpgb_st2(out + i, p0, p1);
     }
+#if defined(HPGB_A2P_QUEUE)
+    // Deferred exact path.  ~2e-4 of the points need it; taken where it arises it runs on ONE lane while the other 31
+    // wait (2.5 % of the warp iterations, ~2x their cost).  Instead a flagged point is parked in a per-warp queue in
+    // shared memory -- its slot in `out` keeps the untrusted fast result for now -- and the exact path runs on 32
+    // parked points at once (dense lanes); the remainder is drained when the CTA runs out of tiles (epilogue).
+    // Ordering of the two stores to one address by different lanes of the warp: __syncwarp() in between.
+    static constexpr bool HAS_EPILOGUE = true;
+    static constexpr int QCAP = 64;  // 31 left over + 32 new, rounded up
+    typedef int64_t QEntry;          // the element's index: its angles are read again from HBM when it is drained
+    static __device__ __forceinline__ QEntry *queue() {
+        __shared__ QEntry q[HPGB_A2P_QBLOCK / 32][QCAP];  // 512 B per warp
+        return q[threadIdx.x >> 5];
+    }
+    __device__ __forceinline__ void drain(QEntry *q, int first, int count, Ctx T, hpgb_bad_t &bad) const {
+        const int lane = threadIdx.x & 31;
+        if (lane < count) {
+            const int64_t i = q[first + lane];
+            hpgb_st1(out + i, slow(g, hpgb_ld1(a + i), hpgb_ld1(b + i), i, T, bad));
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void park(uint32_t gj, int64_t i, int &cnt, Ctx T, hpgb_bad_t &bad) const {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, gj != 0u);
+        if (m == 0u) return;  // warp-uniform
+        QEntry *q = queue();
+        if (gj) q[cnt + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = i;
+        cnt += __popc(m);
+        __syncwarp();
+        if (cnt >= 32) {
+            cnt -= 32;
+            drain(q, cnt, 32, T, bad);
+        }
+    }
+    __device__ __forceinline__ void run4u(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
+                                         hpgb_bad_t &bad) const {
+        int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+        const uint32_t g0 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.x, v0.b.x, p0);
+        const uint32_t g1 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.y, v0.b.y, p1);
+        const uint32_t g2 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.x, v1.b.x, p2);
+        const uint32_t g3 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.y, v1.b.y, p3);
+        hpgb_st2(out + i0, p0, p1);
+        hpgb_st2(out + i1, p2, p3);
+        if (__any_sync(0xFFFFFFFFu, (g0 | g1 | g2 | g3) != 0u)) {  // warp-uniform, 2.5 % of the iterations
+            __syncwarp();
+            int cnt = bad.aux;  // warp-uniform queue length
+            park(g0, i0, cnt, T, bad);
+            park(g1, i0 + 1, cnt, T, bad);
+            park(g2, i1, cnt, T, bad);
+            park(g3, i1 + 1, cnt, T, bad);
+            bad.aux = cnt;
+        }
+    }
+    __device__ __forceinline__ void epilogue(const Ctx &T, hpgb_bad_t &bad) const {
+        __syncwarp();
+        if (bad.aux > 0) drain(queue(), 0, bad.aux, T, bad);
+        bad.aux = 0;
+    }
+#endif
     __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
                                          hpgb_bad_t &bad) const {
         int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
@@ -129,7 +190,9 @@ int launch_a2p_t(const double *a, const double *b, int64_t *out, int64_t n, int6
         return hpgb_launch_map(op, n, vec, st, s);
     }
     OpAng2Pix<NEST, LONLAT, DEGREES, false, false> op{a, b, out, nullptr, base, g, hpgb_make_a2p_fast<LONLAT, DEGREES>(g), hpgb_make_rk(g)};
-    if (vec) return hpgb_launch_stream<decltype(op), HPGB_A2P_ST, HPGB_A2P_H>(op, n, st, s);
+    // RING with a non-power-of-two nside has no fast path: every point takes the exact path, which wants the
+    // occupancy of the plain grid-stride kernel, not the streaming ring
+    if (vec && g.order >= 0) return hpgb_launch_stream<decltype(op), HPGB_A2P_ST, HPGB_A2P_H>(op, n, st, s);
     return hpgb_launch_map(op, n, vec, st, s);
 }
 
@@ -159,7 +222,3 @@ int launch_a2p(const double *a, const double *b, int64_t *out, int64_t n, int64_
 #undef GO
 }
 
-namespace {
-
-
-}  // namespace

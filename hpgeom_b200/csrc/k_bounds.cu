@@ -160,11 +160,8 @@ int launch_boundaries(const int64_t *pix, double *a, double *b, int64_t n, int64
     if (want < grid) grid = want;
 #define GO(N, L, D)                                                                                              \
     do {                                                                                                         \
-        static bool attr = false;                                                                                \
-        if (!attr) {                                                                                             \
-            cudaFuncSetAttribute(k_boundaries<N, L, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      \
-            attr = true;                                                                                         \
-        }                                                                                                        \
+        static hpgb_occ_cache cache; /* per device: the dynamic-smem opt-in is a per-device attribute */        \
+        (void)hpgb_resident_ctas_cached(cache, k_boundaries<N, L, D>, smem, HPGB_BND_BLOCK);                     \
         k_boundaries<N, L, D><<<(unsigned)grid, HPGB_BND_BLOCK, smem, s>>>(pix, a, b, n, step, g, nside_v, base, st); \
     } while (0)
     if (nest) {

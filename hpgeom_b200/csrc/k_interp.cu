@@ -191,11 +191,8 @@ __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_rows(const Op op, 
 template <class Op>
 int launch_interp_rows(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
     const int smem = Op::DYN_SMEM + (HPGB_INTERP_BLOCK / 32) * 256 * 16;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_interp_rows<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr = true;
-    }
+    static hpgb_occ_cache cache;  // per device: the dynamic-smem opt-in is a per-device attribute
+    (void)hpgb_resident_ctas_cached(cache, k_interp_rows<Op>, smem, HPGB_INTERP_BLOCK);
     int64_t grid = hpgb_sm_count();
     const int64_t want = (((n + 63) >> 6) + HPGB_INTERP_BLOCK / 32 - 1) / (HPGB_INTERP_BLOCK / 32);
     if (want < grid) grid = want > 0 ? want : 1;
@@ -251,7 +248,3 @@ int launch_interp(const double *a, const double *b, int64_t *pix, double *wgt, i
 #undef GO
 }
 
-namespace {
-
-
-}  // namespace

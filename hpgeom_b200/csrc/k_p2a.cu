@@ -38,6 +38,15 @@ static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW
 #ifndef HPGB_P2V_BLOCK
 #define HPGB_P2V_BLOCK 640
 #endif
+#ifndef HPGB_P2V_MINB
+#define HPGB_P2V_MINB 2
+#endif
+#ifndef HPGB_P2V_ST
+#define HPGB_P2V_ST 3
+#endif
+#ifndef HPGB_P2V_H
+#define HPGB_P2V_H 2
+#endif
 #ifndef HPGB_V2P_MINB
 #define HPGB_V2P_MINB 2
 #endif
@@ -319,6 +328,7 @@ struct OpPix2Vec {
     typedef longlong2 In2;
     typedef const double *Ctx;
     static constexpr bool FAST = POW2 && !VAR;
+    HPGB_STREAM_IN_I64(pix, HPGB_P2V_MINB)
     __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
     // general path: the reference's branches as they are
@@ -411,19 +421,25 @@ int launch_p2v(const int64_t *pix, double *x, double *y, double *z, int64_t n, i
     if (c) return c;
     const hpgb_geom g = hpgb_make_geom(nside, nest);
     const bool vec = hpgb_aligned16(pix) && hpgb_aligned16(x) && hpgb_aligned16(y) && hpgb_aligned16(z);
+    // power-of-two nside: the TMA-fed streaming skeleton (the pixel tiles arrive through the shared-memory ring, so
+    // load latency is hidden without occupancy and the ~95 registers of the fp64 body are affordable)
     if (nest) {
         OpPix2Vec<true, true, false> op{pix, x, y, z, nullptr, base, g, hpgb_make_rk(g)};
+#if defined(HPGB_P2V_MAP)
         return hpgb_launch_map<decltype(op), HPGB_P2V_BLOCK>(op, n, vec, st, s);
+#else
+        return hpgb_launch_auto<decltype(op), HPGB_P2V_ST, HPGB_P2V_H>(op, n, vec, st, s);
+#endif
     }
     if (g.order >= 0) {
         OpPix2Vec<false, true, false> op{pix, x, y, z, nullptr, base, g, hpgb_make_rk(g)};
+#if defined(HPGB_P2V_MAP)
         return hpgb_launch_map<decltype(op), HPGB_P2V_BLOCK>(op, n, vec, st, s);
+#else
+        return hpgb_launch_auto<decltype(op), HPGB_P2V_ST, HPGB_P2V_H>(op, n, vec, st, s);
+#endif
     }
     OpPix2Vec<false, false, false> op{pix, x, y, z, nullptr, base, g, hpgb_rk()};
     return hpgb_launch_map(op, n, vec, st, s);
 }
 
-namespace {
-
-
-}  // namespace

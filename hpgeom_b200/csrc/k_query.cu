@@ -259,12 +259,14 @@ int build_table(const hpgb_disc_t *plan, int device, DevTable &d, int64_t *total
 extern "C" {
 
 int hpgb_host_query_circle_ring_count(const hpgb_disc_t *plan, int device, int64_t *total) {
+    device = hpgb_host_first_device(device);  // HPGB_DEVICE_ALL: this entry point's scratch lives on one GPU
     if (!total) return HPGB_E_BAD_ARGUMENT;
     DevTable d;
     return build_table(plan, device, d, total);
 }
 
 int hpgb_host_query_circle_ring_fill(const hpgb_disc_t *plan, int64_t *out, int64_t total, int device) {
+    device = hpgb_host_first_device(device);  // HPGB_DEVICE_ALL: this entry point's scratch lives on one GPU
     DevTable d;
     int64_t tot = 0;
     const int rc = build_table(plan, device, d, &tot);
@@ -518,6 +520,7 @@ extern "C" {
 
 int hpgb_query_circle_nest_open(int64_t nside, double a, double b, double radius, int inclusive, int64_t fact, int lonlat,
                                 int degrees, int device, void **handle, int64_t *m, int64_t *total) {
+    device = hpgb_host_first_device(device);  // HPGB_DEVICE_ALL: this entry point's scratch lives on one GPU
     if (!handle || !m || !total) return HPGB_E_BAD_ARGUMENT;
     *handle = nullptr;
     // argument checks in the wrapper's order: hpgeom/hpgeom.c:793-838
@@ -830,6 +833,7 @@ int64_t hpgb_query_circle_ring_batch_prepare(hpgb_disc_t *plans, int64_t D, int6
 // Call with out = NULL to learn the sizes (disc_offsets is filled, *total set), then with the buffer.
 int hpgb_host_query_circle_ring_batch(hpgb_disc_t *plans, int64_t D, int device, int64_t *disc_offsets, int64_t *total,
                                       int64_t *out, int64_t cap) {
+    device = hpgb_host_first_device(device);  // HPGB_DEVICE_ALL: this entry point's scratch lives on one GPU
     if (D < 0 || !total || (D > 0 && (!plans || !disc_offsets))) return HPGB_E_BAD_ARGUMENT;
     *total = 0;
     if (D == 0) {
@@ -1140,6 +1144,7 @@ extern "C" {
 int hpgb_query_circle_nest_batch_open(int64_t nside, const double *a, const double *b, const double *radius, int64_t D,
                                       int inclusive, int64_t fact, int lonlat, int degrees, int device, void **handle,
                                       int64_t *m, int64_t *total, int64_t *first_bad) {
+    device = hpgb_host_first_device(device);  // HPGB_DEVICE_ALL: this entry point's scratch lives on one GPU
     if (!handle || !m || !total || D < 0 || (D > 0 && (!a || !b || !radius))) return HPGB_E_BAD_ARGUMENT;
     *handle = nullptr;
     if (first_bad) *first_bad = -1;

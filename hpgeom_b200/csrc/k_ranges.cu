@@ -288,8 +288,8 @@ int launch_ranges_expand(const int64_t *ranges, const int64_t *offs, int64_t m, 
     if (out_count == 0) return HPGB_OK;
     if (m == 0 || !ranges || !offs || !out || !hpgb_aligned16(ranges)) return HPGB_E_BAD_ARGUMENT;
     const int64_t ntiles = (out_count + RG_TILE - 1) / RG_TILE;
-    static int occ = 0;
-    if (!occ) occ = hpgb_resident_ctas(k_ranges_expand<true>, 0, RG_BLOCK);
+    static hpgb_occ_cache cache;
+    const int occ = hpgb_resident_ctas_cached(cache, k_ranges_expand<true>, 0, RG_BLOCK);
     int64_t grid = (int64_t)hpgb_sm_count() * occ;
     if (grid > ntiles) grid = ntiles;
     const int64_t per = (ntiles + grid - 1) / grid;
@@ -364,11 +364,13 @@ int hpgb_ranges_expand(const int64_t *d_ranges_m2, const int64_t *d_offsets_mp1,
 }
 int hpgb_host_ranges_count(const int64_t *ranges_m2, int64_t m, int inclusive, int device, int64_t *total,
                            int64_t *first_bad) {
+    device = hpgb_host_first_device(device);  // HPGB_DEVICE_ALL: this entry point's scratch lives on one GPU
     if (!total) return HPGB_E_BAD_ARGUMENT;
     DevRanges d;
     return stage_ranges(ranges_m2, m, inclusive, device, d, total, first_bad);
 }
 int hpgb_host_ranges_expand(const int64_t *ranges_m2, int64_t m, int inclusive, int64_t *out, int64_t total, int device) {
+    device = hpgb_host_first_device(device);  // HPGB_DEVICE_ALL: this entry point's scratch lives on one GPU
     DevRanges d;
     int64_t tot = 0, bad = -1;
     int rc = stage_ranges(ranges_m2, m, inclusive, device, d, &tot, &bad);

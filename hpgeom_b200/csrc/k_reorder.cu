@@ -382,10 +382,10 @@ int launch_neighbors(const int64_t *pix, int64_t *out, int64_t n, int64_t nside,
     const hpgb_geom g = hpgb_make_geom(nside, nest);
     const bool vec = hpgb_aligned16(pix);
     if (g.order >= 0 && vec) {
-        static int occ[2] = {0, 0};
-        if (!occ[nest ? 1 : 0])
-            occ[nest ? 1 : 0] = nest ? hpgb_resident_ctas(k_neighbors_rows<true>, 0, HPGB_BLOCK) : hpgb_resident_ctas(k_neighbors_rows<false>, 0, HPGB_BLOCK);
-        int64_t grid = (int64_t)hpgb_sm_count() * occ[nest ? 1 : 0];
+        static hpgb_occ_cache cache[2];
+        const int occ = nest ? hpgb_resident_ctas_cached(cache[1], k_neighbors_rows<true>, 0, HPGB_BLOCK)
+                             : hpgb_resident_ctas_cached(cache[0], k_neighbors_rows<false>, 0, HPGB_BLOCK);
+        int64_t grid = (int64_t)hpgb_sm_count() * occ;
         const int64_t want = ((n >> 6) + HPGB_BLOCK / 32 - 1) / (HPGB_BLOCK / 32);
         if (want < grid) grid = want > 0 ? want : 1;
         if (nest)
@@ -559,11 +559,6 @@ int launch_lonlat(const double *lon, const double *lat, double *theta, double *p
     OpLonLat<false> op{lon, lat, theta, phi, base};
     return hpgb_launch_auto(op, n, vec, st, s);
 }
-
-namespace {
-
-
-}  // namespace
 
 int launch_n2r(const int64_t *in, int64_t *out, int64_t n, int64_t nside, const int64_t *nside_v, int64_t base,
                hpgb_status_t *st, cudaStream_t s) {

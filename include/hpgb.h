@@ -17,7 +17,8 @@
  *    per-element nside values (the reference broadcasts nside against the data);
  *  - hpgb_<fn>()      : DEVICE pointers, asynchronous on `stream`, no allocation, no sync;
  *  - hpgb_host_<fn>() : HOST pointers (pinned or pageable); runs a chunked, multi-stream
- *    H2D -> kernel -> D2H pipeline on `device` and returns when the outputs are complete;
+ *    H2D -> kernel -> D2H pipeline on `device` (or on every GPU of the box, HPGB_DEVICE_ALL) and returns
+ *    when the outputs are complete; slots are sized by a byte budget (HPGB_HOST_SLOT_BYTES, 96 MiB);
  *  - return value: HPGB_OK, an HPGB_E_* argument error, or 1000 + cudaError_t;
  *  - element errors (the reference's ValueError checks) never trap: the kernel writes -1 / NaN
  *    for the offending element and records the SMALLEST failing element index with atomicMin
@@ -47,6 +48,12 @@ extern "C" {
 
 #define HPGB_NO_BAD_ELEMENT 0xFFFFFFFFFFFFFFFFull
 
+/* `device` argument of the hpgb_host_<fn>() entry points: a CUDA device ordinal, or HPGB_DEVICE_ALL = cut the
+ * arrays into contiguous shards over the device set (hpgb_host_set_devices; default every visible GPU), one host
+ * thread and one pipeline per GPU, from this one process.  The split is the reference's split of its element loop
+ * over worker threads (hpgeom/hpgeom.c:272-279).  No collective: the shards are independent. */
+#define HPGB_DEVICE_ALL (-1)
+
 /* element error classes reported by hpgb_explain_* (reference message templates:
  * hpgeom/hpgeom_utils.c:31,36,41,52,56,66,132,134) */
 #define HPGB_BAD_NONE 0
@@ -72,6 +79,9 @@ int hpgb_status_reset(hpgb_status_t *d_status, void *stream);
 int64_t hpgb_launch_count(void);
 /* free the cached device scratch / streams used by the hpgb_host_* entry points */
 int hpgb_host_release(void);
+/* the GPUs HPGB_DEVICE_ALL shards over (n_dev = 0: every visible device); get returns the set's size */
+int hpgb_host_set_devices(const int *devices, int n_dev);
+int hpgb_host_get_devices(int *devices, int cap);
 /* pinned host memory for callers that want zero staging in hpgb_host_* */
 int hpgb_pinned_alloc(void **ptr, int64_t bytes);
 int hpgb_pinned_free(void *ptr);

@@ -14,7 +14,8 @@ _D = ctypes.POINTER(ctypes.c_double)
 class HostSim:
     def __init__(self):
         subprocess.check_call(["make", "-s", "-C", _HERE])
-        self.lib = ctypes.CDLL(os.path.join(_HERE, "libhostsim.so"))
+        # HPGB_HOSTSIM_LIB: an alternative host build (kernel variants compiled with extra -D flags)
+        self.lib = ctypes.CDLL(os.environ.get("HPGB_HOSTSIM_LIB") or os.path.join(_HERE, "libhostsim.so"))
         for n in ("sim_nest_to_ring", "sim_ring_to_nest", "sim_ring_roundtrip_any", "sim_angle_to_pixel",
                   "sim_pixel_to_angle", "sim_pixel_to_vector", "sim_vector_to_pixel", "sim_neighbors", "sim_interp",
                   "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_pixel_to_angle_k", "sim_pixel_to_vector_k", "sim_interp_k", "sim_query_circle_ring", "sim_query_circle_nest"):
