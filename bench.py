@@ -46,6 +46,13 @@ def parse():
     ap.add_argument("--log2-e2e-points", type=int, default=27, help="host-buffer batch per GPU = 2^this")
     ap.add_argument("--log2-ref-points", type=int, default=25, help="reference arm: points per step = 2^this")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="separate", choices=["separate", "carved"],
+                    help="operand placement in HBM: three separately allocated tensors (what a caller has), or "
+                         "lon | lat | pix carved back to back from one allocation")
+    ap.add_argument("--log2-parity-head", type=int, default=24,
+                    help="parity sample per rank = the first 2^this elements of the shard + every 1024th after them")
+    ap.add_argument("--gather", action="store_true",
+                    help="also time the OPTIONAL collective: all-gather of a 2^28-pixel result shard per GPU (NCCL)")
     return ap.parse_args()
 
 
@@ -58,13 +65,31 @@ def measured_peak():
 
 
 def ncu_traffic(kernel, points):
-    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
-    (profiles/ncu_traffic.json holds measured bytes per point at 2^26 points), or None."""
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of THIS kernel at
+    the metric's size (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch over
+    2^30 points, separately allocated operands; profiles/r02a_ncu_headline_2p30_separate.txt), scaled by the point
+    count when the bench runs at another size; None if the file is absent."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f)[kernel + "_bytes_per_point"] * points
+            rec = json.load(f)[kernel]
+        return rec["dram_bytes_per_launch"] * (points / rec["points_per_launch"])
     except Exception:
         return None
+
+
+def boundary_induced(ref, nside, a, b, got, n_threads=1):
+    """True where the reference returns `got` for some <= 2 ulp perturbation of the input angles: the mismatch is
+    a point within 2 ulp of a pixel boundary (BASELINE north_star: such cases are counted and reported)."""
+    import numpy as np
+    ok = np.zeros(a.size, dtype=bool)
+    for da in (-2, -1, 0, 1, 2):
+        for db in (-2, -1, 0, 1, 2):
+            pa, pb = a + da * np.spacing(a), b + db * np.spacing(b)
+            try:
+                ok |= ref(nside, pa, pb) == got
+            except ValueError:
+                pass
+    return ok
 
 
 class ClockSampler:
@@ -224,12 +249,16 @@ def main():
 
     n = 1 << args.log2_points
     gen = torch.Generator(device=dev).manual_seed(12345 + rank)
-    # HBM layout: the three operand arrays are carved from ONE allocation, back to back (2^33 bytes
-    # apart at the default size).  The streaming kernels are ~5-10 % faster when the read and write
-    # streams are congruent modulo 128 MiB than at arbitrary relative offsets (measured);
-    # separately allocated torch tensors land at arbitrary 2 MiB-aligned offsets.
-    pool = torch.empty(3 * n, dtype=torch.float64, device=dev)
-    lon, lat, pix = pool[:n], pool[n:2 * n], pool[2 * n:].view(torch.int64)
+    # HBM layout.  Default: three ordinary, separately allocated tensors -- what a caller of the drop-in has.
+    # (--layout carved = one allocation cut in three, the round-1 layout: a few percent faster on some boxes.)
+    pool = None
+    if args.layout == "carved":
+        pool = torch.empty(3 * n, dtype=torch.float64, device=dev)
+        lon, lat, pix = pool[:n], pool[n:2 * n], pool[2 * n:].view(torch.int64)
+    else:
+        lon = torch.empty(n, dtype=torch.float64, device=dev)
+        lat = torch.empty(n, dtype=torch.float64, device=dev)
+        pix = torch.empty(n, dtype=torch.int64, device=dev)
     torch.rand(n, dtype=torch.float64, device=dev, generator=gen, out=lon).mul_(360.0)
     torch.rand(n, dtype=torch.float64, device=dev, generator=gen, out=lat).mul_(2.0).sub_(1.0).asin_().mul_(180.0 / 3.141592653589793)
     status = torch.empty(2, dtype=torch.int64, device=dev)
@@ -285,8 +314,14 @@ def main():
     value = world * n / (ms_per_step * 1e-3) / 1e9
 
     lon_keep, lat_keep = lon[:1 << 20].clone(), lat[:1 << 20].clone()
+    # parity sample of THIS rank's shard: the first 2^24 elements + every 1024th after them
+    head = min(n, 1 << args.log2_parity_head)
+    sample_idx = torch.cat([torch.arange(head, device=dev), torch.arange(head, n, 1024, device=dev)])
+    s_lon, s_lat, s_pix = lon[sample_idx].cpu().numpy(), lat[sample_idx].cpu().numpy(), pix[sample_idx].cpu().numpy()
     # ---- second headline of the metric: nest_to_ring on the pixels just produced ----
-    ring = lon.view(torch.int64)  # reuse the 8 GiB buffer as the output (lon is no longer needed after e2e setup)
+    ring = torch.empty(n, dtype=torch.int64, device=dev) if args.layout == "separate" else lon.view(torch.int64)
+    if args.layout == "separate":
+        del lon, lat
 
     def step_n2r():
         rc = L.hpgb_nest_to_ring(pix.data_ptr(), ring.data_ptr(), n, NSIDE, None, stp, sp)
@@ -347,22 +382,67 @@ def main():
                  ms8, 40, "upgrade_pixels nside=4096 -> 8192 %s, 2^%d input pixels per GPU" % (tag, ms8.bit_length() - 1))
     assert int(status[0].item()) == -1, "a kernel flagged a bad element in valid synthetic input"
     del f1, f2, f3, i1, o8, w4, p4, p4r, lon4, lat4
-    # parity spot check (outside every timed region): the first 2^20 points of this rank against the oracle
-    parity = None
-    if rank == 0:
-        try:
-            import oracle
-            m = 1 << 20
-            hl, hb = lon_keep[:m].cpu().numpy(), lat_keep[:m].cpu().numpy()
-            if oracle.ref is not None:
-                want = oracle.ref.angle_to_pixel(NSIDE, hl, hb, nest=True, lonlat=True, degrees=True)
-            else:
-                want = oracle.port().angle_to_pixel(NSIDE, hl, hb)
-            parity = {"points": m, "mismatches": int((pix[:m].cpu().numpy() != want).sum()),
-                      "against": "oracle/_ref (reference C)" if oracle.ref is not None else "oracle port"}
-        except Exception as exc:  # the oracle is test infrastructure; its absence must not break the bench
-            parity = {"error": repr(exc)}
-    del ring, lon, lat, pix, pool, lon_keep, lat_keep
+    # ---- parity accounting, every rank, outside every timed region: this rank's sample of BOTH headline kernels
+    # against the reference's own C (oracle/_ref; the port if that build is absent), mismatches classified
+    s_ring = ring[sample_idx].cpu().numpy()
+    par = [0, 0, 0, 0, 0]  # points, a2p mismatches, of which boundary-induced, n2r points, n2r mismatches
+    par_err, against = None, None
+    try:
+        import numpy as np
+        import oracle
+        nth = max(1, (os.cpu_count() or 1) // max(world, 1))
+        if oracle.ref is not None:
+            against = "oracle/_ref (unmodified reference C)"
+            ref_a2p = lambda ns, a, b: oracle.ref.angle_to_pixel(ns, a, b, nest=True, lonlat=True, degrees=True, n_threads=nth)
+            ref_n2r = lambda ns, p: oracle.ref.nest_to_ring(ns, p, n_threads=nth)
+        else:
+            against = "oracle port (C restatement)"
+            port = oracle.port()
+            ref_a2p = lambda ns, a, b: port.angle_to_pixel(ns, a, b)
+            ref_n2r = lambda ns, p: port.nest_to_ring(ns, p)
+        want = ref_a2p(NSIDE, s_lon, s_lat)
+        bad = np.flatnonzero(s_pix != want)
+        explained = int(boundary_induced(ref_a2p, NSIDE, s_lon[bad], s_lat[bad], s_pix[bad]).sum()) if bad.size else 0
+        # nest_to_ring is judged on the pixels the kernel was actually fed (s_pix), bit for bit
+        par = [int(s_pix.size), int(bad.size), explained, int(s_pix.size), int((s_ring != ref_n2r(NSIDE, s_pix)).sum())]
+    except Exception as exc:  # the oracle is test infrastructure; its absence must not break the bench
+        par_err = repr(exc)
+    pt = torch.tensor(par + [1 if par_err else 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(pt, op=dist.ReduceOp.SUM)
+    pt = [int(v) for v in pt.tolist()]
+    parity = {"sample": "per rank: first 2^%d points of the shard + every 1024th after them" % (head.bit_length() - 1),
+              "ranks": world, "ranks_failed_to_check": pt[5], "against": against,
+              "angle_to_pixel": {"points": pt[0], "mismatches": pt[1], "boundary_induced": pt[2], "unexplained": pt[1] - pt[2]},
+              "nest_to_ring": {"points": pt[3], "mismatches": pt[4]}}
+    if par_err:
+        parity["error_rank0"] = par_err
+    # ---- optional collective (never on the data path): all-gather of a result shard over NCCL / NVLink ----
+    gather = None
+    if args.gather and world > 1:
+        from hpgeom_b200 import sharding
+        gn = min(n, 1 << 28)
+        shard_t = pix[:gn]
+        for _ in range(2):
+            full = sharding.gather(shard_t)
+            del full
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(5):
+            full = sharding.gather(shard_t)
+        e1.record(stream)
+        barrier()
+        ok = bool(torch.equal(full[rank * gn:(rank + 1) * gn], shard_t))
+        tg = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        ms_g = float(tg[0])
+        gather = {"bytes_per_rank": 8 * gn, "ms": ms_g, "received_GBps_per_gpu": 8 * gn * (world - 1) / (ms_g * 1e-3) / 1e9,
+                  "busbw_GBps": 8 * gn * (world - 1) / (ms_g * 1e-3) / 1e9, "own_shard_intact": ok,
+                  "nvlink_peer_copy_GBps_measured": 770.0, "api": "sharding.gather -> all_gather_into_tensor (NCCL)"}
+        del full
+    lon = lat = None
+    del ring, lon, lat, pix, pool, lon_keep, lat_keep, sample_idx
     torch.cuda.empty_cache()
 
     # ---- e2e: the C ABI with HOST (pinned) buffers, copies inside the timed region ----
@@ -419,7 +499,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = BYTES_PER_POINT["angle_to_pixel"] * n / (ms_per_step * 1e-3) / 1e9
-        kernel = "k_stream<OpAng2Pix<nest,lonlat,degrees>,3,2>"
+        kernel = "k_stream<OpAng2Pix<nest,lonlat,degrees>,3,2,256,2>"
         line = {
             "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -431,7 +511,9 @@ def main():
                        "e2e_batch_points_per_gpu": ne},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic("angle_to_pixel", n), "kernel": kernel, "peak_source": peak_src,
-                         "bytes_per_point": 24, "points_per_launch": n},
+                         "bytes_per_point": 24, "points_per_launch": n,
+                         "frac_nominal_8tbs": achieved / 8000.0, "peak_nominal": 8000.0,
+                         "traffic_source": "profiles/ncu_traffic.json (ncu --set full of this kernel at 2^30 points)"},
             "e2e": {"value": e2e_value, "unit": "Gpoints/s", "h2d_bytes_per_step": 16 * ne, "d2h_bytes_per_step": 8 * ne,
                     "api": "hpgb_host_angle_to_pixel (C ABI, pinned host buffers)", "steps": e2e_steps,
                     "result_checksum": checksum},
@@ -439,9 +521,12 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "parity": parity,
-            "layout": "lon | lat | pix carved back to back from one allocation",
+            "layout": ("three separately allocated tensors" if args.layout == "separate"
+                       else "lon | lat | pix carved back to back from one allocation"),
+            "gather": gather,
             "also": {"nest_to_ring": {"value": n2r_value, "unit": "Gpoints/s", "ms_per_step": ms_n2r,
                                       "roofline_frac": 16 * n / (ms_n2r * 1e-3) / 1e9 / peak,
+                                      "roofline_frac_nominal_8tbs": 16 * n / (ms_n2r * 1e-3) / 1e9 / 8000.0,
                                       "workload": "nest_to_ring nside=2^29 on the 2^%d pixels per GPU" % args.log2_points}},
         }
         for name, rec in also.items():  # whole-job rate -> per-GPU algorithmic GB/s -> fraction of the measured peak

@@ -10,7 +10,9 @@ the FIRST offending element.  All arithmetic happens in libhpgb.so's CUDA kernel
 numpy in  -> hpgb_host_<fn>() (chunked H2D / kernel / D2H pipeline)      -> numpy out
 torch.cuda in -> hpgb_<fn>() on the tensor's device and current stream   -> torch.cuda out
 """
+import contextlib
 import ctypes
+import threading
 
 import numpy as np
 
@@ -74,8 +76,9 @@ class _NumpyBackend:
     def scalar(a):
         return a[()]  # 0-d array -> numpy scalar, like PyArray_Return
 
-    def call(self, fn, ptr_args, tail_args):
-        """fn = C name without the hpgb_ prefix; returns first_bad (-1 if none)."""
+    def call(self, fn, ptr_args, tail_args, on_bad=None):
+        """fn = C name without the hpgb_ prefix; returns first_bad (-1 if none).  The host pipeline is
+        synchronous (the outputs are numpy arrays), so checks are never deferred here."""
         first_bad = ctypes.c_int64(-1)
         f = getattr(_lib.lib(), "hpgb_host_" + fn)
         rc = f(*ptr_args, *tail_args, self.device, ctypes.byref(first_bad))
@@ -136,17 +139,14 @@ class _TorchBackend:
     def scalar(a):
         return a  # 0-d tensors stay 0-d tensors on the device
 
-    def _status_buf(self):
-        st = self._status.get(self.device)
-        if st is None:
-            st = torch.empty(2, dtype=torch.int64, device=self.dev)
-            self._status[self.device] = st
-        return st
-
-    def call(self, fn, ptr_args, tail_args):
+    def call(self, fn, ptr_args, tail_args, on_bad=None):
+        """Launch on the tensors' device and the current torch stream.  The status word is a fresh 16-byte
+        tensor per call (two threads or two streams never share one).  Normally its 8-byte read-back
+        synchronises the stream, like the reference's return does; inside ``deferred_checks()`` nothing is
+        read: the call returns at once and the check happens when the context's object is asked."""
         L = _lib.lib()
         with torch.cuda.device(self.device):
-            st = self._status_buf()
+            st = torch.empty(2, dtype=torch.int64, device=self.dev)
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             stp = ctypes.c_void_p(st.data_ptr())
             rc = L.hpgb_status_reset(stp, stream)
@@ -154,8 +154,63 @@ class _TorchBackend:
                 rc = getattr(L, "hpgb_" + fn)(*ptr_args, *tail_args, stp, stream)
             if rc != 0:
                 return rc, -1
+            pending = getattr(_tls, "pending", None)
+            if pending is not None:
+                pending._add(st, on_bad)
+                return 0, -1
             first = int(st[0].item())  # 8-byte D2H; synchronises the stream like the numpy path does
         return 0, first  # first == -1 <=> HPGB_NO_BAD_ELEMENT (all ones)
+
+
+_tls = threading.local()
+
+
+class PendingChecks:
+    """Element checks of the device-resident calls made inside ``deferred_checks()``.
+
+    The kernels never trap: a bad element gets -1 / 0 and its index goes to the call's status word.  This object
+    keeps those status words; ``raise_if_bad()`` reads them (ONE synchronisation for the whole chain) and raises
+    the reference's ValueError for the first failing call, in call order."""
+
+    def __init__(self):
+        self._items = []
+
+    def _add(self, status, on_bad):
+        self._items.append((status, on_bad))
+
+    def __len__(self):
+        return len(self._items)
+
+    def raise_if_bad(self):
+        items, self._items = self._items, []
+        if not items:
+            return
+        firsts = torch.stack([st[0] for st, _ in items]).cpu().tolist()  # one D2H copy
+        for first, (_, on_bad) in zip(firsts, items):
+            if first >= 0:
+                if on_bad is not None:
+                    on_bad(int(first))
+                raise ValueError("element %d failed the reference's range check" % first)
+
+
+@contextlib.contextmanager
+def deferred_checks():
+    """Run device-resident (torch CUDA) calls without the per-call stream synchronisation.
+
+        with hpg.deferred_checks() as pending:
+            pix = hpg.angle_to_pixel(nside, lon, lat)      # returns at once, kernel queued
+            ring = hpg.nest_to_ring(nside, pix)            # chained on the same stream
+        pending.raise_if_bad()                             # one sync; ValueError as the reference would raise
+
+    The reference releases the GIL around its loops for the same reason (hpgeom/hpgeom.c:287,320): the caller's
+    thread should not wait per call.  numpy inputs are unaffected (their outputs must be complete on return)."""
+    prev = getattr(_tls, "pending", None)
+    pending = PendingChecks()
+    _tls.pending = pending
+    try:
+        yield pending
+    finally:
+        _tls.pending = prev
 
 
 def pick_backend(*objs):
@@ -177,9 +232,24 @@ def default_device():
 
 
 def set_default_device(index):
-    """GPU used for numpy inputs (torch inputs run where they live)."""
+    """GPU used for numpy inputs (torch inputs run where they live): a device ordinal, or "all" = shard every
+    numpy call over the GPUs of the box from this one process (contiguous shards, one host thread and one
+    H2D / kernel / D2H pipeline per GPU; results land in the returned numpy arrays).  ``set_devices([...])``
+    restricts "all" to a subset."""
     global _default_device
-    _default_device = int(index)
+    _default_device = -1 if (isinstance(index, str) and index.lower() == "all") else int(index)
+
+
+def set_devices(devices=None):
+    """The GPUs ``set_default_device("all")`` shards over (None = every visible device)."""
+    devs = [] if devices is None else [int(d) for d in devices]
+    arr = (ctypes.c_int * max(len(devs), 1))(*devs)
+    _lib.check_rc(_lib.lib().hpgb_host_set_devices(arr, len(devs)))
+
+
+def host_device():
+    """`device` argument for hpgb_host_* calls: the default ordinal, or HPGB_DEVICE_ALL (-1)."""
+    return _default_device
 
 
 def _np_view(o):
@@ -234,11 +304,14 @@ def elementwise(fn, nside, ins, in_kinds, out_kinds, tail, *, nest, bcast_msg, e
         ns_full = be.expand(ns, shape)
     full = [be.expand(a, shape) for a in arrs]
     ptrs = [be.ptr(a) for a in full] + [be.ptr(o) for o in outs]
-    rc, first_bad = be.call(fn, ptrs, [n, nside_val, be.ptr(ns_full)] + list(tail))
-    _lib.check_rc(rc, nside_val, nest)
-    if first_bad >= 0:
+    def on_bad(first_bad):
         ns_i = nside_val if ns_full is None else int(be.item(ns_full, first_bad))
         raise ValueError(explain(ns_i, [be.item(a, first_bad) for a in full]))
+
+    rc, first_bad = be.call(fn, ptrs, [n, nside_val, be.ptr(ns_full)] + list(tail), on_bad)
+    _lib.check_rc(rc, nside_val, nest)
+    if first_bad >= 0:
+        on_bad(first_bad)
     if zero_d:
         outs = [be.scalar(o) if c is None else o for o, c in zip(outs, out_cols)]
     return outs

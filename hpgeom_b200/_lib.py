@@ -53,6 +53,14 @@ _SIGS = {
     "hpgb_host_upgrade_pixels": [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, ctypes.POINTER(c_i64)],
     "hpgb_lonlat_to_thetaphi": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp],
     "hpgb_host_lonlat_to_thetaphi": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, ctypes.POINTER(c_i64)],
+    "hpgb_thetaphi_to_lonlat": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp],
+    "hpgb_host_thetaphi_to_lonlat": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, ctypes.POINTER(c_i64)],
+    "hpgb_angle_to_vector": [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp],
+    "hpgb_host_angle_to_vector": [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_i64)],
+    "hpgb_vector_to_angle": [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp],
+    "hpgb_host_vector_to_angle": [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_i64)],
+    "hpgb_reorder_map": [c_vp, c_vp, c_i64, c_int, c_int, c_vp],
+    "hpgb_host_reorder_map": [c_vp, c_vp, c_i64, c_int, c_int, c_int],
     "hpgb_boundaries": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp],
     "hpgb_host_boundaries": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int,
                              ctypes.POINTER(c_i64)],

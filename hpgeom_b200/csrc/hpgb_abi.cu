@@ -69,6 +69,22 @@ int hpgb_max_pixel_radius(const int64_t *d_nside, double *d_radius, int64_t n, i
     return launch_max_pixrad(d_nside, d_radius, n, degrees, 0, d_status, S(stream));
 }
 
+int hpgb_thetaphi_to_lonlat(const double *d_theta, const double *d_phi, double *d_lon, double *d_lat, int64_t n, int degrees,
+                            hpgb_status_t *d_status, void *stream) {
+    return launch_thetaphi_to_lonlat(d_theta, d_phi, d_lon, d_lat, n, degrees, d_status, S(stream));
+}
+int hpgb_angle_to_vector(const double *d_a, const double *d_b, double *d_vec_n3, int64_t n, int lonlat, int degrees,
+                         hpgb_status_t *d_status, void *stream) {
+    return launch_angle_to_vector(d_a, d_b, d_vec_n3, n, lonlat, degrees, 0, d_status, S(stream));
+}
+int hpgb_vector_to_angle(const double *d_vec_n3, double *d_a, double *d_b, int64_t n, int lonlat, int degrees,
+                         hpgb_status_t *d_status, void *stream) {
+    return launch_vector_to_angle(d_vec_n3, d_a, d_b, n, lonlat, degrees, d_status, S(stream));
+}
+int hpgb_reorder_map(const void *d_map_in, void *d_map_out, int64_t npix, int elem_bytes, int ring_to_nest, void *stream) {
+    return launch_reorder_map(d_map_in, d_map_out, npix, elem_bytes, ring_to_nest, S(stream));
+}
+
 // ---- host-pointer entry points: operands in C-argument order, then the optional nside array ----
 #define IN(p, b) {(cc)(p), nullptr, (b)}
 #define OUT(p, b) {nullptr, (char *)(p), (b)}
@@ -136,6 +152,48 @@ int hpgb_host_lonlat_to_thetaphi(const double *lon, const double *lat, double *t
                                  int degrees, int device, int64_t *first_bad) {
     hpgb_pipe_arr arrs[4] = {IN(lon, 8), IN(lat, 8), OUT(theta, 8), OUT(phi, 8)};
     PIPE(arrs, 4, launch_lonlat((const double *)d[0], (const double *)d[1], (double *)d[2], (double *)d[3], cn, degrees, base, st, s));
+}
+int hpgb_host_thetaphi_to_lonlat(const double *theta, const double *phi, double *lon, double *lat, int64_t n, int degrees,
+                                 int device, int64_t *first_bad) {
+    hpgb_pipe_arr arrs[4] = {IN(theta, 8), IN(phi, 8), OUT(lon, 8), OUT(lat, 8)};
+    PIPE(arrs, 4, launch_thetaphi_to_lonlat((const double *)d[0], (const double *)d[1], (double *)d[2], (double *)d[3], cn, degrees, st, s));
+}
+int hpgb_host_angle_to_vector(const double *a, const double *b, double *vec_n3, int64_t n, int lonlat, int degrees, int device,
+                              int64_t *first_bad) {
+    hpgb_pipe_arr arrs[3] = {IN(a, 8), IN(b, 8), OUT(vec_n3, 24)};
+    PIPE(arrs, 3, launch_angle_to_vector((const double *)d[0], (const double *)d[1], (double *)d[2], cn, lonlat, degrees, base, st, s));
+}
+int hpgb_host_vector_to_angle(const double *vec_n3, double *a, double *b, int64_t n, int lonlat, int degrees, int device,
+                              int64_t *first_bad) {
+    hpgb_pipe_arr arrs[3] = {IN(vec_n3, 24), OUT(a, 8), OUT(b, 8)};
+    PIPE(arrs, 3, launch_vector_to_angle((const double *)d[0], (double *)d[1], (double *)d[2], cn, lonlat, degrees, st, s));
+}
+// the whole map goes to ONE device (a permutation does not shard), is permuted there and comes back
+int hpgb_host_reorder_map(const void *map_in, void *map_out, int64_t npix, int elem_bytes, int ring_to_nest, int device) {
+    if (npix <= 0 || !map_in || !map_out || elem_bytes <= 0) return HPGB_E_BAD_ARGUMENT;
+    device = hpgb_host_first_device(device);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return HPGB_E_CUDA + (int)e;
+    const size_t bytes = (size_t)npix * (size_t)elem_bytes;
+    char *d = nullptr;
+    int rc = HPGB_OK;
+    e = hpgb_dev_alloc((void **)&d, 2 * bytes + 256);
+    if (e != cudaSuccess) {
+        cudaSetDevice(prev);
+        return HPGB_E_CUDA + (int)e;
+    }
+    char *d_out = d + ((bytes + 255) & ~(size_t)255);
+    e = cudaMemcpyAsync(d, map_in, bytes, cudaMemcpyHostToDevice, (cudaStream_t)0);
+    if (e == cudaSuccess) rc = launch_reorder_map(d, d_out, npix, elem_bytes, ring_to_nest, (cudaStream_t)0);
+    if (e == cudaSuccess && rc == HPGB_OK) e = cudaMemcpyAsync(map_out, d_out, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)0);
+    cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)0);
+    hpgb_dev_free(d);
+    cudaSetDevice(prev);
+    if (rc != HPGB_OK) return rc;
+    if (e != cudaSuccess) return HPGB_E_CUDA + (int)e;
+    return e2 == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e2;
 }
 int hpgb_host_boundaries(const int64_t *pix, double *a_n4s, double *b_n4s, int64_t n, int64_t nside, const int64_t *nside_v,
                          int64_t step, int nest, int lonlat, int degrees, int device, int64_t *first_bad) {

@@ -29,6 +29,13 @@ int launch_upgrade(const int64_t *pix, int64_t *out, int64_t n, int64_t nside, i
                    int64_t base, hpgb_status_t *st, cudaStream_t s);
 int launch_lonlat(const double *lon, const double *lat, double *theta, double *phi, int64_t n, int degrees,
                   int64_t base, hpgb_status_t *st, cudaStream_t s);
+int launch_thetaphi_to_lonlat(const double *theta, const double *phi, double *lon, double *lat, int64_t n, int degrees,
+                              hpgb_status_t *st, cudaStream_t s);
+int launch_angle_to_vector(const double *a, const double *b, double *vec3, int64_t n, int lonlat, int degrees, int64_t base,
+                           hpgb_status_t *st, cudaStream_t s);
+int launch_vector_to_angle(const double *vec3, double *a, double *b, int64_t n, int lonlat, int degrees, hpgb_status_t *st,
+                           cudaStream_t s);
+int launch_reorder_map(const void *in, void *out, int64_t npix, int elem_bytes, int ring_to_nest, cudaStream_t s);
 int launch_boundaries(const int64_t *pix, double *a, double *b, int64_t n, int64_t nside, const int64_t *nside_v,
                       int64_t step, int nest, int lonlat, int degrees, int64_t base, hpgb_status_t *st, cudaStream_t s);
 int launch_max_pixrad(const int64_t *nside, double *out, int64_t n, int degrees, int64_t base, hpgb_status_t *st,

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _dispatch as _d
 from . import _lib
-from ._dispatch import F8, I8, set_default_device  # noqa: F401
+from ._dispatch import F8, I8, deferred_checks, set_default_device, set_devices  # noqa: F401
 
 __all__ = [
     'thetaphi_to_lonlat',
@@ -44,10 +44,16 @@ __all__ = [
     'query_circle',
     'query_circle_vec',
     'query_circle_batch',
+    'query_polygon',
+    'query_polygon_vec',
+    'query_ellipse',
+    'query_box',
     'upgrade_pixels',
     'upgrade_pixel_ranges',
     'nside_to_npixel',
     'set_default_device',
+    'set_devices',
+    'deferred_checks',
     'UNSEEN',
 ]
 
@@ -167,10 +173,13 @@ def max_pixel_radius(nside, degrees=True, n_threads=1):
     if n == 0:
         return out
     nsc = be.expand(ns, shape)
-    rc, bad = be.call("max_pixel_radius", [be.ptr(nsc), be.ptr(out)], [n, int(bool(degrees))])
+    def on_bad(bad):
+        raise ValueError(_lib.explain_nside(int(be.item(nsc, bad)), False))
+
+    rc, bad = be.call("max_pixel_radius", [be.ptr(nsc), be.ptr(out)], [n, int(bool(degrees))], on_bad)
     _lib.check_rc(rc)
     if bad >= 0:
-        raise ValueError(_lib.explain_nside(int(be.item(nsc, bad)), False))
+        on_bad(bad)
     return be.scalar(out) if len(shape) == 0 else out
 
 
@@ -210,10 +219,13 @@ def lonlat_to_thetaphi(lon, lat, degrees=True):
         if n == 0:
             return theta, phi
         lo, la = be.expand(lo, be.shape(lo)), be.expand(la, be.shape(la))
-        rc, bad = be.call("lonlat_to_thetaphi", [be.ptr(lo), be.ptr(la), be.ptr(theta), be.ptr(phi)], [n, deg])
+        def on_bad(bad):
+            raise ValueError("Latitude out of range.")
+
+        rc, bad = be.call("lonlat_to_thetaphi", [be.ptr(lo), be.ptr(la), be.ptr(theta), be.ptr(phi)], [n, deg], on_bad)
         _lib.check_rc(rc)
         if bad >= 0:
-            raise ValueError("Latitude out of range.")
+            on_bad(bad)
         return theta, phi
 
     if be.shape(lon_a) == be.shape(lat_a):
@@ -231,17 +243,34 @@ def lonlat_to_thetaphi(lon, lat, degrees=True):
 def thetaphi_to_lonlat(theta, phi, degrees=True):
     """Convert theta/phi (radians) to longitude/latitude (reference: hpgeom/hpgeom.py:91-112).
 
-    One subtraction and one multiplication per element (numpy's ``rad2deg`` = ``x * (180/pi)``);
-    evaluated with numpy for numpy inputs and with torch on the device for CUDA tensors."""
-    if _d._is_torch(theta) or _d._is_torch(phi):
-        torch = _d.torch
-        theta, phi = torch.as_tensor(theta), torch.as_tensor(phi)
-        lon, lat = phi, -(theta - np.pi / 2.)
-        return (torch.rad2deg(lon), torch.rad2deg(lat)) if degrees else (lon, lat)
-    lon = phi
-    lat = -(theta - np.pi / 2.)
-    if degrees:
-        lon, lat = np.rad2deg(lon), np.rad2deg(lat)
+    ``lat = -(theta - pi/2)``, ``rad2deg(x) = x * (180/pi)``: pure IEEE, so the kernel
+    (``hpgb_thetaphi_to_lonlat``) is bit-identical to numpy.  Like the reference, theta and phi are not
+    broadcast against each other: lon has phi's shape, lat has theta's."""
+    be = _d.pick_backend(theta, phi)
+    if be.name == "numpy":
+        theta, phi = _d._np_view(theta), _d._np_view(phi)
+    th, ph = be.coerce(theta, F8), be.coerce(phi, F8)
+    deg = int(bool(degrees))
+
+    def run(t, p_):
+        n = int(np.prod(be.shape(t), dtype=np.int64))
+        lon, lat = be.empty(be.shape(t), F8), be.empty(be.shape(t), F8)
+        if n == 0:
+            return lon, lat
+        t, p_ = be.expand(t, be.shape(t)), be.expand(p_, be.shape(p_))
+        rc, _ = be.call("thetaphi_to_lonlat", [be.ptr(t), be.ptr(p_), be.ptr(lon), be.ptr(lat)], [n, deg])
+        _lib.check_rc(rc)
+        return lon, lat
+
+    if be.shape(th) == be.shape(ph):
+        lon, lat = run(th, ph)
+    else:
+        _, lat = run(th, th * 0.0)
+        lon, _ = run(ph * 0.0, ph)
+    if len(be.shape(lon)) == 0:
+        lon = be.scalar(lon)
+    if len(be.shape(lat)) == 0:
+        lat = be.scalar(lat)
     return lon, lat
 
 
@@ -292,66 +321,91 @@ def order_to_nside(order):
     return 2**order
 
 
-def _check_theta_phi(theta, phi):
-    # reference: hpgeom/hpgeom.py:342-361
-    _theta, _phi = np.atleast_1d(_d._np_view(theta)), np.atleast_1d(_d._np_view(phi))
-    if np.any((_theta < 0.0) | (_theta > np.pi)):
-        raise ValueError("Co-latitude (theta) out of range.")
-    if np.any((_phi < 0.0) | (_phi > 2 * np.pi)):
-        raise ValueError("Longitude (phi) out of range.")
+_A2V_CLASS_PHI = 1 << 62
 
 
 def angle_to_vector(a, b, lonlat=True, degrees=True):
-    """Angles to unit vectors, (N, 3) or (3,) (reference: hpgeom/hpgeom.py:364-393; a numpy helper
-    there too: sin/cos come from the host libm, or from torch for CUDA tensors)."""
-    if lonlat:
-        theta, phi = lonlat_to_thetaphi(a, b, degrees=degrees)
-    else:
-        _check_theta_phi(a, b)
-        theta, phi = a, b
-    if _d._is_torch(theta) or _d._is_torch(phi):
-        torch = _d.torch
-        theta, phi = torch.as_tensor(theta), torch.as_tensor(phi)
-        st = torch.sin(theta)
-        return torch.stack([st * torch.cos(phi), st * torch.sin(phi), torch.cos(theta)]).transpose(0, -1)
-    st = np.sin(theta)
-    return np.array([st * np.cos(phi), st * np.sin(phi), np.cos(theta)]).transpose()
+    """Angles to unit vectors, (N, 3) or (3,) (reference: hpgeom/hpgeom.py:364-393).
+
+    One kernel (``hpgb_angle_to_vector``): numpy's ``lonlat_to_thetaphi`` formulas, then
+    ``(sin t cos p, sin t sin p, cos t)`` with sin / cos correctly rounded in practice (what numpy = glibc
+    returns for ~99.9 % of arguments); the ValueErrors are the reference's (hpgeom/hpgeom.py:86, :342-361)."""
+    be = _d.pick_backend(a, b)
+    if be.name == "numpy":
+        a, b = _d._np_view(a), _d._np_view(b)
+    aa, bb = be.coerce(a, F8), be.coerce(b, F8)
+    shape = np.broadcast_shapes(be.shape(aa), be.shape(bb))  # numpy broadcasting of sin(theta) * cos(phi)
+    n = int(np.prod(shape, dtype=np.int64))
+    vec = be.empty((n, 3), F8)
+    if n:
+        fa, fb = be.expand(aa, shape), be.expand(bb, shape)
+        def on_bad(bad):
+            if lonlat:
+                raise ValueError("Latitude out of range.")
+            raise ValueError("Longitude (phi) out of range." if bad & _A2V_CLASS_PHI else "Co-latitude (theta) out of range.")
+
+        rc, bad = be.call("angle_to_vector", [be.ptr(fa), be.ptr(fb), be.ptr(vec)], [n, int(bool(lonlat)), int(bool(degrees))], on_bad)
+        _lib.check_rc(rc)
+        if bad >= 0:
+            on_bad(bad)
+    # np.array([x, y, z]).transpose(): the component axis goes last, the data axes are REVERSED
+    out = vec.reshape(tuple(shape) + (3,))
+    if len(shape) > 1:
+        perm = tuple(range(len(shape) - 1, -1, -1)) + (len(shape),)
+        out = out.permute(perm) if _d._is_torch(out) else out.transpose(perm)
+    return out
 
 
 def vector_to_angle(vec, lonlat=True, degrees=True):
-    """(N, 3) or (3,) vectors to angles (reference: hpgeom/hpgeom.py:396-422)."""
-    if _d._is_torch(vec):
-        torch = _d.torch
-        v = vec.reshape(-1, 3)
-        theta = torch.acos(v[:, 2] / torch.sqrt(torch.sum(torch.square(v), dim=1)))
-        phi = torch.remainder(torch.atan2(v[:, 1], v[:, 0]), 2. * np.pi)
-    else:
-        v = np.atleast_1d(vec).reshape(-1, 3)
-        theta = np.arccos(v[:, 2] / np.sqrt(np.sum(np.square(v), axis=1)))
-        phi = np.arctan2(v[:, 1], v[:, 0]) % (2. * np.pi)
-    return thetaphi_to_lonlat(theta, phi, degrees=degrees) if lonlat else (theta, phi)
+    """(N, 3) or (3,) vectors to angles (reference: hpgeom/hpgeom.py:396-422); always returns 1-D arrays.
+
+    One kernel (``hpgb_vector_to_angle``): ``theta = acos(z / |v|)``, ``phi = atan2(y, x) mod 2 pi`` with
+    correctly rounded acos / atan2 (numpy's are SVML routines on AVX-512 hosts, within 1 ulp of these)."""
+    be = _d.pick_backend(vec)
+    if be.name == "numpy":
+        vec = np.atleast_1d(_d._np_view(vec))
+    v = be.coerce(vec, F8).reshape(-1, 3)
+    n = int(be.shape(v)[0])
+    a, b = be.empty((n,), F8), be.empty((n,), F8)
+    if n:
+        v = be.expand(v, be.shape(v))
+        rc, _ = be.call("vector_to_angle", [be.ptr(v), be.ptr(a), be.ptr(b)], [n, int(bool(lonlat)), int(bool(degrees))])
+        _lib.check_rc(rc)
+    return a, b
+
+
+_REORDER_SIZES = (1, 2, 4, 8, 16)
 
 
 def reorder(map_in, ring_to_nest=True):
     """Reorder a full-sky map between RING and NEST (reference: hpgeom/hpgeom.py:425-462).
 
-    The permutation comes from the nest_to_ring / ring_to_nest kernels over ALL pixels at once (the
-    reference walks 24 groups to bound its temporaries); the scatter is numpy's / torch's, on the
-    device for CUDA tensors."""
-    npix = map_in.numel() if _d._is_torch(map_in) else map_in.size
+    ONE kernel (``hpgb_reorder_map``): a CTA moves a 64 x 64 block of a base face through shared memory -- one
+    contiguous run on the NEST side, one run per ring on the RING side -- so the map is read once and written
+    once (the reference converts 24 groups of pixel numbers and scatters with fancy indexing)."""
+    is_t = _d._is_torch(map_in)
+    npix = map_in.numel() if is_t else map_in.size
     nside = npixel_to_nside(npix)
     nside_to_order(nside)  # ValueError unless nside is a legal NEST resolution
-    if _d._is_torch(map_in):
+    L = _lib.lib()
+    if is_t and map_in.device.type == "cuda":
         torch = _d.torch
-        pixels = torch.arange(npix, dtype=torch.int64, device=map_in.device)
-        target = globals()['ring_to_nest'](nside, pixels) if ring_to_nest else nest_to_ring(nside, pixels)
-        out = torch.zeros_like(map_in)
-        out[target] = map_in
+        src = map_in.contiguous()
+        if src.element_size() not in _REORDER_SIZES:
+            raise TypeError("reorder: unsupported element size %d" % src.element_size())
+        out = torch.empty_like(src)
+        with torch.cuda.device(src.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)
+            rc = L.hpgb_reorder_map(src.data_ptr(), out.data_ptr(), npix, src.element_size(), int(bool(ring_to_nest)), stream)
+        _lib.check_rc(rc)
         return out
-    pixels = np.arange(npix, dtype=np.int64)
-    target = globals()['ring_to_nest'](nside, pixels) if ring_to_nest else nest_to_ring(nside, pixels)
-    out = np.zeros_like(map_in)
-    out[target] = map_in
+    src = np.ascontiguousarray(_d._np_view(map_in))
+    if src.dtype.itemsize not in _REORDER_SIZES or src.dtype.hasobject:
+        raise TypeError("reorder: unsupported dtype %s" % src.dtype)
+    out = np.empty_like(src)
+    rc = L.hpgb_host_reorder_map(src.ctypes.data, out.ctypes.data, npix, src.dtype.itemsize, int(bool(ring_to_nest)),
+                                 _d.host_device())
+    _lib.check_rc(rc)
     return out
 
 
@@ -399,10 +453,13 @@ def pixel_ranges_to_pixels(pixel_ranges, inclusive=False):
         if r.data_ptr() % 16:
             r = r.clone()
         offs = torch.empty(m + 1, dtype=torch.int64, device=be.dev)
-        rc, first_bad = be.call("ranges_offsets", [be.ptr(r)], [m, inclusive, be.ptr(offs)])
+        def on_bad(bad):
+            raise ValueError(bad_msg)
+
+        rc, first_bad = be.call("ranges_offsets", [be.ptr(r)], [m, inclusive, be.ptr(offs)], on_bad)
         _lib.check_rc(rc)
         if first_bad >= 0:
-            raise ValueError(bad_msg)
+            on_bad(first_bad)
         total = int(offs[m].item())
         out = torch.empty(total, dtype=torch.int64, device=be.dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(be.device).cuda_stream)
@@ -657,22 +714,46 @@ def upgrade_pixels(nside, pixels, nside_upgrade, nest=True):
     if len(be.shape(pix)) != 1:
         raise ValueError("Input pixel_ranges must be of shape (N, 2).")
     n = int(be.shape(pix)[0])
-    ratio = (int(nside_upgrade) // int(nside)) ** 2
-    out = be.empty((n * ratio,), I8)
     if n == 0:
-        if not nest:
-            ring_to_nest(nside, pix)
-        # np.min of an empty array raises in the reference
+        # ring_to_nest of nothing checks nothing; np.min of an empty array raises in the reference
         raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    ns = int(nside)
+    if not nest and (ns <= 0 or ns > max_nside):
+        raise ValueError(_lib.explain_nside(ns, True))  # the reference's ring_to_nest call comes first
+    nside_to_npixel(ns)  # "Illegal nside value ..." for nside < 0 or > 2**29 (hpgeom/hpgeom.py:505 -> :190-206)
+    if ns == 0:
+        raise ValueError("Input pixels/ranges out of range.")  # npix = 0: every pixel is out of range
+    ratio = (int(nside_upgrade) // ns) ** 2
+    out = be.empty((n * ratio,), I8)
     pix = be.expand(pix, be.shape(pix))
-    rc, bad = be.call("upgrade_pixels", [be.ptr(pix), be.ptr(out)], [n, int(nside), int(nside_upgrade), int(nest)])
-    if rc in (1, 2, 3):
-        raise ValueError(_lib.explain_nside(int(nside), True))
-    _lib.check_rc(rc)
-    if bad >= 0:
+    def on_bad(bad):
         # key = (class << 62) | index; class 0 = pixel out of range, class 1 = the last nest pixel
         cls, idx = bad >> 62, bad & ((1 << 62) - 1)
         if not nest and cls == 0:
             raise ValueError(_lib.explain_pixel(int(nside), True, int(be.item(pix, idx))))
         raise ValueError("Input pixels/ranges out of range.")
+
+    rc, bad = be.call("upgrade_pixels", [be.ptr(pix), be.ptr(out)], [n, int(nside), int(nside_upgrade), int(nest)], on_bad)
+    if rc in (1, 2, 3):
+        raise ValueError(_lib.explain_nside(int(nside), True))
+    _lib.check_rc(rc)
+    if bad >= 0:
+        on_bad(bad)
     return out
+
+
+def _out_of_scope(name):
+    def stub(*args, **kwargs):
+        raise NotImplementedError(
+            "hpgeom_b200.%s: the polygon / ellipse / box region queries are outside the accelerated path "
+            "(SURVEY.md section 2 row 6; README 'Scope').  query_circle, query_circle_vec and query_circle_batch "
+            "are available; use the reference package for this call." % name)
+    stub.__name__ = name
+    stub.__doc__ = "Not implemented (out of scope); raises NotImplementedError.  Reference: hpgeom/hpgeom.c:866-1383."
+    return stub
+
+
+query_polygon = _out_of_scope("query_polygon")
+query_polygon_vec = _out_of_scope("query_polygon_vec")
+query_ellipse = _out_of_scope("query_ellipse")
+query_box = _out_of_scope("query_box")

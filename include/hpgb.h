@@ -154,6 +154,35 @@ int hpgb_lonlat_to_thetaphi(const double *d_lon, const double *d_lat, double *d_
 int hpgb_host_lonlat_to_thetaphi(const double *lon, const double *lat, double *theta, double *phi,
                                  int64_t n, int degrees, int device, int64_t *first_bad);
 
+/* ---- thetaphi_to_lonlat: hpgeom/hpgeom.py:91-112 (lat = -(theta - pi/2), numpy rad2deg = x * (180/pi)); no
+ * validation; bit-exact ------------------------------------------------------------------------------------- */
+int hpgb_thetaphi_to_lonlat(const double *d_theta, const double *d_phi, double *d_lon, double *d_lat,
+                            int64_t n, int degrees, hpgb_status_t *d_status, void *stream);
+int hpgb_host_thetaphi_to_lonlat(const double *theta, const double *phi, double *lon, double *lat,
+                                 int64_t n, int degrees, int device, int64_t *first_bad);
+
+/* ---- angle_to_vector: hpgeom/hpgeom.py:364-393; vec is (n,3) row-major.  Element errors: first_bad = index of
+ * the first bad latitude / colatitude; a bad longitude (theta/phi form only, checked after ALL colatitudes like the
+ * reference's np.any) is reported as (1 << 62) | index --------------------------------------------------------- */
+int hpgb_angle_to_vector(const double *d_a, const double *d_b, double *d_vec_n3, int64_t n, int lonlat,
+                         int degrees, hpgb_status_t *d_status, void *stream);
+int hpgb_host_angle_to_vector(const double *a, const double *b, double *vec_n3, int64_t n, int lonlat,
+                              int degrees, int device, int64_t *first_bad);
+
+/* ---- vector_to_angle: hpgeom/hpgeom.py:396-422; vec is (n,3) row-major, need not be normalised; no validation */
+int hpgb_vector_to_angle(const double *d_vec_n3, double *d_a, double *d_b, int64_t n, int lonlat, int degrees,
+                         hpgb_status_t *d_status, void *stream);
+int hpgb_host_vector_to_angle(const double *vec_n3, double *a, double *b, int64_t n, int lonlat, int degrees,
+                              int device, int64_t *first_bad);
+
+/* ---- reorder: hpgeom/hpgeom.py:425-462, the full-map RING <-> NEST permutation as ONE kernel
+ * (map_out[ring_to_nest(i)] = map_in[i], or the converse).  npix = 12 nside^2 elements of elem_bytes = 1, 2, 4, 8
+ * or 16 bytes each, nside a power of two; map_in != map_out.  Returns HPGB_E_BAD_ARGUMENT for an illegal npix. */
+int hpgb_reorder_map(const void *d_map_in, void *d_map_out, int64_t npix, int elem_bytes, int ring_to_nest,
+                     void *stream);
+int hpgb_host_reorder_map(const void *map_in, void *map_out, int64_t npix, int elem_bytes, int ring_to_nest,
+                          int device);
+
 /* ---- boundaries: hpgeom/hpgeom.c:1956-2278 (core hpgeom/healpix_geom.c:807-888); outputs are
  * (n, 4*step) row-major: `step` points along each of the four edges, starting at the north corner
  * and going N->W, W->S, S->E, E->N ---- */

@@ -97,12 +97,84 @@ def test_reorder_and_helpers_through_the_kernels(hpg, g):
         assert_bit_equal(hpg.reorder(m, ring_to_nest=False), g["reorder_n2r_%d" % nside])
         t = hpg.reorder(torch.from_numpy(m).cuda(), ring_to_nest=True)
         assert t.is_cuda and np.array_equal(t.cpu().numpy(), g["reorder_r2n_%d" % nside])
-    assert_bit_equal(hpg.angle_to_vector(g["h_lon"], g["h_lat"]), g["h_a2v_ll"])
-    assert_bit_equal(hpg.angle_to_vector(10.0, 20.0), g["h_a2v_scalar"])
-    # a full-size map on the device: reorder there and back
+    # a full-size map on the device: reorder there and back, and against the permutation kernels
     nside = 2048
     m = torch.arange(12 * nside * nside, dtype=torch.float64, device="cuda")
-    assert torch.equal(hpg.reorder(hpg.reorder(m, ring_to_nest=True), ring_to_nest=False), m)
+    r2n = hpg.reorder(m, ring_to_nest=True)
+    assert torch.equal(hpg.reorder(r2n, ring_to_nest=False), m)
+    pixels = torch.arange(12 * nside * nside, dtype=torch.int64, device="cuda")
+    want = torch.empty_like(m)
+    want[hpg.ring_to_nest(nside, pixels)] = m
+    assert torch.equal(r2n, want)
+    # every supported element size, small and block-sized faces (nside 64 = one 64 x 64 block per face)
+    rng = np.random.default_rng(3)
+    for ns in (1, 2, 16, 64, 128):
+        npix = 12 * ns * ns
+        pix = np.arange(npix)
+        for dt in (np.uint8, np.int16, np.float32, np.float64, np.complex128):
+            mm = rng.integers(0, 200, npix).astype(dt)
+            for r2n_flag in (True, False):
+                ref = np.zeros_like(mm)
+                ref[(hpg.ring_to_nest if r2n_flag else hpg.nest_to_ring)(ns, pix)] = mm
+                assert np.array_equal(hpg.reorder(mm, ring_to_nest=r2n_flag), ref), (ns, dt, r2n_flag)
+    assert hpg.reorder(np.arange(12 * 4 * 4).reshape(12, 16), ring_to_nest=True).shape == (12, 16)
+
+
+def test_angle_vector_helpers_golden(hpg, hpc, g):
+    """thetaphi_to_lonlat / angle_to_vector / vector_to_angle kernels against the reference's numpy results
+    (golden_next.npz): pure-IEEE outputs bit for bit; sin / cos products bit-identical wherever glibc rounds
+    correctly (> 99 %), never more than 1 ulp apart; acos / atan2 within 2 ulp of numpy's SVML routines.
+    numpy inputs and CUDA tensors give the same bits."""
+    import torch
+    for key, kw in (("deg", {}), ("rad", {"degrees": False})):
+        a, b = hpg.thetaphi_to_lonlat(g["h_theta"], g["h_phi"], **kw)
+        assert_bit_equal(a, g["h_tp2ll_%s_a" % key])
+        assert_bit_equal(b, g["h_tp2ll_%s_b" % key])
+        ta, tb = hpg.thetaphi_to_lonlat(torch.from_numpy(g["h_theta"]).cuda(), torch.from_numpy(g["h_phi"]).cuda(), **kw)
+        assert ta.is_cuda and np.array_equal(ta.cpu().numpy(), a) and np.array_equal(tb.cpu().numpy(), b)
+
+    def near(got, ref, max_ulp, frac):
+        assert got.shape == ref.shape
+        big = np.abs(ref) > 1e-300
+        assert ulp_diff(got[big], ref[big]).max() <= max_ulp
+        assert np.abs(got[~big]).max(initial=0.0) < 1e-15
+        assert got.size < 200 or np.mean(got != ref) <= frac
+
+    near(hpg.angle_to_vector(g["h_lon"], g["h_lat"]), g["h_a2v_ll"], 1.0, 0.01)
+    near(hpg.angle_to_vector(g["h_theta"], g["h_phi"], lonlat=False), g["h_a2v_tp"], 1.0, 0.01)
+    near(np.asarray(hpg.angle_to_vector(10.0, 20.0)), g["h_a2v_scalar"], 1.0, 1.0)
+    assert hpg.angle_to_vector(10.0, 20.0).shape == (3,)
+    near(hpc.ang2vec(g["h_theta"], g["h_phi"]), g["hp_ang2vec"], 1.0, 0.01)
+    tv = hpg.angle_to_vector(torch.from_numpy(g["h_lon"]).cuda(), torch.from_numpy(g["h_lat"]).cuda())
+    assert tv.is_cuda and np.array_equal(tv.cpu().numpy(), hpg.angle_to_vector(g["h_lon"], g["h_lat"]))
+    for kw, ka, kb in (({}, "h_v2a_ll_a", "h_v2a_ll_b"), ({"lonlat": False}, "h_v2a_tp_a", "h_v2a_tp_b")):
+        a, b = hpg.vector_to_angle(g["h_vec"], **kw)
+        if kw:
+            near(a, g[ka], 2.0, 0.25)   # theta = acos
+            near(b, g[kb], 2.0, 0.25)   # phi = atan2 mod 2 pi
+        else:
+            near(a, g[ka], 2.0, 0.25)   # lon
+            assert np.abs(b - g[kb]).max() <= 2 * np.spacing(np.pi) * 180 / np.pi  # lat = 90 - theta: ulps of theta
+        ta, tb = hpg.vector_to_angle(torch.from_numpy(g["h_vec"]).cuda(), **kw)
+        assert np.array_equal(ta.cpu().numpy(), a) and np.array_equal(tb.cpu().numpy(), b)
+    a, b = hpc.vec2ang(g["h_vec"])
+    near(a, g["hp_vec2ang_a"], 2.0, 0.25)
+    near(b, g["hp_vec2ang_b"], 2.0, 0.25)
+    # exact cases: the poles and the axes
+    ax = np.array([[0, 0, 1.0], [0, 0, -2.0], [1, 0, 0], [0, 3, 0], [-1, 0, 0], [0, -1, 0]])
+    th, ph = hpg.vector_to_angle(ax, lonlat=False)
+    assert np.array_equal(th, [0.0, np.pi, np.pi / 2, np.pi / 2, np.pi / 2, np.pi / 2])
+    assert np.array_equal(ph, [0.0, 0.0, 0.0, np.pi / 2, np.pi, 1.5 * np.pi])
+    with open(os.path.join(GOLDEN_DIR, "golden_next_errors.json")) as f:
+        errs = json.load(f)
+    for name, fn in (("a2v_theta", lambda: hpg.angle_to_vector(4.0, 1.0, lonlat=False)),
+                     ("a2v_phi", lambda: hpg.angle_to_vector(1.0, 7.0, lonlat=False)),
+                     ("a2v_theta", lambda: hpg.angle_to_vector(np.array([1.0, 1.0, 4.0]), np.array([7.0, 1.0, 1.0]), lonlat=False))):
+        with pytest.raises(ValueError) as e:
+            fn()
+        assert str(e.value) == errs[name][1], name
+    with pytest.raises(ValueError, match="Latitude out of range"):
+        hpg.angle_to_vector(10.0, 91.0)
 
 
 @pytest.mark.parametrize("nest", [True, False])

@@ -248,8 +248,15 @@ def test_pixel_to_angle_branch_free_path(sim, nside):
             a1, b1 = sim.pixel_to_angle_k(nside, pix, nest=nest, **kw)
             assert_bit_equal(a1, a0, "a")
             assert_bit_equal(b1, b0, "b")
-        for got, ref in zip(sim.pixel_to_vector_k(nside, pix, nest=nest), sim.pixel_to_vector(nside, pix, nest=nest)):
-            assert_bit_equal(got, ref, "pixel_to_vector")
+        # the kernel's cos / sin(phi) are plain doubles good to 0.51 ulp (hpgb_sincos_sd), the reference-shaped
+        # routine's are the double-double ones: z identical, x / y identical except where the cheaper routine
+        # mis-rounds (~1e-5 of the pixels), and then by one ulp
+        kx, ky, kz = sim.pixel_to_vector_k(nside, pix, nest=nest)
+        rx, ry, rz = sim.pixel_to_vector(nside, pix, nest=nest)
+        assert_bit_equal(kz, rz, "pixel_to_vector z")
+        for got, ref in ((kx, rx), (ky, ry)):
+            d = np.abs(got - ref) / np.spacing(np.maximum(np.abs(ref), 1e-300))
+            assert d.max() <= 1.0 and np.mean(got != ref) < 1e-3
 
 
 @pytest.mark.parametrize("nside,nest", CASES)

@@ -39,7 +39,7 @@ def _worker(rank, world, port, n, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 1001), (3, 10), (2, 1)])
+@pytest.mark.parametrize("world,n", [(2, 1001), (3, 10), (2, 1), (2, 1000), (3, 0)])
 def test_gather_over_gloo(world, n):
     import torch.multiprocessing as mp
     s = socket.socket()
