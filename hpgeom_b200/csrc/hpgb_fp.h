@@ -1187,6 +1187,104 @@ HPGB_HD bool hpgb_ring_above_fast(const hpgb_geom &g, const hpgb_a2p_fast &f, do
     return ok;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Interpolation, zone by zone (the sorted kernel of k_interp.cu).  hpgb_interpol_rings serves any ring pair
+// with per-ring branches: a warp whose 32 points straddle the caps and the belt runs the acos AND the atan2
+// colatitude, and both ring-length formulas, for every point.  The kernel therefore sorts the points of a warp
+// by the zone of their ring pair and calls one of the two straight-line bodies below on 32 points of ONE zone.
+// Same arithmetic, operation for operation, as hpgb_ring_pair / hpgb_ring_info2 with the hpgb_mp_tab
+// providers (hpgeom/healpix_geom.c:1585-1690); only what a zone makes constant is hoisted:
+//   belt pair (nside <= ir1, ir1 + 1 <= 3 nside): both rings have 4 nside pixels, so dphi = 2 pi / (4 nside) is
+//     a per-nside constant (computed on the host with the same IEEE division) and phi / dphi is shared;
+//   cap pair (both rings strictly inside one polar cap): ring colatitude from atan2, ring length 4 * ring.
+// Everything else (the two pole rows, a pair that straddles a cap edge, a point too close to a ring for the
+// cheap ring choice) is rare and goes to hpgb_interpol / hpgb_interpol_rings.
+// ---------------------------------------------------------------------------------------------
+// zone of the pair (ir1, ir1 + 1): 0 belt, 1 cap, 2 anything else
+HPGB_HD int hpgb_interp_zone(uint32_t ns, int64_t ir1) {
+    const uint32_t r = (uint32_t)ir1;
+    if (ir1 >= (int64_t)ns && ir1 + 1 <= 3 * (int64_t)ns) return 0;
+    if ((ir1 >= 1 && ir1 + 1 <= (int64_t)ns - 1) || (ir1 >= 3 * (int64_t)ns + 1 && ir1 + 1 <= 4 * (int64_t)ns - 1)) return 1;
+    (void)r;
+    return 2;
+}
+
+// floor of a value >= -1 as the reference forms it: (t < 0) ? (int64)t - 1 : (int64)t  (hpgeom/healpix_geom.c:1622)
+// (a ring of nside 2^29 has 2^31 pixels: the index needs 64 bits, like the reference's)
+HPGB_HD int64_t hpgb_interp_floor(double t) { return (t < 0) ? hpgb_d2ll(t) - 1 : hpgb_d2ll(t); }
+
+template <bool NEST>
+HPGB_HD void hpgb_interp_belt(const hpgb_geom &g, const hpgb_rk &rk, const uint64_t *TA, double dphi, double theta, double phi,
+                              uint32_t ir1, int64_t *p, double *w) {
+    const uint32_t ns = (uint32_t)g.nside, nr = 4u * ns;
+    const double tc = hpgb_div_tame(phi, dphi);  // shared by the two rings
+    double th[2], w1[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t r = ir1 + (uint32_t)k;
+        const bool south = r > 2u * ns;
+        const uint32_t nring = south ? 4u * ns - r : r;
+        const double t0 = hpgb_acos_tab(TA, (double)(2u * ns - nring) * g.fact1);
+        th[k] = south ? HPGB_PI - t0 : t0;
+        const double hs = ((nring - ns) & 1u) == 0u ? 0.5 : 0.0;
+        int64_t i1 = hpgb_interp_floor(tc - hs);
+        w1[k] = hpgb_div_tame(phi - ((double)i1 + hs) * dphi, dphi);
+        int64_t i2 = i1 + 1;
+        if (i1 < 0) i1 += (int64_t)nr;
+        if (i2 >= (int64_t)nr) i2 -= (int64_t)nr;
+        if (NEST) {
+            hpgb_ringidx2nest_pair_k(rk, r, (uint32_t)i1, (uint32_t)i2, p[2 * k], p[2 * k + 1]);
+        } else {
+            int64_t sp = g.ncap + (int64_t)((uint64_t)(nring - ns) * (uint64_t)nr);
+            if (south) sp = g.npix - sp - (int64_t)nr;
+            p[2 * k] = sp + i1;
+            p[2 * k + 1] = sp + i2;
+        }
+    }
+    const double wt = hpgb_div_tame(theta - th[0], th[1] - th[0]);
+    w[0] = (1 - w1[0]) * (1 - wt);
+    w[1] = w1[0] * (1 - wt);
+    w[2] = (1 - w1[1]) * wt;
+    w[3] = w1[1] * wt;
+}
+
+template <bool NEST>
+HPGB_HD void hpgb_interp_cap(const hpgb_geom &g, const hpgb_rk &rk, const double *TQ, double theta, double phi, uint32_t ir1,
+                             int64_t *p, double *w) {
+    const uint32_t ns = (uint32_t)g.nside;
+    double th[2], w1[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t r = ir1 + (uint32_t)k;
+        const bool south = r > 2u * ns;
+        const uint32_t nring = south ? 4u * ns - r : r;
+        const double dn = (double)nring;
+        const double t = (dn * dn) * g.fact2;
+        const double t0 = hpgb_atan2_tab(TQ, hpgb_sqrt_tame(t * (2 - t)), 1 - t, HPGB_ATANQ_ROWS);
+        th[k] = south ? HPGB_PI - t0 : t0;
+        const uint32_t nr = 4u * nring;
+        const double dphi = hpgb_div_tame(HPGB_TWOPI, (double)nr);
+        int64_t i1 = hpgb_interp_floor(hpgb_div_tame(phi, dphi) - 0.5);
+        w1[k] = hpgb_div_tame(phi - ((double)i1 + 0.5) * dphi, dphi);
+        int64_t i2 = i1 + 1;
+        if (i1 < 0) i1 += (int64_t)nr;
+        if (i2 >= (int64_t)nr) i2 -= (int64_t)nr;
+        if (NEST) {
+            hpgb_ringidx2nest_pair_k(rk, r, (uint32_t)i1, (uint32_t)i2, p[2 * k], p[2 * k + 1]);
+        } else {
+            int64_t sp = (int64_t)((uint64_t)(2u * nring) * (uint64_t)(nring - 1u));
+            if (south) sp = g.npix - sp - (int64_t)nr;
+            p[2 * k] = sp + i1;
+            p[2 * k + 1] = sp + i2;
+        }
+    }
+    const double wt = hpgb_div_tame(theta - th[0], th[1] - th[0]);
+    w[0] = (1 - w1[0]) * (1 - wt);
+    w[1] = w1[0] * (1 - wt);
+    w[2] = (1 - w1[1]) * wt;
+    w[3] = w1[1] * wt;
+}
+
 // lonlat_to_thetaphi with numpy's formulas (hpgeom/hpgeom.py:75-88): Python-style modulo,
 // deg2rad = x * (pi/180).  Returns false when the latitude is out of range.
 template <bool DEGREES>

@@ -37,6 +37,13 @@ struct hpgb_has_epilogue : std::false_type {};
 template <class T>
 struct hpgb_has_epilogue<T, std::void_t<decltype(T::HAS_EPILOGUE)>> : std::bool_constant<T::HAS_EPILOGUE> {};
 
+// ops whose per-CTA tables live in the streaming kernel's dynamic shared memory (behind the stage ring) declare
+// `static constexpr bool SMEM_PROLOGUE = true` and provide prologue_extra(unsigned char *extra) next to prologue()
+template <class T, class = void>
+struct hpgb_has_smem_prologue : std::false_type {};
+template <class T>
+struct hpgb_has_smem_prologue<T, std::void_t<decltype(T::SMEM_PROLOGUE)>> : std::bool_constant<T::SMEM_PROLOGUE> {};
+
 struct hpgb_bad_t {
     unsigned long long idx;
     int aux;  // per-thread scratch an op may carry through the kernel (e.g. the length of its warp's queue)
@@ -180,7 +187,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_stream(const Op op, const int64
     static_assert(!Op::TILE_HOOK || BLOCK == HPGB_BLOCK, "tile-hook ops are written for HPGB_BLOCK threads");
     extern __shared__ __align__(128) unsigned char hpgb_stage_smem[];
     __shared__ uint64_t full[STAGES], empty[STAGES];
-    const typename Op::Ctx ctx = op.prologue();
+    unsigned char *const extra_smem = hpgb_stage_smem + (size_t)STAGES * NIN * ARR_BYTES;  // Op::EXTRA_SMEM bytes
+    const typename Op::Ctx ctx = [&]() {
+        if constexpr (hpgb_has_smem_prologue<Op>::value)
+            return op.prologue_extra(extra_smem);
+        else
+            return op.prologue();
+    }();
     const int tid = threadIdx.x;
     const int64_t ntiles = n / TILE;
     // this CTA's tiles: t0, t0 + tstep, ... < tend
@@ -240,8 +253,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_stream(const Op op, const int64
         const unsigned char *stage = hpgb_stage_smem + (size_t)s * NIN * ARR_BYTES;
         if constexpr (Op::TILE_HOOK) {
             // the op processes the whole tile itself (warp-cooperative) and arrives on empty[s]
-            op.template tile<TILE>(const_cast<unsigned char *>(stage), hpgb_stage_smem + (size_t)STAGES * NIN * ARR_BYTES,
-                                   t * TILE, tid, ctx, bad, &empty[s]);
+            op.template tile<TILE>(const_cast<unsigned char *>(stage), extra_smem, t * TILE, tid, ctx, bad, &empty[s]);
         } else {
 #pragma unroll
             for (int h = 0; h < H; h++) {

@@ -54,6 +54,7 @@ struct OpInterp {
         const double *TQ;    // atan rows
     };
     static constexpr bool FAST = POW2 && !VAR;
+    static constexpr bool kLonLat = LONLAT, kDegrees = DEGREES;
     static constexpr int DYN_SMEM = FAST ? HPGB_INTERP_TAB_WORDS * 8 : 0;
     HPGB_DEFAULT_RUN4
     __device__ __forceinline__ Ctx prologue() const {
@@ -188,6 +189,150 @@ __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_rows(const Op op, 
     bad.commit(st);
 }
 
+// Scalar power-of-two nside, aligned operands, second generation: the points of a warp are SORTED BY ZONE before
+// the expensive part.  With random points a third of every warp's lanes lie in the polar caps (ring colatitude from
+// the atan2 table, ring length 4 * ring), two thirds in the belt (acos table, 4 nside pixels a ring, one shared
+// phi / dphi): k_interp_rows executed both colatitude routines and both ring set-ups for all of them (22-25 of 32
+// lanes active on average, 935 instructions a point).  Here a lane first does the cheap part of its two points
+// (angle checks, ring pair from the polynomial sine), then parks each point in the warp's BELT or CAP queue in shared
+// memory; whenever a queue holds 32 points the warp runs that zone's straight-line body (hpgb_interp_belt /
+// hpgb_interp_cap, hpgb_fp.h) on them with every lane busy.  Left-overs stay queued for the next chunk and are
+// drained at the end.  The rows go straight to HBM from the lane that computed them: a (4,) int64 row and a (4,)
+// float64 row are one 32-byte sector each, so nothing is gained by transposing them through shared memory first.
+#define HPGB_INTERP_QCAP 64
+#define HPGB_INTERP_QBYTES (HPGB_INTERP_QCAP * (8 + 8 + 8 + 4))
+template <class Op, bool NEST>
+__global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_sorted(const Op op, const int64_t n, const double dphi_belt,
+                                                                    hpgb_status_t *st) {
+    extern __shared__ __align__(16) unsigned long long hpgb_interp_tabs[];
+    const typename Op::Ctx ctx = op.prologue();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *qmem = reinterpret_cast<unsigned char *>(hpgb_interp_tabs + HPGB_INTERP_TAB_WORDS) + warp * (2 * HPGB_INTERP_QBYTES);
+    struct Queue {
+        double *th, *ph;
+        int64_t *idx;
+        uint32_t *ir;
+        __device__ __forceinline__ explicit Queue(unsigned char *m)
+            : th(reinterpret_cast<double *>(m)), ph(th + HPGB_INTERP_QCAP), idx(reinterpret_cast<int64_t *>(ph + HPGB_INTERP_QCAP)),
+              ir(reinterpret_cast<uint32_t *>(idx + HPGB_INTERP_QCAP)) {}
+    };
+    const Queue qb(qmem), qc(qmem + HPGB_INTERP_QBYTES);
+    int nb = 0, nc = 0;  // queue lengths, warp-uniform
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t ns = (uint32_t)op.g.nside;
+    const int64_t gw = (int64_t)blockIdx.x * (HPGB_INTERP_BLOCK / 32) + warp;
+    const int64_t nw = (int64_t)gridDim.x * (HPGB_INTERP_BLOCK / 32);
+    const int64_t nfull = n >> 6, nchunk = (n + 63) >> 6;
+    hpgb_bad_t bad;
+    auto emit = [&](int64_t i, const int64_t *p, const double *w) {
+        hpgb_st2(op.pix + 4 * i, p[0], p[1]);
+        hpgb_st2(op.pix + 4 * i + 2, p[2], p[3]);
+        hpgb_st2(op.wgt + 4 * i, w[0], w[1]);
+        hpgb_st2(op.wgt + 4 * i + 2, w[2], w[3]);
+    };
+    auto run_belt = [&](int first, int count) {
+        if (lane < count) {
+            int64_t p[4];
+            double w[4];
+            hpgb_interp_belt<NEST>(op.g, op.rk, ctx.TA, dphi_belt, qb.th[first + lane], qb.ph[first + lane], qb.ir[first + lane], p, w);
+            emit(qb.idx[first + lane], p, w);
+        }
+        __syncwarp();
+    };
+    auto run_cap = [&](int first, int count) {
+        if (lane < count) {
+            int64_t p[4];
+            double w[4];
+            hpgb_interp_cap<NEST>(op.g, op.rk, ctx.TQ, qc.th[first + lane], qc.ph[first + lane], qc.ir[first + lane], p, w);
+            emit(qc.idx[first + lane], p, w);
+        }
+        __syncwarp();
+    };
+    auto fetch = [&](int64_t c) {
+        typename Op::In2 r;
+        const int64_t i = c * 64 + 2 * lane;
+        if (c < nfull) return op.load2(i);
+        r.a.x = i < n ? hpgb_ld1(op.a + i) : 0.0;
+        r.b.x = i < n ? hpgb_ld1(op.b + i) : 0.0;
+        r.a.y = i + 1 < n ? hpgb_ld1(op.a + i + 1) : 0.0;
+        r.b.y = i + 1 < n ? hpgb_ld1(op.b + i + 1) : 0.0;
+        return r;
+    };
+    int64_t ch = gw;
+    typename Op::In2 v = typename Op::In2();
+    if (ch < nchunk) v = fetch(ch);
+    for (; ch < nchunk; ch += nw) {
+        const typename Op::In2 cur = v;
+        if (ch + nw < nchunk) v = fetch(ch + nw);
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            const int64_t i = ch * 64 + 2 * lane + q;
+            const double va = q ? cur.a.y : cur.a.x, vb = q ? cur.b.y : cur.b.x;
+            double theta = 0.0, phi = 0.0;
+            int64_t ir1 = 0;
+            int zone = 3;  // 0 belt, 1 cap, 2 the reference-shaped routine, 3 nothing to do
+            if (i < n) {
+                if (!hpgb_angles_exact<Op::kLonLat, Op::kDegrees>(va, vb, theta, phi)) {
+                    bad.flag(op.base + i);
+                    const int64_t p[4] = {-1, -1, -1, -1};
+                    const double w[4] = {0.0, 0.0, 0.0, 0.0};
+                    emit(i, p, w);
+                } else if (hpgb_ring_above_fast(op.g, op.f, theta, ir1)) {
+                    zone = hpgb_interp_zone(ns, ir1);
+                } else {
+                    zone = 2;
+                }
+            }
+            const unsigned mb = __ballot_sync(0xFFFFFFFFu, zone == 0);
+            if (zone == 0) {
+                const int pos = nb + __popc(mb & lt);
+                qb.th[pos] = theta, qb.ph[pos] = phi, qb.idx[pos] = i, qb.ir[pos] = (uint32_t)ir1;
+            }
+            nb += __popc(mb);
+            const unsigned mc = __ballot_sync(0xFFFFFFFFu, zone == 1);
+            if (zone == 1) {
+                const int pos = nc + __popc(mc & lt);
+                qc.th[pos] = theta, qc.ph[pos] = phi, qc.idx[pos] = i, qc.ir[pos] = (uint32_t)ir1;
+            }
+            nc += __popc(mc);
+            if (zone == 2) {  // pole rows, pairs straddling a cap edge, points on a ring: rare
+                int64_t p[4];
+                double w[4];
+                Op::slow(op.g, ctx.T, theta, phi, p, w);
+                emit(i, p, w);
+            }
+            __syncwarp();
+            if (nb >= 32) {
+                nb -= 32;
+                run_belt(nb, 32);
+            }
+            if (nc >= 32) {
+                nc -= 32;
+                run_cap(nc, 32);
+            }
+        }
+    }
+    if (nb > 0) run_belt(0, nb);
+    if (nc > 0) run_cap(0, nc);
+    bad.commit(st);
+}
+
+template <class Op, bool NEST>
+int launch_interp_sorted(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
+    const int smem = Op::DYN_SMEM + (HPGB_INTERP_BLOCK / 32) * 2 * HPGB_INTERP_QBYTES;
+    static hpgb_occ_cache cache;  // per device: the dynamic-smem opt-in is a per-device attribute
+    (void)hpgb_resident_ctas_cached(cache, k_interp_sorted<Op, NEST>, smem, HPGB_INTERP_BLOCK);
+    int64_t grid = hpgb_sm_count();
+    const int64_t want = (((n + 63) >> 6) + HPGB_INTERP_BLOCK / 32 - 1) / (HPGB_INTERP_BLOCK / 32);
+    if (want < grid) grid = want > 0 ? want : 1;
+    // 2 pi / (4 nside): the belt rings' pixel spacing, the same IEEE division the reference does per ring
+    const double dphi_belt = HPGB_TWOPI / (double)(4 * op.g.nside);
+    k_interp_sorted<Op, NEST><<<(unsigned)grid, HPGB_INTERP_BLOCK, smem, s>>>(op, n, dphi_belt, st);
+    g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+}
+
 template <class Op>
 int launch_interp_rows(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
     const int smem = Op::DYN_SMEM + (HPGB_INTERP_BLOCK / 32) * 256 * 16;
@@ -213,7 +358,11 @@ int launch_interp_t(const double *a, const double *b, int64_t *pix, double *wgt,
     const bool vec = hpgb_aligned16(a) && hpgb_aligned16(b);
     if (NEST || g.order >= 0) {
         OpInterp<NEST, true, LONLAT, DEGREES, false> op{a, b, pix, wgt, nullptr, base, g, hpgb_make_rk(g), hpgb_make_a2p_fast<false, false>(g)};
+#if defined(HPGB_INTERP_ROWS)
         if (vec) return launch_interp_rows(op, n, st, s);
+#else
+        if (vec) return launch_interp_sorted<decltype(op), NEST>(op, n, st, s);
+#endif
         return hpgb_launch_map<decltype(op), HPGB_INTERP_BLOCK>(op, n, vec, st, s, decltype(op)::DYN_SMEM);
     }
     OpInterp<false, false, LONLAT, DEGREES, false> op{a, b, pix, wgt, nullptr, base, g, hpgb_rk(), hpgb_a2p_fast()};

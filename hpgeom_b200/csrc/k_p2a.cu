@@ -57,6 +57,14 @@ static __device__ const double g_hpgb_atanq_tab[HPGB_ATANQ_ROWS * HPGB_ATANQ_ROW
 #define HPGB_V2P_H 2
 #endif
 #define HPGB_P2A_TAB_DOUBLES (HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + HPGB_ATANQ_ROWS_POLAR * HPGB_ATANQ_ROW_DOUBLES)
+// streaming form: ONE big CTA per SM (the tables are staged once per SM), tiles of 4 * BLOCK pixels
+#ifndef HPGB_P2A_ST
+#define HPGB_P2A_ST 3
+#endif
+#ifndef HPGB_P2A_H
+#define HPGB_P2A_H 1
+#endif
+#define HPGB_P2A_QCAP 64  // per-warp queue of deferred pixels: 31 left over + 32 new, rounded up
 
 template <bool NEST, bool POW2, bool LONLAT, bool DEGREES, bool VAR>
 struct OpPix2Ang {
@@ -73,14 +81,84 @@ struct OpPix2Ang {
     static __device__ __forceinline__ const double *atanq(Ctx T) {
         return reinterpret_cast<const double *>(T + HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS);
     }
-
+    // streaming skeleton: one pixel array in, the tables + the per-warp queues behind the stage ring
+    static constexpr int NIN = 1;
+    static constexpr int MINB = 1;
+    static constexpr bool TILE_HOOK = false;
+    static constexpr bool SMEM_PROLOGUE = true;
+    static constexpr bool HAS_EPILOGUE = FAST;
+    static constexpr int EXTRA_SMEM = DYN_SMEM + (HPGB_P2A_BLOCK / 32) * HPGB_P2A_QCAP * 8;
+    __device__ __forceinline__ const void *src(int) const { return pix; }
+    __device__ __forceinline__ In2 load2s(const unsigned char *stage, int, int e) const {
+        return *reinterpret_cast<const longlong2 *>(stage + 8 * e);
+    }
+    static __device__ __forceinline__ Ctx stage_tables(unsigned long long *dst) {
+        for (int i = threadIdx.x; i < HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS; i += blockDim.x) dst[i] = g_hpgb_acos_tab[i];
+        for (int i = threadIdx.x; i < HPGB_ATANQ_ROWS_POLAR * HPGB_ATANQ_ROW_DOUBLES; i += blockDim.x)
+            dst[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + i] = (unsigned long long)__double_as_longlong(g_hpgb_atanq_tab[i]);
+        __syncthreads();
+        return reinterpret_cast<const uint64_t *>(dst);
+    }
     __device__ __forceinline__ Ctx prologue() const {
         extern __shared__ __align__(16) unsigned long long hpgb_p2a_tabs[];
-        for (int i = threadIdx.x; i < HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS; i += blockDim.x) hpgb_p2a_tabs[i] = g_hpgb_acos_tab[i];
-        for (int i = threadIdx.x; i < HPGB_ATANQ_ROWS_POLAR * HPGB_ATANQ_ROW_DOUBLES; i += blockDim.x)
-            hpgb_p2a_tabs[HPGB_ACOS_ROWS * HPGB_ACOS_ROW_WORDS + i] = (unsigned long long)__double_as_longlong(g_hpgb_atanq_tab[i]);
-        __syncthreads();
-        return reinterpret_cast<const uint64_t *>(hpgb_p2a_tabs);
+        return stage_tables(hpgb_p2a_tabs);
+    }
+    __device__ __forceinline__ Ctx prologue_extra(unsigned char *extra) const {
+        return stage_tables(reinterpret_cast<unsigned long long *>(extra));
+    }
+    // ---- deferred rare pixels (streaming kernel only).  1 % of the pixels have |z| > 0.99 and take theta from
+    // atan2(sin, z); patched where they arise they cost a ~100-instruction pass on ONE lane in 72 % of the warp
+    // iterations.  Instead their indices go to a per-warp queue behind the tables (the output keeps the hot
+    // path's value for now) and are redone 32 at a time -- dense lanes -- by the reference-shaped routine, which
+    // also covers the two rarer cases (isqrt quirk, pixel out of range).
+    static __device__ __forceinline__ int64_t *queue(Ctx T) {
+        return reinterpret_cast<int64_t *>(const_cast<uint64_t *>(T) + HPGB_P2A_TAB_DOUBLES) + (threadIdx.x >> 5) * HPGB_P2A_QCAP;
+    }
+    __device__ __forceinline__ void drain(int64_t *q, int first, int count, Ctx T, hpgb_bad_t &bad) const {
+        const int lane = threadIdx.x & 31;
+        if (lane < count) {
+            const int64_t i = q[first + lane];
+            double va, vb;
+            conv(g, hpgb_ld1(pix + i), i, T, bad, va, vb);
+            hpgb_st1(a + i, va);
+            hpgb_st1(b + i, vb);
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void run4u(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
+                                          hpgb_bad_t &bad) const {
+        Hot h0 = hot(v0.x, T), h1 = hot(v0.y, T), h2 = hot(v1.x, T), h3 = hot(v1.y, T);
+        hpgb_st2(a + i0, h0.va, h1.va);
+        hpgb_st2(b + i0, h0.vb, h1.vb);
+        hpgb_st2(a + i1, h2.va, h3.va);
+        hpgb_st2(b + i1, h2.vb, h3.vb);
+        unsigned pend = (h0.code ? 1u : 0u) | (h1.code ? 2u : 0u) | (h2.code ? 4u : 0u) | (h3.code ? 8u : 0u);
+        if (__any_sync(0xFFFFFFFFu, pend != 0u)) {  // warp-uniform
+            __syncwarp();  // the stores above precede the queued pixels' final stores (other lanes, same addresses)
+            int64_t *q = queue(T);
+            int cnt = bad.aux;
+            const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+            unsigned m;
+            while ((m = __ballot_sync(0xFFFFFFFFu, pend != 0u)) != 0u) {  // one round per flagged pixel of the busiest lane
+                if (pend) {
+                    const unsigned j = (unsigned)__ffs((int)pend) - 1u;
+                    pend &= pend - 1u;
+                    q[cnt + __popc(m & lt)] = (j < 2u ? i0 : i1) + (j & 1u);
+                }
+                cnt += __popc(m);
+                __syncwarp();
+                if (cnt >= 32) {
+                    cnt -= 32;
+                    drain(q, cnt, 32, T, bad);
+                }
+            }
+            bad.aux = cnt;
+        }
+    }
+    __device__ __forceinline__ void epilogue(const Ctx &T, hpgb_bad_t &bad) const {
+        __syncwarp();
+        if (bad.aux > 0) drain(queue(T), 0, bad.aux, T, bad);
+        bad.aux = 0;
     }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
     // general path (any nside, per-element nside): the reference's branches as they are
@@ -186,6 +264,11 @@ int launch_p2a_t(const int64_t *pix, double *a, double *b, int64_t n, int64_t ns
     const bool vec = hpgb_aligned16(pix) && hpgb_aligned16(a) && hpgb_aligned16(b);
     if (NEST || g.order >= 0) {
         OpPix2Ang<NEST, true, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g, hpgb_make_rk(g)};
+#if !defined(HPGB_P2A_MAP)
+        // one 768-thread CTA per SM on the TMA ring (3 stages x 3072 pixels), tables + queues behind the ring
+        if (vec && n >= 4 * 4 * HPGB_P2A_BLOCK * HPGB_P2A_H)
+            return hpgb_launch_stream<decltype(op), HPGB_P2A_ST, HPGB_P2A_H, HPGB_P2A_BLOCK, 1>(op, n, st, s);
+#endif
         return hpgb_launch_map<decltype(op), HPGB_P2A_BLOCK>(op, n, vec, st, s, decltype(op)::DYN_SMEM);
     }
     OpPix2Ang<false, false, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g, hpgb_rk()};

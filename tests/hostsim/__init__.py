@@ -137,7 +137,8 @@ class HostSim:
         return p, w
 
     def get_interpolation_weights_k(self, nside, a, b, nest=True, lonlat=True, degrees=True, exact_only=False):
-        """Power-of-two kernel path (fast ring choice + tables); self.last_slow = points that fell back."""
+        """Power-of-two kernel path (fast ring choice + tables); self.last_slow = points that fell back.
+        exact_only = 2: the zone-sorted bodies of the kernel (hpgb_interp_belt / hpgb_interp_cap)."""
         a, b = self._f(a), self._f(b)
         p = np.empty((a.size, 4), dtype=np.int64)
         w = np.empty((a.size, 4), dtype=np.float64)

@@ -313,6 +313,13 @@ def test_interp_fast_path(sim, oracle_port, nside):
         same = ~flipped
         assert np.mean((w1[same] != w0[same]).any(axis=1)) <= 5e-3
         assert np.abs(w1[same] - w0[same]).max() <= 4 * np.spacing(np.pi) * nside  # one ulp of a ring theta / ring spacing
+        # the zone-sorted bodies the kernel runs (belt pair / cap pair / everything else) are the same arithmetic
+        for kw in ({}, {"degrees": False}):
+            a, b = (lon, lat) if not kw else (np.radians(lon), np.radians(lat))
+            pg, wg = sim.get_interpolation_weights_k(nside, a, b, nest=nest, **kw)
+            ps, ws = sim.get_interpolation_weights_k(nside, a, b, nest=nest, exact_only=2, **kw)
+            assert_bit_equal(ps, pg, "sorted interpolation pixels")
+            assert_bit_equal(ws, wg, "sorted interpolation weights")
         pe, we = sim.get_interpolation_weights_k(nside, lon, lat, nest=nest, exact_only=True)
         assert_bit_equal(p1, pe, "fast vs reference-shaped pixels")
 
