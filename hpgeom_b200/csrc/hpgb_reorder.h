@@ -216,6 +216,43 @@ HPGB_HD void hpgb_r2n_cap(const hpgb_rk &c, const hpgb_geom &g, uint64_t up, boo
     iy = north ? c.nsm1 - q : ir - 1u - q;
 }
 
+// ---- RING -> NEST through FOLDED coordinates (the streaming kernel, OpReorder::tile in k_reorder.cu) ----
+// nest = (face << 2k) + interleave(ix, iy): the four face bits land on bits 2k .. 2k+3 of the pixel number, i.e. on
+// bits k, k+1 of the even (ix) and of the odd (iy) bit plane.  So with
+//     X = ix + ((f0 | f2 << 1) << k),   Y = iy + ((f1 | f3 << 1) << k)        (X, Y < 2^(k+2) <= 2^31)
+// the pixel number is interleave(X, Y): no face arithmetic after the Morton step, the pair (X, Y) is the 8-byte
+// intermediate a shared-memory slot holds between the passes, and ANY 64-bit result v (-1 for a refused pixel, the
+// reference's garbage for its isqrt-quirk pixels) can be stored as deinterleave(v).
+// Belt pixels: the face of the reference's ring2xyf depends only on (ifp, ifm) = (jp >> k, jm >> k), ifm - ifp in
+// {-1, 0, 1}, ifp in 0..4 -> a 16-entry table indexed by 2 ifp + ifm + 1 (128 bytes of shared memory, one entry per
+// pair of banks: conflict-free LDS.64) that holds the two constants of
+//     X = jm + lx,  lx = (fx - ifm) << k          Y = ly - jp,  ly = ((fy + ifp + 1) << k) - 1
+// (jm = ifm nside + ix, jp = ifp nside + (nside-1-iy)): one load and two adds replace the face selection, the two
+// masks and the face multiply-add.
+struct alignas(8) hpgb_u32x2 {
+    uint32_t x, y;
+};
+HPGB_HD void hpgb_r2n_lut_entry(const hpgb_rk &c, uint32_t idx, uint32_t &lx, uint32_t &ly) {
+    // idx = 2 ifp + ifm + 1 with ifm = ifp + d - 1, d in 0..2  ->  ifp = idx / 3, d = idx % 3
+    const uint32_t ifp = idx / 3u, ifm = ifp + idx % 3u - 1u;
+    const uint32_t face = (ifp == ifm) ? (ifp | 4u) : ((ifp < ifm) ? ifp : (ifm + 8u));
+    const uint32_t fx = (face & 1u) | ((face >> 1) & 2u), fy = ((face >> 1) & 1u) | ((face >> 2) & 2u);
+    lx = (fx - ifm) << c.k;
+    ly = ((fy + ifp + 1u) << c.k) - 1u;
+}
+// belt pixel -> (X, Y); lut = the 16 (lx, ly) pairs
+HPGB_HD void hpgb_r2n_belt_fold(const hpgb_rk &c, const hpgb_u32x2 *lut, uint32_t tmp, uint32_t ipb_lo, uint32_t &X, uint32_t &Y) {
+    const uint32_t ip = ipb_lo & c.ns4m1;
+    const uint32_t jp = ip + (tmp >> 1);
+    const uint32_t jm = jp + c.ns - tmp;
+    const hpgb_u32x2 f = lut[2u * (jp >> c.k) + (jm >> c.k) + 1u];
+    X = jm + f.x;
+    Y = f.y - jp;
+}
+// cap pixel -> (X, Y) (hpgb_r2n_cap with the face folded in; the quirk pixels keep the literal 64-bit replay)
+template <bool HI>
+HPGB_HD void hpgb_r2n_cap_fold(const hpgb_rk &c, const hpgb_geom &g, uint64_t up, uint32_t &X, uint32_t &Y);
+
 // RING pixel (must be < npix) -> (ix, iy, face): ring2xyf of the reference (hpgeom/healpix_geom.c:410-454)
 // from the pieces above
 HPGB_HD void hpgb_ring2xyf_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, uint32_t &ix, uint32_t &iy, uint32_t &face) {
@@ -257,6 +294,36 @@ HPGB_HD int64_t hpgb_xyf2nest_k(const hpgb_rk &c, uint32_t ix, uint32_t iy, uint
     HPGB_DSWAP(hi, 0x22222222u, 1);
     if (HI) return (int64_t)(((uint64_t)(hi + face * c.fmul_hi) << 32) | lo);
     return (int64_t)((((uint64_t)hi << 32) | lo) + ((uint64_t)face << c.k2));
+}
+
+template <bool HI>
+HPGB_HD void hpgb_r2n_cap_fold(const hpgb_rk &c, const hpgb_geom &g, uint64_t up, uint32_t &X, uint32_t &Y) {
+    // a cap pixel is north iff it lies in the first half of the map (HI: npix / 2 is a multiple of 2^32)
+    const bool north = HI ? ((uint32_t)(up >> 32) < (c.npix_hi >> 1)) : (up < (((uint64_t)c.ncap_hi << 32) | c.ncap_lo));
+    const uint64_t ipm1 = north ? up : ((((uint64_t)c.npm1_hi << 32) | c.npm1_lo) - up);  // 0-based from the pole
+#if defined(__CUDA_ARCH__)
+    const uint32_t isq = __double2uint_rz(sqrt((double)(int64_t)(2 * ipm1 + 1) + 0.5));  // hpgeom/healpix_geom.c:60
+#else
+    const uint32_t isq = (uint32_t)(int64_t)sqrt((double)(int64_t)(2 * ipm1 + 1) + 0.5);
+#endif
+    const uint32_t ir = (isq + 1u) >> 1;
+    const uint32_t q0 = (uint32_t)ipm1 - ir * (2u * ir - 2u);
+    if (q0 >= 4u * ir) {  // the reference's isqrt mis-rounded: replay its 64-bit arithmetic, store the result de-interleaved
+        int32_t sx, sy;
+        uint32_t face;
+        hpgb_ring2xyf_any(g, (int64_t)up, sx, sy, face);
+        hpgb_deinterleave((uint64_t)hpgb_xyf2nest_k<HI>(c, (uint32_t)sx, (uint32_t)sy, face), X, Y);
+        return;
+    }
+    // face = 2 t1 + t2 (+ 8 south): f0 = t2 rides on X, f1 = t1 and f3 = south on Y
+    uint32_t q = north ? q0 : 4u * ir - 1u - q0;
+    const bool t1 = q >= 2u * ir;
+    q -= t1 ? 2u * ir : 0u;
+    const bool t2 = q >= ir;
+    q -= t2 ? ir : 0u;
+    const uint32_t fy = (t1 ? c.ns : 0u) + (north ? 0u : c.ns2);
+    X = (north ? c.ns - ir + q : q) + (t2 ? c.ns : 0u);
+    Y = (north ? c.nsm1 - q : ir - 1u - q) + fy;
 }
 
 // (ring number 1..4 nside-1, 0-based in-ring index counted eastward) -> NEST pixel: ring2xyf without
@@ -313,6 +380,18 @@ HPGB_HD void hpgb_ringidx2nest_pair_k(const hpgb_rk &c, uint32_t ring, uint32_t 
     } else {
         p2 = hpgb_ringidx2nest_far(c, ring, q2);
     }
+}
+
+// RING pixel (must be < npix) -> NEST pixel the way the streaming kernel's tile routine computes it (fold, then interleave)
+template <bool HI>
+HPGB_HD int64_t hpgb_ring2nest_fold(const hpgb_rk &c, const hpgb_geom &g, const hpgb_u32x2 *lut, int64_t pix) {
+    uint32_t ipb_lo, X, Y;
+    const uint32_t tmp = hpgb_r2n_zone(c, (uint64_t)pix, ipb_lo);
+    if (hpgb_r2n_is_cap(c, tmp))
+        hpgb_r2n_cap_fold<HI>(c, g, (uint64_t)pix, X, Y);
+    else
+        hpgb_r2n_belt_fold(c, lut, tmp, ipb_lo, X, Y);
+    return (int64_t)hpgb_interleave(X, Y);
 }
 
 // RING pixel (must be < npix) -> NEST pixel.  HI: order >= 16.

@@ -20,6 +20,13 @@
 #ifndef HPGB_RE_H
 #define HPGB_RE_H 2
 #endif
+// ring -> nest streaming kernel: min resident CTAs/SM (register cap), two cap pixels per lane in pass B
+#ifndef HPGB_R2N_MINB
+#define HPGB_R2N_MINB 4
+#endif
+#ifndef HPGB_R2N_UNROLL2
+#define HPGB_R2N_UNROLL2 0
+#endif
 
 namespace {
 
@@ -67,85 +74,144 @@ struct OpReorder {
     }
     __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(in + i); }
     static constexpr int NIN = 1;
-    static constexpr int MINB = 1;
+    static constexpr int MINB = TO_RING ? 1 : HPGB_R2N_MINB;
     // ring -> nest runs the warp-cooperative tile routine below; nest -> ring the per-thread run4
     static constexpr bool TILE_HOOK = !TO_RING && !VAR;
-    static constexpr int EXTRA_SMEM = TILE_HOOK ? (HPGB_BLOCK / 32) * 256 * (8 + 2) : 0;
+    static constexpr int EXTRA_SMEM = TILE_HOOK ? 128 + (HPGB_BLOCK / 32) * 256 * 2 : 0;
     __device__ __forceinline__ const void *src(int) const { return in; }
 
     // ---------------------------------------------------------------------------------------
-    // ring -> nest, one tile.  Cap pixels need the (long) isqrt path, belt pixels a dozen
-    // instructions; with random pixels a third of every warp's lanes would drag the other two
-    // thirds through the cap path.  So the warp sorts them instead:
-    //   phase 1  every thread converts its 8 pixels as if they were belt pixels and writes the
-    //            results over the inputs in the shared-memory stage; cap pixels are appended to a
-    //            per-warp queue (ballot + popc) with their slot number;
-    //   phase 2  the warp drains the queue 32 cap pixels at a time (dense lanes) and writes those
-    //            results into their slots;
-    //   phase 3  the finished tile goes to HBM with 128-bit streaming stores.
+    // ring -> nest, one tile, in three passes over the shared-memory stage (hpgb_reorder.h, "folded coordinates":
+    // a slot's 8 bytes go  RING pixel -> (X, Y) -> NEST pixel).  Cap pixels need the isqrt path (~60 instructions),
+    // belt pixels a dozen; with random pixels a third of every warp's lanes would drag the other two thirds through
+    // the cap path.  So the warp sorts them instead:
+    //   pass A  every thread turns its 8 pixels into (X, Y) as if they were belt pixels -- 9 integer-pipe
+    //           instructions, one table load -- and stores the pair over the input unless the pixel is a cap pixel;
+    //           cap pixels set a bit in a per-thread mask; one warp prefix sum of the bit counts gives every thread
+    //           its place in the warp's queue of cap SLOT NUMBERS (2 bytes per entry);
+    //   pass B  the warp drains the queue 32 cap pixels at a time (dense lanes): slot -> pixel -> (X, Y) -> slot;
+    //   pass C  every thread Morton-interleaves its 8 (X, Y) pairs -- the one place the 26-instruction bit shuffle
+    //           exists, executed once per pixel -- and streams the results to HBM with 128-bit stores.
     // A warp only ever touches its own 256 slots, so __syncwarp() is the only synchronisation.
     // ---------------------------------------------------------------------------------------
+    static constexpr bool SMEM_PROLOGUE = TILE_HOOK;
+    static constexpr int LUT_BYTES = 128;
+    __device__ __forceinline__ Ctx prologue_extra(unsigned char *extra) const {
+        if (threadIdx.x < 16) {
+            hpgb_u32x2 e;
+            hpgb_r2n_lut_entry(c, threadIdx.x, e.x, e.y);
+            reinterpret_cast<hpgb_u32x2 *>(extra)[threadIdx.x] = e;
+        }
+        return Ctx();  // visible after the __syncthreads() that follows the mbarrier set-up in k_stream
+    }
     template <int TILE>
     __device__ __forceinline__ void tile(unsigned char *stage, unsigned char *extra, int64_t e_base, int tid, const Ctx &,
                                          hpgb_bad_t &bad, uint64_t *empty_bar) const {
         static_assert(TILE == 2048, "queue sizes assume 8 elements per thread");
         const int lane = tid & 31, warp = tid >> 5;
-        unsigned long long *qpix = reinterpret_cast<unsigned long long *>(extra) + warp * 256;
-        unsigned short *qslot = reinterpret_cast<unsigned short *>(extra + (HPGB_BLOCK / 32) * 256 * 8) + warp * 256;
+        const hpgb_u32x2 *lut = reinterpret_cast<const hpgb_u32x2 *>(extra);
+        unsigned short *qslot = reinterpret_cast<unsigned short *>(extra + LUT_BYTES) + warp * 256;
         longlong2 *st2 = reinterpret_cast<longlong2 *>(stage);
         unsigned long long *st1 = reinterpret_cast<unsigned long long *>(stage);
-        const unsigned lt = (1u << lane) - 1u;
-        int ncap = 0;
-        bool all_ok = true;
+        hpgb_u32x2 *stx = reinterpret_cast<hpgb_u32x2 *>(stage);
+        // ---- pass A ----
+        // "cap" here = not provably a belt pixel: ring - nside > 2 nside, or the pixel is so far out of range that the
+        // 32-bit ring number aliases (bits k+2 .. 31 of the high word of pix - ncap set; negative pixels included).
+        // Every refused pixel is therefore a "cap" pixel and is dealt with in pass B, on dense lanes.
+        uint32_t capm = 0u;
+        longlong2 v[TILE / 512];
+#pragma unroll
+        for (int j = 0; j < TILE / 512; j++) v[j] = st2[j * 256 + tid];
+        const uint32_t lut_s = hpgb_smem_u32(lut) + 8u, slot_s = hpgb_smem_u32(stage) + 16u * (uint32_t)tid;
+        const uint32_t hi_lim = 1u << (c.k + 2u);
 #pragma unroll
         for (int j = 0; j < TILE / 512; j++) {
-            const int slot = j * 512 + 2 * tid;
-            const longlong2 v = st2[slot >> 1];
-            int64_t r[2];
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const int64_t p = e ? v.y : v.x;
-                const bool good = ok(p);
-                all_ok &= good;
-                uint32_t ipb_lo, ix, iy, face;
-                const uint32_t tmp = hpgb_r2n_zone(c, (uint64_t)p, ipb_lo);
-                const bool cap = hpgb_r2n_is_cap(c, tmp) && good;
-                hpgb_r2n_belt(c, tmp, ipb_lo, ix, iy, face);
-                r[e] = hpgb_xyf2nest_k<HI>(c, ix, iy, face);
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, cap);
-                if (cap) {
-                    const int pos = ncap + __popc(m & lt);
-                    qpix[pos] = (unsigned long long)p;
-                    qslot[pos] = (unsigned short)(slot + e);
-                }
-                ncap += __popc(m);
+                const uint64_t ipb = (uint64_t)(e ? v[j].y : v[j].x) - (((uint64_t)c.ncap_hi << 32) | c.ncap_lo);
+                const uint32_t tmp = (uint32_t)((int64_t)ipb >> (c.k + 2u));
+                const uint32_t jp = ((uint32_t)ipb & c.ns4m1) + (tmp >> 1);
+                const uint32_t jm = jp + c.ns - tmp;
+                const uint32_t la = lut_s + 16u * (jp >> c.k) + 8u * (jm >> c.k);  // entry 2 ifp + ifm + 1
+                // X = jm + lx, Y = ly - jp, stored over the input -- all under "not cap" (the table index of a cap
+                // pixel is garbage); cap pixels set their bit in capm
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred q;\n\t"
+                    ".reg .u32 lx, ly;\n\t"
+                    "setp.gt.u32 q, %1, %2;\n\t"
+                    "setp.ge.or.u32 q, %3, %4, q;\n\t"
+                    "@!q ld.shared.v2.u32 {lx, ly}, [%5];\n\t"
+                    "@!q add.u32 lx, %6, lx;\n\t"
+                    "@!q sub.u32 ly, ly, %7;\n\t"
+                    "@!q st.shared.v2.u32 [%8], {lx, ly};\n\t"
+                    "@q add.u32 %0, %0, %9;\n\t"
+                    "}"
+                    : "+r"(capm)
+                    : "r"(tmp), "r"(c.ns2), "r"((uint32_t)(ipb >> 32)), "r"(hi_lim), "r"(la), "r"(jm), "r"(jp),
+                      "r"(slot_s + (uint32_t)(j * 4096 + e * 8)), "r"(1u << (2 * j + e))
+                    : "memory");
             }
-            st2[slot >> 1] = make_longlong2(r[0], r[1]);
+        }
+        // exclusive prefix sum of the per-thread cap counts over the warp
+        const uint32_t mine = (uint32_t)__popc(capm);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)  // shfl.up's predicate = "the source lane exists"
+            asm volatile("{\n\t.reg .pred q;\n\t.reg .u32 u;\n\tshfl.sync.up.b32 u|q, %0, %1, 0, 0xffffffff;\n\t@q add.u32 %0, %0, u;\n\t}"
+                         : "+r"(incl)
+                         : "r"(d));
+        const int ncap = (int)__shfl_sync(0xFFFFFFFFu, incl, 31);
+        unsigned short *qw = qslot + (incl - mine);
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            if (capm & (1u << b)) *qw++ = (unsigned short)((b >> 1) * 512 + 2 * tid + (b & 1));
         }
         __syncwarp();
-        for (int j = lane; j < ncap; j += 32) {
-            const uint64_t p = qpix[j];
-            uint32_t ix, iy, face;
-            hpgb_r2n_cap(c, g, p, p < (((uint64_t)c.ncap_hi << 32) | c.ncap_lo), ix, iy, face);
-            st1[qslot[j]] = (unsigned long long)hpgb_xyf2nest_k<HI>(c, ix, iy, face);
+        // ---- pass B ----  (two cap pixels per lane and step while the queue holds more than 32: the isqrt chain is
+        // ~250 cycles of dependent instructions, a second independent chain hides half of it)
+        auto cap1 = [&](int slot) {
+            const uint64_t p = st1[slot];
+            hpgb_u32x2 r;
+            if (ok((int64_t)p)) {
+                hpgb_r2n_cap_fold<HI>(c, g, p, r.x, r.y);
+            } else {  // refused: result -1 = interleave(~0, ~0)
+                bad.flag(base + e_base + slot);
+                r.x = r.y = ~0u;
+            }
+            stx[slot] = r;
+        };
+#if HPGB_R2N_UNROLL2
+        int j0 = 0;
+        for (; j0 + 32 < ncap; j0 += 64) {  // warp-uniform condition: the second half-step has at least one entry
+            const int ja = j0 + lane, jb = ja + 32;
+            const bool vb = jb < ncap;
+            const int sa = qslot[ja], sb = qslot[vb ? jb : ja];
+            const uint64_t pa = st1[sa], pb = st1[sb];
+            hpgb_u32x2 ra, rb;
+            const bool oka = ok((int64_t)pa), okb = ok((int64_t)pb);
+            hpgb_r2n_cap_fold<HI>(c, g, oka ? pa : 0ull, ra.x, ra.y);
+            hpgb_r2n_cap_fold<HI>(c, g, okb ? pb : 0ull, rb.x, rb.y);
+            if (!(oka && okb)) {
+                if (!oka) bad.flag(base + e_base + sa), ra.x = ra.y = ~0u;
+                if (!okb) bad.flag(base + e_base + sb), rb.x = rb.y = ~0u;
+            }
+            stx[sa] = ra;
+            if (vb) stx[sb] = rb;
         }
-        if (!all_ok) {  // rare: out-of-range pixels among this thread's 8 -> re-read them from HBM, flag, patch
-#pragma unroll 1
-            for (int j = 0; j < TILE / 512; j++)
-                for (int e = 0; e < 2; e++) {
-                    const int slot = j * 512 + 2 * tid + e;
-                    if (!ok(in[e_base + slot])) {
-                        bad.flag(base + e_base + slot);
-                        st1[slot] = ~0ull;
-                    }
-                }
-        }
+        if (j0 + lane < ncap) cap1(qslot[j0 + lane]);
+#else
+        for (int j = lane; j < ncap; j += 32) cap1(qslot[j]);
+#endif
         __syncwarp();
+        // ---- pass C ----
 #pragma unroll
         for (int j = 0; j < TILE / 512; j++) {
             const int slot = j * 512 + 2 * tid;
             const longlong2 v = st2[slot >> 1];
-            hpgb_st2(out + e_base + slot, v.x, v.y);
+            const uint64_t a = hpgb_interleave((uint32_t)(uint64_t)v.x, (uint32_t)((uint64_t)v.x >> 32));
+            const uint64_t b = hpgb_interleave((uint32_t)(uint64_t)v.y, (uint32_t)((uint64_t)v.y >> 32));
+            hpgb_st2(out + e_base + slot, (int64_t)a, (int64_t)b);
         }
         // generic-proxy writes to the stage must be ordered before the TMA refill (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

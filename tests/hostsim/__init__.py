@@ -18,7 +18,7 @@ class HostSim:
         self.lib = ctypes.CDLL(os.environ.get("HPGB_HOSTSIM_LIB") or os.path.join(_HERE, "libhostsim.so"))
         for n in ("sim_nest_to_ring", "sim_ring_to_nest", "sim_ring_roundtrip_any", "sim_angle_to_pixel",
                   "sim_pixel_to_angle", "sim_pixel_to_vector", "sim_vector_to_pixel", "sim_neighbors", "sim_interp",
-                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_pixel_to_angle_k", "sim_pixel_to_vector_k", "sim_interp_k", "sim_query_circle_ring", "sim_query_circle_nest"):
+                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_ring_to_nest_fold", "sim_pixel_to_angle_k", "sim_pixel_to_vector_k", "sim_interp_k", "sim_query_circle_ring", "sim_query_circle_nest"):
             getattr(self.lib, n).restype = ctypes.c_int64
         self.last_slow = 0
 
@@ -61,6 +61,10 @@ class HostSim:
 
     def ring_to_nest_k(self, nside, pix, hi=None):
         return self._conv_k("sim_ring_to_nest_k", nside, pix, nside >= 2 ** 16 if hi is None else hi)
+
+    def ring_to_nest_fold(self, nside, pix, hi=None):
+        """the folded-coordinate path of the streaming ring -> nest kernel (hpgb_reorder.h)"""
+        return self._conv_k("sim_ring_to_nest_fold", nside, pix, nside >= 2 ** 16 if hi is None else hi)
 
     def ring_roundtrip_any(self, nside, pix):
         return self._conv("sim_ring_roundtrip_any", nside, pix)

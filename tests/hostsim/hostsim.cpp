@@ -58,6 +58,19 @@ int64_t sim_ring_to_nest_k(int64_t nside, const int64_t *in, int64_t n, int64_t 
     return -1;
 }
 
+// the folded-coordinate form of the streaming kernel's tile routine (lookup table built exactly as the kernel's prologue does)
+int64_t sim_ring_to_nest_fold(int64_t nside, const int64_t *in, int64_t n, int64_t *out, int hi) {
+    hpgb_geom g = hpgb_make_geom(nside, 1);
+    hpgb_rk c = hpgb_make_rk(g);
+    hpgb_u32x2 lut[16];
+    for (uint32_t i = 0; i < 16; i++) hpgb_r2n_lut_entry(c, i, lut[i].x, lut[i].y);
+    for (int64_t i = 0; i < n; i++) {
+        if (!hpgb_pixel_ok(g, in[i])) return i;
+        out[i] = hi ? hpgb_ring2nest_fold<true>(c, g, lut, in[i]) : hpgb_ring2nest_fold<false>(c, g, lut, in[i]);
+    }
+    return -1;
+}
+
 // ring -> (ix,iy,face) -> ring through the general-nside path (non powers of two)
 int64_t sim_ring_roundtrip_any(int64_t nside, const int64_t *in, int64_t n, int64_t *out) {
     hpgb_geom g = hpgb_make_geom(nside, 0);

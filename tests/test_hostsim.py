@@ -36,6 +36,8 @@ def test_reorder_golden(sim, nside):
     assert_bit_equal(sim.ring_to_nest_k(nside, pix), g["r2n_%d" % nside], "r2n (kernel core)")
     assert_bit_equal(sim.nest_to_ring_k(nside, pix, hi=False), g["n2r_%d" % nside], "n2r (kernel core, general)")
     assert_bit_equal(sim.ring_to_nest_k(nside, pix, hi=False), g["r2n_%d" % nside], "r2n (kernel core, general)")
+    assert_bit_equal(sim.ring_to_nest_fold(nside, pix), g["r2n_%d" % nside], "r2n (folded coordinates)")
+    assert_bit_equal(sim.ring_to_nest_fold(nside, pix, hi=False), g["r2n_%d" % nside], "r2n (folded coordinates, general)")
 
 
 def test_reorder_isqrt_quirk_region(sim, oracle_port):
@@ -52,6 +54,8 @@ def test_reorder_isqrt_quirk_region(sim, oracle_port):
         assert_bit_equal(sim.ring_to_nest(nside, pix), ref)
         assert_bit_equal(sim.ring_to_nest_k(nside, pix), ref)
         assert_bit_equal(sim.ring_to_nest_k(nside, pix, hi=False), ref)
+        assert_bit_equal(sim.ring_to_nest_fold(nside, pix), ref)
+        assert_bit_equal(sim.ring_to_nest_fold(nside, pix, hi=False), ref)
 
 
 @pytest.mark.parametrize("nside", [1, 2, 4, 8, 64, 256])
@@ -62,6 +66,7 @@ def test_reorder_all_pixels(sim, oracle_port, nside):
     assert_bit_equal(sim.ring_to_nest(nside, pix), r2n)
     assert_bit_equal(sim.nest_to_ring_k(nside, pix), n2r)
     assert_bit_equal(sim.ring_to_nest_k(nside, pix), r2n)
+    assert_bit_equal(sim.ring_to_nest_fold(nside, pix), r2n)
 
 
 @pytest.mark.parametrize("nside", [2 ** 15, 2 ** 16, 2 ** 17, 2 ** 24, 2 ** 28, 2 ** 29])
@@ -79,6 +84,7 @@ def test_reorder_kernel_cores_random(sim, oracle_port, nside):
     for hi in ([False, True] if nside >= 2 ** 16 else [False]):
         assert_bit_equal(sim.nest_to_ring_k(nside, pix, hi=hi), n2r, "n2r hi=%s" % hi)
         assert_bit_equal(sim.ring_to_nest_k(nside, pix, hi=hi), r2n, "r2n hi=%s" % hi)
+        assert_bit_equal(sim.ring_to_nest_fold(nside, pix, hi=hi), r2n, "r2n folded hi=%s" % hi)
 
 
 @pytest.mark.parametrize("nside", [3, 5, 12, 924, 2 ** 29 - 1])
@@ -380,6 +386,7 @@ def test_reorder_isqrt_quirk_known_pixels(sim, oracle_port, oracle_ref):
     want = np.array([-2888003994884788701, -2888003994884788696, -2888003994884788700], dtype=np.int64)
     assert_bit_equal(oracle_port.ring_to_nest(nside, ring), want)
     assert_bit_equal(sim.ring_to_nest_k(nside, ring), want)
+    assert_bit_equal(sim.ring_to_nest_fold(nside, ring), want)
     assert_bit_equal(sim.ring_to_nest(nside, ring), want)
     if oracle_ref is not None:
         assert_bit_equal(oracle_ref.ring_to_nest(nside, ring), want)
