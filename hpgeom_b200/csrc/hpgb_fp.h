@@ -1200,6 +1200,9 @@ HPGB_HD bool hpgb_ring_above_fast(const hpgb_geom &g, const hpgb_a2p_fast &f, do
 // Everything else (the two pole rows, a pair that straddles a cap edge, a point too close to a ring for the
 // cheap ring choice) is rare and goes to hpgb_interpol / hpgb_interpol_rings.
 // ---------------------------------------------------------------------------------------------
+// the branch-free divisions of the zone bodies (hpgb_div_tame, hpgb_div_const) are IEEE-exact away from underflow;
+// phi / dphi with a subnormal-range phi is not: such points (0 < phi < 1e-290) go to the reference-shaped routine
+HPGB_HD bool hpgb_interp_phi_tame(double phi) { return !(phi > 0.0 && phi < 1e-290); }
 // zone of the pair (ir1, ir1 + 1): 0 belt, 1 cap, 2 anything else
 HPGB_HD int hpgb_interp_zone(uint32_t ns, int64_t ir1) {
     const uint32_t r = (uint32_t)ir1;
@@ -1276,6 +1279,147 @@ HPGB_HD void hpgb_interp_cap(const hpgb_geom &g, const hpgb_rk &rk, const double
             if (south) sp = g.npix - sp - (int64_t)nr;
             p[2 * k] = sp + i1;
             p[2 * k + 1] = sp + i2;
+        }
+    }
+    const double wt = hpgb_div_tame(theta - th[0], th[1] - th[0]);
+    w[0] = (1 - w1[0]) * (1 - wt);
+    w[1] = w1[0] * (1 - wt);
+    w[2] = (1 - w1[1]) * wt;
+    w[3] = w1[1] * wt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Interpolation for SMALL nside (<= HPGB_INTERP_LUT_MAX_NSIDE), third generation: what depends only on the RING is
+// computed once per launch into a shared-memory table instead of once per point --
+//   th[nring]            colatitude of ring nring, 1 <= nring <= 2 nside (the southern rings are pi - th, as in the
+//                        reference's get_ring_info2, hpgeom/healpix_geom.c:1585-1610)
+//   cap[nring] = (d, inv) d = 2 pi / (4 nring), the pixel spacing of a polar-cap ring, and inv = RN(1 / d)
+// -- by the SAME routines the per-point bodies above call (hpgb_acos_tab / hpgb_atan2_tab / IEEE division), so every
+// value is bit-identical; the table is the reference's "ring info" hoisted out of the point loop (two correctly
+// rounded inverse trig evaluations, ~200 instructions, leave the body of a point).
+// Also here: 32-bit ring indices (a ring has at most 4 nside <= 2^14 pixels), NEST numbers through the folded
+// coordinates of hpgb_reorder.h with a ONE-word Morton step (X, Y < 2^14), and divisions by the per-ring constant
+// d as q = RN(a inv), q' = RN(q + (a - d q) inv) -- correctly rounded when inv = RN(1/d) and d's significand is not
+// all ones (Markstein's theorem; d = pi / (2 nring)); checked against IEEE division in tests/test_hostsim.py.
+// ---------------------------------------------------------------------------------------------
+#define HPGB_INTERP_LUT_MAX_NSIDE 4096
+struct hpgb_cdiv {
+    double d, inv;
+};
+HPGB_HD double hpgb_div_const(double a, const hpgb_cdiv &c) {
+    const double q = a * c.inv;
+    return fma(fma(-c.d, q, a), c.inv, q);
+}
+HPGB_HD int32_t hpgb_d2i(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2int_rz(v);
+#else
+    return (int32_t)v;
+#endif
+}
+// one table entry (run by the kernel's prologue and by the host simulation): ring nring in 1 .. 2 nside
+HPGB_HD void hpgb_interp_ring_entry(const hpgb_geom &g, const uint64_t *TA, const double *TQ, uint32_t nring, double &theta,
+                                    hpgb_cdiv &cap) {
+    const uint32_t ns = (uint32_t)g.nside;
+    cap.d = cap.inv = 0.0;
+    if (nring < ns) {
+        const double dn = (double)nring;
+        const double t = (dn * dn) * g.fact2;
+        theta = hpgb_atan2_tab(TQ, hpgb_sqrt_tame(t * (2 - t)), 1 - t, HPGB_ATANQ_ROWS);
+        cap.d = HPGB_TWOPI / (double)(4u * nring);
+        cap.inv = 1.0 / cap.d;
+    } else {
+        theta = hpgb_acos_tab(TA, (double)(2u * ns - nring) * g.fact1);
+    }
+}
+// Morton code of two coordinates below 2^16 in one word
+HPGB_HD uint32_t hpgb_interleave16(uint32_t x, uint32_t y) {
+    uint32_t lo = hpgb_prmt(x, y, 0x5140);
+    HPGB_DSWAP(lo, 0x00F000F0u, 4);
+    HPGB_DSWAP(lo, 0x0C0C0C0Cu, 2);
+    HPGB_DSWAP(lo, 0x22222222u, 1);
+    return lo;
+}
+// (belt ring r, nside <= r <= 3 nside; 0-based in-ring index q) -> NEST pixel; flut = the 16 (lx, ly) pairs of
+// hpgb_r2n_lut_entry
+HPGB_HD int64_t hpgb_beltidx2nest_fold(const hpgb_rk &c, const hpgb_u32x2 *flut, uint32_t r, uint32_t q) {
+    uint32_t X, Y;
+    hpgb_r2n_belt_fold(c, flut, r - c.ns, q, X, Y);  // q < 4 nside: the mask inside is a no-op
+    return (int64_t)hpgb_interleave16(X, Y);
+}
+// (cap ring: nring < nside from the nearest pole, south or north; 0-based in-ring index q) -> NEST pixel
+HPGB_HD int64_t hpgb_capidx2nest_fold(const hpgb_rk &c, uint32_t nring, bool south, uint32_t q) {
+    const bool t1 = q >= 2u * nring;
+    q -= t1 ? 2u * nring : 0u;
+    const bool t2 = q >= nring;
+    q -= t2 ? nring : 0u;
+    const uint32_t X = (south ? q : c.ns - nring + q) + (t2 ? c.ns : 0u);
+    const uint32_t Y = (south ? nring - 1u - q : c.nsm1 - q) + (t1 ? c.ns : 0u) + (south ? c.ns2 : 0u);
+    return (int64_t)hpgb_interleave16(X, Y);
+}
+// floor of t >= -1/2 the way the reference forms it, 32-bit
+HPGB_HD int32_t hpgb_interp_floor32(double t) { return (t < 0) ? hpgb_d2i(t) - 1 : hpgb_d2i(t); }
+
+template <bool NEST>
+HPGB_HD void hpgb_interp_belt_lut(const hpgb_geom &g, const hpgb_rk &rk, const hpgb_u32x2 *flut, const double *th_tab,
+                                  const hpgb_cdiv &dphi, double theta, double phi, uint32_t ir1, int64_t *p, double *w) {
+    const uint32_t ns = rk.ns, nr = rk.ns4;
+    const double tc = hpgb_div_const(phi, dphi);  // shared by the two rings
+    double th[2], w1[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t r = ir1 + (uint32_t)k;
+        const bool south = r > rk.ns2;
+        const uint32_t nring = south ? nr - r : r;
+        const double t0 = th_tab[nring];
+        th[k] = south ? HPGB_PI - t0 : t0;
+        const double hs = ((nring - ns) & 1u) == 0u ? 0.5 : 0.0;
+        const int32_t i1 = hpgb_interp_floor32(tc - hs);
+        w1[k] = hpgb_div_const(phi - ((double)i1 + hs) * dphi.d, dphi);
+        const uint32_t q1 = i1 < 0 ? (uint32_t)i1 + nr : (uint32_t)i1;
+        const uint32_t q2 = (uint32_t)(i1 + 1) >= nr ? (uint32_t)(i1 + 1) - nr : (uint32_t)(i1 + 1);
+        if (NEST) {
+            p[2 * k] = hpgb_beltidx2nest_fold(rk, flut, r, q1);
+            p[2 * k + 1] = hpgb_beltidx2nest_fold(rk, flut, r, q2);
+        } else {
+            uint32_t sp = rk.ncap_lo + (nring - ns) * nr;
+            if (south) sp = rk.npix_lo - sp - nr;
+            p[2 * k] = (int64_t)(sp + q1);
+            p[2 * k + 1] = (int64_t)(sp + q2);
+        }
+    }
+    const double wt = hpgb_div_tame(theta - th[0], th[1] - th[0]);
+    w[0] = (1 - w1[0]) * (1 - wt);
+    w[1] = w1[0] * (1 - wt);
+    w[2] = (1 - w1[1]) * wt;
+    w[3] = w1[1] * wt;
+}
+
+template <bool NEST>
+HPGB_HD void hpgb_interp_cap_lut(const hpgb_geom &g, const hpgb_rk &rk, const double *th_tab, const hpgb_cdiv *cap_tab,
+                                 double theta, double phi, uint32_t ir1, int64_t *p, double *w) {
+    double th[2], w1[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t r = ir1 + (uint32_t)k;
+        const bool south = r > rk.ns2;
+        const uint32_t nring = south ? rk.ns4 - r : r;
+        const double t0 = th_tab[nring];
+        th[k] = south ? HPGB_PI - t0 : t0;
+        const hpgb_cdiv dphi = cap_tab[nring];
+        const uint32_t nr = 4u * nring;
+        const int32_t i1 = hpgb_interp_floor32(hpgb_div_const(phi, dphi) - 0.5);
+        w1[k] = hpgb_div_const(phi - ((double)i1 + 0.5) * dphi.d, dphi);
+        const uint32_t q1 = i1 < 0 ? (uint32_t)i1 + nr : (uint32_t)i1;
+        const uint32_t q2 = (uint32_t)(i1 + 1) >= nr ? (uint32_t)(i1 + 1) - nr : (uint32_t)(i1 + 1);
+        if (NEST) {
+            p[2 * k] = hpgb_capidx2nest_fold(rk, nring, south, q1);
+            p[2 * k + 1] = hpgb_capidx2nest_fold(rk, nring, south, q2);
+        } else {
+            uint32_t sp = 2u * nring * (nring - 1u);
+            if (south) sp = rk.npix_lo - sp - nr;
+            p[2 * k] = (int64_t)(sp + q1);
+            p[2 * k + 1] = (int64_t)(sp + q2);
         }
     }
     const double wt = hpgb_div_tame(theta - th[0], th[1] - th[0]);

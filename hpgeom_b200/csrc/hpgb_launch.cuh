@@ -433,6 +433,15 @@ __device__ __forceinline__ void hpgb_st2(double *p, double a, double b) { __stwt
 __device__ __forceinline__ void hpgb_st2(int64_t *p, int64_t a, int64_t b) { __stcs(reinterpret_cast<longlong2 *>(p), make_longlong2(a, b)); }
 __device__ __forceinline__ void hpgb_st2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
 #endif
+// 256-bit streaming stores (sm_100: st.global.v4.b64 -> STG.E.EF.256): a lane writes one whole 32-byte sector -- a (4,)
+// row of int64 / float64 -- in ONE request instead of two half-sector ones.  p must be 32-byte aligned.
+__device__ __forceinline__ void hpgb_st4(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d) {
+    asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+__device__ __forceinline__ void hpgb_st4(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+static inline bool hpgb_aligned32(const void *p) { return (((uintptr_t)p) & 31u) == 0; }
 __device__ __forceinline__ int64_t hpgb_ld1(const int64_t *p) { return __ldcs(p); }
 __device__ __forceinline__ double hpgb_ld1(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void hpgb_st1(int64_t *p, int64_t a) { __stcs(p, a); }

@@ -73,6 +73,13 @@ struct OpInterp {
         c.T = sT;
         return c;
     }
+    // the ring-table kernel keeps the acos / atan2 tables in global memory (only its prologue reads them)
+    __device__ __forceinline__ Ctx prologue_global_tables() const {
+        __shared__ double sT[4 * HPGB_SINCOS_ROWS];
+        for (int i = threadIdx.x; i < 4 * HPGB_SINCOS_ROWS; i += blockDim.x) sT[i] = g_hpgb_sincos[i];
+        __syncthreads();
+        return Ctx{sT, reinterpret_cast<const uint64_t *>(g_hpgb_acos_tab), g_hpgb_atanq_tab};
+    }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(a + i), hpgb_ld2(b + i)}; }
     static __device__ __noinline__ void slow(const hpgb_geom &gg, const double *T, double theta, double phi, int64_t *p,
                                              double *w) {
@@ -201,13 +208,42 @@ __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_rows(const Op op, 
 // float64 row are one 32-byte sector each, so nothing is gained by transposing them through shared memory first.
 #define HPGB_INTERP_QCAP 64
 #define HPGB_INTERP_QBYTES (HPGB_INTERP_QCAP * (8 + 8 + 8 + 4))
-template <class Op, bool NEST>
+// LUT (nside <= HPGB_INTERP_LUT_MAX_NSIDE, enough points to pay for it): what depends only on the ring -- its colatitude,
+// a cap ring's pixel spacing and the reciprocal of that -- is computed ONCE per CTA into shared memory by the prologue
+// (2 nside ring entries spread over the CTA's threads, the acos / atan2 tables read from global memory) and the zone
+// bodies are the hpgb_interp_*_lut ones of hpgb_fp.h: no inverse trigonometry in the point loop at all.
+//   dynamic shared memory: th[2 nside + 2] | cap[nside] (16 B) | 16 fold entries | the warps' queues
+static __host__ __device__ inline int hpgb_interp_lut_bytes(int64_t nside) { return (int)((2 * nside + 2) * 8 + nside * 16 + 128); }
+template <class Op, bool NEST, bool LUT>
 __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_sorted(const Op op, const int64_t n, const double dphi_belt,
                                                                     hpgb_status_t *st) {
     extern __shared__ __align__(16) unsigned long long hpgb_interp_tabs[];
-    const typename Op::Ctx ctx = op.prologue();
+    const typename Op::Ctx ctx = LUT ? op.prologue_global_tables() : op.prologue();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *qmem = reinterpret_cast<unsigned char *>(hpgb_interp_tabs + HPGB_INTERP_TAB_WORDS) + warp * (2 * HPGB_INTERP_QBYTES);
+    const uint32_t ns_l = (uint32_t)op.g.nside;
+    double *th_tab = reinterpret_cast<double *>(hpgb_interp_tabs);
+    hpgb_cdiv *cap_tab = reinterpret_cast<hpgb_cdiv *>(th_tab + 2 * ns_l + 2);
+    hpgb_u32x2 *flut = reinterpret_cast<hpgb_u32x2 *>(cap_tab + ns_l);
+    hpgb_cdiv dphi_c;
+    dphi_c.d = dphi_belt;
+    dphi_c.inv = 1.0 / dphi_belt;
+    if (LUT) {
+        for (uint32_t nring = 1u + threadIdx.x; nring <= 2u * ns_l; nring += blockDim.x) {
+            double th;
+            hpgb_cdiv cd;
+            hpgb_interp_ring_entry(op.g, ctx.TA, ctx.TQ, nring, th, cd);
+            th_tab[nring] = th;
+            if (nring < ns_l) cap_tab[nring] = cd;
+        }
+        if (threadIdx.x < 16) {
+            hpgb_u32x2 e;
+            hpgb_r2n_lut_entry(op.rk, threadIdx.x, e.x, e.y);
+            flut[threadIdx.x] = e;
+        }
+        __syncthreads();
+    }
+    unsigned char *qmem = reinterpret_cast<unsigned char *>(hpgb_interp_tabs) +
+                          (LUT ? hpgb_interp_lut_bytes(op.g.nside) : HPGB_INTERP_TAB_WORDS * 8) + warp * (2 * HPGB_INTERP_QBYTES);
     struct Queue {
         double *th, *ph;
         int64_t *idx;
@@ -224,17 +260,29 @@ __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_sorted(const Op op
     const int64_t nw = (int64_t)gridDim.x * (HPGB_INTERP_BLOCK / 32);
     const int64_t nfull = n >> 6, nchunk = (n + 63) >> 6;
     hpgb_bad_t bad;
+    // a (4,) row is one 32-byte sector: one 256-bit store when the arrays are 32-byte aligned (every allocation is;
+    // a caller's odd 16-byte-aligned view takes the two-halves form).  The points of a queue are not in index order, so
+    // a warp's store instruction touches 32 different sectors either way -- the 256-bit form halves the requests.
+    const bool st256 = (((uintptr_t)op.pix | (uintptr_t)op.wgt) & 31u) == 0;
     auto emit = [&](int64_t i, const int64_t *p, const double *w) {
-        hpgb_st2(op.pix + 4 * i, p[0], p[1]);
-        hpgb_st2(op.pix + 4 * i + 2, p[2], p[3]);
-        hpgb_st2(op.wgt + 4 * i, w[0], w[1]);
-        hpgb_st2(op.wgt + 4 * i + 2, w[2], w[3]);
+        if (st256) {
+            hpgb_st4(op.pix + 4 * i, p[0], p[1], p[2], p[3]);
+            hpgb_st4(op.wgt + 4 * i, w[0], w[1], w[2], w[3]);
+        } else {
+            hpgb_st2(op.pix + 4 * i, p[0], p[1]);
+            hpgb_st2(op.pix + 4 * i + 2, p[2], p[3]);
+            hpgb_st2(op.wgt + 4 * i, w[0], w[1]);
+            hpgb_st2(op.wgt + 4 * i + 2, w[2], w[3]);
+        }
     };
     auto run_belt = [&](int first, int count) {
         if (lane < count) {
             int64_t p[4];
             double w[4];
-            hpgb_interp_belt<NEST>(op.g, op.rk, ctx.TA, dphi_belt, qb.th[first + lane], qb.ph[first + lane], qb.ir[first + lane], p, w);
+            if (LUT)
+                hpgb_interp_belt_lut<NEST>(op.g, op.rk, flut, th_tab, dphi_c, qb.th[first + lane], qb.ph[first + lane], qb.ir[first + lane], p, w);
+            else
+                hpgb_interp_belt<NEST>(op.g, op.rk, ctx.TA, dphi_belt, qb.th[first + lane], qb.ph[first + lane], qb.ir[first + lane], p, w);
             emit(qb.idx[first + lane], p, w);
         }
         __syncwarp();
@@ -243,7 +291,10 @@ __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_sorted(const Op op
         if (lane < count) {
             int64_t p[4];
             double w[4];
-            hpgb_interp_cap<NEST>(op.g, op.rk, ctx.TQ, qc.th[first + lane], qc.ph[first + lane], qc.ir[first + lane], p, w);
+            if (LUT)
+                hpgb_interp_cap_lut<NEST>(op.g, op.rk, th_tab, cap_tab, qc.th[first + lane], qc.ph[first + lane], qc.ir[first + lane], p, w);
+            else
+                hpgb_interp_cap<NEST>(op.g, op.rk, ctx.TQ, qc.th[first + lane], qc.ph[first + lane], qc.ir[first + lane], p, w);
             emit(qc.idx[first + lane], p, w);
         }
         __syncwarp();
@@ -264,24 +315,38 @@ __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_sorted(const Op op
     for (; ch < nchunk; ch += nw) {
         const typename Op::In2 cur = v;
         if (ch + nw < nchunk) v = fetch(ch + nw);
-#pragma unroll 1
+        // the cheap part of BOTH points first, as one straight-line block (two independent dependency chains per lane:
+        // this part is latency-bound at 20 warps per SM), then the queueing point by point
+        double theta2[2], phi2[2];
+        int64_t ir2[2];
+        int zone2[2];  // 0 belt, 1 cap, 2 the reference-shaped routine, 3 nothing to do
+#pragma unroll
         for (int q = 0; q < 2; q++) {
             const int64_t i = ch * 64 + 2 * lane + q;
             const double va = q ? cur.a.y : cur.a.x, vb = q ? cur.b.y : cur.b.x;
-            double theta = 0.0, phi = 0.0;
-            int64_t ir1 = 0;
-            int zone = 3;  // 0 belt, 1 cap, 2 the reference-shaped routine, 3 nothing to do
+            theta2[q] = phi2[q] = 0.0;
+            ir2[q] = 0;
+            zone2[q] = 3;
             if (i < n) {
-                if (!hpgb_angles_exact<Op::kLonLat, Op::kDegrees>(va, vb, theta, phi)) {
-                    bad.flag(op.base + i);
-                    const int64_t p[4] = {-1, -1, -1, -1};
-                    const double w[4] = {0.0, 0.0, 0.0, 0.0};
-                    emit(i, p, w);
-                } else if (hpgb_ring_above_fast(op.g, op.f, theta, ir1)) {
-                    zone = hpgb_interp_zone(ns, ir1);
-                } else {
-                    zone = 2;
-                }
+                if (!hpgb_angles_exact<Op::kLonLat, Op::kDegrees>(va, vb, theta2[q], phi2[q]))
+                    zone2[q] = 4;  // refused
+                else if (hpgb_ring_above_fast(op.g, op.f, theta2[q], ir2[q]) && hpgb_interp_phi_tame(phi2[q]))
+                    zone2[q] = hpgb_interp_zone(ns, ir2[q]);
+                else
+                    zone2[q] = 2;
+            }
+        }
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            const int64_t i = ch * 64 + 2 * lane + q;
+            const double theta = q ? theta2[1] : theta2[0], phi = q ? phi2[1] : phi2[0];
+            const int64_t ir1 = q ? ir2[1] : ir2[0];
+            const int zone = q ? zone2[1] : zone2[0];
+            if (zone == 4) {
+                bad.flag(op.base + i);
+                const int64_t p[4] = {-1, -1, -1, -1};
+                const double w[4] = {0.0, 0.0, 0.0, 0.0};
+                emit(i, p, w);
             }
             const unsigned mb = __ballot_sync(0xFFFFFFFFu, zone == 0);
             if (zone == 0) {
@@ -317,20 +382,32 @@ __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_sorted(const Op op
     bad.commit(st);
 }
 
-template <class Op, bool NEST>
-int launch_interp_sorted(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
-    const int smem = Op::DYN_SMEM + (HPGB_INTERP_BLOCK / 32) * 2 * HPGB_INTERP_QBYTES;
+// points below which the ring table does not pay for itself (its prologue costs ~13 ring entries per thread)
+#ifndef HPGB_INTERP_LUT_MIN_N
+#define HPGB_INTERP_LUT_MIN_N (1 << 20)
+#endif
+template <class Op, bool NEST, bool LUT>
+int launch_interp_sorted_t(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
+    const int smem = (LUT ? hpgb_interp_lut_bytes(HPGB_INTERP_LUT_MAX_NSIDE) : Op::DYN_SMEM) + (HPGB_INTERP_BLOCK / 32) * 2 * HPGB_INTERP_QBYTES;
     static hpgb_occ_cache cache;  // per device: the dynamic-smem opt-in is a per-device attribute
-    (void)hpgb_resident_ctas_cached(cache, k_interp_sorted<Op, NEST>, smem, HPGB_INTERP_BLOCK);
+    (void)hpgb_resident_ctas_cached(cache, k_interp_sorted<Op, NEST, LUT>, smem, HPGB_INTERP_BLOCK);
     int64_t grid = hpgb_sm_count();
     const int64_t want = (((n + 63) >> 6) + HPGB_INTERP_BLOCK / 32 - 1) / (HPGB_INTERP_BLOCK / 32);
     if (want < grid) grid = want > 0 ? want : 1;
     // 2 pi / (4 nside): the belt rings' pixel spacing, the same IEEE division the reference does per ring
     const double dphi_belt = HPGB_TWOPI / (double)(4 * op.g.nside);
-    k_interp_sorted<Op, NEST><<<(unsigned)grid, HPGB_INTERP_BLOCK, smem, s>>>(op, n, dphi_belt, st);
+    const int smem_launch = (LUT ? hpgb_interp_lut_bytes(op.g.nside) : Op::DYN_SMEM) + (HPGB_INTERP_BLOCK / 32) * 2 * HPGB_INTERP_QBYTES;
+    k_interp_sorted<Op, NEST, LUT><<<(unsigned)grid, HPGB_INTERP_BLOCK, smem_launch, s>>>(op, n, dphi_belt, st);
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+}
+template <class Op, bool NEST>
+int launch_interp_sorted(const Op &op, int64_t n, hpgb_status_t *st, cudaStream_t s) {
+#if !defined(HPGB_INTERP_NO_LUT)
+    if (op.g.nside <= HPGB_INTERP_LUT_MAX_NSIDE && n >= HPGB_INTERP_LUT_MIN_N) return launch_interp_sorted_t<Op, NEST, true>(op, n, st, s);
+#endif
+    return launch_interp_sorted_t<Op, NEST, false>(op, n, st, s);
 }
 
 template <class Op>

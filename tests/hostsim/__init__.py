@@ -153,6 +153,12 @@ class HostSim:
         self.last_slow = ns.value
         return p, w
 
+    def div_const_mismatches(self, a, d):
+        """hpgb_div_const(a, d) != a / d, counted over the array a"""
+        a = self._f(a)
+        self.lib.sim_div_const_check.restype = ctypes.c_int64
+        return self.lib.sim_div_const_check(a.ctypes.data_as(_D), ctypes.c_int64(a.size), ctypes.c_double(d))
+
     def lonlat_to_thetaphi(self, lon, lat, degrees=True):
         lon, lat = self._f(lon), self._f(lat)
         th, ph = np.empty(lon.size), np.empty(lon.size)

@@ -255,6 +255,34 @@ def test_config4_neighbors_interp_upgrade(hpg, oracle_port, nest):
     assert np.abs(w.sum(axis=1) - 1.0).max() < 1e-12
 
 
+@pytest.mark.parametrize("nside", [4096, 1024, 64, 2, 1])
+@pytest.mark.parametrize("nest", [True, False])
+def test_interp_ring_table_kernel(hpg, oracle_port, nside, nest):
+    """Launches of >= 2^20 points at nside <= 4096 run the ring-table kernel (per-ring colatitudes / pixel spacings
+    computed once per CTA, k_interp.cu): bit-identical to the per-point kernel (the same points in launches below the
+    threshold), pixels equal to the oracle's, weights within the usual bound."""
+    import torch
+    rng = np.random.default_rng(nside + 99)
+    n = (1 << 20) + 12345
+    theta = np.arccos(rng.uniform(-1, 1, n))
+    phi = rng.uniform(0, 2 * np.pi, n)
+    phi[:1000] = rng.choice([0.0, 2 * np.pi - 1e-15, 1e-300, 5e-324, np.pi / 2, np.pi], 1000)
+    theta[1000:2000] = rng.choice([0.0, np.pi, 1e-9, np.pi - 1e-9, np.pi / 2], 1000)
+    tt, tp = torch.from_numpy(theta).cuda(), torch.from_numpy(phi).cuda()
+    p, w = hpg.get_interpolation_weights(nside, tt, tp, nest=nest, lonlat=False, degrees=False)
+    half = n // 2
+    parts = [hpg.get_interpolation_weights(nside, tt[a:b], tp[a:b], nest=nest, lonlat=False, degrees=False)
+             for a, b in ((0, half), (half, n))]
+    assert torch.equal(p, torch.cat([q[0] for q in parts])), "ring-table kernel pixels differ from the per-point kernel"
+    assert torch.equal(w.view(torch.int64), torch.cat([q[1] for q in parts]).view(torch.int64)), "weights differ"
+    rp, rw = oracle_port.get_interpolation_weights(nside, theta, phi, nest=nest, lonlat=False, degrees=False)
+    p, w = p.cpu().numpy(), w.cpu().numpy()
+    same = (p == rp).all(axis=1)
+    assert np.mean(~same) <= 1e-5
+    assert np.mean(w[same] != rw[same]) < 5e-3
+    assert np.abs(w[same] - rw[same]).max() <= 8 * np.spacing(np.pi) * max(nside, 2)
+
+
 def test_vector_to_pixel_random(hpg, oracle_port):
     rng = np.random.default_rng(12345)
     x, y, z = rng.uniform(-1, 1, (3, 2_000_000))

@@ -326,8 +326,41 @@ def test_interp_fast_path(sim, oracle_port, nside):
             ps, ws = sim.get_interpolation_weights_k(nside, a, b, nest=nest, exact_only=2, **kw)
             assert_bit_equal(ps, pg, "sorted interpolation pixels")
             assert_bit_equal(ws, wg, "sorted interpolation weights")
+            if nside <= 4096:  # the ring-table kernel: per-ring constants from a table, 32-bit indices, folded NEST numbers
+                pt, wt = sim.get_interpolation_weights_k(nside, a, b, nest=nest, exact_only=3, **kw)
+                assert_bit_equal(pt, pg, "ring-table interpolation pixels")
+                assert_bit_equal(wt, wg, "ring-table interpolation weights")
         pe, we = sim.get_interpolation_weights_k(nside, lon, lat, nest=nest, exact_only=True)
         assert_bit_equal(p1, pe, "fast vs reference-shaped pixels")
+
+
+@pytest.mark.parametrize("nside", [1, 2, 16, 64, 1024, 4096])
+def test_interp_ring_table_dense(sim, nside):
+    """The ring-table bodies against the per-point ones on points spread over every ring, the ring centres themselves
+    and the phi wrap (first / last pixel of a ring), both schemes."""
+    rng = np.random.default_rng(nside + 5)
+    n = 300_000
+    theta = np.arccos(rng.uniform(-1, 1, n))
+    phi = rng.uniform(0, 2 * np.pi, n)
+    phi[: n // 10] = rng.choice([0.0, 2 * np.pi - 1e-15, 1e-300, np.pi / 2, np.pi, 6.283185307179586], n // 10)
+    phi[n // 10: n // 5] = 2 * np.pi * (rng.integers(0, 4 * nside, n // 10) + rng.choice([0.0, 0.5], n // 10)) / (4 * nside)
+    for nest in (True, False):
+        pg, wg = sim.get_interpolation_weights_k(nside, theta, phi, nest=nest, lonlat=False, degrees=False)
+        pt, wt = sim.get_interpolation_weights_k(nside, theta, phi, nest=nest, lonlat=False, degrees=False, exact_only=3)
+        assert_bit_equal(pt, pg, "ring-table interpolation pixels")
+        assert_bit_equal(wt, wg, "ring-table interpolation weights")
+
+
+def test_div_const_is_ieee_division(sim):
+    """hpgb_div_const (multiply by RN(1/d), one fma residual correction) returns the IEEE quotient for the divisors the
+    interpolation uses -- d = 2 pi / (4 nring) -- over the numerators it meets (phi in [0, 2 pi], residuals near 0)."""
+    rng = np.random.default_rng(11)
+    a = np.concatenate([rng.uniform(0, 2 * np.pi, 400_000), rng.uniform(0, 1, 100_000) * 10.0 ** rng.uniform(-12, 0, 100_000),
+                        np.nextafter(np.linspace(0, 2 * np.pi, 4097), 7.0)[1:], [0.0, 1e-290, 2 * np.pi]])  # (subnormal-range phi never gets here)
+    for nring in [1, 2, 3, 5, 7, 100, 1000, 1023, 2047, 4095, 4096, 2 ** 20, 2 ** 29]:
+        d = 2 * np.pi / (4 * nring)
+        assert sim.div_const_mismatches(a, d) == 0
+        assert sim.div_const_mismatches(a * d, d) == 0  # quotients near integers (the floor() of the pixel index)
 
 
 def test_lonlat_golden(sim):
