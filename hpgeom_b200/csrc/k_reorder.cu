@@ -401,6 +401,17 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_neighbors_rows(const int64_t *__
 #pragma unroll
         for (int a = 0; a + 1 < HPGB_NB_AHEAD; a++) v[a] = v[a + 1];
         if (ch + HPGB_NB_AHEAD * nw < nchunk) v[HPGB_NB_AHEAD - 1] = hpgb_ld2(pix + (ch + HPGB_NB_AHEAD * nw) * 64 + 2 * lane);
+#if defined(HPGB_NB_DIRECT256)
+        // A/B: rows straight from the computing lane as two 256-bit stores each (no staging)
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            int64_t r[8];
+            const int64_t i = ch * 64 + 2 * lane + q;
+            convert(q ? cur.y : cur.x, i, r);
+            hpgb_st4(out + 8 * i, r[0], r[1], r[2], r[3]);
+            hpgb_st4(out + 8 * i + 4, r[4], r[5], r[6], r[7]);
+        }
+#else
 #pragma unroll 1
         for (int q = 0; q < 2; q++) {
             int64_t r[8];
@@ -416,6 +427,7 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_neighbors_rows(const int64_t *__
             hpgb_row_st(dst + idx, ws[src * 8 + (j ^ (src & 7))]);
         }
         __syncwarp();
+#endif
     }
     // tail (< 64 pixels): one pixel per thread, direct stores
     const int64_t t = (nchunk << 6) + (int64_t)blockIdx.x * HPGB_BLOCK + threadIdx.x;
@@ -489,7 +501,7 @@ namespace {
 // 512 contiguous bytes; RING: 4 = two 128-bit stores).  The parent is converted ring -> nest once per group,
 // each child nest -> ring with the minimum-instruction cores of hpgb_reorder.h.  For
 // nside_upgrade == nside (one child) the group is the single child.
-template <bool NEST, int C>
+template <bool NEST, int C, bool ST256 = false>
 __global__ void __launch_bounds__(HPGB_BLOCK) k_upgrade(const int64_t *__restrict__ pix, int64_t *__restrict__ out,
                                                         const int64_t n_groups, const int gshift, const hpgb_geom g,
                                                         const hpgb_rk c, const hpgb_rk cu, const int64_t base,
@@ -517,8 +529,12 @@ __global__ void __launch_bounds__(HPGB_BLOCK) k_upgrade(const int64_t *__restric
             }
         }
         if (C == 4) {
-            hpgb_st2(out + 4 * w, r[0], r[1]);
-            hpgb_st2(out + 4 * w + 2, r[2], r[3]);
+            if (ST256) {  // four children = one 32-byte sector: one 256-bit store
+                hpgb_st4(out + 4 * w, r[0], r[1], r[2], r[3]);
+            } else {
+                hpgb_st2(out + 4 * w, r[0], r[1]);
+                hpgb_st2(out + 4 * w + 2, r[2], r[3]);
+            }
         } else if (C == 2) {
             hpgb_st2(out + 2 * w, r[0], r[C - 1]);
         } else {
@@ -561,17 +577,23 @@ int launch_upgrade(const int64_t *pix, int64_t *out, int64_t n, int64_t nside, i
     const int shift = 2 * (gu.order - g.order);
     // children per thread: NEST 2 (one fully coalesced 16-byte unit per lane), RING 4 (the parent's
     // ring -> nest conversion is shared by the four), 1 when nside_upgrade == nside or `out` is misaligned
-    const bool four = shift >= 2 && hpgb_aligned16(out) && !nest, two = shift >= 2 && hpgb_aligned16(out) && nest;
+    // (out 32-byte aligned: four children per thread in both schemes, written by one 256-bit store)
+#if defined(HPGB_UPG_NO256)
+    const bool st256 = false;
+#else
+    const bool st256 = shift >= 2 && hpgb_aligned32(out);
+#endif
+    const bool four = shift >= 2 && hpgb_aligned16(out) && (!nest || st256), two = shift >= 2 && hpgb_aligned16(out) && nest && !four;
     const int gshift = four ? shift - 2 : (two ? shift - 1 : shift);  // log2(groups per parent)
     const int64_t n_groups = n << gshift;
     int64_t grid = (int64_t)hpgb_sm_count() * 8;
     const int64_t want = (n_groups + HPGB_BLOCK - 1) / HPGB_BLOCK;
     if (want < grid) grid = want;
-#define GO(N, C) k_upgrade<N, C><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n_groups, gshift, g, rk, rku, base, st)
+#define GO(N, C, S) k_upgrade<N, C, S><<<(unsigned)grid, HPGB_BLOCK, 0, s>>>(pix, out, n_groups, gshift, g, rk, rku, base, st)
     if (nest) {
-        if (two) GO(true, 2); else GO(true, 1);
+        if (four) GO(true, 4, true); else if (two) GO(true, 2, false); else GO(true, 1, false);
     } else {
-        if (four) GO(false, 4); else GO(false, 1);
+        if (four && st256) GO(false, 4, true); else if (four) GO(false, 4, false); else GO(false, 1, false);
     }
 #undef GO
     g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);

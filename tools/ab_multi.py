@@ -1,7 +1,7 @@
 """A/B timing of kernel variants IN ONE PROCESS: several builds of libhpgb.so are loaded side by side and the same
 kernel is launched from each in turn (round robin), so that clock / power drift of the box hits every variant alike.
 usage: python tools/ab_multi.py <log2n> <kernel> <reps> <rounds> <lib> [<lib> ...]     (lib = path, or 'default')
-kernels: a2p a2p_ring n2r r2n p2a p2a_ring p2v v2p interp interp_ring neigh neigh_ring"""
+kernels: a2p a2p_ring n2r r2n p2a p2a_ring p2v v2p interp interp_ring neigh neigh_ring upg upg_ring"""
 import ctypes
 import os
 import sys
@@ -61,7 +61,11 @@ else:
     p4 = torch.randint(0, 12 * 4096 * 4096, (m,), dtype=torch.int64, device="cuda", generator=g)
     o8 = torch.empty((m, 8), dtype=torch.int64, device="cuda")
     w4 = torch.empty((m, 4), dtype=torch.float64, device="cuda")
-    if kern.startswith("interp"):
+    if kern.startswith("upg"):
+        o4 = torch.empty((m, 4), dtype=torch.int64, device="cuda")
+        p4 = p4 % (12 * 4096 * 4096 - 1)
+        call, outs, bpe = (lambda L: L.hpgb_upgrade_pixels(P(p4), P(o4), m, 4096, 8192, nest, P(st), s)), [o4], 40
+    elif kern.startswith("interp"):
         call, outs, bpe = (lambda L: L.hpgb_interp_weights(P(lon), P(lat), P(o8), P(w4), m, 4096, None, nest, 1, 1, P(st), s)), [o8[: m // 2], w4], 80
     else:
         call, outs, bpe = (lambda L: L.hpgb_neighbors(P(p4), P(o8), m, 4096, None, nest, P(st), s)), [o8], 72
