@@ -662,13 +662,14 @@ HPGB_HD void hpgb_pix2loc(const hpgb_geom &g, int64_t pix, double &z, double &ph
 // `tcap` is the reference's `tmp` = nr^2 * fact2 (sth = sqrt(tcap (2 - tcap))), `polar` tells
 // whether the reference would have set have_sth.  Returns false for the ~1e-8 of RING cap pixels
 // where the reference's uncorrected isqrt mis-rounds (the caller then uses hpgb_pix2loc).
+// integer part of hpgb_pix2loc_k: zone flags, ring size / 4 (`nr`), the integer the reference converts for phi
+// (`tphi`, minus `phi_off` in the RING scheme), 2 nside - ring for the belt (`zb`) and the ring number itself
+// (`ring`, 1 .. 4 nside - 1 counted from the north pole)
 template <bool NEST>
-HPGB_HD bool hpgb_pix2loc_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, double &z, double &phi, double &tcap,
-                            bool &polar) {
-    uint32_t nr, tphi;    // ring size / 4, and the integer the reference converts for phi
-    int32_t zb;           // belt: 2 nside - ring
-    bool north, cap, ok = true;
-    double phi_off = 0.0;  // RING: subtracted from the in-ring index before scaling
+HPGB_HD bool hpgb_pix2zone_k(const hpgb_rk &c, int64_t pix, uint32_t &nr, uint32_t &tphi, int32_t &zb, bool &north,
+                             bool &cap, double &phi_off, uint32_t &ring) {
+    bool ok = true;
+    phi_off = 0.0;  // RING: subtracted from the in-ring index before scaling
     if (NEST) {
         const uint32_t lo = (uint32_t)(uint64_t)pix, hi = (uint32_t)((uint64_t)pix >> 32);
         const uint32_t face = (uint32_t)((uint64_t)pix >> c.k2);
@@ -685,6 +686,7 @@ HPGB_HD bool hpgb_pix2loc_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, d
         cap = t > c.ns2;  // jr > 3 nside, or jr < nside (wraps)
         nr = hpgb_sel(cap, hpgb_sel(north, t + c.ns, c.ns3 - t), c.ns);
         zb = (int32_t)(c.ns - t);
+        ring = t + c.ns;
         // jpll * nr + ix - iy, + 8 nr when negative (only face row 1, jpll = 0, can be negative)
         const uint32_t jp = 2u * (face & 3u) + 1u - ((face >> 2) & 1u);
         const uint32_t v = jp * nr + ix - iy;
@@ -708,25 +710,56 @@ HPGB_HD bool hpgb_pix2loc_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, d
         const uint32_t iphi_cap = hpgb_sel(north, q0 + 1u, 4u * ir - q0);
         nr = hpgb_sel(cap, ir, c.ns);
         zb = (int32_t)(c.ns - tmp);
+        ring = hpgb_sel(cap, hpgb_sel(north, ir, c.ns4 - ir), tmp + c.ns);
         tphi = hpgb_sel(cap, iphi_cap, (ipb_lo & c.ns4m1) + 1u);
         phi_off = cap ? 0.5 : ((tmp & 1u) ? 1.0 : 0.5);  // belt: (iring + nside) & 1 ? 1 : 0.5, iring + nside = tmp + 2 nside
     }
-    const double dnr = (double)nr;
-    tcap = (dnr * dnr) * g.fact2;  // RN(nr^2) either way: same double as (double)(nr * nr)
-    const double zc = north ? 1.0 - tcap : tcap - 1.0;
-    z = cap ? zc : (double)zb * g.fact1;
-    polar = cap && fabs(zc) > 0.99;
+    return ok;
+}
+// phi of a pixel centre from the integers above (hpgeom/healpix_geom.c:319,338,345 / :369-376)
+template <bool NEST>
+HPGB_HD double hpgb_zone_phi_k(const hpgb_geom &g, bool cap, uint32_t tphi, double phi_off, double dnr) {
     const double dt = (double)tphi;
     if (NEST) {
         const double pb = 0.75 * HPGB_HALFPI * dt * g.fact1;
         const double pc = hpgb_div_tame(0.5 * HPGB_HALFPI * dt, dnr);
-        phi = cap ? pc : pb;
-    } else {
-        const double d = dt - phi_off;
-        const double pb = d * HPGB_PI * 0.75 * g.fact1;
-        const double pc = hpgb_div_tame(d * HPGB_HALFPI, dnr);
-        phi = cap ? pc : pb;
+        return cap ? pc : pb;
     }
+    const double d = dt - phi_off;
+    const double pb = d * HPGB_PI * 0.75 * g.fact1;
+    const double pc = hpgb_div_tame(d * HPGB_HALFPI, dnr);
+    return cap ? pc : pb;
+}
+
+template <bool NEST>
+HPGB_HD bool hpgb_pix2loc_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, double &z, double &phi, double &tcap,
+                            bool &polar) {
+    uint32_t nr, tphi, ring;  // ring size / 4, and the integer the reference converts for phi
+    int32_t zb;               // belt: 2 nside - ring
+    bool north, cap;
+    double phi_off;
+    const bool ok = hpgb_pix2zone_k<NEST>(c, pix, nr, tphi, zb, north, cap, phi_off, ring);
+    const double dnr = (double)nr;
+    tcap = (dnr * dnr) * g.fact2;  // RN(nr^2) either way: same double as (double)(nr * nr)
+    const double zn = 1.0 - tcap;
+    const double zc = north ? zn : -zn;  // tcap - 1 = -(1 - tcap) exactly
+    z = cap ? zc : (double)zb * g.fact1;
+    polar = cap && nr <= c.nr_polar;  // <=> |zc| > 0.99
+    phi = hpgb_zone_phi_k<NEST>(g, cap, tphi, phi_off, dnr);
+    return ok;
+}
+
+// pixel -> (ring number, phi) only, for the kernels that take the ring-dependent outputs (colatitude, z, sin theta)
+// from a per-launch ring table: same integers and the same phi as hpgb_pix2loc_k
+template <bool NEST>
+HPGB_HD bool hpgb_pix2ringphi_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, uint32_t &ring, bool &north,
+                                double &phi) {
+    uint32_t nr, tphi;
+    int32_t zb;
+    bool cap;
+    double phi_off;
+    const bool ok = hpgb_pix2zone_k<NEST>(c, pix, nr, tphi, zb, north, cap, phi_off, ring);
+    phi = hpgb_zone_phi_k<NEST>(g, cap, tphi, phi_off, (double)nr);
     return ok;
 }
 
@@ -818,6 +851,8 @@ HPGB_HD bool hpgb_pix2vec_k(const hpgb_rk &c, const hpgb_geom &g, const double *
     double s, co;
 #if defined(HPGB_P2V_DD)
     hpgb_sincos_cr(T, phi, s, co);
+#elif defined(HPGB_P2V_SINCOS_P)
+    hpgb_sincos_p(T, phi, s, co);
 #else
     hpgb_sincos_sd(T, phi, s, co);
 #endif
@@ -825,6 +860,47 @@ HPGB_HD bool hpgb_pix2vec_k(const hpgb_rk &c, const hpgb_geom &g, const double *
     y = sth * s;
     zz = z;
     return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ring tables (nside = 2^k <= 2^20, large batches).  Everything pixel_to_angle / pixel_to_vector derive from z --
+// the colatitude (acos / atan2) resp. sin(theta) (sqrt) -- depends on the RING NUMBER only, and a map has 4 nside - 1
+// rings against 12 nside^2 pixels.  A launch that converts many more pixels than there are rings first fills a
+// table with one entry per ring, computed by the very routine the per-pixel path uses on the first pixel of the
+// ring (so the values are the same doubles), and the streaming kernel gathers from it (the table -- <= 32 MB --
+// stays in L2) instead of redoing ~40 fp64 operations per pixel.
+// ---------------------------------------------------------------------------------------------
+// first pixel (RING scheme) of ring `ring`, 1 <= ring <= 4 nside - 1   (hpgeom/healpix_geom.c:304-345 inverted)
+HPGB_HD int64_t hpgb_ring_first_pixel(const hpgb_geom &g, int64_t ring) {
+    const int64_t ns = g.nside;
+    if (ring < ns) return 2 * ring * (ring - 1);
+    if (ring <= 3 * ns) return g.ncap + (ring - ns) * 4 * ns;
+    const int64_t nr = 4 * ns - ring;
+    return g.npix - 2 * nr * (nr + 1);
+}
+// pixel_to_angle table entry: the theta-derived output (theta, or latitude in radians / degrees) of every pixel of
+// the ring.  `gr` = geometry of the RING scheme for this nside.
+template <bool LONLAT, bool DEGREES>
+HPGB_HD double hpgb_ringtab_angle(const hpgb_geom &gr, const uint64_t *TA, const double *TQ, int64_t ring) {
+    double va, vb;
+    hpgb_pix2ang<false, true, LONLAT, DEGREES>(gr, TA, TQ, hpgb_ring_first_pixel(gr, ring), va, vb);
+    return LONLAT ? vb : va;
+}
+// pixel_to_vector table entry for ring m <= 2 nside (northern half; z(4 nside - m) = -z(m) exactly and sin(theta)
+// is the same double: hpgeom/healpix_geom.c:193,317,336)
+HPGB_HD void hpgb_ringtab_zsth(const hpgb_geom &gr, int64_t ring, double &z, double &sth) {
+    double phi;
+    bool have_sth;
+    hpgb_pix2loc<false, true>(gr, hpgb_ring_first_pixel(gr, ring), z, phi, sth, have_sth);
+    if (!have_sth) sth = sqrt((1 - z) * (1 + z));
+}
+// pixel_to_angle / pixel_to_vector of one pixel given its table entries
+template <bool NEST, bool LONLAT, bool DEGREES>
+HPGB_HD void hpgb_pix2ang_tab(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, uint32_t &ring, double &phi_out) {
+    bool north;
+    double phi;
+    hpgb_pix2ringphi_k<NEST>(c, g, pix, ring, north, phi);
+    phi_out = (LONLAT && DEGREES) ? phi * (180.0 / HPGB_PI) : phi;
 }
 
 // vector -> pixel: hpgeom/healpix_geom.c:161-170 (+ vec3_length, hpgeom/hpgeom_stack.c:396).

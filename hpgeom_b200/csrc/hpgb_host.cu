@@ -37,7 +37,7 @@ int hpgb_sm_count() {
     return sms[dev];
 }
 
-cudaError_t hpgb_dev_alloc(void **p, size_t bytes) {
+static void hpgb_tune_pool() {
     static bool tuned[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -50,7 +50,18 @@ cudaError_t hpgb_dev_alloc(void **p, size_t bytes) {
         cudaGetLastError();
         tuned[dev] = true;
     }
+}
+cudaError_t hpgb_dev_alloc(void **p, size_t bytes) {
+    hpgb_tune_pool();
     return cudaMallocAsync(p, bytes ? bytes : 16, (cudaStream_t)0);
+}
+// scratch that lives between two launches on the caller's stream (per-launch ring tables)
+cudaError_t hpgb_dev_alloc_on(void **p, size_t bytes, cudaStream_t s) {
+    hpgb_tune_pool();
+    return cudaMallocAsync(p, bytes ? bytes : 16, s);
+}
+void hpgb_dev_free_on(void *p, cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
 }
 void hpgb_dev_free(void *p) {
     if (!p) return;

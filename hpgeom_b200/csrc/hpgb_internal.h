@@ -44,4 +44,7 @@ int launch_ranges_offsets(const int64_t *ranges, int64_t m, int inclusive, int64
 int launch_ranges_expand(const int64_t *ranges, const int64_t *offs, int64_t m, int64_t out_begin, int64_t out_count,
                          int64_t *out, cudaStream_t s);
 int launch_qc_ring_ranges(const hpgb_disc_t *plan, int64_t *ranges, int64_t *work, cudaStream_t s);
+// stream-ordered device scratch (cudaMallocAsync / cudaFreeAsync on `s`; hpgb_host.cu)
+cudaError_t hpgb_dev_alloc_on(void **p, size_t bytes, cudaStream_t s);
+void hpgb_dev_free_on(void *p, cudaStream_t s);
 #endif

@@ -187,6 +187,39 @@ HPGB_HD void hpgb_sincos_sd(const double *T, double x, double &s, double &c) {
     if ((q + 1) & 2) c = -c;
 }
 
+// The same with the angle-addition sums evaluated in plain fma arithmetic (no exact products / sums): the terms
+// below the table value are < 2^-6 of it except in the first two table cells, so the result is within 0.52 ulp for
+// |r| >= 1/32 and 0.8 ulp below (r = the reduced argument).  28 fp64 operations.  For pixel_to_vector, whose contract
+// is "x, y within 2 ulp": a cosine within 1.5 ulp of the true value is within 1 ulp of glibc's, and the product with
+// sin(theta) then within 2 ulp of the reference's.
+HPGB_HD void hpgb_sincos_p(const double *T, double x, double &s, double &c) {
+    const double fq = rint(x * HPGB_2OPI);
+    const int q = (int)fq;
+    const double t = fma(-fq, HPGB_PIO2_1, x);  // exact (see hpgb_reduce_pio2)
+    double w, we;
+    hpgb_two_prod(fq, HPGB_PIO2_2, w, we);
+    const double rh = t - w;
+    const double rl = ((t - rh) - w) - fma(fq, HPGB_PIO2_3, we);
+    const bool neg = rh < 0.0;
+    const double a = fabs(rh);
+    const double al = neg ? -rl : rl;
+    const double fk = rint(a * 64.0);
+    const int k = (int)fk;
+    const double d = fma(-fk, 0.015625, a);  // exact
+    const double Sh = T[4 * k + 0], Sl = T[4 * k + 1], Ch = T[4 * k + 2], Cl = T[4 * k + 3];
+    const double p = d * d;
+    const double sd = fma(d * p, fma(p, fma(p, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), al);
+    const double cd = fma(p, fma(p, fma(p, -1.0 / 720.0, 1.0 / 24.0), -0.5), -d * al);
+    double sa = Sh + fma(Ch, d, fma(Ch, sd, fma(Sh, cd, fma(Cl, d, Sl))));
+    const double ca = Ch + fma(-Sh, d, fma(-Sh, sd, fma(Ch, cd, fma(-Sl, d, Cl))));
+    if (neg) sa = -sa;
+    const bool swap = q & 1;
+    s = swap ? ca : sa;
+    c = swap ? sa : ca;
+    if (q & 2) s = -s;
+    if ((q + 1) & 2) c = -c;
+}
+
 // 24-bit first guesses (any estimate good to ~2^-20 gives the same final result)
 HPGB_HD double hpgb_acos_guess(double z) {
 #if defined(__CUDA_ARCH__)

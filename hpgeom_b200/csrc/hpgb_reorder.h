@@ -43,6 +43,7 @@ struct hpgb_rk {
     uint32_t k, k2;                     // order, 2 * order
     uint32_t fsh_hi, fmul_hi;           // order >= 16: 2k - 32 and 1 << (2k - 32)
     uint32_t ns3p1, dnr;                // 3 nside + 1, nside - (3 nside + 1)
+    uint32_t nr_polar;                  // cap rings with nr <= nr_polar have |z| > 0.99 (hpgeom/healpix_geom.c:317,336)
 };
 
 HPGB_HD hpgb_rk hpgb_make_rk(const hpgb_geom &g) {
@@ -71,6 +72,15 @@ HPGB_HD hpgb_rk hpgb_make_rk(const hpgb_geom &g) {
     c.fmul_hi = k >= 16 ? (1u << (2u * k - 32u)) : 0u;
     c.ns3p1 = 3u * ns + 1u;
     c.dnr = ns - (3u * ns + 1u);
+    // |z| = 1 - nr^2 fact2 decreases with nr: the largest nr for which the reference's test z > 0.99 holds,
+    // evaluated with the reference's own expression
+    uint32_t lo = 0u, hi = ns;  // P(lo) true (z = 1), hi exclusive
+    while (hi - lo > 1u) {
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        const double t = ((double)mid * (double)mid) * g.fact2;
+        if (1.0 - t > 0.99) lo = mid; else hi = mid;
+    }
+    c.nr_polar = lo;
     return c;
 }
 

@@ -253,6 +253,146 @@ struct OpPix2Ang {
     }
 };
 
+// ---- ring-table form (hpgb_fp.h "Ring tables"): nside = 2^k <= 2^HPGB_RINGTAB_MAX_ORDER and a batch of at least
+// HPGB_RINGTAB_MIN_PER_RING pixels per ring.  k_ringtab_angle fills tab[ring] (one thread per ring, the per-pixel
+// routine on the ring's first pixel), the streaming kernel decodes (ring, phi) and gathers tab[ring] from L2.
+#ifndef HPGB_RINGTAB_MAX_ORDER
+#define HPGB_RINGTAB_MAX_ORDER 20
+#endif
+#ifndef HPGB_RINGTAB_P2V_MAX_ORDER
+#define HPGB_RINGTAB_P2V_MAX_ORDER 12
+#endif
+#ifndef HPGB_RINGTAB_MIN_PER_RING
+#define HPGB_RINGTAB_MIN_PER_RING 8
+#endif
+#ifndef HPGB_P2AT_MINB
+#define HPGB_P2AT_MINB 3
+#endif
+#ifndef HPGB_P2AT_ST
+#define HPGB_P2AT_ST 3
+#endif
+#ifndef HPGB_P2AT_H
+#define HPGB_P2AT_H 1  // small stage ring: the gathers want the L1 (measured: 228 vs 188 Gpix/s at nside 4096, 150 vs 138 at 2^20)
+#endif
+// gather from a ring table (A/B switch HPGB_TAB_LD: 0 = read-only path, 1 = L2 only, 2 = read-only, no L1 allocation)
+#ifndef HPGB_TAB_LD
+#define HPGB_TAB_LD 0
+#endif
+__device__ __forceinline__ double hpgb_tab_ld(const double *p) {
+#if HPGB_TAB_LD == 1
+    return __ldcg(p);
+#elif HPGB_TAB_LD == 2
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ double2 hpgb_tab_ld(const double2 *p) {
+#if HPGB_TAB_LD == 1
+    return __ldcg(p);
+#elif HPGB_TAB_LD == 2
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+template <bool LONLAT, bool DEGREES>
+__global__ void __launch_bounds__(HPGB_P2A_BLOCK) k_ringtab_angle(const hpgb_geom gr, double *tab, const int64_t nrings) {
+    extern __shared__ __align__(16) unsigned long long hpgb_p2a_tabs[];
+    typedef OpPix2Ang<false, true, LONLAT, DEGREES, false> Gen;
+    const uint64_t *T = Gen::stage_tables(hpgb_p2a_tabs);
+    for (int64_t ring = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ring < nrings; ring += (int64_t)gridDim.x * blockDim.x)
+        tab[ring] = ring == 0 ? 0.0 : hpgb_ringtab_angle<LONLAT, DEGREES>(gr, T, Gen::atanq(T), ring);
+}
+
+template <bool NEST, bool LONLAT, bool DEGREES>
+struct OpPix2AngTab {
+    const int64_t *pix;
+    double *a, *b;
+    int64_t base;
+    hpgb_geom g;
+    hpgb_rk c;
+    const double *tab;  // 4 nside entries, [ring]
+    typedef longlong2 In2;
+    typedef hpgb_no_ctx Ctx;
+    HPGB_STREAM_IN_I64(pix, HPGB_P2AT_MINB)
+    __device__ __forceinline__ Ctx prologue() const { return Ctx(); }
+    __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
+    __device__ __forceinline__ void one(int64_t p, int64_t i, hpgb_bad_t &bad, double &va, double &vb) const {
+        const bool okp = hpgb_pixel_ok(g, p);
+        uint32_t ring;
+        double ph;
+        hpgb_pix2ang_tab<NEST, LONLAT, DEGREES>(c, g, okp ? p : 0, ring, ph);
+        const double th = hpgb_tab_ld(tab + ring);
+        va = LONLAT ? ph : th;
+        vb = LONLAT ? th : ph;
+        if (!okp) {
+            bad.flag(base + i);
+            va = vb = 0.0;
+        }
+    }
+    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &, hpgb_bad_t &bad) const {
+        double a0, b0, a1, b1;
+        one(v.x, i, bad, a0, b0);
+        one(v.y, i + 1, bad, a1, b1);
+        hpgb_st2(a + i, a0, a1);
+        hpgb_st2(b + i, b0, b1);
+    }
+    HPGB_DEFAULT_RUN4
+    __device__ __forceinline__ void run1(int64_t i, const Ctx &, hpgb_bad_t &bad) const {
+        double va, vb;
+        one(hpgb_ld1(pix + i), i, bad, va, vb);
+        hpgb_st1(a + i, va);
+        hpgb_st1(b + i, vb);
+    }
+};
+
+// does a batch of n pixels at this geometry take the ring-table form?
+// (max_order: pixel_to_angle gains up to nside 2^20 -- 228 / 164 / 157 Gpix/s at nside 4096 / 2^16 / 2^20 against 140
+// per pixel: beyond the L1 the gather costs one L2 sector per pixel --, pixel_to_vector only while the table stays in
+// the L1, its sin / cos(phi) dominate either way)
+static inline bool hpgb_use_ringtab(const hpgb_geom &g, int64_t n, int max_order) {
+#if defined(HPGB_NO_RINGTAB)
+    return false;
+#else
+    return g.order >= 0 && g.order <= max_order && n >= (int64_t)HPGB_RINGTAB_MIN_PER_RING * 4 * g.nside && n >= (1 << 20);
+#endif
+}
+
+template <bool NEST, bool LONLAT, bool DEGREES>
+int launch_p2a_ringtab(const int64_t *pix, double *a, double *b, int64_t n, const hpgb_geom &g, int64_t base,
+                       hpgb_status_t *st, cudaStream_t s) {
+    const int64_t nrings = 4 * g.nside;
+    double *tab = nullptr;
+    cudaError_t e = hpgb_dev_alloc_on((void **)&tab, (size_t)nrings * 8, s);
+    if (e != cudaSuccess) return HPGB_E_CUDA + (int)e;
+    typedef OpPix2Ang<false, true, LONLAT, DEGREES, false> Gen;
+    static hpgb_occ_cache cache;
+    hpgb_resident_ctas_cached(cache, k_ringtab_angle<LONLAT, DEGREES>, Gen::DYN_SMEM, HPGB_P2A_BLOCK);
+    int64_t grid = (nrings + HPGB_P2A_BLOCK - 1) / HPGB_P2A_BLOCK;
+    if (grid > hpgb_sm_count()) grid = hpgb_sm_count();
+    hpgb_geom gr = g;
+    gr.nest = 0;
+    k_ringtab_angle<LONLAT, DEGREES><<<(unsigned)grid, HPGB_P2A_BLOCK, Gen::DYN_SMEM, s>>>(gr, tab, nrings);
+    g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    int rc = e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+    if (rc == HPGB_OK) {
+        OpPix2AngTab<NEST, LONLAT, DEGREES> op{pix, a, b, base, g, hpgb_make_rk(g), tab};
+#if defined(HPGB_P2AT_MAP)
+        rc = hpgb_launch_map(op, n, true, st, s);
+#else
+        rc = hpgb_launch_stream<decltype(op), HPGB_P2AT_ST, HPGB_P2AT_H>(op, n, st, s);
+#endif
+    }
+    hpgb_dev_free_on(tab, s);
+    return rc;
+}
+
 template <bool NEST, bool LONLAT, bool DEGREES>
 int launch_p2a_t(const int64_t *pix, double *a, double *b, int64_t n, int64_t nside, const int64_t *nside_v,
                  int64_t base, hpgb_status_t *st, cudaStream_t s) {
@@ -263,6 +403,7 @@ int launch_p2a_t(const int64_t *pix, double *a, double *b, int64_t n, int64_t ns
     const hpgb_geom g = hpgb_make_geom(nside, NEST);
     const bool vec = hpgb_aligned16(pix) && hpgb_aligned16(a) && hpgb_aligned16(b);
     if (NEST || g.order >= 0) {
+        if (vec && hpgb_use_ringtab(g, n, HPGB_RINGTAB_MAX_ORDER)) return launch_p2a_ringtab<NEST, LONLAT, DEGREES>(pix, a, b, n, g, base, st, s);
         OpPix2Ang<NEST, true, LONLAT, DEGREES, false> op{pix, a, b, nullptr, base, g, hpgb_make_rk(g)};
 #if !defined(HPGB_P2A_MAP)
         // one 768-thread CTA per SM on the TMA ring (3 stages x 3072 pixels), tables + queues behind the ring
@@ -486,6 +627,103 @@ struct OpPix2Vec {
     }
 };
 
+// ring-table form of pixel_to_vector (hpgb_fp.h "Ring tables"): tab[m] = {z, sin(theta)} of ring m <= 2 nside, the
+// southern rings mirror them exactly; cos / sin(phi) per pixel as before
+__global__ void __launch_bounds__(256) k_ringtab_zsth(const hpgb_geom gr, double2 *tab, const int64_t nrings) {
+    for (int64_t ring = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ring < nrings; ring += (int64_t)gridDim.x * blockDim.x) {
+        double z = 0.0, sth = 0.0;
+        if (ring > 0) hpgb_ringtab_zsth(gr, ring, z, sth);
+        tab[ring] = make_double2(z, sth);
+    }
+}
+#ifndef HPGB_P2VT_MINB
+#define HPGB_P2VT_MINB 2
+#endif
+#ifndef HPGB_P2VT_ST
+#define HPGB_P2VT_ST 3
+#endif
+#ifndef HPGB_P2VT_H
+#define HPGB_P2VT_H 2
+#endif
+template <bool NEST>
+struct OpPix2VecTab {
+    const int64_t *pix;
+    double *x, *y, *z;
+    int64_t base;
+    hpgb_geom g;
+    hpgb_rk c;
+    const double2 *tab;  // 2 nside + 1 entries
+    typedef longlong2 In2;
+    typedef const double *Ctx;
+    HPGB_STREAM_IN_I64(pix, HPGB_P2VT_MINB)
+    __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
+    __device__ __forceinline__ In2 load2(int64_t i) const { return hpgb_ld2(pix + i); }
+    __device__ __forceinline__ void one(int64_t p, int64_t i, Ctx T, hpgb_bad_t &bad, double &vx, double &vy, double &vz) const {
+        const bool okp = hpgb_pixel_ok(g, p);
+        uint32_t ring;
+        bool north;
+        double phi, s, co;
+        hpgb_pix2ringphi_k<NEST>(c, g, okp ? p : 0, ring, north, phi);
+        const bool upper = ring <= c.ns2;
+        const double2 zs = hpgb_tab_ld(tab + (upper ? ring : c.ns4 - ring));
+#if defined(HPGB_P2V_SINCOS_P)  // A/B switch: plain-fma sums, 28 fp64 operations, <= 0.8 ulp
+        hpgb_sincos_p(T, phi, s, co);
+#else
+        hpgb_sincos_sd(T, phi, s, co);
+#endif
+        vx = zs.y * co;
+        vy = zs.y * s;
+        vz = upper ? zs.x : -zs.x;
+        if (!okp) {
+            bad.flag(base + i);
+            vx = vy = vz = 0.0;
+        }
+    }
+    __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &bad) const {
+        double x0, y0, z0, x1, y1, z1;
+        one(v.x, i, T, bad, x0, y0, z0);
+        one(v.y, i + 1, T, bad, x1, y1, z1);
+        hpgb_st2(x + i, x0, x1);
+        hpgb_st2(y + i, y0, y1);
+        hpgb_st2(z + i, z0, z1);
+    }
+    HPGB_DEFAULT_RUN4
+    __device__ __forceinline__ void run1(int64_t i, const Ctx &T, hpgb_bad_t &bad) const {
+        double vx, vy, vz;
+        one(hpgb_ld1(pix + i), i, T, bad, vx, vy, vz);
+        hpgb_st1(x + i, vx);
+        hpgb_st1(y + i, vy);
+        hpgb_st1(z + i, vz);
+    }
+};
+
+template <bool NEST>
+int launch_p2v_ringtab(const int64_t *pix, double *x, double *y, double *z, int64_t n, const hpgb_geom &g, int64_t base,
+                       hpgb_status_t *st, cudaStream_t s) {
+    const int64_t nrings = 2 * g.nside + 1;
+    double2 *tab = nullptr;
+    cudaError_t e = hpgb_dev_alloc_on((void **)&tab, (size_t)nrings * 16, s);
+    if (e != cudaSuccess) return HPGB_E_CUDA + (int)e;
+    int64_t grid = (nrings + 255) / 256;
+    if (grid > 8 * (int64_t)hpgb_sm_count()) grid = 8 * (int64_t)hpgb_sm_count();
+    hpgb_geom gr = g;
+    gr.nest = 0;
+    k_ringtab_zsth<<<(unsigned)grid, 256, 0, s>>>(gr, tab, nrings);
+    g_hpgb_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    int rc = e == cudaSuccess ? HPGB_OK : HPGB_E_CUDA + (int)e;
+    if (rc == HPGB_OK) {
+        OpPix2VecTab<NEST> op{pix, x, y, z, base, g, hpgb_make_rk(g), tab};
+#if defined(HPGB_P2AT_MAP)
+        rc = hpgb_launch_map(op, n, true, st, s);
+#else
+        rc = hpgb_launch_stream<decltype(op), HPGB_P2VT_ST, HPGB_P2VT_H>(op, n, st, s);
+#endif
+    }
+    hpgb_dev_free_on(tab, s);
+    return rc;
+}
+
 }  // namespace
 
 int launch_p2v(const int64_t *pix, double *x, double *y, double *z, int64_t n, int64_t nside, const int64_t *nside_v,
@@ -506,6 +744,9 @@ int launch_p2v(const int64_t *pix, double *x, double *y, double *z, int64_t n, i
     const bool vec = hpgb_aligned16(pix) && hpgb_aligned16(x) && hpgb_aligned16(y) && hpgb_aligned16(z);
     // power-of-two nside: the TMA-fed streaming skeleton (the pixel tiles arrive through the shared-memory ring, so
     // load latency is hidden without occupancy and the ~95 registers of the fp64 body are affordable)
+    if (vec && hpgb_use_ringtab(g, n, HPGB_RINGTAB_P2V_MAX_ORDER))
+        return nest ? launch_p2v_ringtab<true>(pix, x, y, z, n, g, base, st, s)
+                    : launch_p2v_ringtab<false>(pix, x, y, z, n, g, base, st, s);
     if (nest) {
         OpPix2Vec<true, true, false> op{pix, x, y, z, nullptr, base, g, hpgb_make_rk(g)};
 #if defined(HPGB_P2V_MAP)

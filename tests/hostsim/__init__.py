@@ -18,7 +18,7 @@ class HostSim:
         self.lib = ctypes.CDLL(os.environ.get("HPGB_HOSTSIM_LIB") or os.path.join(_HERE, "libhostsim.so"))
         for n in ("sim_nest_to_ring", "sim_ring_to_nest", "sim_ring_roundtrip_any", "sim_angle_to_pixel",
                   "sim_pixel_to_angle", "sim_pixel_to_vector", "sim_vector_to_pixel", "sim_neighbors", "sim_interp",
-                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_ring_to_nest_fold", "sim_pixel_to_angle_k", "sim_pixel_to_vector_k", "sim_interp_k", "sim_query_circle_ring", "sim_query_circle_nest"):
+                  "sim_lonlat", "sim_nest_to_ring_k", "sim_ring_to_nest_k", "sim_ring_to_nest_fold", "sim_pixel_to_angle_k", "sim_pixel_to_vector_k", "sim_pixel_to_angle_tab", "sim_pixel_to_vector_tab", "sim_interp_k", "sim_query_circle_ring", "sim_query_circle_nest"):
             getattr(self.lib, n).restype = ctypes.c_int64
         self.last_slow = 0
 
@@ -106,6 +106,25 @@ class HostSim:
         if r < 0:
             raise ValueError("bad element %d" % (-1 - r))
         self.last_slow = r
+        return x, y, z
+
+    def pixel_to_angle_tab(self, nside, pix, nest=True, lonlat=True, degrees=True):
+        """The ring-table form of the kernels (per-ring colatitude table + per-pixel ring number and phi)."""
+        pix = self._i(pix)
+        a, b = np.empty(pix.size), np.empty(pix.size)
+        r = self.lib.sim_pixel_to_angle_tab(ctypes.c_int64(nside), pix.ctypes.data_as(_I), ctypes.c_int64(pix.size),
+                                            int(nest), int(lonlat), int(degrees), a.ctypes.data_as(_D), b.ctypes.data_as(_D))
+        if r < 0:
+            raise ValueError("bad element %d" % (-1 - r))
+        return a, b
+
+    def pixel_to_vector_tab(self, nside, pix, nest=True, sincos=0):
+        pix = self._i(pix)
+        x, y, z = np.empty(pix.size), np.empty(pix.size), np.empty(pix.size)
+        r = self.lib.sim_pixel_to_vector_tab(ctypes.c_int64(nside), pix.ctypes.data_as(_I), ctypes.c_int64(pix.size), int(nest),
+                                             int(sincos), x.ctypes.data_as(_D), y.ctypes.data_as(_D), z.ctypes.data_as(_D))
+        if r < 0:
+            raise ValueError("bad element %d" % (-1 - r))
         return x, y, z
 
     def pixel_to_vector(self, nside, pix, nest=True):

@@ -265,6 +265,42 @@ def test_pixel_to_angle_branch_free_path(sim, nside):
             assert d.max() <= 1.0 and np.mean(got != ref) < 1e-3
 
 
+@pytest.mark.parametrize("nside", [1, 2, 8, 64, 1024, 2 ** 16, 2 ** 18])
+def test_pixel_to_angle_vector_ring_table_form(sim, nside):
+    """The ring-table form of pixel_to_angle / pixel_to_vector (large batches at nside <= 2^20: per-ring colatitude /
+    (z, sin theta) table + per-pixel ring number and phi) gives the same bits as the reference-shaped routines: every
+    pixel of the small maps, zone boundaries + random pixels of the large ones, both schemes, all angle conventions.
+    With hpgb_sincos_sd the vector form equals the per-pixel kernel path bit for bit; with the cheaper hpgb_sincos_p
+    (the kernel's choice) x / y stay within 1 ulp of it."""
+    rng = np.random.default_rng(nside + 11)
+    npix = 12 * nside * nside
+    ncap = 2 * nside * (nside - 1)
+    if npix < 200000:
+        pix = np.arange(npix)
+    else:
+        pix = np.concatenate([rng.integers(0, npix, 60000), np.arange(500), npix - 1 - np.arange(500),
+                              ncap + np.arange(-500, 500), npix - ncap + np.arange(-500, 500),
+                              npix // 2 + np.arange(-500, 500)])
+    for nest in (True, False):
+        for kw in ({}, {"degrees": False}, {"lonlat": False, "degrees": False}):
+            a0, b0 = sim.pixel_to_angle(nside, pix, nest=nest, **kw)
+            a1, b1 = sim.pixel_to_angle_tab(nside, pix, nest=nest, **kw)
+            assert_bit_equal(a1, a0, "a")
+            assert_bit_equal(b1, b0, "b")
+        kx, ky, kz = sim.pixel_to_vector_k(nside, pix, nest=nest)
+        tx, ty, tz = sim.pixel_to_vector_tab(nside, pix, nest=nest, sincos=1)
+        assert_bit_equal(tz, kz, "z")
+        assert_bit_equal(tx, kx, "x")
+        assert_bit_equal(ty, ky, "y")
+        px, py, pz = sim.pixel_to_vector_tab(nside, pix, nest=nest, sincos=0)
+        rx, ry, rz = sim.pixel_to_vector(nside, pix, nest=nest)
+        assert_bit_equal(pz, rz, "z")
+        for got, ref in ((px, rx), (py, ry)):
+            d = np.abs(got - ref) / np.spacing(np.maximum(np.abs(ref), 1e-300))
+            print(nside, nest, "max ulp", d.max(), "fraction differing", np.mean(got != ref))
+            assert d.max() <= 2.0 and np.mean(got != ref) < 0.2
+
+
 @pytest.mark.parametrize("nside,nest", CASES)
 def test_pixel_to_vector_golden(sim, nside, nest):
     g = load_golden("pixel_to_vector")

@@ -23,7 +23,7 @@ for p in paths:
             fn.restype = _lib._RESTYPES.get(name, ctypes.c_int)
     libs.append(L)
 n = 1 << log2
-nside = 2 ** 29
+nside = int(os.environ.get("HPGB_AB_NSIDE", 2 ** 29))
 g = torch.Generator(device="cuda").manual_seed(1)
 P = lambda t: ctypes.c_void_p(t.data_ptr())
 st = torch.empty(2, dtype=torch.int64, device="cuda")
