@@ -70,6 +70,24 @@ HPGB_HD hpgb_geom hpgb_make_geom(int64_t nside, int nest) {
     return g;
 }
 
+// uint32 / int32 -> double.  With HPGB_MAGIC_CVT the device version splices the integer into the mantissa of 2^52
+// and subtracts 2^52 (exact: one fixed-latency DADD on the fp64 pipe instead of an I2F on the quarter-rate
+// conversion unit, whose variable latency also costs a scoreboard wait).  Same double either way.
+HPGB_HD double hpgb_u2d(uint32_t v) {
+#if defined(__CUDA_ARCH__) && defined(HPGB_MAGIC_CVT)
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+#else
+    return (double)v;
+#endif
+}
+HPGB_HD double hpgb_i2d(int32_t v) {
+#if defined(__CUDA_ARCH__) && defined(HPGB_MAGIC_CVT)
+    return __hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+#else
+    return (double)v;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------
 // byte permute (PRMT on the device)
 // ---------------------------------------------------------------------------------------

@@ -719,7 +719,7 @@ HPGB_HD bool hpgb_pix2zone_k(const hpgb_rk &c, int64_t pix, uint32_t &nr, uint32
 // phi of a pixel centre from the integers above (hpgeom/healpix_geom.c:319,338,345 / :369-376)
 template <bool NEST>
 HPGB_HD double hpgb_zone_phi_k(const hpgb_geom &g, bool cap, uint32_t tphi, double phi_off, double dnr) {
-    const double dt = (double)tphi;
+    const double dt = hpgb_u2d(tphi);
     if (NEST) {
         const double pb = 0.75 * HPGB_HALFPI * dt * g.fact1;
         const double pc = hpgb_div_tame(0.5 * HPGB_HALFPI * dt, dnr);
@@ -739,11 +739,11 @@ HPGB_HD bool hpgb_pix2loc_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pix, d
     bool north, cap;
     double phi_off;
     const bool ok = hpgb_pix2zone_k<NEST>(c, pix, nr, tphi, zb, north, cap, phi_off, ring);
-    const double dnr = (double)nr;
+    const double dnr = hpgb_u2d(nr);
     tcap = (dnr * dnr) * g.fact2;  // RN(nr^2) either way: same double as (double)(nr * nr)
     const double zn = 1.0 - tcap;
     const double zc = north ? zn : -zn;  // tcap - 1 = -(1 - tcap) exactly
-    z = cap ? zc : (double)zb * g.fact1;
+    z = cap ? zc : hpgb_i2d(zb) * g.fact1;
     polar = cap && nr <= c.nr_polar;  // <=> |zc| > 0.99
     phi = hpgb_zone_phi_k<NEST>(g, cap, tphi, phi_off, dnr);
     return ok;
@@ -759,7 +759,7 @@ HPGB_HD bool hpgb_pix2ringphi_k(const hpgb_rk &c, const hpgb_geom &g, int64_t pi
     bool cap;
     double phi_off;
     const bool ok = hpgb_pix2zone_k<NEST>(c, pix, nr, tphi, zb, north, cap, phi_off, ring);
-    phi = hpgb_zone_phi_k<NEST>(g, cap, tphi, phi_off, (double)nr);
+    phi = hpgb_zone_phi_k<NEST>(g, cap, tphi, phi_off, hpgb_u2d(nr));
     return ok;
 }
 
@@ -846,15 +846,17 @@ HPGB_HD bool hpgb_pix2vec_k(const hpgb_rk &c, const hpgb_geom &g, const double *
     // sin(theta): hpgeom/healpix_geom.c:317 (polar, from tmp) or :193 (from z); the argument is never 0
     // for a pixel centre, so the branch-free square root applies
     const double sth = hpgb_sqrt_tame(polar ? tcap * (2. - tcap) : (1 - z) * (1 + z));
-    // cos(phi), sin(phi) to <= 0.51 ulp in plain doubles: x, y end up within 2 ulp of the reference's (which
-    // multiplies glibc's correctly rounded values by the same sth), bit-identical for ~98 % of the pixels
+    // cos(phi), sin(phi) in plain doubles (hpgb_sincos_p, 28 fp64 operations, <= 0.8 ulp): x, y end up within 2 ulp of
+    // the reference's (which multiplies glibc's values by the same sth) -- measured over 1.6e7 pixels at nside 2^10 ..
+    // 2^29: max 2 ulp, 99.5 % bit-identical.  A/B switches: HPGB_P2V_SINCOS_SD (<= 0.51 ulp, 40 operations: 99.87 %
+    // identical, -7 % throughput), HPGB_P2V_DD (double-double, correctly rounded).
     double s, co;
 #if defined(HPGB_P2V_DD)
     hpgb_sincos_cr(T, phi, s, co);
-#elif defined(HPGB_P2V_SINCOS_P)
-    hpgb_sincos_p(T, phi, s, co);
-#else
+#elif defined(HPGB_P2V_SINCOS_SD)
     hpgb_sincos_sd(T, phi, s, co);
+#else
+    hpgb_sincos_p(T, phi, s, co);
 #endif
     x = sth * co;
     y = sth * s;

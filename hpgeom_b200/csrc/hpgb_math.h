@@ -46,10 +46,24 @@ HPGB_HD void hpgb_two_sum(double a, double b, double &s, double &e) {
     e = (a - (s - bb)) + (b - bb);
 }
 
+// rint(p) and the same value as an int, |p| < 2^31.  With HPGB_MAGIC_CVT the device version adds and subtracts
+// 1.5 2^52 (round-to-nearest-even at the integer position: the same value as rint) and reads the integer out of
+// the low mantissa word -- two fixed-latency DADDs instead of a round + a double -> int on the conversion unit.
+HPGB_HD double hpgb_rint_i(double p, int &i) {
+#if defined(__CUDA_ARCH__) && defined(HPGB_MAGIC_CVT)
+    const double t = p + 6755399441055744.0;
+    i = __double2loint(t);
+    return t - 6755399441055744.0;
+#else
+    const double f = rint(p);
+    i = (int)f;
+    return f;
+#endif
+}
+
 // x -> quadrant q and r = x - q*pi/2 as rh + rl, |r| <= pi/4 (1 + 2^-50).  Valid for |x| < 2^20.
 HPGB_HD void hpgb_reduce_pio2(double x, int &q, double &rh, double &rl) {
-    const double fq = rint(x * HPGB_2OPI);
-    q = (int)fq;
+    const double fq = hpgb_rint_i(x * HPGB_2OPI, q);
     const double t = fma(-fq, HPGB_PIO2_1, x);  // exact: |t| < 1 and t is a multiple of ulp(x)/4
     double p, pe, e1;
     hpgb_two_prod(fq, HPGB_PIO2_2, p, pe);
@@ -63,8 +77,8 @@ HPGB_HD void hpgb_sincos_dd(const double *T, double rh, double rl, double &sh, d
     const bool neg = rh < 0.0;
     const double a = fabs(rh);
     const double al = neg ? -rl : rl;
-    const double fk = rint(a * 64.0);
-    const int k = (int)fk;
+    int k;
+    const double fk = hpgb_rint_i(a * 64.0, k);
     const double d = a - fk * 0.015625;  // exact
     const double Sh = T[4 * k + 0], Sl = T[4 * k + 1], Ch = T[4 * k + 2], Cl = T[4 * k + 3];
     // powers of the offset
@@ -148,8 +162,8 @@ HPGB_HD void hpgb_sincos_cr(const double *T, double x, double &s, double &c) {
 // ---------------------------------------------------------------------------------------------
 HPGB_HD void hpgb_sincos_sd(const double *T, double x, double &s, double &c) {
     // x = q pi/2 + r, r = rh + rl
-    const double fq = rint(x * HPGB_2OPI);
-    const int q = (int)fq;
+    int q;
+    const double fq = hpgb_rint_i(x * HPGB_2OPI, q);
     const double t = fma(-fq, HPGB_PIO2_1, x);  // exact (see hpgb_reduce_pio2)
     double w, we;
     hpgb_two_prod(fq, HPGB_PIO2_2, w, we);
@@ -158,8 +172,8 @@ HPGB_HD void hpgb_sincos_sd(const double *T, double x, double &s, double &c) {
     const bool neg = rh < 0.0;
     const double a = fabs(rh);
     const double al = neg ? -rl : rl;
-    const double fk = rint(a * 64.0);
-    const int k = (int)fk;
+    int k;
+    const double fk = hpgb_rint_i(a * 64.0, k);
     const double d = fma(-fk, 0.015625, a);  // exact
     const double Sh = T[4 * k + 0], Sl = T[4 * k + 1], Ch = T[4 * k + 2], Cl = T[4 * k + 3];
     const double p = d * d;
@@ -193,8 +207,8 @@ HPGB_HD void hpgb_sincos_sd(const double *T, double x, double &s, double &c) {
 // is "x, y within 2 ulp": a cosine within 1.5 ulp of the true value is within 1 ulp of glibc's, and the product with
 // sin(theta) then within 2 ulp of the reference's.
 HPGB_HD void hpgb_sincos_p(const double *T, double x, double &s, double &c) {
-    const double fq = rint(x * HPGB_2OPI);
-    const int q = (int)fq;
+    int q;
+    const double fq = hpgb_rint_i(x * HPGB_2OPI, q);
     const double t = fma(-fq, HPGB_PIO2_1, x);  // exact (see hpgb_reduce_pio2)
     double w, we;
     hpgb_two_prod(fq, HPGB_PIO2_2, w, we);
@@ -203,8 +217,8 @@ HPGB_HD void hpgb_sincos_p(const double *T, double x, double &s, double &c) {
     const bool neg = rh < 0.0;
     const double a = fabs(rh);
     const double al = neg ? -rl : rl;
-    const double fk = rint(a * 64.0);
-    const int k = (int)fk;
+    int k;
+    const double fk = hpgb_rint_i(a * 64.0, k);
     const double d = fma(-fk, 0.015625, a);  // exact
     const double Sh = T[4 * k + 0], Sl = T[4 * k + 1], Ch = T[4 * k + 2], Cl = T[4 * k + 3];
     const double p = d * d;
@@ -376,6 +390,7 @@ HPGB_HD double hpgb_sqrt_tame(double x) {
 }
 
 // acos(z) as hi + lo, |z| <= 0.99.  TA: rows of HPGB_ACOS_ROW_WORDS 64-bit words (see tools/gen_tables.py)
+#if defined(HPGB_ACOS_V1)
 HPGB_HD void hpgb_acos_tab_dd(const uint64_t *TA, double z, double &hi, double &lo) {
     const double a = fabs(z);
     const double u = 1.0 - a;  // exact for a >= 1/2
@@ -414,6 +429,58 @@ HPGB_HD void hpgb_acos_tab_dd(const uint64_t *TA, double z, double &hi, double &
     hi = neg ? nh : h;
     lo = neg ? ne + (HPGB_PI_2 - l) : l;
 }
+#else
+// Row = nine doubles { a0 hi, lo, a1 hi, lo, a2 .. a6 } and one word whose 64 bits ARE a7 (its low mantissa half is
+// the high word of a8, accounted for when the table was generated) -- no float -> double conversions; the cell
+// number of |z| <= 1/2 comes out of the mantissa of |z| 256 + 1.5 2^52 (no rint / double -> int / int -> double
+// conversions either: those run on the quarter-rate conversion unit).
+HPGB_HD void hpgb_acos_tab_dd(const uint64_t *TA, double z, double &hi, double &lo) {
+    const double a = fabs(z);
+    const double u = 1.0 - a;  // exact for a >= 1/2
+    const double am = fma(a, 256.0, 6755399441055744.0);  // 1.5 2^52 + RN(256 a): the integer sits in the low word
+    const double fk = am - 6755399441055744.0;
+#if defined(__CUDA_ARCH__)
+    const int ia = __double2loint(am);
+#else
+    union {
+        double d;
+        uint64_t w;
+    } cv;
+    cv.d = am;
+    const int ia = (int)(uint32_t)cv.w;
+#endif
+    const int ib = 129 + (int)(hpgb_math_hi32(u) >> 13) - 1016 * 128;
+    int idx = a <= 0.5 ? ia : ib;
+    idx = idx < 0 ? 0 : (idx > HPGB_ACOS_ROWS - 1 ? HPGB_ACOS_ROWS - 1 : idx);  // NaN / out-of-domain input: stay inside the table
+    const uint64_t *roww = TA + idx * HPGB_ACOS_ROW_WORDS;
+    double row[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) row[j] = hpgb_w2d(roww[j]);
+    const uint64_t w9 = roww[9];
+    const double a7 = hpgb_w2d(w9), a8 = hpgb_w2d(w9 << 32);
+    // r = |z| - zc, exact.  |z| <= 1/2: zc = cell / 256.  Beyond: zc = 1 - uc, uc = the cell's lower edge
+    // (u with all but 7 mantissa bits cleared) + half a cell (the next mantissa bit), so r = uc - u.
+    const double uc = hpgb_w2d((uint64_t)((hpgb_math_hi32(u) & 0xFFFFE000u) | 0x00001000u) << 32);
+    const double r = a <= 0.5 ? fma(-fk, 0.00390625, a) : uc - u;
+    double s = fma(a8, r, a7);
+    s = fma(s, r, row[8]);
+    s = fma(s, r, row[7]);
+    s = fma(s, r, row[6]);
+    s = fma(s, r, row[5]);
+    s = fma(s, r, row[4]);
+    double p, pe, h, hl;
+    hpgb_two_prod(row[2], r, p, pe);
+    const double low = row[1] + (pe + fma(row[3], r, (r * r) * s));
+    hpgb_fast_two_sum(row[0], p, h, hl);  // |a1 r| < acos(zc)
+    const double l = hl + low;
+    // z < 0: pi - (h + l), pi as a double-double; both variants computed, two selects
+    double nh, ne;
+    hpgb_fast_two_sum(HPGB_PI_1, -h, nh, ne);  // pi_1 > h
+    const bool neg = z < 0.0;
+    hi = neg ? nh : h;
+    lo = neg ? ne + (HPGB_PI_2 - l) : l;
+}
+#endif
 HPGB_HD double hpgb_acos_tab(const uint64_t *TA, double z) {
     double hi, lo;
     hpgb_acos_tab_dd(TA, z, hi, lo);

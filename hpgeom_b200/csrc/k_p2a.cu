@@ -666,10 +666,10 @@ struct OpPix2VecTab {
         hpgb_pix2ringphi_k<NEST>(c, g, okp ? p : 0, ring, north, phi);
         const bool upper = ring <= c.ns2;
         const double2 zs = hpgb_tab_ld(tab + (upper ? ring : c.ns4 - ring));
-#if defined(HPGB_P2V_SINCOS_P)  // A/B switch: plain-fma sums, 28 fp64 operations, <= 0.8 ulp
-        hpgb_sincos_p(T, phi, s, co);
-#else
+#if defined(HPGB_P2V_SINCOS_SD)  // A/B switch, see hpgb_pix2vec_k
         hpgb_sincos_sd(T, phi, s, co);
+#else
+        hpgb_sincos_p(T, phi, s, co);
 #endif
         vx = zs.y * co;
         vy = zs.y * s;

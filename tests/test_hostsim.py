@@ -254,15 +254,15 @@ def test_pixel_to_angle_branch_free_path(sim, nside):
             a1, b1 = sim.pixel_to_angle_k(nside, pix, nest=nest, **kw)
             assert_bit_equal(a1, a0, "a")
             assert_bit_equal(b1, b0, "b")
-        # the kernel's cos / sin(phi) are plain doubles good to 0.51 ulp (hpgb_sincos_sd), the reference-shaped
+        # the kernel's cos / sin(phi) are plain doubles good to 0.8 ulp (hpgb_sincos_p), the reference-shaped
         # routine's are the double-double ones: z identical, x / y identical except where the cheaper routine
-        # mis-rounds (~1e-5 of the pixels), and then by one ulp
+        # mis-rounds (< 2 % of the pixels), and then by at most two ulp (north_star: <= 2 ulp)
         kx, ky, kz = sim.pixel_to_vector_k(nside, pix, nest=nest)
         rx, ry, rz = sim.pixel_to_vector(nside, pix, nest=nest)
         assert_bit_equal(kz, rz, "pixel_to_vector z")
         for got, ref in ((kx, rx), (ky, ry)):
             d = np.abs(got - ref) / np.spacing(np.maximum(np.abs(ref), 1e-300))
-            assert d.max() <= 1.0 and np.mean(got != ref) < 1e-3
+            assert d.max() <= 2.0 and np.mean(got != ref) < 0.02
 
 
 @pytest.mark.parametrize("nside", [1, 2, 8, 64, 1024, 2 ** 16, 2 ** 18])
@@ -270,8 +270,8 @@ def test_pixel_to_angle_vector_ring_table_form(sim, nside):
     """The ring-table form of pixel_to_angle / pixel_to_vector (large batches at nside <= 2^20: per-ring colatitude /
     (z, sin theta) table + per-pixel ring number and phi) gives the same bits as the reference-shaped routines: every
     pixel of the small maps, zone boundaries + random pixels of the large ones, both schemes, all angle conventions.
-    With hpgb_sincos_sd the vector form equals the per-pixel kernel path bit for bit; with the cheaper hpgb_sincos_p
-    (the kernel's choice) x / y stay within 1 ulp of it."""
+    The vector form equals the per-pixel kernel path bit for bit (both use hpgb_sincos_p) and stays within 2 ulp of
+    the reference-shaped routine (double-double sin / cos)."""
     rng = np.random.default_rng(nside + 11)
     npix = 12 * nside * nside
     ncap = 2 * nside * (nside - 1)
@@ -288,11 +288,11 @@ def test_pixel_to_angle_vector_ring_table_form(sim, nside):
             assert_bit_equal(a1, a0, "a")
             assert_bit_equal(b1, b0, "b")
         kx, ky, kz = sim.pixel_to_vector_k(nside, pix, nest=nest)
-        tx, ty, tz = sim.pixel_to_vector_tab(nside, pix, nest=nest, sincos=1)
+        tx, ty, tz = sim.pixel_to_vector_tab(nside, pix, nest=nest, sincos=0)
         assert_bit_equal(tz, kz, "z")
         assert_bit_equal(tx, kx, "x")
         assert_bit_equal(ty, ky, "y")
-        px, py, pz = sim.pixel_to_vector_tab(nside, pix, nest=nest, sincos=0)
+        px, py, pz = tx, ty, tz
         rx, ry, rz = sim.pixel_to_vector(nside, pix, nest=nest)
         assert_bit_equal(pz, rz, "z")
         for got, ref in ((px, rx), (py, ry)):
