@@ -361,6 +361,18 @@ def main():
     add_also("vector_to_pixel", lambda: ck(L.hpgb_vector_to_pixel(f1.data_ptr(), f2.data_ptr(), f3.data_ptr(), i1.data_ptr(), m, NSIDE, None, 1, stp, sp)),
              m, 32, "vector_to_pixel nside=2^29 nest on the vectors just produced, 2^%d per GPU" % (m.bit_length() - 1))
     assert torch.equal(i1[:1 << 20], pix[:1 << 20]), "vector_to_pixel(pixel_to_vector(p)) != p"
+    # BASELINE config 2 as written: nside 2^20, 10^8 random pixels, both schemes (ring-table form of pixel_to_angle:
+    # >= 8 pixels per ring)
+    m2 = min(m, 100_000_000)
+    p20 = pix[:m2] % (12 * (1 << 20) ** 2)
+    for nest_flag, tag in ((1, "nest"), (0, "ring")):
+        add_also("pixel_to_angle_config2_" + tag,
+                 lambda nf=nest_flag: ck(L.hpgb_pixel_to_angle(p20.data_ptr(), f1.data_ptr(), f2.data_ptr(), m2, 1 << 20, None, nf, 1, 1, stp, sp)),
+                 m2, 24, "pixel_to_angle nside=2^20 %s lonlat degrees, %d random pixels per GPU (BASELINE config 2)" % (tag, m2))
+        add_also("pixel_to_vector_config2_" + tag,
+                 lambda nf=nest_flag: ck(L.hpgb_pixel_to_vector(p20.data_ptr(), f1.data_ptr(), f2.data_ptr(), f3.data_ptr(), m2, 1 << 20, None, nf, stp, sp)),
+                 m2, 32, "pixel_to_vector nside=2^20 %s, %d random pixels per GPU (BASELINE config 2)" % (tag, m2))
+    del p20
     p4 = pix[:ms8] % (12 * 4096 * 4096 - 1)
     # upgrade_pixels refuses the LAST NEST pixel like the reference (hpgeom/hpgeom.py:505); in the RING scheme that
     # is one particular pixel inside the range: keep it out of the RING batch (p4 never holds npix-1 itself)
