@@ -1290,6 +1290,33 @@ HPGB_HD int hpgb_interp_zone(uint32_t ns, int64_t ir1) {
     return 2;
 }
 
+// hpgb_ring_above_fast + hpgb_interp_zone for the sorted kernel, in 32-bit integers and without conversion-unit
+// instructions: floor(v) is RN(v - 1/2) read off the mantissa of (v - 1/2) + 1.5 2^52 (v - 1/2 is exact for v >= 1 and
+// the two disagree only where frac(v) is 0 -- inside the guard band, which then fails), `dns` = (double)nside is
+// computed once per kernel, the zone is three unsigned compares.  Returns 0 = both rings in the belt, 1 = both in
+// one polar cap, 2 = anything else (guard failed, pole rows, pairs straddling a cap edge): same ring and the same
+// verdict as the two routines above (tests/test_hostsim.py runs both).
+HPGB_HD int hpgb_ring_zone_fast(const hpgb_rk &rk, const hpgb_a2p_fast &f, double dns, double theta, uint32_t &ir1) {
+    const double lat = (HPGB_PIO2_1 - theta) + HPGB_PIO2_2;
+    const bool north = theta < HPGB_PIO2_1;
+    const double colat = north ? theta : (HPGB_PI_1 - theta) + HPGB_PI_2;  // from the nearest pole
+    const double al = fabs(lat);
+    const bool eq = al <= f.asin23;
+    bool ok = (colat > 0.0102) & !(fabs(al - f.asin23) < 1e-11);
+    const double s = hpgb_sin_poly(f, eq ? lat : 0.5 * colat);
+    const double v = eq ? dns * (2.0 - 1.5 * s) : dns * (2.4494897427831780981972840747059 * s);
+    const double t = (v - 0.5) + 6755399441055744.0;
+    const double fl = t - 6755399441055744.0;
+    const double fr = v - fl, m = dns * 5.6843418860808015e-14;  // 2^-44
+    ok &= (fr > m) & (fr < 1.0 - m);
+    const uint32_t iv = hpgb_lo32(t);
+    ir1 = (eq | north) ? iv : rk.ns4 - iv - 1u;
+    const bool belt = (ir1 - rk.ns) <= rk.ns2 - 1u;
+    const uint32_t capw = rk.ns > 2u ? rk.ns - 2u : 0u;
+    const bool cap = (ir1 - 1u) < capw || (ir1 - rk.ns3p1) < capw;
+    return ok ? (belt ? 0 : (cap ? 1 : 2)) : 2;
+}
+
 // floor of a value >= -1 as the reference forms it: (t < 0) ? (int64)t - 1 : (int64)t  (hpgeom/healpix_geom.c:1622)
 // (a ring of nside 2^29 has 2^31 pixels: the index needs 64 bits, like the reference's)
 HPGB_HD int64_t hpgb_interp_floor(double t) { return (t < 0) ? hpgb_d2ll(t) - 1 : hpgb_d2ll(t); }
@@ -1444,6 +1471,9 @@ HPGB_HD void hpgb_interp_belt_lut(const hpgb_geom &g, const hpgb_rk &rk, const h
     const uint32_t ns = rk.ns, nr = rk.ns4;
     const double tc = hpgb_div_const(phi, dphi);  // shared by the two rings
     double th[2], w1[2];
+    int32_t ii[2] = {0, 0};
+    uint32_t qq[4] = {0u, 0u, 0u, 0u};
+    bool sw = false;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const uint32_t r = ir1 + (uint32_t)k;
@@ -1457,8 +1487,15 @@ HPGB_HD void hpgb_interp_belt_lut(const hpgb_geom &g, const hpgb_rk &rk, const h
         const uint32_t q1 = i1 < 0 ? (uint32_t)i1 + nr : (uint32_t)i1;
         const uint32_t q2 = (uint32_t)(i1 + 1) >= nr ? (uint32_t)(i1 + 1) - nr : (uint32_t)(i1 + 1);
         if (NEST) {
+#if defined(HPGB_INTERP_NO_DIAMOND)
             p[2 * k] = hpgb_beltidx2nest_fold(rk, flut, r, q1);
             p[2 * k + 1] = hpgb_beltidx2nest_fold(rk, flut, r, q2);
+#else
+            ii[k] = i1;
+            qq[2 * k] = q1;
+            qq[2 * k + 1] = q2;
+            sw = k == 0 ? (hs != 0.0) : sw;  // hs of ring r
+#endif
         } else {
             uint32_t sp = rk.ncap_lo + (nring - ns) * nr;
             if (south) sp = rk.npix_lo - sp - nr;
@@ -1466,6 +1503,39 @@ HPGB_HD void hpgb_interp_belt_lut(const hpgb_geom &g, const hpgb_rk &rk, const h
             p[2 * k + 1] = (int64_t)(sp + q2);
         }
     }
+#if !defined(HPGB_INTERP_NO_DIAMOND)
+    if (NEST) {
+        // The four pixels are a diamond of the pixel grid: with (ix, iy) the in-face coordinates of the first one,
+        // its ring mate is the EAST neighbour (ix + 1, iy - 1), the first pixel of the ring below is its SOUTH-WEST
+        // (ix - 1, iy) or SOUTH-EAST (ix, iy - 1) neighbour -- one ring further south the edge-line coordinates
+        // change by jm - 1 (ring - nside even) or jp + 1 (odd) at equal in-ring index, and the index itself moves by
+        // 0 / +1 resp. -1 / 0 because the rings are shifted by half a pixel against each other -- and the fourth
+        // is that one's east neighbour.  Inside a base face each step is +-1 on one bit plane of the Morton code
+        // (the face bits ride above, hpgb_reorder.h "folded coordinates"): one conversion and three 5-instruction
+        // steps instead of four conversions.  A step that would leave the face (2-3 pixels in nside) converts
+        // directly.
+        const uint32_t EV = 0x55555555u & rk.lmask, OD = 0xAAAAAAAAu & rk.lmask;
+        const uint32_t v0 = (uint32_t)hpgb_beltidx2nest_fold(rk, flut, ir1, qq[0]);
+        const bool use_sw = sw ? (ii[1] == ii[0]) : (ii[1] != ii[0]);
+        // east of v: x + 1, y - 1 (needs x < nside - 1, y > 0)
+        const uint32_t e0 = (v0 & ~rk.lmask) | (((v0 | ~EV) + 1u) & EV) | (((v0 & OD) - 2u) & OD);
+        const bool e0_ok = (v0 & EV) != EV && (v0 & OD) != 0u;
+        // south-west: x - 1 (needs x > 0); south-east: y - 1 (needs y > 0)
+        const uint32_t s0 = use_sw ? ((v0 & ~EV) | (((v0 & EV) - 1u) & EV)) : ((v0 & ~OD) | (((v0 & OD) - 2u) & OD));
+        const bool s0_ok = use_sw ? ((v0 & EV) != 0u) : ((v0 & OD) != 0u);
+        const uint32_t e1 = (s0 & ~rk.lmask) | (((s0 | ~EV) + 1u) & EV) | (((s0 & OD) - 2u) & OD);
+        const bool e1_ok = s0_ok && (s0 & EV) != EV && (s0 & OD) != 0u;
+        p[0] = (int64_t)v0;
+        p[1] = (int64_t)e0;
+        p[2] = (int64_t)s0;
+        p[3] = (int64_t)e1;
+        if (!(e0_ok && e1_ok)) {  // s0_ok is implied by e1_ok
+            if (!e0_ok) p[1] = hpgb_beltidx2nest_fold(rk, flut, ir1, qq[1]);
+            if (!s0_ok) p[2] = hpgb_beltidx2nest_fold(rk, flut, ir1 + 1u, qq[2]);
+            if (!e1_ok) p[3] = hpgb_beltidx2nest_fold(rk, flut, ir1 + 1u, qq[3]);
+        }
+    }
+#endif
     const double wt = hpgb_div_tame(theta - th[0], th[1] - th[0]);
     w[0] = (1 - w1[0]) * (1 - wt);
     w[1] = w1[0] * (1 - wt);

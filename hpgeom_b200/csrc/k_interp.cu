@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_sorted(const Op op
     int nb = 0, nc = 0;  // queue lengths, warp-uniform
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t ns = (uint32_t)op.g.nside;
+    const double dns = (double)op.g.nside;
+    (void)ns;
     const int64_t gw = (int64_t)blockIdx.x * (HPGB_INTERP_BLOCK / 32) + warp;
     const int64_t nw = (int64_t)gridDim.x * (HPGB_INTERP_BLOCK / 32);
     const int64_t nfull = n >> 6, nchunk = (n + 63) >> 6;
@@ -318,29 +320,35 @@ __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_sorted(const Op op
         // the cheap part of BOTH points first, as one straight-line block (two independent dependency chains per lane:
         // this part is latency-bound at 20 warps per SM), then the queueing point by point
         double theta2[2], phi2[2];
-        int64_t ir2[2];
+        uint32_t ir2[2];
         int zone2[2];  // 0 belt, 1 cap, 2 the reference-shaped routine, 3 nothing to do
 #pragma unroll
         for (int q = 0; q < 2; q++) {
             const int64_t i = ch * 64 + 2 * lane + q;
             const double va = q ? cur.a.y : cur.a.x, vb = q ? cur.b.y : cur.b.x;
             theta2[q] = phi2[q] = 0.0;
-            ir2[q] = 0;
+            ir2[q] = 0u;
             zone2[q] = 3;
             if (i < n) {
-                if (!hpgb_angles_exact<Op::kLonLat, Op::kDegrees>(va, vb, theta2[q], phi2[q]))
+                if (!hpgb_angles_exact<Op::kLonLat, Op::kDegrees>(va, vb, theta2[q], phi2[q])) {
                     zone2[q] = 4;  // refused
-                else if (hpgb_ring_above_fast(op.g, op.f, theta2[q], ir2[q]) && hpgb_interp_phi_tame(phi2[q]))
-                    zone2[q] = hpgb_interp_zone(ns, ir2[q]);
-                else
-                    zone2[q] = 2;
+                } else {
+#if defined(HPGB_INTERP_ZONE_V1)
+                    int64_t ir64 = 0;
+                    zone2[q] = (hpgb_ring_above_fast(op.g, op.f, theta2[q], ir64) && hpgb_interp_phi_tame(phi2[q])) ? hpgb_interp_zone(ns, ir64) : 2;
+                    ir2[q] = (uint32_t)ir64;
+#else
+                    const int z = hpgb_ring_zone_fast(op.rk, op.f, dns, theta2[q], ir2[q]);
+                    zone2[q] = hpgb_interp_phi_tame(phi2[q]) ? z : 2;
+#endif
+                }
             }
         }
 #pragma unroll 1
         for (int q = 0; q < 2; q++) {
             const int64_t i = ch * 64 + 2 * lane + q;
             const double theta = q ? theta2[1] : theta2[0], phi = q ? phi2[1] : phi2[0];
-            const int64_t ir1 = q ? ir2[1] : ir2[0];
+            const uint32_t ir1 = q ? ir2[1] : ir2[0];
             const int zone = q ? zone2[1] : zone2[0];
             if (zone == 4) {
                 bad.flag(op.base + i);
@@ -348,17 +356,18 @@ __global__ void __launch_bounds__(HPGB_INTERP_BLOCK) k_interp_sorted(const Op op
                 const double w[4] = {0.0, 0.0, 0.0, 0.0};
                 emit(i, p, w);
             }
+            // one set of stores for both queues: the cap queue lies HPGB_INTERP_QBYTES behind the belt queue
             const unsigned mb = __ballot_sync(0xFFFFFFFFu, zone == 0);
-            if (zone == 0) {
-                const int pos = nb + __popc(mb & lt);
-                qb.th[pos] = theta, qb.ph[pos] = phi, qb.idx[pos] = i, qb.ir[pos] = (uint32_t)ir1;
+            const unsigned mc = __ballot_sync(0xFFFFFFFFu, zone == 1);
+            if ((unsigned)zone <= 1u) {
+                const int pos = zone ? nc + __popc(mc & lt) : nb + __popc(mb & lt);
+                unsigned char *qz = qmem + (zone ? HPGB_INTERP_QBYTES : 0);
+                reinterpret_cast<double *>(qz)[pos] = theta;
+                reinterpret_cast<double *>(qz + 8 * HPGB_INTERP_QCAP)[pos] = phi;
+                reinterpret_cast<int64_t *>(qz + 16 * HPGB_INTERP_QCAP)[pos] = i;
+                reinterpret_cast<uint32_t *>(qz + 24 * HPGB_INTERP_QCAP)[pos] = ir1;
             }
             nb += __popc(mb);
-            const unsigned mc = __ballot_sync(0xFFFFFFFFu, zone == 1);
-            if (zone == 1) {
-                const int pos = nc + __popc(mc & lt);
-                qc.th[pos] = theta, qc.ph[pos] = phi, qc.idx[pos] = i, qc.ir[pos] = (uint32_t)ir1;
-            }
             nc += __popc(mc);
             if (zone == 2) {  // pole rows, pairs straddling a cap edge, points on a ring: rare
                 int64_t p[4];
