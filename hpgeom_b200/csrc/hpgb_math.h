@@ -46,11 +46,28 @@ HPGB_HD void hpgb_two_sum(double a, double b, double &s, double &e) {
     e = (a - (s - bb)) + (b - bb);
 }
 
+// v with its sign flipped when s is negative (rh < 0 and "sign bit of rh set" agree for every rh the reductions
+// produce: they never yield -0), resp. when bit 31 of `m` is set: one LOP3 on the high word
+HPGB_HD double hpgb_flip_sign_bit(double v, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (int)(m & 0x80000000u), __double2loint(v));
+#else
+    return (m & 0x80000000u) ? -v : v;
+#endif
+}
+HPGB_HD double hpgb_flip_sign_if_neg(double v, double s) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (__double2hiint(s) & (int)0x80000000), __double2loint(v));
+#else
+    return (s < 0.0) ? -v : v;
+#endif
+}
+
 // rint(p) and the same value as an int, |p| < 2^31.  With HPGB_MAGIC_CVT the device version adds and subtracts
 // 1.5 2^52 (round-to-nearest-even at the integer position: the same value as rint) and reads the integer out of
 // the low mantissa word -- two fixed-latency DADDs instead of a round + a double -> int on the conversion unit.
 HPGB_HD double hpgb_rint_i(double p, int &i) {
-#if defined(__CUDA_ARCH__) && defined(HPGB_MAGIC_CVT)
+#if defined(__CUDA_ARCH__) && (defined(HPGB_MAGIC_CVT) || defined(HPGB_MAGIC_RINT))
     const double t = p + 6755399441055744.0;
     i = __double2loint(t);
     return t - 6755399441055744.0;
@@ -214,9 +231,13 @@ HPGB_HD void hpgb_sincos_p(const double *T, double x, double &s, double &c) {
     hpgb_two_prod(fq, HPGB_PIO2_2, w, we);
     const double rh = t - w;
     const double rl = ((t - rh) - w) - fma(fq, HPGB_PIO2_3, we);
-    const bool neg = rh < 0.0;
     const double a = fabs(rh);
+#if defined(HPGB_SINCOS_SELECTS)
+    const bool neg = rh < 0.0;
     const double al = neg ? -rl : rl;
+#else
+    const double al = hpgb_flip_sign_if_neg(rl, rh);  // sign handling on the high words: one LOP3 each instead of selects
+#endif
     int k;
     const double fk = hpgb_rint_i(a * 64.0, k);
     const double d = fma(-fk, 0.015625, a);  // exact
@@ -226,12 +247,18 @@ HPGB_HD void hpgb_sincos_p(const double *T, double x, double &s, double &c) {
     const double cd = fma(p, fma(p, fma(p, -1.0 / 720.0, 1.0 / 24.0), -0.5), -d * al);
     double sa = Sh + fma(Ch, d, fma(Ch, sd, fma(Sh, cd, fma(Cl, d, Sl))));
     const double ca = Ch + fma(-Sh, d, fma(-Sh, sd, fma(Ch, cd, fma(-Sl, d, Cl))));
-    if (neg) sa = -sa;
     const bool swap = q & 1;
+#if defined(HPGB_SINCOS_SELECTS)
+    if (neg) sa = -sa;
     s = swap ? ca : sa;
     c = swap ? sa : ca;
     if (q & 2) s = -s;
     if ((q + 1) & 2) c = -c;
+#else
+    sa = hpgb_flip_sign_if_neg(sa, rh);
+    s = hpgb_flip_sign_bit(swap ? ca : sa, (uint32_t)q << 30);        // quadrants 2, 3: sin negative
+    c = hpgb_flip_sign_bit(swap ? sa : ca, (uint32_t)(q + 1) << 30);  // quadrants 1, 2: cos negative
+#endif
 }
 
 // 24-bit first guesses (any estimate good to ~2^-20 gives the same final result)
