@@ -63,11 +63,11 @@ HPGB_HD double hpgb_flip_sign_if_neg(double v, double s) {
 #endif
 }
 
-// rint(p) and the same value as an int, |p| < 2^31.  With HPGB_MAGIC_CVT the device version adds and subtracts
+// rint(p) and the same value as an int, |p| < 2^31.  The device version adds and subtracts
 // 1.5 2^52 (round-to-nearest-even at the integer position: the same value as rint) and reads the integer out of
 // the low mantissa word -- two fixed-latency DADDs instead of a round + a double -> int on the conversion unit.
 HPGB_HD double hpgb_rint_i(double p, int &i) {
-#if defined(__CUDA_ARCH__) && (defined(HPGB_MAGIC_CVT) || defined(HPGB_MAGIC_RINT))
+#if defined(__CUDA_ARCH__) && !defined(HPGB_NO_MAGIC_RINT)
     const double t = p + 6755399441055744.0;
     i = __double2loint(t);
     return t - 6755399441055744.0;

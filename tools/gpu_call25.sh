@@ -1,0 +1,14 @@
+set -x
+O=gpurun_out/r02z
+mkdir -p $O
+V=variants
+timeout 300 python tools/ab_multi.py 28 p2v 5 3 default $V/lib_p2v_mrint.so > $O/ab_p2v.log 2>&1; cat $O/ab_p2v.log
+prof() {  # name kernel log2 regex
+  timeout 200 python tools/ncu_one.py $2 $3 1 > $O/plain_$1.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:$4 -c 1 -f -o $O/prof_$1 python tools/ncu_one.py $2 $3 1 > $O/ncu_$1.log 2>&1
+  python tools/ncu_summary.py $O/prof_$1.ncu-rep > $O/prof_$1.summary.txt 2>&1
+  ncu -i $O/prof_$1.ncu-rep --page source --csv > $O/prof_$1.source.csv 2>/dev/null
+  rm -f $O/prof_$1.ncu-rep
+}
+prof r2n r2n 27 k_stream
+prof v2p v2p 27 'k_stream.*Vec2Pix'
+prof p2v p2v 27 k_stream
