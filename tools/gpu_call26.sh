@@ -1,0 +1,12 @@
+set -x
+O=gpurun_out/r03a
+mkdir -p $O
+prof() {  # name kernel log2 regex
+  timeout 200 python tools/ncu_one.py $2 $3 1 > $O/plain_$1.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:$4 -c 1 -f -o $O/prof_$1 python tools/ncu_one.py $2 $3 1 > $O/ncu_$1.log 2>&1
+  python tools/ncu_summary.py $O/prof_$1.ncu-rep > $O/prof_$1.summary.txt 2>&1
+  ncu -i $O/prof_$1.ncu-rep --page source --csv > $O/prof_$1.source.csv 2>/dev/null
+  rm -f $O/prof_$1.ncu-rep
+}
+prof neigh neigh 27 k_neighbors
+prof upg upg 27 k_upgrade
+timeout 300 python tools/quickbench.py 28 p2a,p2v,interp,neigh,upgrade > $O/qb.txt 2>&1; cat $O/qb.txt
