@@ -567,8 +567,17 @@ HPGB_HD uint32_t hpgb_vector_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_
     const double ax = fabs(x), ay = fabs(y);
     const bool swap = ay > ax;
     const double num = swap ? ax : ay, den = swap ? ay : ax;  // 0 <= num <= den, den > 0
+#if defined(HPGB_V2P_RINT_V1)
     double fk = rint(16.0 * (num * hpgb_rcp_rough(den)));
     fk = fk >= 0.0 ? (fk <= 16.0 ? fk : 16.0) : 0.0;  // NaN / zero vectors (guarded above) must still index the table safely
+    const int ik = (int)fk;
+#else
+    // table row = RN(16 num / den), read off a mantissa (hpgb_rint_i); only the INDEX is clamped -- a NaN / zero
+    // vector is guarded above and merely has to address the table safely
+    int ik;
+    const double fk = hpgb_rint_i(16.0 * (num * hpgb_rcp_rough(den)), ik);
+    ik = ik < 0 ? 0 : (ik > 16 ? 16 : ik);
+#endif
     const double c = fk * 0.0625;
     const double r = fma(-c, den, num) * hpgb_rcp_fast(fma(c, num, den));
     const double rr = r * r;
@@ -576,12 +585,13 @@ HPGB_HD uint32_t hpgb_vector_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_
     p = fma(p, rr, -1.0 / 7.0);
     p = fma(p, rr, 1.0 / 5.0);
     p = fma(p, rr, -1.0 / 3.0);
-    const double at = T[4 * HPGB_SINCOS_ROWS + (int)fk] + fma(r * rr, p, r);  // atan(num/den) in [0, pi/4]
+    const double at = T[4 * HPGB_SINCOS_ROWS + ik] + fma(r * rr, p, r);  // atan(num/den) in [0, pi/4]
     const double u = at * HPGB_INV_HALFPI;                                    // in quarter turns, [0, 1/2]
     // quadrant: floor(tt) from the signs alone; tp = u or 1 - u by the parity of (swap, x < 0, y < 0)
     const uint32_t xs = hpgb_hi32(x) >> 31, ys = hpgb_hi32(y) >> 31;
     const bool flip = ((uint32_t)swap ^ xs ^ ys) != 0u;
-    const double tq = flip ? 0.5 - u : u - 0.5;  // tp - 1/2
+    // tp - 1/2 = u - 1/2, or its exact negative 1/2 - u: one subtraction and a sign flip on the high word
+    const double tq = hpgb_flip_sign_bit(u - 0.5, (uint32_t)flip << 31);
     guard |= (unsigned)!(fabs(tq) < 0.5 - 3.8146972656250000e-06);  // tt within 2^-18 of an integer (face edge / wrap)
 #if defined(HPGB_A2P_V1)
     const double xn = xs ? 1.0 : 0.0;
