@@ -30,6 +30,7 @@ _SIGS = {
     "hpgb_host_get_devices": [ctypes.POINTER(c_int), c_int],
     "hpgb_pinned_alloc": [ctypes.POINTER(c_vp), c_i64],
     "hpgb_pinned_free": [c_vp],
+    "hpgb_host_copy": [c_vp, c_vp, c_i64],
     "hpgb_nest_to_ring": [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],
     "hpgb_ring_to_nest": [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],
     "hpgb_host_nest_to_ring": [c_vp, c_vp, c_i64, c_i64, c_vp, c_int, ctypes.POINTER(c_i64)],

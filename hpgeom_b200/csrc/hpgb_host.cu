@@ -564,3 +564,12 @@ extern "C" int hpgb_explain_pixel(int64_t nside, int nest, int64_t pix, char *ms
     }
     return HPGB_BAD_NONE;
 }
+
+// The staging copy of the host pipeline on its own (the pool's parallel memcpy): exported so that the CPU test tier can
+// check it without a GPU and tools/host_copy_rate.py can time it.  (Measured and rejected: non-temporal SSE2 stores for
+// the shares -- 44.6 against 55.3 GB/s for glibc's memcpy on 8 threads.)
+extern "C" int hpgb_host_copy(void *dst, const void *src, int64_t bytes) {
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) return HPGB_E_BAD_ARGUMENT;
+    if (bytes) CopyPool::get().copy((char *)dst, (const char *)src, (size_t)bytes);
+    return HPGB_OK;
+}

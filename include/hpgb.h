@@ -85,6 +85,8 @@ int hpgb_host_get_devices(int *devices, int cap);
 /* pinned host memory for callers that want zero staging in hpgb_host_* */
 int hpgb_pinned_alloc(void **ptr, int64_t bytes);
 int hpgb_pinned_free(void *ptr);
+/* the parallel staging copy the hpgb_host_* entry points use for pageable buffers (host only, no GPU needed) */
+int hpgb_host_copy(void *dst, const void *src, int64_t bytes);
 
 /* ---- nest_to_ring / ring_to_nest: hpgeom/hpgeom.c:1406-1653, :1676-1927 ------------------ */
 int hpgb_nest_to_ring(const int64_t *d_nest, int64_t *d_ring, int64_t n, int64_t nside,

@@ -138,3 +138,24 @@ def test_no_cpu_fallback_without_device():
         hpg.query_circle(1024, 10.0, 20.0, 1.0, nest=False)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         hpg.query_circle(1024, 10.0, 20.0, 1.0)
+
+
+def test_host_copy_pool_is_a_memcpy():
+    """hpgb_host_copy -- the parallel staging copy of the hpgb_host_* pipelines -- on sizes around its split points,
+    odd sizes and misaligned pointers (host only: no GPU involved)."""
+    import ctypes
+
+    import numpy as np
+
+    from hpgeom_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    for nbytes in (0, 1, 63, 64, 65, (1 << 20) - 1, (1 << 20) + 1, 3 * (1 << 20) + 17, 37 * (1 << 20) + 5):
+        for shift_src, shift_dst in ((0, 0), (1, 0), (0, 3), (5, 7)):
+            src = rng.integers(0, 255, nbytes + 16, dtype=np.uint8)
+            dst = np.full(nbytes + 32, 0xAB, dtype=np.uint8)
+            rc = L.hpgb_host_copy(ctypes.c_void_p(dst.ctypes.data + 8 + shift_dst), ctypes.c_void_p(src.ctypes.data + shift_src), nbytes)
+            assert rc == 0
+            assert np.array_equal(dst[8 + shift_dst:8 + shift_dst + nbytes], src[shift_src:shift_src + nbytes])
+            assert (dst[:8 + shift_dst] == 0xAB).all() and (dst[8 + shift_dst + nbytes:] == 0xAB).all()
+    assert L.hpgb_host_copy(None, None, -1) != 0
