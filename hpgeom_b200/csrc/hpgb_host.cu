@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -163,13 +164,18 @@ int64_t chunk_points(size_t bytes_per_point) {
 // the pipeline stages through its own pinned buffers, filled / drained by a small pool of host threads
 // (parallel memcpy), so the PCIe engines see pinned memory and the host copies of chunk i+1 overlap the
 // DMA of chunk i.
+// Workers and the submitting thread SPIN for a short while (HPGB_HOST_SPIN_US, default 500 us) before they sleep on a
+// condition variable: a pipeline posts three copy jobs per chunk a few hundred microseconds apart, and waking fifteen
+// sleeping threads (futex + a scheduler round trip, slow inside a VM) cost ~0.4 ms per job -- 1.3 ms per chunk, as much
+// as the chunk's DMA (measured: a 10M-point numpy call got SLOWER when cut into more chunks).  Only callers that pass
+// pageable buffers ever post a job, so processes that use pinned buffers never spin.
 class CopyPool {
   public:
     static CopyPool &get() {
         static CopyPool *p = new CopyPool;  // never destroyed: its threads sleep on the condition variable at exit
         return *p;
     }
-    // dst[0..bytes) = src[0..bytes), split over the pool (the caller takes the first share).  One job at a
+    // dst[0..bytes) = src[0..bytes), split over the pool (the caller copies shares too).  One job at a
     // time (submit_): pipelines of different devices take turns, each job uses the whole pool.
     void copy(char *dst, const char *src, size_t bytes) {
         std::lock_guard<std::mutex> job(submit_);
@@ -185,12 +191,29 @@ class CopyPool {
             std::lock_guard<std::mutex> lk(m_);
             dst_ = dst, src_ = src, bytes_ = bytes, per_ = per;
             next_ = 1, parts_ = parts, pending_ = parts - 1;
+            avail_.store(true, std::memory_order_release);
         }
-        cv_.notify_all();
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
         memcpy(dst, src, per < bytes ? per : bytes);
         std::unique_lock<std::mutex> lk(m_);
-        done_.wait(lk, [&] { return pending_ == 0; });
+        while (next_ < parts_) {  // shares nobody has taken yet: the submitting thread helps
+            const int part = take_();
+            lk.unlock();
+            share_(part, dst, src, per, bytes);
+            lk.lock();
+            --pending_;
+        }
+        if (pending_ != 0) {  // the last shares are in flight on other threads: they take < 100 us
+            lk.unlock();
+            const auto t0 = std::chrono::steady_clock::now();
+            while (!done_flag_.load(std::memory_order_acquire) &&
+                   std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(spin_us_))
+                relax_();
+            lk.lock();
+            done_.wait(lk, [&] { return pending_ == 0; });
+        }
         parts_ = 0, next_ = 0;
+        done_flag_.store(false, std::memory_order_relaxed);
     }
 
   private:
@@ -199,30 +222,73 @@ class CopyPool {
         int n = e ? atoi(e) : (int)std::thread::hardware_concurrency();  // HPGB_HOST_THREADS overrides
         if (!e && n > 16) n = 16;
         if (n < 1) n = 1;
+        const char *sp = getenv("HPGB_HOST_SPIN_US");
+        spin_us_ = sp ? atoi(sp) : 500;
+        if (spin_us_ < 0) spin_us_ = 0;
         nworkers_ = n - 1;  // the caller is one of the copiers
         for (int i = 0; i < nworkers_; i++) std::thread([this] { worker(); }).detach();
+    }
+    static void relax_() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    int take_() {  // m_ held, next_ < parts_
+        const int part = next_++;
+        if (next_ >= parts_) avail_.store(false, std::memory_order_release);
+        return part;
+    }
+    static void share_(int part, char *d, const char *s, size_t per, size_t bytes) {
+        const size_t off = (size_t)part * per;
+        if (off < bytes) memcpy(d + off, s + off, (off + per <= bytes) ? per : bytes - off);
     }
     void worker() {
         std::unique_lock<std::mutex> lk(m_);
         for (;;) {
-            cv_.wait(lk, [&] { return next_ < parts_; });
-            const int part = next_++;
+            if (!(next_ < parts_)) {
+                lk.unlock();
+                bool got = false;
+                if (spin_us_ > 0) {
+                    const auto t0 = std::chrono::steady_clock::now();
+                    do {
+                        for (int k = 0; k < 64 && !got; k++) {
+                            got = avail_.load(std::memory_order_acquire);
+                            if (!got) relax_();
+                        }
+                    } while (!got && std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(spin_us_));
+                }
+                lk.lock();
+                if (!got) {
+                    sleepers_.fetch_add(1, std::memory_order_acq_rel);
+                    cv_.wait(lk, [&] { return next_ < parts_; });
+                    sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+                } else if (!(next_ < parts_)) {
+                    continue;  // somebody else took the share
+                }
+            }
+            const int part = take_();
             char *d = dst_;
             const char *s = src_;
             const size_t per = per_, bytes = bytes_;
             lk.unlock();
-            const size_t off = (size_t)part * per;
-            if (off < bytes) memcpy(d + off, s + off, (off + per <= bytes) ? per : bytes - off);
+            share_(part, d, s, per, bytes);
             lk.lock();
-            if (--pending_ == 0) done_.notify_all();
+            if (--pending_ == 0) {
+                done_flag_.store(true, std::memory_order_release);
+                done_.notify_all();
+            }
         }
     }
     std::mutex m_, submit_;
     std::condition_variable cv_, done_;
+    std::atomic<bool> avail_{false}, done_flag_{false};
+    std::atomic<int> sleepers_{0};
     char *dst_ = nullptr;
     const char *src_ = nullptr;
     size_t bytes_ = 0, per_ = 0;
-    int next_ = 0, parts_ = 0, pending_ = 0, nworkers_ = 0;
+    int next_ = 0, parts_ = 0, pending_ = 0, nworkers_ = 0, spin_us_ = 500;
 };
 
 bool is_pageable(const void *p) {
@@ -271,7 +337,21 @@ static int pipeline_one(int device, int64_t n, const hpgb_pipe_arr *arrs, int na
 
     size_t bpp = 0;
     for (int a = 0; a < narr; a++) bpp += (size_t)arrs[a].bytes_per_point;
-    const int64_t cpb = chunk_points(bpp);
+    // HPGB_HOST_MIN_CHUNKS (default 1 = off): cut mid-sized calls (BASELINE config 1 is 10M points = 2.4 default chunks)
+    // into at least that many pieces so that more of the first copy-in / last copy-out overlaps.  Measured and NOT
+    // adopted: 10M pageable points take 7.1 ms as three chunks and 8.2 / 10.4 ms as eight (a chunk's fixed host cost --
+    // three pool jobs, four CUDA calls, an event wait -- outweighs the overlap), 1e8 points are unaffected.
+    int64_t cpb = chunk_points(bpp);
+    {
+        static const int64_t min_chunks = [] {
+            const char *e = getenv("HPGB_HOST_MIN_CHUNKS");
+            const int64_t v = e ? atoll(e) : 1;
+            return v < 1 ? (int64_t)1 : v;
+        }();
+        const int64_t want = ((n + min_chunks - 1) / min_chunks + 1) & ~(int64_t)1;
+        const int64_t floor_pts = (int64_t)1 << 18;
+        if (want < cpb) cpb = want > floor_pts ? want : (floor_pts < cpb ? floor_pts : cpb);
+    }
     const int64_t cp = cpb < n ? cpb : ((n + 1) & ~(int64_t)1);
     const int64_t nchunks = (n + cp - 1) / cp;
     const int nslots = nchunks < HPGB_PIPE_SLOTS ? (int)nchunks : HPGB_PIPE_SLOTS;  // no more slots than chunks
