@@ -67,7 +67,7 @@ def measured_peak():
 def ncu_traffic(kernel, points):
     """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of THIS kernel at
     the metric's size (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch over
-    2^30 points, separately allocated operands; profiles/r02a_ncu_headline_2p30_separate.txt), scaled by the point
+    2^30 points, separately allocated operands; the json names its source capture under profiles/), scaled by the point
     count when the bench runs at another size; None if the file is absent."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
