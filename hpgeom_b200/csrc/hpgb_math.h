@@ -461,7 +461,7 @@ HPGB_HD void hpgb_acos_tab_dd(const uint64_t *TA, double z, double &hi, double &
 // the high word of a8, accounted for when the table was generated) -- no float -> double conversions; the cell
 // number of |z| <= 1/2 comes out of the mantissa of |z| 256 + 1.5 2^52 (no rint / double -> int / int -> double
 // conversions either: those run on the quarter-rate conversion unit).
-HPGB_HD void hpgb_acos_tab_dd(const uint64_t *TA, double z, double &hi, double &lo) {
+HPGB_HD void hpgb_acos_tab_abs(const uint64_t *TA, double z, double &h, double &l) {  // acos(|z|) = h + l
     const double a = fabs(z);
     const double u = 1.0 - a;  // exact for a >= 1/2
     const double am = fma(a, 256.0, 6755399441055744.0);  // 1.5 2^52 + RN(256 a): the integer sits in the low word
@@ -495,13 +495,16 @@ HPGB_HD void hpgb_acos_tab_dd(const uint64_t *TA, double z, double &hi, double &
     s = fma(s, r, row[6]);
     s = fma(s, r, row[5]);
     s = fma(s, r, row[4]);
-    double p, pe, h, hl;
+    double p, pe, hl;
     hpgb_two_prod(row[2], r, p, pe);
     const double low = row[1] + (pe + fma(row[3], r, (r * r) * s));
     hpgb_fast_two_sum(row[0], p, h, hl);  // |a1 r| < acos(zc)
-    const double l = hl + low;
-    // z < 0: pi - (h + l), pi as a double-double; both variants computed, two selects
-    double nh, ne;
+    l = hl + low;
+}
+// z < 0: pi - (h + l), pi as a double-double
+HPGB_HD void hpgb_acos_tab_dd(const uint64_t *TA, double z, double &hi, double &lo) {
+    double h, l, nh, ne;
+    hpgb_acos_tab_abs(TA, z, h, l);
     hpgb_fast_two_sum(HPGB_PI_1, -h, nh, ne);  // pi_1 > h
     const bool neg = z < 0.0;
     hi = neg ? nh : h;
@@ -509,9 +512,18 @@ HPGB_HD void hpgb_acos_tab_dd(const uint64_t *TA, double z, double &hi, double &
 }
 #endif
 HPGB_HD double hpgb_acos_tab(const uint64_t *TA, double z) {
+#if defined(HPGB_ACOS_V1) || defined(HPGB_ACOS_SELECT_PARTS)
     double hi, lo;
     hpgb_acos_tab_dd(TA, z, hi, lo);
     return hi + lo;
+#else
+    // the same two sums as hi + lo of hpgb_acos_tab_dd, selected AFTER the additions: one select instead of two
+    double h, l, nh, ne;
+    hpgb_acos_tab_abs(TA, z, h, l);
+    hpgb_fast_two_sum(HPGB_PI_1, -h, nh, ne);  // pi_1 > h
+    const double pos = h + l, negv = nh + (ne + (HPGB_PI_2 - l));
+    return z < 0.0 ? negv : pos;
+#endif
 }
 
 // atan2(s, c) as hi + lo for 0 <= s <= 0.156 |c| (result pi - atan2(s, |c|) when c < 0)

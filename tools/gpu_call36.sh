@@ -12,5 +12,7 @@ prof() {  # name kernel log2 regex
   python tools/ncu_summary.py $O/prof_$1.ncu-rep > $O/prof_$1.summary.txt 2>&1
   rm -f $O/prof_$1.ncu-rep
 }
+timeout 300 python tools/ab_multi.py 28 p2a 5 3 default variants/lib_p2a_selparts.so > $O/ab_p2a.log 2>&1; cat $O/ab_p2a.log
+timeout 300 python tools/ab_multi.py 28 p2a_ring 5 3 default variants/lib_p2a_selparts.so > $O/ab_p2a_ring.log 2>&1; cat $O/ab_p2a_ring.log
 prof v2p v2p 27 'k_stream.*Vec2Pix'
 cat $O/prof_v2p.summary.txt
