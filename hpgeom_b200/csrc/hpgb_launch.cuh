@@ -167,11 +167,19 @@ __device__ __forceinline__ void hpgb_mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = hpgb_smem_u32(bar);
     uint32_t ok;
     do {
+#if defined(HPGB_TRYWAIT_HINT_NS)  // A/B: ask the hardware to suspend the warp for up to this long per attempt
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"((uint32_t)HPGB_TRYWAIT_HINT_NS)
+            : "memory");
+#else
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(addr), "r"(parity)
             : "memory");
+#endif
     } while (!ok);
 }
 
