@@ -330,7 +330,7 @@ def main():
                      "ms_per_launch": ms_s / args.sustained_launches, "clocks": c2,
                      "note": "back-to-back launches right after the timed region: the kernel runs into the board power "
                              "limit (sw_power_cap), the SM clock drops and the issue-limited kernel with it"}
-        time.sleep(0.5)  # let the clocks recover before the other kernels are timed
+        time.sleep(1.0)  # let the clocks recover before the other kernels are timed
 
     lon_keep, lat_keep = lon[:1 << 20].clone(), lat[:1 << 20].clone()
     # parity sample of THIS rank's shard: the first 2^24 elements + every 1024th after them
