@@ -351,8 +351,18 @@ HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, cons
     const unsigned guard = (unsigned)((((uint32_t)x1 + f.margin) & f.mask_hi) == 0u) | (unsigned)((((uint32_t)x2 + f.margin) & f.mask_hi) == 0u);
     const uint32_t j1 = (uint32_t)(x1 >> f.fbits), j2 = (uint32_t)(x2 >> f.fbits);
 #endif
-    const uint32_t nsm1 = (uint32_t)g.nside - 1u;
     const uint32_t ifp = j1 >> f.ord, ifm = j2 >> f.ord;
+    if (NEST && flut) {
+        // j1, j2 ARE the edge-line coordinates jp, jm of ring_to_nest's belt pass (hpgb_reorder.h, "folded coordinates"):
+        // the 16-entry table indexed by (ifp, ifm) supplies the two constants of X = jm + lx, Y = ly - jp, whose Morton
+        // interleave is the pixel number with the face bits already in place -- one load and two adds instead of the face
+        // selection, the two masks and the face shift-add.  The index is masked: an untrusted point (guard set, result
+        // discarded) may carry any j1, j2 and must not read outside the table.
+        const hpgb_u32x2 fl = flut[(2u * ifp + ifm + 1u) & 15u];
+        pix = (int64_t)hpgb_interleave(j2 + fl.x, fl.y - j1);
+        return guard;
+    }
+    const uint32_t nsm1 = (uint32_t)g.nside - 1u;
     const uint32_t face = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
     const uint32_t ix = j2 & nsm1;
     const uint32_t iy = ~j1 & nsm1;  // nside - 1 - (j1 mod nside)
@@ -381,7 +391,7 @@ HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, cons
 // bit 51 and falls off the 32-bit result of the shift.  ntt * nside is added to both integer parts afterwards.
 template <bool NEST, bool HI>
 HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, uint32_t ntt, double tq,
-                                bool eq, double v, double hemi, int64_t &pix) {
+                                bool eq, double v, double hemi, int64_t &pix, const hpgb_u32x2 *flut = nullptr) {
     const double W = eq ? f.ns_s : v;
     const double S = fma(tq, W, f.ns_s_magic);
     const double Dp = hpgb_copysign_xor(fma(0.5, v, -f.ns_s), hemi);  // +-(w/2 - nside)
@@ -392,8 +402,18 @@ HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, cons
     const unsigned guard = (unsigned)(((l1 + f.margin) & 0xFFFFFu) < f.margin2) | (unsigned)(((l2 + f.margin) & 0xFFFFFu) < f.margin2);
     const uint32_t turn = ntt << f.ord;  // ntt * nside
     const uint32_t j1 = hpgb_funnel_r(l1, hpgb_hi32(r1), 20) + turn, j2 = hpgb_funnel_r(l2, hpgb_hi32(r2), 20) + turn;
-    const uint32_t nsm1 = (uint32_t)g.nside - 1u;
     const uint32_t ifp = j1 >> f.ord, ifm = j2 >> f.ord;
+    if (NEST && flut) {
+        // j1, j2 ARE the edge-line coordinates jp, jm of ring_to_nest's belt pass (hpgb_reorder.h, "folded coordinates"):
+        // the 16-entry table indexed by (ifp, ifm) supplies the two constants of X = jm + lx, Y = ly - jp, whose Morton
+        // interleave is the pixel number with the face bits already in place -- one load and two adds instead of the face
+        // selection, the two masks and the face shift-add.  The index is masked: an untrusted point (guard set, result
+        // discarded) may carry any j1, j2 and must not read outside the table.
+        const hpgb_u32x2 fl = flut[(2u * ifp + ifm + 1u) & 15u];
+        pix = (int64_t)hpgb_interleave(j2 + fl.x, fl.y - j1);
+        return guard;
+    }
+    const uint32_t nsm1 = (uint32_t)g.nside - 1u;
     const uint32_t face = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
     const uint32_t ix = j2 & nsm1;
     const uint32_t iy = ~j1 & nsm1;  // nside - 1 - (j1 mod nside)
@@ -464,7 +484,7 @@ HPGB_HD uint32_t hpgb_angle_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_f
 #define HPGB_RND_MAGIC 6755399441055744.0
 template <bool NEST, bool LONLAT, bool DEGREES, bool HI>
 HPGB_HD uint32_t hpgb_angle_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, double a,
-                                            double b, int64_t &pix) {
+                                            double b, int64_t &pix, const hpgb_u32x2 *flut = nullptr) {
     // ---- latitude (radians, signed), half colatitude from the nearest pole, tt - 1/2 ----
     double lat, hcth, u;
     unsigned guard;
@@ -492,7 +512,7 @@ HPGB_HD uint32_t hpgb_angle_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_f
     // ---- one sine for both zones: z = sin(lat) (equatorial), w = sqrt(6) nside sin(colat / 2) (polar) ----
     const double s = hpgb_sin_poly(f, eq ? lat : hcth);
     const double v = (eq ? f.ns_075_s : f.ns_sqrt6_s) * s;  // (3/4) nside z   or   w
-    guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, ntt, tq, eq, v, lat, pix);
+    guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, ntt, tq, eq, v, lat, pix, flut);
     return guard | (f.enabled ^ 1u);
 }
 #endif
@@ -544,7 +564,7 @@ HPGB_HD double hpgb_rcp_rough(double x) {  // ~2^-20 relative: only used to pick
 
 template <bool NEST, bool HI>
 HPGB_HD uint32_t hpgb_vector_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, const double *T,
-                                             double x, double y, double z, int64_t &pix) {
+                                             double x, double y, double z, int64_t &pix, const hpgb_u32x2 *flut = nullptr) {
     const double r2 = fma(y, y, x * x);
     const double len2 = fma(z, z, r2);
     // squares must stay normal numbers; |x| = |y| = 0 (phi = 0 by convention) goes to the exact path
@@ -598,7 +618,7 @@ HPGB_HD uint32_t hpgb_vector_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_
     const double nttd = ys ? 3.0 - xn : xn;
     guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, nttd, tq, e, v, nz, pix);
 #else
-    guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, ys ? 3u - xs : xs, tq, eq, v, nz, pix);
+    guard |= hpgb_sd_to_pix<NEST, HI>(g, f, rk, ys ? 3u - xs : xs, tq, eq, v, nz, pix, flut);
 #endif
     return guard | (f.enabled ^ 1u);
 }

@@ -54,9 +54,27 @@ struct OpAng2Pix {
     struct In2 {
         double2 a, b;
     };
-    typedef const double *Ctx;
-
-    __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
+    // per-CTA context: the sin / cos table of the exact path, and (NEST, scalar nside) the 16-entry table that folds the
+    // face into the edge-line coordinates (hpgb_sd_to_pix, hpgb_reorder.h "folded coordinates")
+    struct Ctx {
+        const double *T;
+        const hpgb_u32x2 *flut;
+    };
+    static constexpr bool FOLD = NEST && !VAR;
+    __device__ __forceinline__ Ctx prologue() const {
+        __shared__ hpgb_u32x2 s_flut[16];
+        if (FOLD && threadIdx.x < 16) {
+            hpgb_u32x2 e;
+            hpgb_r2n_lut_entry(rk, threadIdx.x, e.x, e.y);
+            s_flut[threadIdx.x] = e;
+        }
+        const double *T = hpgb_stage_table();  // ends with __syncthreads(): the table above is visible too
+#if defined(HPGB_A2P_NO_FOLD)
+        return Ctx{T, nullptr};
+#else
+        return Ctx{T, FOLD ? s_flut : nullptr};
+#endif
+    }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(a + i), hpgb_ld2(b + i)}; }
     static constexpr int NIN = 2;
     static constexpr bool TILE_HOOK = false;
@@ -71,13 +89,13 @@ struct OpAng2Pix {
     __device__ __forceinline__ int64_t slow(const hpgb_geom &gg, double va, double vb, int64_t i, Ctx T,
                                             hpgb_bad_t &bad) const {
         int64_t pix;
-        if (!hpgb_angle_to_pixel_exact<NEST, LONLAT, DEGREES>(gg, T, va, vb, pix)) bad.flag(base + i);
+        if (!hpgb_angle_to_pixel_exact<NEST, LONLAT, DEGREES>(gg, T.T, va, vb, pix)) bad.flag(base + i);
         return pix;
     }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &bad) const {
         int64_t p0 = 0, p1 = 0;  // both fast paths first (independent -> the fp64 chains interleave), exact path after
-        const uint32_t g0 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v.a.x, v.b.x, p0);
-        const uint32_t g1 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v.a.y, v.b.y, p1);
+        const uint32_t g0 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v.a.x, v.b.x, p0, T.flut);
+        const uint32_t g1 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v.a.y, v.b.y, p1, T.flut);
         if (g0) p0 = slow(g, v.a.x, v.b.x, i, T, bad);
         if (g1) p1 = slow(g, v.a.y, v.b.y, i + 1, T, bad);
         hpgb_st2(out + i, p0, p1);
@@ -118,10 +136,10 @@ struct OpAng2Pix {
     __device__ __forceinline__ void run4u(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
                                          hpgb_bad_t &bad) const {
         int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-        const uint32_t g0 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.x, v0.b.x, p0);
-        const uint32_t g1 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.y, v0.b.y, p1);
-        const uint32_t g2 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.x, v1.b.x, p2);
-        const uint32_t g3 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.y, v1.b.y, p3);
+        const uint32_t g0 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.x, v0.b.x, p0, T.flut);
+        const uint32_t g1 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.y, v0.b.y, p1, T.flut);
+        const uint32_t g2 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.x, v1.b.x, p2, T.flut);
+        const uint32_t g3 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.y, v1.b.y, p3, T.flut);
         hpgb_st2(out + i0, p0, p1);
         hpgb_st2(out + i1, p2, p3);
         if (__any_sync(0xFFFFFFFFu, (g0 | g1 | g2 | g3) != 0u)) {  // warp-uniform, 2.5 % of the iterations
@@ -144,10 +162,10 @@ struct OpAng2Pix {
                                          hpgb_bad_t &bad) const {
         int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
         // guard words: 0 = the fast result can be trusted
-        const uint32_t g0 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.x, v0.b.x, p0);
-        const uint32_t g1 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.y, v0.b.y, p1);
-        const uint32_t g2 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.x, v1.b.x, p2);
-        const uint32_t g3 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.y, v1.b.y, p3);
+        const uint32_t g0 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.x, v0.b.x, p0, T.flut);
+        const uint32_t g1 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v0.a.y, v0.b.y, p1, T.flut);
+        const uint32_t g2 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.x, v1.b.x, p2, T.flut);
+        const uint32_t g3 = hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(g, f, rk, v1.a.y, v1.b.y, p3, T.flut);
         if ((g0 | g1 | g2 | g3) != 0u) {
             if (g0) p0 = slow(g, v0.a.x, v0.b.x, i0, T, bad);
             if (g1) p1 = slow(g, v0.a.y, v0.b.y, i0 + 1, T, bad);
@@ -170,7 +188,7 @@ struct OpAng2Pix {
         }
         const double va = hpgb_ld1(a + i), vb = hpgb_ld1(b + i);
         int64_t pix;
-        if (VAR || hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(gg, ff, rk, va, vb, pix) != 0u) pix = slow(gg, va, vb, i, T, bad);
+        if (VAR || hpgb_angle_to_pixel_fast_g<NEST, LONLAT, DEGREES, HI>(gg, ff, rk, va, vb, pix, T.flut) != 0u) pix = slow(gg, va, vb, i, T, bad);
         hpgb_st1(out + i, pix);
     }
 };

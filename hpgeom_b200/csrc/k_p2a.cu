@@ -461,17 +461,36 @@ struct OpVec2Pix {
     struct In2 {
         double2 x, y, z;
     };
-    typedef const double *Ctx;
+    // per-CTA context: the sin / cos + atan rows, and (NEST, scalar nside) the 16-entry table of the folded face
+    // (hpgb_sd_to_pix, hpgb_reorder.h "folded coordinates")
+    struct Ctx {
+        const double *T;
+        const hpgb_u32x2 *flut;
+    };
+    static constexpr bool FOLD = NEST && !VAR;
     HPGB_STREAM_IN_F64x3(x, y, z, HPGB_V2P_MINB)
-    __device__ __forceinline__ Ctx prologue() const { return hpgb_stage_table(); }
+    __device__ __forceinline__ Ctx prologue() const {
+        __shared__ hpgb_u32x2 s_flut[16];
+        if (FOLD && threadIdx.x < 16) {
+            hpgb_u32x2 e;
+            hpgb_r2n_lut_entry(rk, threadIdx.x, e.x, e.y);
+            s_flut[threadIdx.x] = e;
+        }
+        const double *T = hpgb_stage_table();  // ends with __syncthreads(): the table above is visible too
+#if defined(HPGB_A2P_NO_FOLD)
+        return Ctx{T, nullptr};
+#else
+        return Ctx{T, FOLD ? s_flut : nullptr};
+#endif
+    }
     __device__ __forceinline__ In2 load2(int64_t i) const { return In2{hpgb_ld2(x + i), hpgb_ld2(y + i), hpgb_ld2(z + i)}; }
     static __device__ __noinline__ int64_t slow(const hpgb_geom &gg, Ctx T, double vx, double vy, double vz) {
-        return hpgb_vec2pix<NEST>(gg, T, vx, vy, vz);
+        return hpgb_vec2pix<NEST>(gg, T.T, vx, vy, vz);
     }
     __device__ __forceinline__ void run2(int64_t i, const In2 &v, const Ctx &T, hpgb_bad_t &) const {
         int64_t p0 = 0, p1 = 0;
-        const uint32_t g0 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v.x.x, v.y.x, v.z.x, p0);
-        const uint32_t g1 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v.x.y, v.y.y, v.z.y, p1);
+        const uint32_t g0 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T.T, v.x.x, v.y.x, v.z.x, p0, T.flut);
+        const uint32_t g1 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T.T, v.x.y, v.y.y, v.z.y, p1, T.flut);
         if ((g0 | g1) != 0u) {
             if (g0) p0 = slow(g, T, v.x.x, v.y.x, v.z.x);
             if (g1) p1 = slow(g, T, v.x.y, v.y.y, v.z.y);
@@ -481,10 +500,10 @@ struct OpVec2Pix {
     __device__ __forceinline__ void run4(int64_t i0, const In2 &v0, int64_t i1, const In2 &v1, const Ctx &T,
                                          hpgb_bad_t &) const {
         int64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-        const uint32_t g0 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v0.x.x, v0.y.x, v0.z.x, p0);
-        const uint32_t g1 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v0.x.y, v0.y.y, v0.z.y, p1);
-        const uint32_t g2 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v1.x.x, v1.y.x, v1.z.x, p2);
-        const uint32_t g3 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T, v1.x.y, v1.y.y, v1.z.y, p3);
+        const uint32_t g0 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T.T, v0.x.x, v0.y.x, v0.z.x, p0, T.flut);
+        const uint32_t g1 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T.T, v0.x.y, v0.y.y, v0.z.y, p1, T.flut);
+        const uint32_t g2 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T.T, v1.x.x, v1.y.x, v1.z.x, p2, T.flut);
+        const uint32_t g3 = hpgb_vector_to_pixel_fast_g<NEST, HI>(g, f, rk, T.T, v1.x.y, v1.y.y, v1.z.y, p3, T.flut);
         if ((g0 | g1 | g2 | g3) != 0u) {
             if (g0) p0 = slow(g, T, v0.x.x, v0.y.x, v0.z.x);
             if (g1) p1 = slow(g, T, v0.x.y, v0.y.y, v0.z.y);
@@ -503,7 +522,7 @@ struct OpVec2Pix {
         }
         const double vx = hpgb_ld1(x + i), vy = hpgb_ld1(y + i), vz = hpgb_ld1(z + i);
         int64_t pix = 0;
-        if (VAR || hpgb_vector_to_pixel_fast_g<NEST, HI>(gg, f, rk, T, vx, vy, vz, pix) != 0u) pix = slow(gg, T, vx, vy, vz);
+        if (VAR || hpgb_vector_to_pixel_fast_g<NEST, HI>(gg, f, rk, T.T, vx, vy, vz, pix, T.flut) != 0u) pix = slow(gg, T, vx, vy, vz);
         hpgb_st1(out + i, pix);
     }
 };

@@ -141,6 +141,8 @@ class HostSim:
         self.last_slow = self.lib.sim_vector_to_pixel(ctypes.c_int64(nside), x.ctypes.data_as(_D), y.ctypes.data_as(_D),
                                                       z.ctypes.data_as(_D), ctypes.c_int64(x.size), int(nest),
                                                       int(exact_only), out.ctypes.data_as(_I))
+        if self.last_slow < 0:
+            raise ValueError("folded-face and direct-face fast paths disagree at element %d" % (-self.last_slow - 4000000000000))
         return out
 
     def neighbors(self, nside, pix, nest=True):
