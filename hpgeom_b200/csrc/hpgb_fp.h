@@ -389,6 +389,19 @@ HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, cons
 // S +- D lands in [2^52, 2^53), where one ulp is one fixed-point unit: the sum's mantissa IS the coordinate (20
 // fraction bits, rounded to nearest), its integer part one funnel shift away -- the exponent field sits above
 // bit 51 and falls off the 32-bit result of the shift.  ntt * nside is added to both integer parts afterwards.
+// entry e = 8 ntt + i of the 32-entry folded-face table of the NEST fast paths (see hpgb_sd_to_pix): i = 2 (jf1 >> k) +
+// (jf2 >> k) + 1 with the coordinates taken WITHOUT their quarter turn (jf1 >> k in {0, 1}, jf2 >> k - jf1 >> k in {-1, 0, 1}:
+// i = 1 .. 5); the entry is ring_to_nest's (lx, ly) for (jp >> k, jm >> k) = (jf1 >> k + ntt, jf2 >> k + ntt) with the turn
+// ntt nside added to lx and taken from ly
+HPGB_HD void hpgb_a2p_fold_entry(const hpgb_rk &c, uint32_t e, uint32_t &x, uint32_t &y) {
+    const uint32_t t = e >> 3, i = e & 7u;
+    x = y = 0u;
+    if (i < 1u || i > 5u) return;
+    uint32_t lx, ly;
+    hpgb_r2n_lut_entry(c, i + 3u * t, lx, ly);
+    x = lx + (t << c.k);
+    y = ly - (t << c.k);
+}
 template <bool NEST, bool HI>
 HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, const hpgb_rk &rk, uint32_t ntt, double tq,
                                 bool eq, double v, double hemi, int64_t &pix, const hpgb_u32x2 *flut = nullptr) {
@@ -400,19 +413,22 @@ HPGB_HD unsigned hpgb_sd_to_pix(const hpgb_geom &g, const hpgb_a2p_fast &f, cons
     const uint32_t l1 = hpgb_lo32(r1), l2 = hpgb_lo32(r2);
     // within `margin` units of an integer?
     const unsigned guard = (unsigned)(((l1 + f.margin) & 0xFFFFFu) < f.margin2) | (unsigned)(((l2 + f.margin) & 0xFFFFFu) < f.margin2);
-    const uint32_t turn = ntt << f.ord;  // ntt * nside
-    const uint32_t j1 = hpgb_funnel_r(l1, hpgb_hi32(r1), 20) + turn, j2 = hpgb_funnel_r(l2, hpgb_hi32(r2), 20) + turn;
-    const uint32_t ifp = j1 >> f.ord, ifm = j2 >> f.ord;
+    const uint32_t jf1 = hpgb_funnel_r(l1, hpgb_hi32(r1), 20), jf2 = hpgb_funnel_r(l2, hpgb_hi32(r2), 20);
     if (NEST && flut) {
-        // j1, j2 ARE the edge-line coordinates jp, jm of ring_to_nest's belt pass (hpgb_reorder.h, "folded coordinates"):
-        // the 16-entry table indexed by (ifp, ifm) supplies the two constants of X = jm + lx, Y = ly - jp, whose Morton
-        // interleave is the pixel number with the face bits already in place -- one load and two adds instead of the face
-        // selection, the two masks and the face shift-add.  The index is masked: an untrusted point (guard set, result
-        // discarded) may carry any j1, j2 and must not read outside the table.
-        const hpgb_u32x2 fl = flut[(2u * ifp + ifm + 1u) & 15u];
-        pix = (int64_t)hpgb_interleave(j2 + fl.x, fl.y - j1);
+        // jf1 + ntt nside, jf2 + ntt nside ARE the edge-line coordinates jp, jm of ring_to_nest's belt pass (hpgb_reorder.h,
+        // "folded coordinates"): a table indexed by (jp >> k, jm >> k) supplies the two constants of X = jm + lx,
+        // Y = ly - jp, whose Morton interleave is the pixel number with the face bits already in place -- one load and two
+        // adds instead of the face selection, the two masks and the face shift-add.  The quarter turn rides in the table
+        // as well (hpgb_a2p_fold_entry: 4 x 8 entries, lx + ntt nside, ly - ntt nside), so it is never added to the
+        // coordinates, and the index is masked instead of ntt: an untrusted point (guard set, result discarded) may carry
+        // any coordinates and must not read outside the table.
+        const hpgb_u32x2 fl = flut[(8u * ntt + 2u * (jf1 >> f.ord) + (jf2 >> f.ord) + 1u) & 31u];
+        pix = (int64_t)hpgb_interleave(jf2 + fl.x, fl.y - jf1);
         return guard;
     }
+    const uint32_t turn = (ntt & 3u) << f.ord;  // ntt * nside
+    const uint32_t j1 = jf1 + turn, j2 = jf2 + turn;
+    const uint32_t ifp = j1 >> f.ord, ifm = j2 >> f.ord;
     const uint32_t nsm1 = (uint32_t)g.nside - 1u;
     const uint32_t face = hpgb_sel(ifp == ifm, ifp | 4u, hpgb_sel(ifp < ifm, ifp, ifm + 8u));
     const uint32_t ix = j2 & nsm1;
@@ -507,7 +523,7 @@ HPGB_HD uint32_t hpgb_angle_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_f
     // read off the sum's low word, so a negative or wrapped longitude needs nothing extra: ntt = floor(tt) mod 4.
     const double r = u + HPGB_RND_MAGIC;
     const double tq = u - (r - HPGB_RND_MAGIC);  // frac(tt) - 1/2, exact
-    const uint32_t ntt = hpgb_lo32(r) & 3u;
+    const uint32_t ntt = hpgb_lo32(r);  // floor(tt) modulo 2^32: hpgb_sd_to_pix takes it modulo 4
     guard |= (unsigned)!(fabs(tq) < 0.5 - 3.8146972656250000e-06);  // tt within 2^-18 of an integer
     // ---- one sine for both zones: z = sin(lat) (equatorial), w = sqrt(6) nside sin(colat / 2) (polar) ----
     const double s = hpgb_sin_poly(f, eq ? lat : hcth);

@@ -54,7 +54,7 @@ struct OpAng2Pix {
     struct In2 {
         double2 a, b;
     };
-    // per-CTA context: the sin / cos table of the exact path, and (NEST, scalar nside) the 16-entry table that folds the
+    // per-CTA context: the sin / cos table of the exact path, and (NEST, scalar nside) the 32-entry table that folds the
     // face into the edge-line coordinates (hpgb_sd_to_pix, hpgb_reorder.h "folded coordinates")
     struct Ctx {
         const double *T;
@@ -62,10 +62,10 @@ struct OpAng2Pix {
     };
     static constexpr bool FOLD = NEST && !VAR;
     __device__ __forceinline__ Ctx prologue() const {
-        __shared__ hpgb_u32x2 s_flut[16];
-        if (FOLD && threadIdx.x < 16) {
+        __shared__ hpgb_u32x2 s_flut[32];
+        if (FOLD && threadIdx.x < 32) {
             hpgb_u32x2 e;
-            hpgb_r2n_lut_entry(rk, threadIdx.x, e.x, e.y);
+            hpgb_a2p_fold_entry(rk, threadIdx.x, e.x, e.y);
             s_flut[threadIdx.x] = e;
         }
         const double *T = hpgb_stage_table();  // ends with __syncthreads(): the table above is visible too

@@ -461,7 +461,7 @@ struct OpVec2Pix {
     struct In2 {
         double2 x, y, z;
     };
-    // per-CTA context: the sin / cos + atan rows, and (NEST, scalar nside) the 16-entry table of the folded face
+    // per-CTA context: the sin / cos + atan rows, and (NEST, scalar nside) the 32-entry table of the folded face
     // (hpgb_sd_to_pix, hpgb_reorder.h "folded coordinates")
     struct Ctx {
         const double *T;
@@ -470,10 +470,10 @@ struct OpVec2Pix {
     static constexpr bool FOLD = NEST && !VAR;
     HPGB_STREAM_IN_F64x3(x, y, z, HPGB_V2P_MINB)
     __device__ __forceinline__ Ctx prologue() const {
-        __shared__ hpgb_u32x2 s_flut[16];
-        if (FOLD && threadIdx.x < 16) {
+        __shared__ hpgb_u32x2 s_flut[32];
+        if (FOLD && threadIdx.x < 32) {
             hpgb_u32x2 e;
-            hpgb_r2n_lut_entry(rk, threadIdx.x, e.x, e.y);
+            hpgb_a2p_fold_entry(rk, threadIdx.x, e.x, e.y);
             s_flut[threadIdx.x] = e;
         }
         const double *T = hpgb_stage_table();  // ends with __syncthreads(): the table above is visible too
