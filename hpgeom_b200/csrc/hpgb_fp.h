@@ -269,6 +269,7 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
     f.ns_075_s = 0.75 * dns * scale;
     f.ns_sqrt6_s = 2.4494897427831780981972840747059 * dns * scale;
     f.d_ns_m = f.ns_075_s - f.ns_sqrt6_s;
+#if defined(HPGB_SIN_TAYLOR15)
     f.c3 = -1.6666666666666666667e-1;
     f.c5 = 8.3333333333333333333e-3;
     f.c7 = -1.9841269841269841270e-4;
@@ -276,6 +277,17 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
     f.c11 = -2.5052108385441718775e-8;
     f.c13 = 1.6059043836821614599e-10;
     f.c15 = -7.6471637318198164759e-13;
+#else
+    // degree 13, interpolated at the Chebyshev nodes of a^2 in [0, 0.74^2] (mpmath, 200 bits): max relative error
+    // 2^-57.3 over |a| <= 0.74 -- what the Taylor coefficients need degree 15 for; one DFMA (two issue cycles) less
+    f.c3 = -0x1.5555555555555p-3;
+    f.c5 = 0x1.1111111110e1bp-7;
+    f.c7 = -0x1.a01a019f1d752p-13;
+    f.c9 = 0x1.71de3869568b0p-19;
+    f.c11 = -0x1.ae60f378ed40dp-26;
+    f.c13 = 0x1.5e63d28acf0d3p-33;
+    f.c15 = 0.0;
+#endif
     if (LONLAT && DEGREES) {
         f.k_lat = 1.7453292519943295769e-2;   // pi/180
         f.k_hcth = 8.7266462599716478846e-3;  // pi/360
@@ -307,8 +319,12 @@ HPGB_HD hpgb_a2p_fast hpgb_make_a2p_fast(const hpgb_geom &g) {
 
 HPGB_HD double hpgb_sin_poly(const hpgb_a2p_fast &f, double a) {  // |a| <= 0.74, error < 1 ulp
     const double a2 = a * a;
+#if defined(HPGB_SIN_TAYLOR15)
     double p = fma(a2, f.c15, f.c13);
     p = fma(p, a2, f.c11);
+#else
+    double p = fma(a2, f.c13, f.c11);
+#endif
     p = fma(p, a2, f.c9);
     p = fma(p, a2, f.c7);
     p = fma(p, a2, f.c5);
@@ -515,9 +531,13 @@ HPGB_HD uint32_t hpgb_angle_to_pixel_fast_g(const hpgb_geom &g, const hpgb_a2p_f
         u = fma(b, f.k_lon, -0.5);
         guard = (unsigned)!(a > 0.0102) | (unsigned)!(a < 3.1313) | (unsigned)!(b >= 0.0) | (unsigned)!(b < 6.2831853);
     }
-    const double al = fabs(lat);
-    const bool eq = al <= f.asin23;
-    guard |= (unsigned)(fabs(al - f.asin23) < 1e-11);
+    // equatorial / polar split on the HIGH WORD of |lat| (one LOP3 + two 32-bit compares instead of two fp64 compares
+    // and a subtraction, each of which costs two issue cycles): every latitude whose high word is that of asin(2/3) or
+    // one of its two neighbours -- within 2^-20 relative of the split, 1.5e-6 of the sphere -- goes to the exact path,
+    // and outside that band the high words alone order |lat| and asin(2/3) correctly
+    const uint32_t alh = hpgb_hi32(lat) & 0x7FFFFFFFu, a23h = hpgb_hi32(f.asin23);
+    const bool eq = alh < a23h;
+    guard |= (unsigned)(alh - (a23h - 1u) < 3u);
     // floor(tt) = RN(tt - 1/2) unless tt is (nearly) an integer -- and then the point is on a face edge / the wrap
     // and goes to the exact path anyway (|tq| guard).  The rounding is one addition of 1.5 * 2^52; the integer is
     // read off the sum's low word, so a negative or wrapped longitude needs nothing extra: ntt = floor(tt) mod 4.
